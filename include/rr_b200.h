@@ -1,0 +1,203 @@
+/*
+ * rr_b200.h -- C ABI of librr_b200.so, the B200 (sm_100a) replacement for the routing hot
+ * path of rileyhales/river-route.  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference repository root).  All functions return 0 on success, non-zero on failure;
+ * rr_last_error() returns a thread-local description of the last failure.
+ *
+ * Conventions
+ *   - fp64 arithmetic everywhere; index arrays are int32 (scipy's run-time dtype for the
+ *     reference's CSC arrays), reach counts are int64.
+ *   - 2-D arrays are time-major with an explicit leading dimension in ELEMENTS:
+ *     a[t * ld + reach], exactly the reference's C-contiguous (T, n) layout when ld == n.
+ *   - "host" entry points take host pointers (pageable or pinned) and stream chunks of
+ *     time steps through pinned double buffers; "dev" entry points take device pointers
+ *     (e.g. torch.Tensor.data_ptr()) and a cudaStream_t passed as void*.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef RR_B200_H
+#define RR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rr_plan rr_plan;
+
+/* Router variants (the three numba kernels of river_route/routers/_numba_kernels.py). */
+enum {
+    RR_MODE_MUSKINGUM = 0, /* muskingum_route, _numba_kernels.py:9-46   */
+    RR_MODE_RAPID     = 1, /* rapid_route,     _numba_kernels.py:49-84  */
+    RR_MODE_UNIT      = 2  /* unit_route,      _numba_kernels.py:88-171 */
+};
+
+/* Tunables of the wavefront solve; zero / negative fields mean "choose for me". */
+typedef struct rr_plan_opts {
+    int32_t time_tile;      /* runoff/output rows advanced per work item (default 32)        */
+    int32_t tile_stride;    /* ticket-key distance between consecutive tiles of one block;
+                               0 = smallest power of two whose exchange rings fit the budget */
+    int32_t device;         /* CUDA device ordinal (default: current device)                 */
+    int32_t threads_per_cta;/* persistent CTA size, multiple of 32 (default 256)             */
+    int64_t raw_budget_bytes;/* cap for the exchange buffer (default 16 GiB)                 */
+} rr_plan_opts;
+
+/* Host-visible description of a built plan (for tests, DESIGN.md numbers and bench.py). */
+typedef struct rr_plan_info {
+    int64_t n;               /* reaches                                                     */
+    int64_t n_edges;         /* reaches with a downstream reach                              */
+    int64_t n_blocks;        /* 32-reach blocks                                              */
+    int64_t n_export;        /* reaches whose downstream lives in another block              */
+    int64_t n_internal_edges;/* edges served by in-warp shuffles                             */
+    int32_t max_skew;        /* largest in-block systolic delay                              */
+    int32_t max_indegree;    /* largest number of upstream reaches of one reach              */
+    int32_t max_block_level; /* depth of the block dependency DAG                            */
+    int32_t n_outlets_lo;    /* number of outlets (low 32 bits)                              */
+    int64_t n_dep_edges;     /* distinct (block -> upstream block) dependencies              */
+    int64_t device_bytes;    /* bytes of plan-owned device memory (after first upload)       */
+} rr_plan_info;
+
+const char *rr_last_error(void);
+int  rr_version(void);
+/* 1 when a CUDA device is usable from this process, else 0 (never falls back to CPU). */
+int  rr_cuda_available(void);
+
+/* ---- topology --------------------------------------------------------------------------
+ * Replaces river_route.tools.adjacency_matrix (tools.py:75-109) and the pre-checks of
+ * Muskingum._set_network_dependent_vectors (routers/Muskingum.py:153-167).
+ * Writes down_idx[i] = index of the reach downstream of i, or -1 for outlets
+ * (downstream_id < 0, tools.py:98-99).  Status codes mirror the reference's ValueErrors:
+ *   1 duplicate river id (Muskingum.py:153-154)        -> *bad = the id
+ *   2 unknown downstream id (tools.py:101-102)         -> *bad = the id
+ *   3 not topologically sorted (tools.py:103-104)      -> *bad = the upstream index
+ * The first offending row in file order is reported, as the reference's loop does. */
+int rr_downstream_index(int64_t n, const int64_t *river_ids, const int64_t *downstream_ids,
+                        int32_t *down_idx, int64_t *bad);
+
+/* Basin (connected component) label of every reach = index of its terminal outlet, and
+ * optional LPT bin-packing of basins over n_parts devices by reach count
+ * (docs/references/parallelism.md:67-75 names watersheds as the unit of parallelism).
+ * basin[i] in [0, n_basins); part[i] in [0, n_parts) (part may be NULL). */
+int rr_label_basins(int64_t n, const int32_t *down_idx, int32_t *basin, int64_t *n_basins,
+                    int32_t n_parts, int32_t *part);
+
+/* ---- plan -------------------------------------------------------------------------------
+ * A plan owns everything derived from the network alone: the upstream-CSR in ascending
+ * upstream order, 32-reach blocks, in-block systolic delays, block dependency lists, the
+ * wavefront ticket order and (lazily) their device copies and the exchange buffer.
+ * It plays the role of the reference's cached CSC arrays
+ * (Muskingum._set_muskingum_coefficients, routers/Muskingum.py:187-193). Host only; needs
+ * no GPU until the first route call. */
+int  rr_plan_create(int64_t n, const int32_t *down_idx, const rr_plan_opts *opts, rr_plan **out);
+void rr_plan_destroy(rr_plan *p);
+int  rr_plan_get_info(const rr_plan *p, rr_plan_info *info);
+
+/* Coefficients c1,c2,c3 (Muskingum.py:176-179) and c4_dt = (c1+c2)/dt_runoff
+ * (TransformMuskingum.py:104, RapidMuskingum.py:25); host pointers, length n, computed by
+ * the caller with the reference's exact numpy expressions so they are bit-identical.
+ * c4_dt may be NULL for RR_MODE_MUSKINGUM / RR_MODE_UNIT. */
+int rr_plan_set_coefficients(rr_plan *p, const double *c1, const double *c2, const double *c3,
+                             const double *c4_dt);
+
+/* ---- routing ----------------------------------------------------------------------------
+ * One call == one call of the reference kernel:
+ *   RR_MODE_RAPID     rapid_route(csc..., c2, c3, c4_dt, q_t, qlateral, discharge_array,
+ *                                 num_substeps)                       _numba_kernels.py:50-55
+ *   RR_MODE_MUSKINGUM muskingum_route(csc..., c2, c3, q_t, discharge_array,
+ *                                 num_output_steps, num_routing_per_output)        :9-14
+ *                     (T = num_output_steps, substeps = num_routing_per_output, lateral NULL)
+ *   RR_MODE_UNIT      unit_route(...)                                              :89-99
+ *                     lateral = convolved lateral over ALL reaches; q_state = full-length
+ *                     channel state; headwater/inner split is derived inside the plan
+ *                     (UnitMuskingum._hook_before_route, routers/UnitMuskingum.py:39-46) and
+ *                     the returned state is the recombined vector of :94-98.
+ * q_state [n] is read as the initial state and overwritten with the final state (the
+ * reference mutates q_t in place).  out is [T][ldo] and fully overwritten.
+ * q_full is used by RR_MODE_UNIT only and may be NULL:
+ *   NULL      router-level semantics: q_ch = q_full = q_state on entry
+ *             (UnitMuskingum.py:78-79), q_state = recombined final vector on exit (:94-98);
+ *   non-NULL  kernel-level semantics of unit_route's q_ch / q_full argument pair, both
+ *             full length n: q_state is q_ch, q_full is q_full, both read and both updated
+ *             (entries of headwater reaches are ignored and left untouched).
+ * Device variant: all pointers are device pointers on the plan's device; the call is
+ * asynchronous on `stream`. */
+int rr_route_dev(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,
+                 int64_t ldl, double *out, int64_t ldo, int64_t T, int64_t substeps, void *stream);
+
+/* Host variant: host pointers; time is cut into chunks that are copied through pinned
+ * double buffers (cudaMemcpyAsync) overlapping H2D, compute and D2H.  Synchronous. */
+int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,
+                  int64_t ldl, double *out, int64_t ldo, int64_t T, int64_t substeps);
+
+/* Ensemble: n_members independent lateral arrays routed from the SAME initial state in one
+ * launch (TransformMuskingum._execute_routing 'ensemble' mode, TransformMuskingum.py:121-126).
+ * lateral[m], out[m], q_final[m] are device pointers per member; q_init [n] is shared. */
+int rr_route_ensemble_dev(rr_plan *p, int mode, const double *q_init, int32_t n_members,
+                          const double *const *lateral, int64_t ldl, double *const *out, int64_t ldo,
+                          double *const *q_final, int64_t T, int64_t substeps, void *stream);
+
+/* Kernel launches issued by this library on this thread since the last reset (bench.py's
+ * gpu_launches claim). */
+int64_t rr_launch_count(int reset);
+
+/* ---- unit hydrograph ----------------------------------------------------------------------
+ * Replaces UnitHydrograph.convolve (river_route/uhkernels/UnitHydrograph.py:77-107):
+ * out[t,b] = carry-in + sum_tau kernel[tau,b] * lateral[t-tau,b], accumulated oldest
+ * contribution first (the order of convolve_incrementally, :64-75); state [n_ks][lds] is
+ * updated in place with the tail that spills past T (:100-105).  Device pointers. */
+int rr_uh_convolve_dev(int64_t n, int64_t n_ks, int64_t T,
+                       const double *lateral, int64_t ldl, const double *kernel, int64_t ldk,
+                       double *state, int64_t lds, double *out, int64_t ldo, void *stream);
+int rr_uh_convolve_host(int64_t n, int64_t n_ks, int64_t T,
+                        const double *lateral, int64_t ldl, const double *kernel, int64_t ldk,
+                        double *state, int64_t lds, double *out, int64_t ldo);
+
+/* ---- grid weights -------------------------------------------------------------------------
+ * Replaces the SpMM core and in-place tail of runoff_to_qlateral (river_route/runoff.py:292-337):
+ * y[t,r] = sum_j w[j] * x[t, col[j]] over CSR row r in stored order, then
+ * cumulative->incremental, optional clip at 0, NaN->0, optional multiply by area[r].
+ * x is the gathered grid runoff [T][ldx], float32 (x_is_f32 != 0) or float64; the product
+ * is formed in fp64 as the reference's scipy call does.  Device pointers. */
+int rr_weights_transform_dev(int64_t n_rivers, int64_t T, const int32_t *indptr,
+                             const int32_t *indices, const double *w, const void *x, int x_is_f32,
+                             int64_t ldx, double *y, int64_t ldy, int cumulative, int force_positive,
+                             const double *area, void *stream);
+int rr_weights_transform_host(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr,
+                              const int32_t *indices, const double *w, const void *x, int x_is_f32,
+                              int64_t ldx, double *y, int64_t ldy, int cumulative, int force_positive,
+                              const double *area);
+
+/* ---- pinned host memory for the streaming path ---------------------------------------------- */
+int rr_host_alloc(void **ptr, int64_t bytes);
+int rr_host_free(void *ptr);
+
+/* ---- synthetic networks (used by tests and bench.py) -------------------
+ * Forest grown upstream from outlets; final index = reverse growth order, so down[i] > i.
+ * basin sizes ~ lognormal(sigma) normalised to n.  main_stem > 0 pre-seeds a chain of that
+ * length in the first basin.  Deterministic for a given seed on every platform. */
+int rr_synth_forest(int64_t n, int64_t n_basins, uint64_t seed, double depth_bias,
+                    int64_t main_stem, double sigma, int32_t *down_idx);
+
+/* ---- plan introspection for tests (host copies; pointers valid until rr_plan_destroy) -------- */
+int rr_plan_get_arrays(const rr_plan *p,
+                       const int32_t **up_ptr,   /* [n+1]   upstream-CSR row pointers            */
+                       const int32_t **up_idx,   /* [edges] upstream reach indices, ascending    */
+                       const uint8_t **skew,     /* [n]     in-block systolic delay              */
+                       const int32_t **slot_src, /* [edges] >=0 export id of an external upstream,
+                                                            <0: -(lane+1) of an in-block upstream */
+                       const int32_t **export_id,/* [n]     compact id in the exchange buffer or -1 */
+                       const int32_t **blk_level,/* [n_blocks] level in the block DAG            */
+                       const int32_t **dep_ptr,  /* [n_blocks+1]                                 */
+                       const int32_t **dep_idx,  /* distinct upstream blocks                     */
+                       const int32_t **exp_span  /* [n_export] block-level distance producer -> consumer */);
+/* Ticket -> (block, tile) decode used by the kernel, for schedule-validity tests. */
+int rr_plan_schedule(const rr_plan *p, int64_t n_tiles, int32_t tile_stride, int64_t *n_items,
+                     int32_t *item_block /* [n_blocks*n_tiles] or NULL */,
+                     int32_t *item_tile  /* same */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RR_B200_H */

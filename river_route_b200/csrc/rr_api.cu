@@ -1,0 +1,362 @@
+// rr_api.cu -- C-ABI entry points that touch the GPU: plan upload, route launches (device and
+// host-streaming variants), ensembles, pinned host memory.  Interfaces are documented in
+// include/rr_b200.h together with the reference functions they replace.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rr_route.cuh"
+
+cudaError_t rr_launch_wavefront(int mode, const rr_route_params &P, int grid, int block, cudaStream_t stream);
+int rr_wavefront_occupancy(int mode, int block);
+
+static thread_local int64_t g_launches = 0;
+extern "C" int64_t rr_launch_count(int reset) {
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+void rr_count_launch(int64_t k) { g_launches += k; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            rr_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+            return 200;                                                                            \
+        }                                                                                          \
+    } while (0)
+
+extern "C" int rr_cuda_available(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n > 0 ? 1 : 0;
+}
+
+struct rr_device_state {
+    int device = 0, sm_count = 0;
+    // plan arrays
+    int32_t *up_ptr = nullptr, *up_idx = nullptr, *slot_src = nullptr, *export_id = nullptr;
+    int32_t *dep_ptr = nullptr, *dep_idx = nullptr, *down = nullptr, *exp_off = nullptr, *exp_ring = nullptr;
+    int32_t *lvl_ptr = nullptr, *lvl_blk = nullptr;
+    uint8_t *skew = nullptr;
+    rr_blk_meta *meta = nullptr;
+    double *coef = nullptr;  // c1|c2|c3|c4, each n
+    uint64_t coeff_version = 0;
+    // launch scratch
+    int64_t *key_start = nullptr;
+    size_t key_cap = 0;
+    int64_t sched_tiles = -1, sched_budget_rows = -1;
+    rr_schedule sched;
+    double *raw = nullptr;
+    size_t raw_bytes = 0;
+    int32_t *done = nullptr;
+    size_t done_cap = 0;
+    unsigned long long *ticket = nullptr;
+    int occ[3] = {0, 0, 0};
+    // host streaming path
+    cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    double *d_lat[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
+    size_t chunk_cap = 0;  // doubles per chunk buffer
+    double *d_q = nullptr, *d_qfull = nullptr;
+    size_t bytes = 0;
+};
+
+template <typename T>
+static int upload(T **dst, const std::vector<T> &src, size_t &bytes) {
+    const size_t nb = std::max<size_t>(src.size(), 1) * sizeof(T);
+    CK(cudaMalloc((void **)dst, nb));
+    if (!src.empty()) CK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    bytes += nb;
+    return 0;
+}
+
+static int ensure_device(rr_plan *p) {
+    if (!rr_cuda_available()) {
+        rr_set_error("no CUDA device available: librr_b200 has no CPU fallback");
+        return 201;
+    }
+    if (p->dev) { CK(cudaSetDevice(p->dev->device)); }
+    else {
+        rr_device_state *d = new rr_device_state();
+        p->dev = d;
+        if (p->opts.device >= 0) CK(cudaSetDevice(p->opts.device));
+        CK(cudaGetDevice(&d->device));
+        CK(cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, d->device));
+        int rc = 0;
+        rc |= upload(&d->up_ptr, p->up_ptr, d->bytes);
+        rc |= upload(&d->up_idx, p->up_idx, d->bytes);
+        rc |= upload(&d->slot_src, p->slot_src, d->bytes);
+        rc |= upload(&d->export_id, p->export_id, d->bytes);
+        rc |= upload(&d->dep_ptr, p->dep_ptr, d->bytes);
+        rc |= upload(&d->dep_idx, p->dep_idx, d->bytes);
+        rc |= upload(&d->down, p->down, d->bytes);
+        rc |= upload(&d->lvl_ptr, p->lvl_ptr, d->bytes);
+        rc |= upload(&d->lvl_blk, p->lvl_blk, d->bytes);
+        rc |= upload(&d->skew, p->skew, d->bytes);
+        rc |= upload(&d->meta, p->meta, d->bytes);
+        if (rc) return rc;
+        CK(cudaMalloc((void **)&d->coef, sizeof(double) * 4 * (size_t)p->n));
+        d->bytes += sizeof(double) * 4 * (size_t)p->n;
+        CK(cudaMalloc((void **)&d->ticket, sizeof(unsigned long long)));
+        CK(cudaStreamCreateWithFlags(&d->s_comp, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaEventCreateWithFlags(&d->ev_in[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&d->ev_comp[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&d->ev_out[k], cudaEventDisableTiming));
+        }
+    }
+    rr_device_state *d = p->dev;
+    if (d->coeff_version != p->coeff_version) {
+        if (p->c1.empty()) { rr_set_error("coefficients not set: call rr_plan_set_coefficients first"); return 100; }
+        const size_t nb = sizeof(double) * (size_t)p->n;
+        CK(cudaMemcpy(d->coef, p->c1.data(), nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d->coef + p->n, p->c2.data(), nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d->coef + 2 * p->n, p->c3.data(), nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d->coef + 3 * p->n, p->c4.data(), nb, cudaMemcpyHostToDevice));
+        d->coeff_version = p->coeff_version;
+    }
+    return 0;
+}
+
+void rr_device_release(rr_plan *p) {
+    rr_device_state *d = p->dev;
+    if (!d) return;
+    cudaSetDevice(d->device);
+    cudaDeviceSynchronize();
+    void *ptrs[] = {d->up_ptr, d->up_idx, d->slot_src, d->export_id, d->dep_ptr, d->dep_idx, d->down, d->exp_off, d->exp_ring,
+                    d->lvl_ptr, d->lvl_blk, d->skew, d->meta, d->coef, d->key_start, d->raw, d->done, d->ticket,
+                    d->d_lat[0], d->d_lat[1], d->d_out[0], d->d_out[1], d->d_q, d->d_qfull};
+    for (void *q : ptrs)
+        if (q) cudaFree(q);
+    if (d->s_comp) cudaStreamDestroy(d->s_comp);
+    if (d->s_in) cudaStreamDestroy(d->s_in);
+    if (d->s_out) cudaStreamDestroy(d->s_out);
+    for (int k = 0; k < 2; ++k) {
+        if (d->ev_in[k]) cudaEventDestroy(d->ev_in[k]);
+        if (d->ev_comp[k]) cudaEventDestroy(d->ev_comp[k]);
+        if (d->ev_out[k]) cudaEventDestroy(d->ev_out[k]);
+    }
+    delete d;
+    p->dev = nullptr;
+}
+
+// One kernel launch == one reference call (or one time chunk of it).
+static int launch_route(rr_plan *p, int mode, int n_members, const double *q_init, const double *const *lateral,
+                        int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
+                        int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream) {
+    if (mode < 0 || mode > 2) { rr_set_error("unknown router mode"); return 100; }
+    if (T <= 0 || K <= 0 || T > 0x7fffffff || K > 0x7fffffff) { rr_set_error("T and substeps must be positive"); return 100; }
+    if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
+    if (mode == RR_MODE_RAPID && !p->have_c4) { rr_set_error("RapidMuskingum needs c4_dt coefficients"); return 100; }
+    if (mode != RR_MODE_MUSKINGUM && ldl < p->n) { rr_set_error("lateral leading dimension smaller than n"); return 100; }
+    if (ldo < p->n) { rr_set_error("output leading dimension smaller than n"); return 100; }
+    int rc = ensure_device(p);
+    if (rc) return rc;
+    rr_device_state *d = p->dev;
+
+    // tile geometry: aim for `time_tile` routing substeps per work item
+    const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(T, p->opts.time_tile / K));
+    const int64_t n_tiles = (T + rows - 1) / rows;
+    const int64_t pitch = ((rows * K + 2 + 3) / 4) * 4;
+    const int64_t budget_rows = std::max<int64_t>(1, p->opts.raw_budget_bytes / (int64_t)(pitch * sizeof(double) * n_members));
+    if (d->sched_tiles != n_tiles || d->sched_budget_rows != budget_rows) {
+        if ((double)n_tiles * (double)(p->max_level + 1) > 2e9) {
+            rr_set_error("network too deep for the ticket scheduler at this tile size; raise time_tile");
+            return 100;
+        }
+        rr_build_schedule(*p, n_tiles, p->opts.tile_stride, budget_rows, d->sched);
+        // the previous launch may still be reading the old tables on another stream
+        CK(cudaDeviceSynchronize());
+        if (d->sched.key_start.size() > d->key_cap) {
+            if (d->key_start) CK(cudaFree(d->key_start));
+            d->key_start = nullptr; d->key_cap = 0;
+            CK(cudaMalloc((void **)&d->key_start, d->sched.key_start.size() * sizeof(int64_t)));
+            d->key_cap = d->sched.key_start.size();
+        }
+        CK(cudaMemcpy(d->key_start, d->sched.key_start.data(), d->sched.key_start.size() * sizeof(int64_t),
+                      cudaMemcpyHostToDevice));
+        const size_t ne = std::max<size_t>(d->sched.exp_ring.size(), 1);
+        if (!d->exp_off) {
+            CK(cudaMalloc((void **)&d->exp_off, ne * sizeof(int32_t)));
+            CK(cudaMalloc((void **)&d->exp_ring, ne * sizeof(int32_t)));
+        }
+        if (!d->sched.exp_ring.empty()) {
+            CK(cudaMemcpy(d->exp_off, d->sched.exp_off.data(), d->sched.exp_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d->exp_ring, d->sched.exp_ring.data(), d->sched.exp_ring.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
+        d->sched_tiles = n_tiles;
+        d->sched_budget_rows = budget_rows;
+    }
+    const size_t raw_need = (size_t)n_members * (size_t)d->sched.raw_rows * pitch * sizeof(double);
+    if (raw_need > d->raw_bytes) {
+        CK(cudaDeviceSynchronize());
+        if (d->raw) CK(cudaFree(d->raw));
+        d->raw = nullptr; d->raw_bytes = 0;
+        CK(cudaMalloc((void **)&d->raw, raw_need));
+        d->raw_bytes = raw_need;
+    }
+    const size_t done_need = (size_t)n_members * p->n_blocks;
+    if (done_need > d->done_cap) {
+        CK(cudaDeviceSynchronize());
+        if (d->done) CK(cudaFree(d->done));
+        d->done = nullptr; d->done_cap = 0;
+        CK(cudaMalloc((void **)&d->done, done_need * sizeof(int32_t)));
+        d->done_cap = done_need;
+    }
+
+    rr_route_params P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = p->n; P.n_blocks = (int32_t)p->n_blocks; P.max_level = p->max_level;
+    P.up_ptr = d->up_ptr; P.up_idx = d->up_idx; P.slot_src = d->slot_src; P.skew = d->skew;
+    P.export_id = d->export_id; P.meta = d->meta;
+    P.dep_ptr = d->dep_ptr; P.dep_idx = d->dep_idx; P.down = d->down;
+    P.exp_off = d->exp_off; P.exp_ring = d->exp_ring; P.raw_rows = d->sched.raw_rows;
+    P.lvl_ptr = d->lvl_ptr; P.lvl_blk = d->lvl_blk;
+    P.c1 = d->coef; P.c2 = d->coef + p->n; P.c3 = d->coef + 2 * p->n; P.c4 = d->coef + 3 * p->n;
+    P.key_start = d->key_start; P.n_keys = d->sched.n_keys; P.n_items = d->sched.n_items;
+    P.delta = d->sched.delta; P.n_tiles = (int32_t)n_tiles;
+    P.T = (int32_t)T; P.K = (int32_t)K; P.tile_rows = (int32_t)rows;
+    P.raw_pitch = (int32_t)pitch; P.n_members = n_members; P.first_call = first_call; P.last_call = last_call;
+    P.ldl = ldl; P.ldo = ldo;
+    P.raw = d->raw; P.done = d->done; P.ticket = d->ticket; P.q_init = q_init;
+    for (int m = 0; m < n_members; ++m) {
+        P.lateral[m] = lateral ? lateral[m] : nullptr;
+        P.out[m] = out[m];
+        P.q_state[m] = q_state[m];
+        P.q_full[m] = q_full ? q_full[m] : nullptr;
+    }
+    CK(cudaMemsetAsync(d->done, 0, done_need * sizeof(int32_t), stream));
+    CK(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), stream));
+    const int block = p->opts.threads_per_cta;
+    if (!d->occ[mode]) {
+        d->occ[mode] = rr_wavefront_occupancy(mode, block);
+        if (d->occ[mode] <= 0) { rr_set_error("occupancy query failed for the wavefront kernel"); return 200; }
+    }
+    const int64_t warps_per_cta = block / 32;
+    const int64_t total_items = d->sched.n_items * n_members;
+    int64_t grid = (int64_t)d->sm_count * d->occ[mode];
+    grid = std::max<int64_t>(1, std::min<int64_t>(grid, (total_items + warps_per_cta - 1) / warps_per_cta));
+    CK(rr_launch_wavefront(mode, P, (int)grid, block, stream));
+    rr_count_launch(1);
+    return 0;
+}
+
+extern "C" int rr_route_dev(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,
+                            int64_t ldl, double *out, int64_t ldo, int64_t T, int64_t substeps, void *stream) {
+    if (!p || !q_state || !out || (mode != RR_MODE_MUSKINGUM && !lateral)) { rr_set_error("null argument"); return 100; }
+    int rc = ensure_device(p);
+    if (rc) return rc;
+    rr_device_state *d = p->dev;
+    double *qf = nullptr;
+    const int router_level = (mode != RR_MODE_UNIT) || q_full == nullptr;
+    if (mode == RR_MODE_UNIT) {
+        if (!q_full && !d->d_qfull) CK(cudaMalloc((void **)&d->d_qfull, sizeof(double) * (size_t)p->n));
+        qf = q_full ? q_full : d->d_qfull;
+    }
+    const double *lat1[1] = {lateral};
+    double *out1[1] = {out}, *qs1[1] = {q_state}, *qf1[1] = {qf};
+    return launch_route(p, mode, 1, q_state, lat1, ldl, out1, ldo, qs1, qf1, T, substeps, router_level, router_level,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int rr_route_ensemble_dev(rr_plan *p, int mode, const double *q_init, int32_t n_members,
+                                     const double *const *lateral, int64_t ldl, double *const *out, int64_t ldo,
+                                     double *const *q_final, int64_t T, int64_t substeps, void *stream) {
+    if (!p || !q_init || !out || !q_final || (mode != RR_MODE_MUSKINGUM && !lateral)) { rr_set_error("null argument"); return 100; }
+    if (mode == RR_MODE_UNIT) { rr_set_error("ensemble launch supports Muskingum / RapidMuskingum"); return 100; }
+    return launch_route(p, mode, n_members, q_init, lateral, ldl, out, ldo, q_final, nullptr, T, substeps, 1, 1,
+                        (cudaStream_t)stream);
+}
+
+// Host arrays: stream time chunks through two device buffers per direction.
+//   s_in : H2D of chunk c+1        (cudaMemcpy2DAsync, pinned source gives full PCIe rate)
+//   s_comp: route chunk c          (one wavefront launch, state carried on the device)
+//   s_out: D2H of chunk c-1
+extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,
+                             int64_t ldl, double *out, int64_t ldo, int64_t T, int64_t substeps) {
+    if (!p || !q_state || !out || (mode != RR_MODE_MUSKINGUM && !lateral)) { rr_set_error("null argument"); return 100; }
+    if (T <= 0 || substeps <= 0) { rr_set_error("T and substeps must be positive"); return 100; }
+    int rc = ensure_device(p);
+    if (rc) return rc;
+    rr_device_state *d = p->dev;
+    const int64_t n = p->n;
+    const int64_t ldd = ((n + 31) / 32) * 32;  // device rows start on 256-byte boundaries
+    const int64_t rows_tile = std::max<int64_t>(1, p->opts.time_tile / substeps);
+    int64_t chunk = std::max<int64_t>(1, (1ll << 30) / (ldd * 8));      // ~1 GiB per buffer
+    chunk = std::max<int64_t>(rows_tile, (chunk / rows_tile) * rows_tile);
+    chunk = std::min<int64_t>(chunk, T);
+    const size_t need = (size_t)chunk * ldd;
+    if (need > d->chunk_cap) {
+        for (int k = 0; k < 2; ++k) {
+            if (d->d_lat[k]) CK(cudaFree(d->d_lat[k]));
+            if (d->d_out[k]) CK(cudaFree(d->d_out[k]));
+            d->d_lat[k] = d->d_out[k] = nullptr;
+        }
+        d->chunk_cap = 0;
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaMalloc((void **)&d->d_lat[k], need * sizeof(double)));
+            CK(cudaMalloc((void **)&d->d_out[k], need * sizeof(double)));
+        }
+        d->chunk_cap = need;
+    }
+    if (!d->d_q) CK(cudaMalloc((void **)&d->d_q, sizeof(double) * (size_t)n));
+    if (mode == RR_MODE_UNIT && !d->d_qfull) CK(cudaMalloc((void **)&d->d_qfull, sizeof(double) * (size_t)n));
+    CK(cudaMemcpyAsync(d->d_q, q_state, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, d->s_comp));
+    const int router_level = (mode != RR_MODE_UNIT) || q_full == nullptr;
+    if (!router_level)
+        CK(cudaMemcpyAsync(d->d_qfull, q_full, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, d->s_comp));
+
+    const int64_t n_chunks = (T + chunk - 1) / chunk;
+    auto rows_of = [&](int64_t c) { return std::min<int64_t>(chunk, T - c * chunk); };
+    auto copy_in = [&](int64_t c) -> int {
+        if (mode == RR_MODE_MUSKINGUM) return 0;
+        const int k = (int)(c & 1);
+        if (c >= 2) CK(cudaStreamWaitEvent(d->s_in, d->ev_comp[k], 0));  // buffer free once chunk c-2 was routed
+        CK(cudaMemcpy2DAsync(d->d_lat[k], ldd * 8, lateral + (size_t)c * chunk * ldl, ldl * 8, n * 8, rows_of(c),
+                             cudaMemcpyHostToDevice, d->s_in));
+        CK(cudaEventRecord(d->ev_in[k], d->s_in));
+        return 0;
+    };
+    if ((rc = copy_in(0))) return rc;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int k = (int)(c & 1);
+        if (c + 1 < n_chunks && (rc = copy_in(c + 1))) return rc;
+        if (mode != RR_MODE_MUSKINGUM) CK(cudaStreamWaitEvent(d->s_comp, d->ev_in[k], 0));
+        if (c >= 2) CK(cudaStreamWaitEvent(d->s_comp, d->ev_out[k], 0));  // out buffer drained
+        const double *lat1[1] = {d->d_lat[k]};
+        double *out1[1] = {d->d_out[k]}, *qs1[1] = {d->d_q}, *qf1[1] = {d->d_qfull};
+        rc = launch_route(p, mode, 1, d->d_q, lat1, ldd, out1, ldd, qs1, qf1, rows_of(c), substeps,
+                          router_level && c == 0, router_level && c == n_chunks - 1, d->s_comp);
+        if (rc) return rc;
+        CK(cudaEventRecord(d->ev_comp[k], d->s_comp));
+        CK(cudaStreamWaitEvent(d->s_out, d->ev_comp[k], 0));
+        CK(cudaMemcpy2DAsync(out + (size_t)c * chunk * ldo, ldo * 8, d->d_out[k], ldd * 8, n * 8, rows_of(c),
+                             cudaMemcpyDeviceToHost, d->s_out));
+        CK(cudaEventRecord(d->ev_out[k], d->s_out));
+    }
+    CK(cudaMemcpyAsync(q_state, d->d_q, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, d->s_comp));
+    if (!router_level)
+        CK(cudaMemcpyAsync(q_full, d->d_qfull, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, d->s_comp));
+    CK(cudaStreamSynchronize(d->s_comp));
+    CK(cudaStreamSynchronize(d->s_out));
+    CK(cudaStreamSynchronize(d->s_in));
+    return 0;
+}
+
+extern "C" int rr_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) { rr_set_error("bad argument"); return 100; }
+    CK(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return 0;
+}
+extern "C" int rr_host_free(void *ptr) {
+    CK(cudaFreeHost(ptr));
+    return 0;
+}

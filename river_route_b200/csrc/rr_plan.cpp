@@ -1,0 +1,446 @@
+// Host-side (CPU, no CUDA) part of librr_b200: topology validation, basin labelling, the
+// wavefront plan (upstream-CSR, 32-reach blocks, systolic delays, block dependency DAG, ticket
+// schedule) and the synthetic network generator.  Reference citations are in include/rr_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "rr_internal.h"
+
+static thread_local std::string g_err;
+void rr_set_error(const std::string &msg) { g_err = msg; }
+extern "C" const char *rr_last_error(void) { return g_err.c_str(); }
+extern "C" int rr_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------
+// id -> index hash (open addressing, splitmix finaliser)
+// ------------------------------------------------------------------------------------------
+namespace {
+inline uint64_t mix64(uint64_t x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+struct IdTable {
+    std::vector<int64_t> key;
+    std::vector<int32_t> val;
+    uint64_t mask = 0;
+    explicit IdTable(int64_t n) {
+        uint64_t cap = 16;
+        while (cap < (uint64_t)n * 2 + 2) cap <<= 1;
+        key.assign(cap, 0);
+        val.assign(cap, -1);
+        mask = cap - 1;
+    }
+    // returns previous index if the id was already present, else -1
+    int32_t insert(int64_t id, int32_t idx) {
+        uint64_t h = mix64((uint64_t)id) & mask;
+        while (val[h] >= 0) {
+            if (key[h] == id) return val[h];
+            h = (h + 1) & mask;
+        }
+        key[h] = id;
+        val[h] = idx;
+        return -1;
+    }
+    int32_t find(int64_t id) const {
+        uint64_t h = mix64((uint64_t)id) & mask;
+        while (val[h] >= 0) {
+            if (key[h] == id) return val[h];
+            h = (h + 1) & mask;
+        }
+        return -1;
+    }
+};
+}  // namespace
+
+extern "C" int rr_downstream_index(int64_t n, const int64_t *river_ids, const int64_t *downstream_ids,
+                                   int32_t *down_idx, int64_t *bad) {
+    if (n < 0 || n > 0x7fffffff) { rr_set_error("reach count out of int32 range"); return 100; }
+    IdTable tab(n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (tab.insert(river_ids[i], (int32_t)i) >= 0) {
+            if (bad) *bad = river_ids[i];
+            rr_set_error("params_file contains duplicate river IDs.");
+            return 1;
+        }
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t d = downstream_ids[i];
+        if (d < 0) { down_idx[i] = -1; continue; }
+        const int32_t di = tab.find(d);
+        if (di < 0) {
+            if (bad) *bad = d;
+            rr_set_error("Unknown downstream_river_id: " + std::to_string(d));
+            return 2;
+        }
+        if (di <= (int32_t)i) {
+            if (bad) *bad = i;
+            rr_set_error("params_file must be topologically sorted upstream to downstream");
+            return 3;
+        }
+        down_idx[i] = di;
+    }
+    return 0;
+}
+
+extern "C" int rr_label_basins(int64_t n, const int32_t *down, int32_t *basin, int64_t *n_basins,
+                               int32_t n_parts, int32_t *part) {
+    int64_t nb = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (down[i] < 0) basin[i] = (int32_t)nb++;
+    for (int64_t i = n - 1; i >= 0; --i)
+        if (down[i] >= 0) {
+            if (down[i] <= i || down[i] >= n) { rr_set_error("down_idx is not topologically sorted"); return 3; }
+            basin[i] = basin[down[i]];
+        }
+    if (n_basins) *n_basins = nb;
+    if (part && n_parts > 0) {
+        std::vector<int64_t> size(nb, 0);
+        for (int64_t i = 0; i < n; ++i) size[basin[i]]++;
+        std::vector<int32_t> order(nb);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return size[a] > size[b]; });
+        std::vector<int64_t> load(n_parts, 0);
+        std::vector<int32_t> owner(nb, 0);
+        for (int32_t b : order) {  // LPT greedy: largest basin to the least-loaded part
+            int32_t best = 0;
+            for (int32_t g = 1; g < n_parts; ++g)
+                if (load[g] < load[best]) best = g;
+            owner[b] = best;
+            load[best] += size[b];
+        }
+        for (int64_t i = 0; i < n; ++i) part[i] = owner[basin[i]];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Plan
+// ------------------------------------------------------------------------------------------
+extern "C" int rr_plan_create(int64_t n, const int32_t *down, const rr_plan_opts *opts, rr_plan **out) {
+    if (!out) { rr_set_error("null output pointer"); return 100; }
+    *out = nullptr;
+    if (n <= 0 || n > 0x7ffffff0ll) { rr_set_error("reach count must be in [1, 2^31)"); return 100; }
+    for (int64_t i = 0; i < n; ++i) {
+        if (down[i] >= 0 && (down[i] <= i || down[i] >= n)) {
+            rr_set_error("params_file must be topologically sorted upstream to downstream");
+            return 3;
+        }
+    }
+    rr_plan *p = new rr_plan();
+    if (opts) p->opts = *opts;
+    if (p->opts.time_tile <= 0) p->opts.time_tile = 32;
+    if (p->opts.threads_per_cta <= 0) p->opts.threads_per_cta = 256;
+    p->opts.threads_per_cta = std::max(32, (p->opts.threads_per_cta / 32) * 32);
+    if (p->opts.raw_budget_bytes <= 0) p->opts.raw_budget_bytes = 16ll << 30;
+    if (!opts || opts->device < 0) p->opts.device = -1;
+    p->n = n;
+    p->n_blocks = (n + RR_BLOCK - 1) / RR_BLOCK;
+    const int64_t nb = p->n_blocks;
+    p->down.assign(down, down + n);
+
+    // upstream-CSR: counting sort by downstream index keeps upstream indices ascending per row
+    p->up_ptr.assign(n + 1, 0);
+    for (int64_t i = 0; i < n; ++i)
+        if (down[i] >= 0) { p->up_ptr[down[i] + 1]++; p->n_edges++; } else p->n_outlets++;
+    for (int64_t i = 0; i < n; ++i) p->up_ptr[i + 1] += p->up_ptr[i];
+    p->up_idx.resize(p->n_edges);
+    {
+        std::vector<int32_t> fill(p->up_ptr.begin(), p->up_ptr.end() - 1);
+        for (int64_t i = 0; i < n; ++i)
+            if (down[i] >= 0) p->up_idx[fill[down[i]]++] = (int32_t)i;
+    }
+    p->is_hw.resize(n);
+    for (int64_t i = 0; i < n; ++i) p->is_hw[i] = p->up_ptr[i + 1] == p->up_ptr[i];
+
+    // in-block systolic delays: every in-block edge gets lag exactly 1
+    //   height[i] = longest in-block chain ending at i; roots (reaches whose downstream is in
+    //   another block) start at skew = height, every in-block upstream is one less than its
+    //   downstream, so a consumer lane always finds the value produced one step earlier.
+    std::vector<uint8_t> height(n, 0);
+    auto blk = [](int64_t i) { return i / RR_BLOCK; };
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t d = down[i];
+        if (d >= 0 && blk(d) == blk(i)) height[d] = std::max<uint8_t>(height[d], height[i] + 1);
+    }
+    p->skew.resize(n);
+    for (int64_t i = n - 1; i >= 0; --i) {
+        const int32_t d = down[i];
+        if (d >= 0 && blk(d) == blk(i)) { p->skew[i] = p->skew[d] - 1; p->n_internal++; }
+        else p->skew[i] = height[i];
+    }
+
+    // exchange-buffer ids: only reaches whose downstream sits in another block export a series
+    p->export_id.assign(n, -1);
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t d = down[i];
+        if (d >= 0 && blk(d) != blk(i)) p->export_id[i] = (int32_t)p->n_export++;
+    }
+
+    // encoded upstream slots + block metadata + block dependency lists
+    p->slot_src.resize(p->n_edges);
+    p->meta.assign(nb, rr_blk_meta{0, 0, 0, 0});
+    p->dep_ptr.assign(nb + 1, 0);
+    p->dep_idx.clear();
+    std::vector<int32_t> tmp;
+    for (int64_t b = 0; b < nb; ++b) {
+        rr_blk_meta &m = p->meta[b];
+        tmp.clear();
+        const int64_t lo = b * RR_BLOCK, hi = std::min<int64_t>(n, lo + RR_BLOCK);
+        for (int64_t i = lo; i < hi; ++i) {
+            const int32_t deg = p->up_ptr[i + 1] - p->up_ptr[i];
+            if (deg > 65535) { delete p; rr_set_error("in-degree above 65535 is not supported"); return 100; }
+            m.max_skew = std::max(m.max_skew, p->skew[i]);
+            m.max_deg = std::max<uint16_t>(m.max_deg, (uint16_t)deg);
+            for (int32_t k = 0; k < deg; ++k) {
+                const int32_t e = p->up_ptr[i] + k;
+                const int32_t u = p->up_idx[e];
+                if (blk(u) == b) {
+                    p->slot_src[e] = -(int32_t)(u - lo + 1) - (p->is_hw[u] ? 64 : 0);
+                    m.int_mask |= (uint8_t)(k < RR_MAX_FAST_DEG ? (1u << k) : 0x80u);
+                } else {
+                    p->slot_src[e] = p->export_id[u] | (p->is_hw[u] ? RR_SLOT_HW_BIT : 0);
+                    tmp.push_back((int32_t)blk(u));
+                }
+            }
+        }
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        int32_t lvl = 0;
+        for (int32_t ub : tmp) lvl = std::max(lvl, p->meta[ub].level + 1);
+        m.level = lvl;
+        p->dep_idx.insert(p->dep_idx.end(), tmp.begin(), tmp.end());
+        p->dep_ptr[b + 1] = (int32_t)p->dep_idx.size();
+        p->max_level = std::max(p->max_level, lvl);
+        p->max_skew = std::max<int32_t>(p->max_skew, m.max_skew);
+        p->max_deg = std::max<int32_t>(p->max_deg, m.max_deg);
+    }
+    p->blk_level.resize(nb);
+    for (int64_t b = 0; b < nb; ++b) p->blk_level[b] = p->meta[b].level;
+
+    // span of every exported series in block levels (producer block -> its single consumer block);
+    // it sizes that series' ring in the exchange buffer (rr_build_schedule)
+    p->exp_span.resize(p->n_export);
+    for (int64_t i = 0; i < n; ++i)
+        if (p->export_id[i] >= 0) p->exp_span[p->export_id[i]] = p->blk_level[blk(down[i])] - p->blk_level[blk(i)];
+
+    // level buckets
+    p->lvl_ptr.assign(p->max_level + 2, 0);
+    for (int64_t b = 0; b < nb; ++b) p->lvl_ptr[p->blk_level[b] + 1]++;
+    for (int32_t l = 0; l <= p->max_level; ++l) p->lvl_ptr[l + 1] += p->lvl_ptr[l];
+    p->lvl_blk.resize(nb);
+    {
+        std::vector<int32_t> fill(p->lvl_ptr.begin(), p->lvl_ptr.end() - 1);
+        for (int64_t b = 0; b < nb; ++b) p->lvl_blk[fill[p->blk_level[b]]++] = (int32_t)b;
+    }
+    *out = p;
+    return 0;
+}
+
+extern "C" void rr_plan_destroy(rr_plan *p) {
+    if (!p) return;
+    rr_device_release(p);
+    delete p;
+}
+
+extern "C" int rr_plan_get_info(const rr_plan *p, rr_plan_info *info) {
+    if (!p || !info) { rr_set_error("null argument"); return 100; }
+    std::memset(info, 0, sizeof(*info));
+    info->n = p->n;
+    info->n_edges = p->n_edges;
+    info->n_blocks = p->n_blocks;
+    info->n_export = p->n_export;
+    info->n_internal_edges = p->n_internal;
+    info->max_skew = p->max_skew;
+    info->max_indegree = p->max_deg;
+    info->max_block_level = p->max_level;
+    info->n_outlets_lo = (int32_t)p->n_outlets;
+    info->n_dep_edges = (int64_t)p->dep_idx.size();
+    info->device_bytes = 0;
+    return 0;
+}
+
+extern "C" int rr_plan_set_coefficients(rr_plan *p, const double *c1, const double *c2, const double *c3,
+                                        const double *c4_dt) {
+    if (!p || !c1 || !c2 || !c3) { rr_set_error("null argument"); return 100; }
+    p->c1.assign(c1, c1 + p->n);
+    p->c2.assign(c2, c2 + p->n);
+    p->c3.assign(c3, c3 + p->n);
+    p->have_c4 = c4_dt != nullptr;
+    if (c4_dt) p->c4.assign(c4_dt, c4_dt + p->n); else p->c4.assign(p->n, 0.0);
+    p->coeff_version++;
+    return 0;
+}
+
+extern "C" int rr_plan_get_arrays(const rr_plan *p, const int32_t **up_ptr, const int32_t **up_idx,
+                                  const uint8_t **skew, const int32_t **slot_src, const int32_t **export_id,
+                                  const int32_t **blk_level, const int32_t **dep_ptr, const int32_t **dep_idx,
+                                  const int32_t **exp_span) {
+    if (!p) { rr_set_error("null plan"); return 100; }
+    if (up_ptr) *up_ptr = p->up_ptr.data();
+    if (up_idx) *up_idx = p->up_idx.data();
+    if (skew) *skew = p->skew.data();
+    if (slot_src) *slot_src = p->slot_src.data();
+    if (export_id) *export_id = p->export_id.data();
+    if (blk_level) *blk_level = p->blk_level.data();
+    if (dep_ptr) *dep_ptr = p->dep_ptr.data();
+    if (dep_idx) *dep_idx = p->dep_idx.data();
+    if (exp_span) *exp_span = p->exp_span.data();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Ticket schedule.  Item (block b, tile j) gets key = level(b) + j * delta; tickets are handed
+// out in key order.  Every dependency of an item has a strictly smaller key:
+//   upstream block, same tile      level(b') < level(b)
+//   same block, previous tile      delta >= 1
+//   exchange-ring reuse (WAR)      the series of reach u lives in a ring of depth
+//                                  R_u = span_u / delta + 1 (span_u = level(consumer) - level(producer));
+//                                  producer (b', j) overwrites what consumer (c, j - R_u) read, and
+//                                  key(c, j - R_u) < key(b', j)  <=>  span_u < R_u * delta.
+// so the warp holding the lowest unfinished ticket can always finish: no deadlock, for any grid
+// size, without a cooperative launch.  A small delta lets many tiles be in flight at once (the
+// wavefront through deep networks); the budget bounds the ring memory that costs.
+// ------------------------------------------------------------------------------------------
+static int64_t ring_rows(const rr_plan &p, int64_t n_tiles, int64_t delta) {
+    int64_t rows = 0;
+    for (int32_t sp : p.exp_span) rows += std::min<int64_t>(sp / delta + 1, n_tiles);
+    return rows;
+}
+
+void rr_build_schedule(const rr_plan &p, int64_t n_tiles, int32_t delta, int64_t budget_rows, rr_schedule &s) {
+    if (delta <= 0) {
+        int64_t d = 1;
+        while (d <= p.max_level && ring_rows(p, n_tiles, d) > budget_rows) d <<= 1;
+        delta = (int32_t)std::min<int64_t>(d, (int64_t)p.max_level + 1);
+    }
+    s.delta = delta;
+    s.exp_ring.resize(p.n_export);
+    s.exp_off.resize(p.n_export);
+    int64_t rows = 0;
+    for (int64_t e = 0; e < p.n_export; ++e) {
+        s.exp_off[e] = (int32_t)rows;
+        s.exp_ring[e] = (int32_t)std::min<int64_t>(p.exp_span[e] / delta + 1, n_tiles);
+        rows += s.exp_ring[e];
+    }
+    s.raw_rows = std::max<int64_t>(rows, 1);
+    s.n_keys = (int64_t)p.max_level + (n_tiles - 1) * (int64_t)s.delta + 1;
+    s.key_start.assign(s.n_keys + 1, 0);
+    for (int64_t j = 0; j < n_tiles; ++j)
+        for (int32_t l = 0; l <= p.max_level; ++l)
+            s.key_start[l + j * s.delta + 1] += p.lvl_ptr[l + 1] - p.lvl_ptr[l];
+    for (int64_t k = 0; k < s.n_keys; ++k) s.key_start[k + 1] += s.key_start[k];
+    s.n_items = s.key_start[s.n_keys];
+}
+
+void rr_decode_ticket(const rr_plan &p, const rr_schedule &s, int64_t n_tiles, int64_t ticket,
+                      int32_t *block, int32_t *tile) {
+    int64_t lo = 0, hi = s.n_keys;  // largest key with key_start[key] <= ticket
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (s.key_start[mid] <= ticket) lo = mid; else hi = mid;
+    }
+    int64_t r = ticket - s.key_start[lo];
+    int64_t j = lo > p.max_level ? (lo - p.max_level + s.delta - 1) / s.delta : 0;
+    const int64_t jhi = std::min<int64_t>(n_tiles - 1, lo / s.delta);
+    for (; j <= jhi; ++j) {
+        const int64_t l = lo - j * s.delta;
+        const int64_t w = p.lvl_ptr[l + 1] - p.lvl_ptr[l];
+        if (r < w) { *block = p.lvl_blk[p.lvl_ptr[l] + r]; *tile = (int32_t)j; return; }
+        r -= w;
+    }
+    *block = -1; *tile = -1;
+}
+
+extern "C" int rr_plan_schedule(const rr_plan *p, int64_t n_tiles, int32_t tile_stride, int64_t *n_items,
+                                int32_t *item_block, int32_t *item_tile) {
+    if (!p || n_tiles <= 0 || tile_stride <= 0) { rr_set_error("bad argument"); return 100; }
+    rr_schedule s;
+    rr_build_schedule(*p, n_tiles, tile_stride, INT64_MAX, s);
+    if (n_items) *n_items = s.n_items;
+    if (item_block && item_tile)
+        for (int64_t t = 0; t < s.n_items; ++t) rr_decode_ticket(*p, s, n_tiles, t, item_block + t, item_tile + t);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Synthetic forests
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Rng {
+    uint64_t s[4];
+    explicit Rng(uint64_t seed) {
+        for (int i = 0; i < 4; ++i) { seed += 0x9e3779b97f4a7c15ull; s[i] = mix64(seed); }
+    }
+    static inline uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    uint64_t next() {  // xoshiro256**
+        const uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
+        return r;
+    }
+    double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    uint64_t below(uint64_t n) { return (uint64_t)(uniform() * (double)n) % n; }
+    double normal() {
+        double u1 = uniform(), u2 = uniform();
+        if (u1 < 1e-300) u1 = 1e-300;
+        return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+    }
+};
+}  // namespace
+
+extern "C" int rr_synth_forest(int64_t n, int64_t n_basins, uint64_t seed, double depth_bias,
+                               int64_t main_stem, double sigma, int32_t *down) {
+    if (n <= 0 || n_basins <= 0 || n_basins > n || n > 0x7ffffff0ll) { rr_set_error("bad forest size"); return 100; }
+    Rng rng(seed);
+    // basin sizes: lognormal(sigma) normalised to n, each at least 1
+    std::vector<double> w(n_basins);
+    double tot = 0;
+    for (auto &x : w) { x = std::exp(sigma * rng.normal()); tot += x; }
+    std::vector<int64_t> size(n_basins);
+    int64_t used = 0;
+    for (int64_t b = 0; b < n_basins; ++b) {
+        size[b] = std::max<int64_t>(1, (int64_t)std::floor(w[b] / tot * (double)(n - n_basins)) + 1);
+        used += size[b];
+    }
+    {   // hand the rounding remainder to the largest basin (or take it back from it)
+        int64_t big = std::max_element(size.begin(), size.end()) - size.begin();
+        size[big] += n - used;
+        if (size[big] < 1) { rr_set_error("basin size normalisation failed"); return 100; }
+    }
+    if (main_stem > 0) std::swap(size[0], *std::max_element(size.begin(), size.end()));
+    std::vector<int32_t> parent, tips;
+    std::vector<uint8_t> half;  // tip may take only one more child (pre-seeded stem)
+    int64_t off = 0;
+    for (int64_t b = 0; b < n_basins; ++b) {
+        const int64_t m = size[b];
+        parent.assign(m, -1);
+        half.assign(m, 0);
+        tips.clear();
+        int64_t cnt = 1;
+        const int64_t stem = (b == 0 && main_stem > 0) ? std::min<int64_t>(main_stem, m) : 0;
+        if (stem > 1) {
+            for (int64_t g = 1; g < stem; ++g) { parent[g] = (int32_t)(g - 1); half[g - 1] = 1; tips.push_back((int32_t)(g - 1)); }
+            tips.push_back((int32_t)(stem - 1));
+            cnt = stem;
+        } else tips.push_back(0);
+        while (cnt < m) {
+            size_t pick = tips.size() - 1;
+            if (!(rng.uniform() < depth_bias)) pick = (size_t)rng.below(tips.size());
+            const int32_t t = tips[pick];
+            tips[pick] = tips.back();
+            tips.pop_back();
+            int64_t kids = (half[t] || rng.uniform() >= 0.7) ? 1 : 2;
+            kids = std::min<int64_t>(kids, m - cnt);
+            for (int64_t c = 0; c < kids; ++c) { parent[cnt] = t; tips.push_back((int32_t)cnt); cnt++; }
+        }
+        for (int64_t g = 0; g < m; ++g) {
+            const int64_t idx = off + (m - 1 - g);
+            down[idx] = parent[g] < 0 ? -1 : (int32_t)(off + (m - 1 - parent[g]));
+        }
+        off += m;
+    }
+    return 0;
+}

@@ -1,0 +1,377 @@
+// rr_route.cu -- the Muskingum wavefront solve for sm_100a.
+//
+// Replaces the three numba loops of river_route/routers/_numba_kernels.py
+// (muskingum_route :9-46, rapid_route :49-84, unit_route :88-171).
+//
+// Formulation (per reach i, upstream set U(i) in ascending index order, one routing substep):
+//     q'[i] = c3*q[i] + c4_dt*ql[t,i] + sum_u c2[i]*q[u] + sum_u c1[i]*q'[u]
+// which is the reference's push / forward-substitution pair written as a pull; the two sums are
+// accumulated one after the other in ascending upstream order exactly as the reference's
+// column-ascending scatters deliver them.
+//
+// Parallel decomposition
+//   * A work item is (block b of 32 consecutive reaches, tile j of `tile_rows` output rows) and is
+//     executed by ONE WARP, lane = reach.  Consecutive reaches keep the lateral / discharge rows
+//     coalesced in the reference's own (T, n) layout -- no permutation of the user's arrays.
+//   * Inside an item the warp is a systolic array: lane l runs `skew[l]` steps behind, and the plan
+//     guarantees that every in-block upstream lane is exactly ONE step ahead, so its newest and
+//     previous discharge are fetched with warp shuffles -- no shared memory, no in-block flags.
+//   * Between blocks, a reach whose downstream lives in another block exports its raw (unclamped)
+//     substep series for the tile to the exchange buffer raw[slot][export_id][1 + s] (entry 0 is
+//     the carry-in value).  Consumers read those series; the producer publishes "tile j done" with
+//     a release store on done[b], consumers acquire it.  A reach therefore advances to tile j+1 as
+//     soon as its upstream blocks and its own tile j are done: the wavefront pipelines time through
+//     deep networks with no grid-wide barrier and one kernel launch per call.
+//   * Persistent warps take tickets from a global counter; the ticket order (rr_plan.cpp) is a
+//     linear extension of all dependencies, so the lowest unfinished ticket can always finish.
+#include <cuda_runtime.h>
+
+#include "rr_route.cuh"
+
+#define FULL_MASK 0xffffffffu
+#define SLOT_NONE ((int32_t)0x80000000)
+
+namespace {
+
+__device__ __forceinline__ int32_t ld_acquire(const int32_t *p) {
+    int32_t v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int32_t *p, int32_t v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_ge(const int32_t *flag, int32_t want) {
+    unsigned ns = 20;
+    while (ld_acquire(flag) < want) {
+        __nanosleep(ns);
+        if (ns < 640) ns <<= 1;
+    }
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// streaming read of data that is never written during the launch
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldg(p); }
+
+}  // namespace
+
+template <int MODE>
+__global__ void __launch_bounds__(256) rr_wavefront_kernel(const __grid_constant__ rr_route_params P) {
+    constexpr bool HAS_LAT = (MODE != RR_MODE_MUSKINGUM);
+    constexpr bool UNIT = (MODE == RR_MODE_UNIT);
+    const int lane = threadIdx.x & 31;
+    const int K = P.K;
+    const double inv_k = 1.0 / (double)K;  // _numba_kernels.py:19, :60, :104
+
+    for (;;) {
+        // ---------------- ticket -> (member, block, tile) ----------------
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(P.ticket, 1ull);
+        tk = __shfl_sync(FULL_MASK, tk, 0);
+        if (tk >= (unsigned long long)P.n_items * (unsigned)P.n_members) break;
+        int m = 0;
+        int64_t ticket = (int64_t)tk;
+        if (P.n_members > 1) { m = (int)(tk % (unsigned)P.n_members); ticket = (int64_t)(tk / (unsigned)P.n_members); }
+        int b, j;
+        {
+            int64_t lo = 0, hi = P.n_keys;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(P.key_start + mid) <= ticket) lo = mid; else hi = mid;
+            }
+            int64_t r = ticket - __ldg(P.key_start + lo);
+            int64_t jj = lo > P.max_level ? (lo - P.max_level + P.delta - 1) / P.delta : 0;
+            for (;; ++jj) {
+                const int64_t l = lo - jj * P.delta;
+                const int32_t base = __ldg(P.lvl_ptr + l);
+                const int64_t w = __ldg(P.lvl_ptr + l + 1) - base;
+                if (r < w) { b = __ldg(P.lvl_blk + base + r); break; }
+                r -= w;
+            }
+            j = (int)jj;
+        }
+
+        // ---------------- per-lane constants ----------------
+        const int64_t i = (int64_t)b * RR_BLOCK + lane;
+        const bool valid = i < P.n;
+        const int64_t ic = valid ? i : P.n - 1;
+        const double c1 = __ldg(P.c1 + ic), c2 = __ldg(P.c2 + ic), c3 = __ldg(P.c3 + ic);
+        const double c4 = HAS_LAT && !UNIT ? __ldg(P.c4 + ic) : 0.0;
+        const int d = __ldg(P.skew + ic);
+        const int e0 = __ldg(P.up_ptr + ic);
+        const int deg = valid ? __ldg(P.up_ptr + ic + 1) - e0 : 0;
+        const int ex = valid ? __ldg(P.export_id + ic) : -1;
+        const rr_blk_meta M = P.meta[b];
+        const int nfast = M.max_deg < RR_MAX_FAST_DEG ? M.max_deg : RR_MAX_FAST_DEG;
+
+        const int t0 = j * P.tile_rows;
+        const int rows = min(P.tile_rows, P.T - t0);
+        const int TT = rows * K;
+        double *raw_m = P.raw + (size_t)m * (size_t)P.raw_rows * P.raw_pitch;
+        // row of exported series e for this tile: its private ring, indexed by tile
+        auto raw_row = [&](int32_t e) -> double * {
+            const int32_t ring = __ldg(P.exp_ring + e);
+            return raw_m + ((size_t)__ldg(P.exp_off + e) + (size_t)(j % ring)) * P.raw_pitch;
+        };
+
+        int32_t src[RR_MAX_FAST_DEG];
+        const double *rp[RR_MAX_FAST_DEG];   // exported series of an external upstream
+        int ilane[RR_MAX_FAST_DEG];          // lane of an in-block upstream (own lane if none)
+        int64_t ug[RR_MAX_FAST_DEG];         // UNIT: global index of the upstream reach
+#pragma unroll
+        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+            src[k] = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
+            rp[k] = nullptr;
+            ilane[k] = lane;
+            ug[k] = 0;
+            if (src[k] != SLOT_NONE) {
+                if (src[k] >= 0) rp[k] = raw_row(src[k] & ~RR_SLOT_HW_BIT);
+                else ilane[k] = (-src[k] - 1) & 31;
+                if (UNIT) ug[k] = __ldg(P.up_idx + e0 + k);
+            }
+        }
+        const double *lat = nullptr;
+        if (HAS_LAT) {
+            lat = P.lateral[m] + (size_t)t0 * P.ldl + (size_t)b * RR_BLOCK;
+            // pull this item's lateral tile towards L2 before the dependency wait hides the latency
+            const int64_t left = P.n - (int64_t)b * RR_BLOCK;
+            const int row_bytes = (int)(left < RR_BLOCK ? left : RR_BLOCK) * 8;
+            for (int r = lane; r < rows; r += 32) {
+                const char *a = (const char *)(lat + (size_t)r * P.ldl);
+                prefetch_l2(a);
+                if (row_bytes > 128) prefetch_l2(a + 128);
+                prefetch_l2(a + row_bytes - 1);
+            }
+            lat += lane;
+        }
+        double *outp = P.out[m] + (size_t)t0 * P.ldo + i;
+
+        // ---------------- dependencies ----------------
+        int32_t *done = P.done + (size_t)m * P.n_blocks;
+        if (lane == 0 && j > 0) wait_ge(done + b, j);                       // own previous tile
+        for (int e = P.dep_ptr[b] + lane; e < P.dep_ptr[b + 1]; e += 32)    // upstream blocks, this tile
+            wait_ge(done + P.dep_idx[e], j + 1);
+        if (ex >= 0) {                                                      // exchange-ring reuse
+            const int32_t ring = __ldg(P.exp_ring + ex);
+            if (j >= ring) wait_ge(done + __ldg(P.down + i) / RR_BLOCK, j - ring + 1);
+        }
+        __syncwarp();
+
+        // ---------------- state ----------------
+        // first tile of a reference call: every member starts from the shared initial state and
+        // (UNIT) q_ch = q_full = state (UnitMuskingum.py:78-79); later tiles / chunks continue
+        // from the member's own running state.
+        const bool use_init = (j == 0) && P.first_call;
+        double qcur = 0.0;   // q_t (UNIT: q_ch)
+        if (valid) qcur = use_init ? P.q_init[i] : P.q_state[m][i];
+        double qprev = qcur;
+        double qf_cur = 0.0, qf_prev = 0.0;  // UNIT: q_full and its previous value
+        if (UNIT && valid) {
+            qf_cur = use_init ? qcur : P.q_full[m][i];
+            qf_prev = qf_cur;
+        }
+        double *myraw = nullptr;
+        if (ex >= 0) {
+            myraw = raw_row(ex);
+            myraw[0] = qcur;                               // carry-in for consumers
+            if (UNIT) myraw[P.raw_pitch - 1] = qf_cur;     // q_full carry-in
+        }
+
+        // one-step lookahead registers for the external series and the lateral row
+        double eo[RR_MAX_FAST_DEG], en[RR_MAX_FAST_DEG];
+        double lu[RR_MAX_FAST_DEG], lu_old[RR_MAX_FAST_DEG];   // UNIT: upstream lateral (this / previous row)
+#pragma unroll
+        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+            eo[k] = en[k] = lu[k] = lu_old[k] = 0.0;
+            if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) {
+                eo[k] = UNIT ? rp[k][P.raw_pitch - 1] : rp[k][0];
+                en[k] = rp[k][1];
+            }
+        }
+        double ql = 0.0, ql_nx = 0.0;
+        if (HAS_LAT && valid) ql_nx = ld_stream(lat);
+        double acc = 0.0, base = 0.0;
+        int sub = 0, row = 0;
+
+        const int nsteps = TT + M.max_skew;
+        for (int sig = 0; sig < nsteps; ++sig) {
+            const int s = sig - d;
+            const bool act = valid && s >= 0 && s < TT;
+            const bool row_start = act && sub == 0;
+
+            // ---- gather upstream values (shuffles are executed by every lane) ----
+            double vo[RR_MAX_FAST_DEG], vn[RR_MAX_FAST_DEG];
+#pragma unroll
+            for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+                vo[k] = eo[k];
+                vn[k] = en[k];
+                if (k < nfast && (M.int_mask >> k) & 1) {
+                    const double so = __shfl_sync(FULL_MASK, UNIT ? qf_prev : qprev, ilane[k]);
+                    const double sn = __shfl_sync(FULL_MASK, qcur, ilane[k]);
+                    if (src[k] < 0 && src[k] != SLOT_NONE) { vo[k] = so; vn[k] = sn; }
+                }
+            }
+
+            double r = 0.0;
+            if (UNIT) {
+                if (row_start) {
+                    // _numba_kernels.py:116-143: lateral gathers, A_inner@ql and A_hw@ql in ascending
+                    // column order, c1*(a_inner + a_hw); rhs base = c1_A_ql + c2*a_hw (:151)
+                    ql = ql_nx;
+                    double a_in = 0.0, a_hw = 0.0;
+#pragma unroll
+                    for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+                        if (k < deg) {
+                            lu_old[k] = lu[k];
+                            lu[k] = ld_stream(P.lateral[m] + (size_t)(t0 + row) * P.ldl + ug[k]);
+                            const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
+                            if (hw) a_hw += lu[k]; else a_in += lu[k];
+                        }
+                    }
+                    for (int k = RR_MAX_FAST_DEG; k < deg; ++k) {
+                        const int32_t sk = __ldg(P.slot_src + e0 + k);
+                        const double l = ld_stream(P.lateral[m] + (size_t)(t0 + row) * P.ldl + __ldg(P.up_idx + e0 + k));
+                        const bool hw = sk >= 0 ? (sk & RR_SLOT_HW_BIT) != 0 : (((-sk - 1) >> 6) & 1) != 0;
+                        if (hw) a_hw += l; else a_in += l;
+                    }
+                    base = c1 * (a_in + a_hw) + c2 * a_hw;
+                }
+                r = base + c3 * qcur;
+            } else {
+                if (row_start) ql = ql_nx;
+                r = c3 * qcur;                      // :27-28 / :68-69
+                if (HAS_LAT) r = fma(c4, ql, r);
+            }
+
+            // ---- pass A: c2 * (previous-substep discharge of each upstream), ascending ----
+#pragma unroll
+            for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+                if (k < deg) {
+                    if (UNIT) {
+                        const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
+                        if (!hw) {
+                            // external inner upstream: q_full_old = q_ch_old + lateral of the row that substep
+                            // belonged to; at s == 0 the exported carry already is q_full
+                            double qfo = vo[k];
+                            if (src[k] >= 0 && s > 0) qfo = vo[k] + (sub == 0 ? lu_old[k] : lu[k]);
+                            r = fma(c2, qfo, r);
+                        }
+                    } else {
+                        r = fma(c2, vo[k], r);
+                    }
+                }
+            }
+            if (M.max_deg > RR_MAX_FAST_DEG) {
+                for (int k = RR_MAX_FAST_DEG; k < M.max_deg; ++k) {
+                    const int32_t sk = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
+                    const int il = (sk < 0 && sk != SLOT_NONE) ? ((-sk - 1) & 31) : lane;
+                    double v = __shfl_sync(FULL_MASK, UNIT ? qf_prev : qprev, il);
+                    bool use = act && k < deg;
+                    if (use && sk >= 0) {
+                        const double *q = raw_row(sk & ~RR_SLOT_HW_BIT);
+                        if (UNIT) {
+                            if (sk & RR_SLOT_HW_BIT) use = false;
+                            else if (s == 0) v = q[P.raw_pitch - 1];
+                            else {
+                                const int prow = (sub == 0) ? row - 1 : row;
+                                v = q[s] + ld_stream(P.lateral[m] + (size_t)(t0 + prow) * P.ldl + __ldg(P.up_idx + e0 + k));
+                            }
+                        } else v = q[s];
+                    } else if (use && UNIT && (((-sk - 1) >> 6) & 1)) use = false;
+                    if (use) r = fma(c2, v, r);
+                }
+            }
+            // ---- pass B: c1 * (this-substep discharge of each upstream), ascending ----
+#pragma unroll
+            for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+                if (k < deg) {
+                    if (UNIT) {
+                        const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
+                        if (!hw) r = fma(c1, vn[k], r);
+                    } else {
+                        r = fma(c1, vn[k], r);      // rhs -= lhs_off * q_new with lhs_off = -c1 (:36-39)
+                    }
+                }
+            }
+            if (M.max_deg > RR_MAX_FAST_DEG) {
+                for (int k = RR_MAX_FAST_DEG; k < M.max_deg; ++k) {
+                    const int32_t sk = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
+                    const int il = (sk < 0 && sk != SLOT_NONE) ? ((-sk - 1) & 31) : lane;
+                    double v = __shfl_sync(FULL_MASK, qcur, il);
+                    bool use = act && k < deg;
+                    if (use && sk >= 0) {
+                        if (UNIT && (sk & RR_SLOT_HW_BIT)) use = false;
+                        else v = raw_row(sk & ~RR_SLOT_HW_BIT)[s + 1];
+                    } else if (use && UNIT && (((-sk - 1) >> 6) & 1)) use = false;
+                    if (use) r = fma(c1, v, r);
+                }
+            }
+
+            // ---- commit ----
+            if (act) {
+                const bool inner = !UNIT || deg > 0;
+                if (inner) {
+                    qprev = qcur;
+                    qcur = r;
+                    if (UNIT) {
+                        qf_prev = qf_cur;
+                        qf_cur = r + ql;            // :165-166
+                        acc += qf_cur;
+                    } else acc += r;                // :41-42 / :79-80
+                    if (myraw) myraw[1 + s] = r;
+                }
+                if (++sub == K) {
+                    double v;
+                    if (UNIT && !inner) v = ql;     // headwater: lateral inflow, unclamped (:122-123)
+                    else { v = acc * inv_k; v = v > 0.0 ? v : 0.0; }   // :44-46 / :82-84 / :169-171
+                    outp[(size_t)row * P.ldo] = v;
+                    acc = 0.0;
+                    sub = 0;
+                    ++row;
+                }
+                // lookahead for the next step of this lane
+                if (s + 1 < TT) {
+#pragma unroll
+                    for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+                        if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) { eo[k] = en[k]; en[k] = rp[k][s + 2]; }
+                    }
+                    if (HAS_LAT && sub == 0) ql_nx = ld_stream(lat + (size_t)row * P.ldl);
+                }
+            }
+        }
+
+        // ---------------- publish ----------------
+        if (valid) {
+            const bool last = (j == P.n_tiles - 1);
+            if (UNIT) {
+                if (last && P.last_call) P.q_state[m][i] = deg > 0 ? qf_cur : ql;   // UnitMuskingum.py:94-98
+                else { P.q_state[m][i] = qcur; P.q_full[m][i] = qf_cur; }
+            } else P.q_state[m][i] = qcur;
+        }
+        __syncwarp();
+        if (lane == 0) st_release(done + b, j + 1);
+    }
+}
+
+// Host-callable launcher (used by rr_api.cu).
+cudaError_t rr_launch_wavefront(int mode, const rr_route_params &P, int grid, int block, cudaStream_t stream) {
+    switch (mode) {
+        case RR_MODE_MUSKINGUM: rr_wavefront_kernel<RR_MODE_MUSKINGUM><<<grid, block, 0, stream>>>(P); break;
+        case RR_MODE_RAPID: rr_wavefront_kernel<RR_MODE_RAPID><<<grid, block, 0, stream>>>(P); break;
+        case RR_MODE_UNIT: rr_wavefront_kernel<RR_MODE_UNIT><<<grid, block, 0, stream>>>(P); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+int rr_wavefront_occupancy(int mode, int block) {
+    int nb = 0;
+    cudaError_t e;
+    switch (mode) {
+        case RR_MODE_MUSKINGUM: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_wavefront_kernel<RR_MODE_MUSKINGUM>, block, 0); break;
+        case RR_MODE_RAPID: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_wavefront_kernel<RR_MODE_RAPID>, block, 0); break;
+        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_wavefront_kernel<RR_MODE_UNIT>, block, 0); break;
+    }
+    return e == cudaSuccess ? nb : -1;
+}

@@ -1,0 +1,50 @@
+// Device-side parameter block of the wavefront routing kernel (shared by rr_route.cu / rr_api.cu).
+#pragma once
+#include <cstdint>
+
+#include "rr_internal.h"
+
+#define RR_MAX_MEMBERS 64
+
+struct rr_route_params {
+    // ---- network (plan) ----
+    int64_t n;
+    int32_t n_blocks;
+    int32_t max_level;
+    const int32_t *up_ptr;
+    const int32_t *up_idx;
+    const int32_t *slot_src;
+    const uint8_t *skew;
+    const int32_t *export_id;
+    const rr_blk_meta *meta;
+    const int32_t *dep_ptr, *dep_idx;
+    const int32_t *down;      // [n] downstream reach (-1 outlet): the consumer of an exported series
+    const int32_t *lvl_ptr, *lvl_blk;
+    const double *c1, *c2, *c3, *c4;
+    // ---- ticket schedule ----
+    const int64_t *key_start;
+    int64_t n_keys;
+    int64_t n_items;      // per member
+    int32_t delta;
+    int32_t n_tiles;
+    // ---- problem ----
+    int32_t T;            // output rows
+    int32_t K;            // routing substeps per row
+    int32_t tile_rows;    // rows per work item
+    int32_t raw_pitch;    // doubles per exported series (1 carry + tile_rows*K, padded to 4)
+    int32_t n_members;
+    int32_t first_call;   // UNIT: 1 when q_state holds the start-of-file state (q_ch = q_full = state)
+    int32_t last_call;    // UNIT: 1 when q_state must end as the recombined vector (hw: lateral, inner: q_full)
+    const int32_t *exp_off;   // [n_export] first row of each exported series' ring
+    const int32_t *exp_ring;  // [n_export] ring depth (tiles) of each exported series
+    int64_t raw_rows;     // rows of the exchange buffer per ensemble member
+    int64_t ldl, ldo;
+    double *raw;          // [member][raw_rows][raw_pitch]
+    int32_t *done;        // [member][n_blocks] tiles completed
+    unsigned long long *ticket;
+    const double *q_init;                       // shared initial state
+    const double *lateral[RR_MAX_MEMBERS];
+    double *out[RR_MAX_MEMBERS];
+    double *q_state[RR_MAX_MEMBERS];            // per-member running / final state (UNIT: q_ch)
+    double *q_full[RR_MAX_MEMBERS];             // UNIT only: running q_full = q_ch + lateral
+};

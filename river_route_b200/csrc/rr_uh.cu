@@ -1,0 +1,174 @@
+// rr_uh.cu -- unit-hydrograph causal convolution for sm_100a.
+//
+// Replaces UnitHydrograph.convolve (river_route/uhkernels/UnitHydrograph.py:77-107):
+//     out[t,b] = carry[t,b] (t < n_ks) + sum_{tau} kernel[tau,b] * lateral[t-tau,b]
+// accumulated oldest contribution first, which is the order of the reference's exact
+// direct form convolve_incrementally (:64-75; the FFT path agrees with it to 1e-12,
+// tests/test_uhkernels.py:52-78).  Not a dense contraction: each basin has its own taps, so
+// there is nothing for tensor cores; it is a register-blocked FIR, one thread per basin,
+// all arrays (time, basin) row-major so every warp access is a coalesced 256-byte row segment.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+
+#include "rr_internal.h"
+
+void rr_count_launch(int64_t k);
+
+#define CK(call)                                                                \
+    do {                                                                        \
+        cudaError_t e_ = (call);                                                \
+        if (e_ != cudaSuccess) {                                                \
+            rr_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));   \
+            return 200;                                                         \
+        }                                                                       \
+    } while (0)
+
+namespace {
+
+// Taps and a circular window of the last NK inputs live in registers; the time loop is
+// unrolled NK-fold so every window index is a compile-time constant (no register moves).
+// grid.y splits time into chunks; a chunk warms its window from the NK-1 inputs before it.
+template <int NK>
+__global__ void __launch_bounds__(128) uh_conv_kernel(int64_t n, int n_ks, int64_t T, int64_t chunk,
+                                                      const double *__restrict__ lat, int64_t ldl,
+                                                      const double *__restrict__ ker, int64_t ldk,
+                                                      const double *__restrict__ state, int64_t lds,
+                                                      double *__restrict__ out, int64_t ldo) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const int64_t tb = (int64_t)blockIdx.y * chunk;
+    const int64_t te = min(T, tb + chunk);
+    double kq[NK], win[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) kq[k] = k < n_ks ? __ldg(ker + (int64_t)k * ldk + b) : 0.0;
+    // window slot u holds the input of time (tb + u) mod NK-periodic; warm-up: inputs tb-NK+1 .. tb-1
+#pragma unroll
+    for (int u = 1; u < NK; ++u) {
+        const int64_t t = tb - NK + u;
+        win[u] = t >= 0 ? __ldg(lat + t * ldl + b) : 0.0;
+    }
+    win[0] = 0.0;
+    for (int64_t t = tb; t < te; t += NK) {
+#pragma unroll
+        for (int u = 0; u < NK; ++u) {
+            const int64_t tt = t + u;
+            if (tt < te) {
+                win[u] = __ldg(lat + tt * ldl + b);
+                double acc = tt < n_ks ? state[tt * lds + b] : 0.0;   // UnitHydrograph.py:100
+#pragma unroll
+                for (int tau = NK - 1; tau >= 0; --tau)               // oldest input first
+                    acc = fma(kq[tau], win[(u - tau + 2 * NK) % NK], acc);
+                out[tt * ldo + b] = acc;
+            }
+        }
+    }
+}
+
+// Any kernel length: taps and inputs re-read through L1/L2.
+__global__ void __launch_bounds__(128) uh_conv_generic(int64_t n, int n_ks, int64_t T, int64_t chunk,
+                                                       const double *__restrict__ lat, int64_t ldl,
+                                                       const double *__restrict__ ker, int64_t ldk,
+                                                       const double *__restrict__ state, int64_t lds,
+                                                       double *__restrict__ out, int64_t ldo) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const int64_t tb = (int64_t)blockIdx.y * chunk;
+    const int64_t te = min(T, tb + chunk);
+    for (int64_t t = tb; t < te; ++t) {
+        double acc = t < n_ks ? state[t * lds + b] : 0.0;
+        const int tau_hi = (int)(t < (int64_t)n_ks - 1 ? t : (int64_t)n_ks - 1);
+        for (int tau = tau_hi; tau >= 0; --tau)
+            acc = fma(__ldg(ker + (int64_t)tau * ldk + b), __ldg(lat + (t - tau) * ldl + b), acc);
+        out[t * ldo + b] = acc;
+    }
+}
+
+// Carry-over state: rows 0..n_ks-2 = the full convolution at times T..T+n_ks-2, last row = 0
+// (UnitHydrograph.py:103-105).  Reads of the old state run ahead of the writes (row T+j > j).
+__global__ void __launch_bounds__(128) uh_state_kernel(int64_t n, int n_ks, int64_t T,
+                                                       const double *__restrict__ lat, int64_t ldl,
+                                                       const double *__restrict__ ker, int64_t ldk,
+                                                       double *state, int64_t lds) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    for (int j = 0; j < n_ks - 1; ++j) {
+        const int64_t t = T + j;
+        double acc = t < n_ks ? state[t * lds + b] : 0.0;
+        const int64_t s_lo = t - n_ks + 1 > 0 ? t - n_ks + 1 : 0;
+        for (int64_t s = s_lo; s < T; ++s)
+            acc = fma(__ldg(ker + (t - s) * ldk + b), __ldg(lat + s * ldl + b), acc);
+        state[(int64_t)j * lds + b] = acc;
+    }
+    state[(int64_t)(n_ks - 1) * lds + b] = 0.0;
+}
+
+}  // namespace
+
+extern "C" int rr_uh_convolve_dev(int64_t n, int64_t n_ks, int64_t T, const double *lateral, int64_t ldl,
+                                  const double *kernel, int64_t ldk, double *state, int64_t lds, double *out,
+                                  int64_t ldo, void *stream_) {
+    if (n <= 0 || n_ks <= 0 || T <= 0) { rr_set_error("n, n_ks and T must be positive"); return 100; }
+    if (!lateral || !kernel || !state || !out) { rr_set_error("null argument"); return 100; }
+    if (n_ks > 0x7fffffff) { rr_set_error("kernel too long"); return 100; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int threads = 128;
+    const unsigned gx = (unsigned)((n + threads - 1) / threads);
+    // enough time chunks to fill the machine when there are few basins; a chunk re-reads NK-1 rows
+    int sms = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t want_y = std::max<int64_t>(1, ((int64_t)sms * 16 + gx - 1) / gx);
+    int64_t chunk = std::max<int64_t>(std::max<int64_t>(8 * n_ks, 64), (T + want_y - 1) / want_y);
+    chunk = std::min<int64_t>(chunk, T);
+    const unsigned gy = (unsigned)((T + chunk - 1) / chunk);
+    dim3 grid(gx, gy);
+    const int nk = (int)n_ks;
+#define RR_UH_LAUNCH(NKT) \
+    uh_conv_kernel<NKT><<<grid, threads, 0, stream>>>(n, nk, T, chunk, lateral, ldl, kernel, ldk, state, lds, out, ldo)
+    if (nk <= 8) RR_UH_LAUNCH(8);
+    else if (nk <= 16) RR_UH_LAUNCH(16);
+    else if (nk <= 24) RR_UH_LAUNCH(24);
+    else if (nk <= 32) RR_UH_LAUNCH(32);
+    else uh_conv_generic<<<grid, threads, 0, stream>>>(n, nk, T, chunk, lateral, ldl, kernel, ldk, state, lds, out, ldo);
+#undef RR_UH_LAUNCH
+    CK(cudaGetLastError());
+    uh_state_kernel<<<gx, threads, 0, stream>>>(n, nk, T, lateral, ldl, kernel, ldk, state, lds);
+    CK(cudaGetLastError());
+    rr_count_launch(2);
+    return 0;
+}
+
+extern "C" int rr_uh_convolve_host(int64_t n, int64_t n_ks, int64_t T, const double *lateral, int64_t ldl,
+                                   const double *kernel, int64_t ldk, double *state, int64_t lds, double *out,
+                                   int64_t ldo) {
+    if (n <= 0 || n_ks <= 0 || T <= 0) { rr_set_error("n, n_ks and T must be positive"); return 100; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        rr_set_error("no CUDA device available: librr_b200 has no CPU fallback");
+        return 201;
+    }
+    const int64_t ldd = ((n + 31) / 32) * 32;
+    double *d_lat = nullptr, *d_ker = nullptr, *d_state = nullptr, *d_out = nullptr;
+    CK(cudaMalloc((void **)&d_lat, sizeof(double) * (size_t)T * ldd));
+    CK(cudaMalloc((void **)&d_out, sizeof(double) * (size_t)T * ldd));
+    CK(cudaMalloc((void **)&d_ker, sizeof(double) * (size_t)n_ks * ldd));
+    CK(cudaMalloc((void **)&d_state, sizeof(double) * (size_t)n_ks * ldd));
+    int rc = 0;
+    auto fail = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && !rc) { rr_set_error(std::string(what) + ": " + cudaGetErrorString(e)); rc = 200; }
+    };
+    fail(cudaMemcpy2D(d_lat, ldd * 8, lateral, ldl * 8, n * 8, T, cudaMemcpyHostToDevice), "H2D lateral");
+    fail(cudaMemcpy2D(d_ker, ldd * 8, kernel, ldk * 8, n * 8, n_ks, cudaMemcpyHostToDevice), "H2D kernel");
+    fail(cudaMemcpy2D(d_state, ldd * 8, state, lds * 8, n * 8, n_ks, cudaMemcpyHostToDevice), "H2D state");
+    if (!rc) rc = rr_uh_convolve_dev(n, n_ks, T, d_lat, ldd, d_ker, ldd, d_state, ldd, d_out, ldd, nullptr);
+    if (!rc) {
+        fail(cudaMemcpy2D(out, ldo * 8, d_out, ldd * 8, n * 8, T, cudaMemcpyDeviceToHost), "D2H out");
+        fail(cudaMemcpy2D(state, lds * 8, d_state, ldd * 8, n * 8, n_ks, cudaMemcpyDeviceToHost), "D2H state");
+    }
+    cudaFree(d_lat); cudaFree(d_out); cudaFree(d_ker); cudaFree(d_state);
+    return rc;
+}

@@ -1,0 +1,187 @@
+"""
+Host-side handle of the wavefront plan (``rr_plan`` in include/rr_b200.h) and the topology helpers.
+
+The plan plays the role of the reference's cached sparse arrays
+(``Muskingum._set_network_dependent_vectors`` / ``_set_muskingum_coefficients``,
+river_route/routers/Muskingum.py:141-193): it is built once per network and reused for every file.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+
+MODE_MUSKINGUM, MODE_RAPID, MODE_UNIT = 0, 1, 2
+
+
+def downstream_index(river_ids, downstream_ids) -> np.ndarray:
+    """
+    int32 index of each reach's downstream reach (-1 for outlets) with the reference's checks and
+    error messages: duplicate ids (routers/Muskingum.py:153-154), downstream ids that are not river
+    ids (Muskingum.py:161-166, river_route/tools.py:101-102) and topological order (tools.py:103-104).
+    """
+    river_ids = np.ascontiguousarray(river_ids, dtype=np.int64)
+    downstream_ids = np.ascontiguousarray(downstream_ids, dtype=np.int64)
+    if river_ids.ndim != 1 or river_ids.shape != downstream_ids.shape:
+        raise ValueError('river_ids and downstream_ids must be 1D arrays of the same length')
+    down = np.empty(river_ids.shape[0], dtype=np.int32)
+    bad = C.c_int64(0)
+    rc = lib.rr_downstream_index(river_ids.shape[0], _lib.as_i64p(river_ids), _lib.as_i64p(downstream_ids),
+                                 _lib.as_i32p(down), C.byref(bad))
+    if rc == 2 and bad.value > 0:
+        # Muskingum.py:161-166 runs before adjacency_matrix and lists every positive unknown id
+        unknown = np.setdiff1d(downstream_ids[downstream_ids > 0], river_ids)
+        raise ValueError(f'params_file has downstream IDs not in river_id column: {unknown[:10].tolist()}')
+    check(rc)
+    return down
+
+
+def label_basins(down: np.ndarray, n_parts: int = 0):
+    """
+    Drainage-basin label of every reach (basins numbered by ascending outlet index) and, when
+    ``n_parts`` > 0, the LPT bin-packing of basins over that many GPUs by reach count.
+    Returns (basin, n_basins, part-or-None).
+    """
+    down = np.ascontiguousarray(down, dtype=np.int32)
+    basin = np.empty(down.shape[0], dtype=np.int32)
+    nb = C.c_int64(0)
+    part = np.empty(down.shape[0], dtype=np.int32) if n_parts > 0 else None
+    check(lib.rr_label_basins(down.shape[0], _lib.as_i32p(down), _lib.as_i32p(basin), C.byref(nb), int(n_parts),
+                              _lib.as_i32p(part) if part is not None else None))
+    return basin, int(nb.value), part
+
+
+def down_from_csc(indptr, indices, n: int) -> np.ndarray:
+    """
+    Recover the downstream-index vector from the CSC arrays the reference passes to its kernels
+    (A[downstream, upstream] = 1, one entry per non-outlet column; tools.py:108-109).
+    """
+    indptr = np.asarray(indptr)
+    indices = np.asarray(indices)
+    if indptr.shape[0] != n + 1:
+        raise ValueError('csc_indptr has the wrong length for this state vector')
+    counts = np.diff(indptr)
+    if counts.size and counts.max() > 1:
+        raise ValueError('a river segment has more than one downstream segment; not a valid routing network')
+    down = np.full(n, -1, dtype=np.int32)
+    has = counts == 1
+    down[has] = indices[indptr[:-1][has]]
+    return down
+
+
+class Plan:
+    """Owns an ``rr_plan``.  ``down`` is the int32 downstream-index vector (-1 = outlet)."""
+
+    def __init__(self, down, time_tile: int = 0, tile_stride: int = 0, device: int = -1, threads_per_cta: int = 0,
+                 raw_budget_bytes: int = 0):
+        down = np.ascontiguousarray(down, dtype=np.int32)
+        self.n = int(down.shape[0])
+        self.down = down
+        opts = _lib.PlanOpts(int(time_tile), int(tile_stride), int(device), int(threads_per_cta), int(raw_budget_bytes))
+        handle = C.c_void_p()
+        check(lib.rr_plan_create(self.n, _lib.as_i32p(down), C.byref(opts), C.byref(handle)))
+        self._h = handle
+        self._coeff_key = None
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib.rr_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def info(self) -> dict:
+        inf = _lib.PlanInfo()
+        check(lib.rr_plan_get_info(self._h, C.byref(inf)))
+        return {k: getattr(inf, k) for k, _ in inf._fields_}
+
+    def set_coefficients(self, c1, c2, c3, c4_dt=None):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (c1, c2, c3)]
+        c4 = None if c4_dt is None else np.ascontiguousarray(c4_dt, dtype=np.float64)
+        for a in arrs + ([c4] if c4 is not None else []):
+            if a.shape != (self.n,):
+                raise ValueError('coefficient vectors must have one value per river segment')
+        check(lib.rr_plan_set_coefficients(self._h, *[_lib.as_f64p(a) for a in arrs],
+                                           _lib.as_f64p(c4) if c4 is not None else None))
+
+    # ---- host arrays (numpy) : H2D / route / D2H streamed inside the library ----
+    def route_host(self, mode: int, q_state: np.ndarray, lateral, out: np.ndarray, substeps: int, q_full=None):
+        """
+        One reference kernel call on host arrays.  ``q_state`` (n,) is updated in place with the final state,
+        ``out`` (T, n) is overwritten.  ``lateral`` is (T, n) or None for MODE_MUSKINGUM.
+        """
+        if q_state.dtype != np.float64 or not q_state.flags.c_contiguous or q_state.shape != (self.n,):
+            raise ValueError('q_state must be a contiguous float64 vector with one value per river segment')
+        if out.dtype != np.float64 or out.ndim != 2 or out.shape[1] != self.n:
+            raise ValueError('discharge array must be float64 with shape (T, n)')
+        T = out.shape[0]
+        ldo = _lib.rows_ld(out)
+        p_lat, ldl = None, self.n
+        if mode != MODE_MUSKINGUM:
+            if lateral.shape != (T, self.n):
+                raise ValueError(f'lateral inflow shape {lateral.shape} does not match (T, n) = {(T, self.n)}')
+            if lateral.dtype != np.float64 or (self.n > 1 and lateral.strides[1] != 8):
+                # the reference's grid path hands over an F-ordered transposed view (runoff.py:298)
+                lateral = np.ascontiguousarray(lateral, dtype=np.float64)
+            ldl = _lib.rows_ld(lateral)
+            p_lat = _lib.as_f64p(lateral)
+        p_qf = None
+        if q_full is not None:
+            if q_full.dtype != np.float64 or not q_full.flags.c_contiguous or q_full.shape != (self.n,):
+                raise ValueError('q_full must be a contiguous float64 vector with one value per river segment')
+            p_qf = _lib.as_f64p(q_full)
+        check(lib.rr_route_host(self._h, int(mode), _lib.as_f64p(q_state), p_qf, p_lat, ldl, _lib.as_f64p(out), ldo,
+                                T, int(substeps)))
+
+    # ---- device pointers (torch tensors used purely as device buffers) ----
+    def route_dev(self, mode: int, q_state_ptr: int, lateral_ptr: int, ldl: int, out_ptr: int, ldo: int, T: int,
+                  substeps: int, stream: int = 0, q_full_ptr: int = 0):
+        check(lib.rr_route_dev(self._h, int(mode), C.c_void_p(q_state_ptr), C.c_void_p(q_full_ptr or None),
+                               C.c_void_p(lateral_ptr or None), int(ldl), C.c_void_p(out_ptr), int(ldo), int(T),
+                               int(substeps), C.c_void_p(stream or None)))
+
+    def route_ensemble_dev(self, mode: int, q_init_ptr: int, lateral_ptrs, ldl: int, out_ptrs, ldo: int,
+                           q_final_ptrs, T: int, substeps: int, stream: int = 0):
+        m = len(out_ptrs)
+        arr = C.c_void_p * m
+        lat = arr(*lateral_ptrs) if lateral_ptrs else None
+        check(lib.rr_route_ensemble_dev(self._h, int(mode), C.c_void_p(q_init_ptr), m, lat, int(ldl), arr(*out_ptrs),
+                                        int(ldo), arr(*q_final_ptrs), int(T), int(substeps),
+                                        C.c_void_p(stream or None)))
+
+    # ---- introspection (tests, DESIGN.md numbers) ----
+    def arrays(self) -> dict:
+        inf = self.info
+        ptrs = [_lib.c_i32p(), _lib.c_i32p(), _lib.c_u8p()] + [_lib.c_i32p() for _ in range(6)]
+        check(lib.rr_plan_get_arrays(self._h, *[C.byref(p) for p in ptrs]))
+        n, e, nb, nd = inf['n'], inf['n_edges'], inf['n_blocks'], inf['n_dep_edges']
+        sizes = [n + 1, e, n, e, n, nb, nb + 1, nd, inf['n_export']]
+        names = ['up_ptr', 'up_idx', 'skew', 'slot_src', 'export_id', 'blk_level', 'dep_ptr', 'dep_idx', 'exp_span']
+        out = {}
+        for name, p, sz in zip(names, ptrs, sizes):
+            out[name] = np.ctypeslib.as_array(p, shape=(sz,)).copy() if sz > 0 else np.zeros(0, dtype=np.int32)
+        return out
+
+    def schedule(self, n_tiles: int, tile_stride: int):
+        """Ticket order as (block, tile) pairs -- the kernel decodes tickets with the same table."""
+        nb = self.info['n_blocks']
+        blocks = np.empty(nb * n_tiles, dtype=np.int32)
+        tiles = np.empty(nb * n_tiles, dtype=np.int32)
+        n_items = C.c_int64(0)
+        check(lib.rr_plan_schedule(self._h, int(n_tiles), int(tile_stride), C.byref(n_items), _lib.as_i32p(blocks),
+                                   _lib.as_i32p(tiles)))
+        assert n_items.value == nb * n_tiles
+        return blocks, tiles
+
+
+def launch_count(reset: bool = False) -> int:
+    """Kernel launches issued by the library on this thread (bench.py's gpu_launches)."""
+    return int(lib.rr_launch_count(1 if reset else 0))

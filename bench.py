@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""
+bench.py -- reach-timesteps/sec of the RapidMuskingum routing hot path (BASELINE.json metric).
+
+Workload (config.workload = "C4"): the GEOGLOWS-scale configuration of BASELINE.json configs[3] --
+a synthetic 7M-reach forest in 5000 independent basins (SURVEY.md 8d generator, seed 4), hourly
+lateral inflow volumes, dt_routing = dt_runoff = 3600 s, fp64.  One "step" routes one resident chunk
+of `--rows` hourly time steps over the whole network, chained in time through the channel state
+(a 1-year run is 8760/rows such steps).  The 7M-reach network fits one B200, so it is the N=1
+workload; with N GPUs the basins are bin-packed over the ranks (no collective in the time loop) and
+the total work stays the same ("scaling": "strong").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU algorithm (oracle port)
+
+Prints ONE JSON line on rank 0.  `value` is timed with CUDA events around device-resident launches;
+`e2e` is the same metric through the host-array API (pinned H2D + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_ALG = 56.0  # algorithmic bytes per reach-timestep: 8 lateral + 8 discharge + 32 coefficients + 8 topology
+DT = 3600
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--reaches', type=int, default=7_000_000)
+    ap.add_argument('--basins', type=int, default=5000)
+    ap.add_argument('--rows', type=int, default=240, help='hourly time steps resident per step')
+    ap.add_argument('--e2e-rows', type=int, default=48, help='time steps per end-to-end (host array) step')
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--ref-rows', type=int, default=24, help='time steps per step of the CPU reference arm')
+    ap.add_argument('--cpu-sample-reaches', type=int, default=1_000_000)
+    ap.add_argument('--depth-bias', type=float, default=0.5)
+    ap.add_argument('--time-tile', type=int, default=0)
+    ap.add_argument('--tile-stride', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--order', default='growth', choices=['growth', 'level'],
+                    help='reach order of the synthetic params file: generator order or sorted by topological level')
+    return ap.parse_args()
+
+
+def network(args):
+    """C4 network + Muskingum parameters, identical on every rank."""
+    from river_route_b200 import synth
+    down = synth.forest(args.reaches, args.basins, seed=4, depth_bias=args.depth_bias)
+    k, x = synth.muskingum_params(args.reaches, 4)
+    if args.order == 'level':
+        down = synth.relabel(down, synth.level_sorted_order(down))
+    return down, k, x
+
+
+def coefficients(k, x, dt_routing, dt_runoff):
+    """The reference's exact expressions (routers/Muskingum.py:174-179, TransformMuskingum.py:104)."""
+    dt_div_k = dt_routing / k
+    denominator = dt_div_k + (2 * (1 - x))
+    _2x = 2 * x
+    c1 = (dt_div_k - _2x) / denominator
+    c2 = (dt_div_k + _2x) / denominator
+    c3 = ((2 * (1 - x)) - dt_div_k) / denominator
+    return c1, c2, c3, (c1 + c2) / dt_runoff
+
+
+def shard(down, n_parts, part_id):
+    """Reaches of this rank's basins, in their original relative order, and the local downstream index."""
+    import river_route_b200 as rr
+    from river_route_b200 import synth
+    if n_parts == 1:
+        return np.arange(down.shape[0]), down
+    _, _, part = rr.label_basins(down, n_parts)
+    idx = np.flatnonzero(part == part_id)
+    new_of_old = np.full(down.shape[0], -1, dtype=np.int64)
+    new_of_old[idx] = np.arange(idx.shape[0])
+    d = down[idx]
+    local = np.where(d >= 0, new_of_old[np.where(d >= 0, d, 0)], -1).astype(np.int32)
+    return idx, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for l in self.lines:
+            f = [s.strip() for s in l.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the routing kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def cpu_baseline(down, k, x, target_reaches, rows, threads=1):
+    """The oracle port of rapid_route on the host cores, on a bounded sample of the same workload:
+    the first whole basins of the network (basins are contiguous index ranges) x `rows` hourly steps."""
+    from oracle import oracle
+    from river_route_b200 import synth
+    outlets = np.flatnonzero(down < 0)
+    m = int(outlets[np.searchsorted(outlets, min(target_reaches, down.shape[0]) - 1)]) + 1
+    sub = down[:m]
+    c1, c2, c3, c4 = coefficients(k[:m], x[:m], DT, DT)
+    indptr, indices = oracle.csc_from_down(sub)
+    lhs = oracle.lhs_off_data(c1, indices)
+    ql = synth.lateral_volumes(rows, m, 99)
+    out = np.zeros((rows, m))
+    q = np.zeros(m)
+    oracle.rapid_route(indptr, indices, lhs, c2, c3, c4, q, ql[:2], out[:2], 1)   # warm caches / page in
+    t = time.perf_counter()
+    oracle.rapid_route(indptr, indices, lhs, c2, c3, c4, q, ql, out, 1)
+    dt = time.perf_counter() - t
+    return {'value': m * rows / dt, 'unit': 'reach-timesteps/s', 'cores': threads, 'kind': 'port',
+            'sample': f'first {m} reaches (whole basins) x {rows} hourly steps, oracle/rr_oracle.c (-O3, scalar), '
+                      f'{dt:.2f} s; host has {os.cpu_count()} cores'}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm with every host core, parallel over independent basins as
+    the reference documents (docs/references/parallelism.md:67-112).  The reference is Python+numba and cannot
+    travel to the GPU box, so this is the oracle port (kind = "port")."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import river_route_b200 as rr
+    from river_route_b200 import synth
+    from oracle import oracle
+    down, k, x = network(args)
+    cores = os.cpu_count() or 1
+    _, _, part = rr.label_basins(down, cores)
+    shards = []
+    rows = args.ref_rows
+    for c in range(cores):
+        idx = np.flatnonzero(part == c)
+        new_of_old = np.full(down.shape[0], -1, dtype=np.int64)
+        new_of_old[idx] = np.arange(idx.shape[0])
+        d = down[idx]
+        local = np.where(d >= 0, new_of_old[np.where(d >= 0, d, 0)], -1)
+        c1, c2, c3, c4 = coefficients(k[idx], x[idx], DT, DT)
+        indptr, indices = oracle.csc_from_down(local)
+        shards.append(dict(indptr=indptr, indices=indices, lhs_off=oracle.lhs_off_data(c1, indices), c2=c2, c3=c3,
+                           c4_dt=c4, q_t=np.zeros(idx.shape[0]), ql=synth.lateral_volumes(rows, idx.shape[0], 100 + c),
+                           out=np.zeros((rows, idx.shape[0]))))
+    for _ in range(args.warmup):
+        oracle.rapid_route_sharded(shards, 1, cores)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.rapid_route_sharded(shards, 1, cores)
+    dt = time.perf_counter() - t
+    value = args.reaches * rows * args.steps / dt
+    sample = (f'{args.reaches} reaches x {rows} hourly steps per step, basins bin-packed over {cores} threads, '
+              f'oracle/rr_oracle.c rapid_route')
+    line = {
+        'impl': 'reference', 'metric': 'reach-timesteps/sec (RapidMuskingum, fp64)', 'value': value,
+        'unit': 'reach-timesteps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, rows),
+        'cpu_baseline': {'value': value, 'unit': 'reach-timesteps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'reach-timesteps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, rows):
+    return {'workload': 'C4', 'router': 'RapidMuskingum', 'reaches': args.reaches, 'basins': args.basins,
+            'network': f'synthetic forest seed 4 depth_bias {args.depth_bias} (SURVEY.md 8d), reach order: {args.order}',
+            'rows_per_step': rows, 'dt_runoff_s': DT, 'dt_routing_s': DT, 'substeps': 1,
+            'parallelism': f'basin-sharded x{args.gpus}, no collective in the time loop',
+            'l2': 'inputs larger than L2: every step streams rows x reaches x 16 B'}
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import river_route_b200 as rr
+    from river_route_b200 import synth  # noqa: F401
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
+    if not rr.cuda_available():
+        raise SystemExit('bench.py needs a CUDA device: river_route_b200 has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    # ---- network, shard, plan ----
+    down, k, x = network(args)
+    idx, local_down = shard(down, world, rank)
+    n = int(idx.shape[0])
+    plan = rr.Plan(local_down, time_tile=args.time_tile, tile_stride=args.tile_stride, device=local_rank)
+    c1, c2, c3, c4 = coefficients(k[idx], x[idx], DT, DT)
+    plan.set_coefficients(c1, c2, c3, c4)
+    info = plan.info
+
+    # ---- device-resident inputs (synthetic lateral volumes: gamma(0.3, 5e4 m3), half zeros) ----
+    rows = args.rows
+    ld = ((n + 31) // 32) * 32
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    d_lat = torch.empty((rows, ld), dtype=torch.float64, device=dev)
+    conc = torch.full((ld,), 0.3, dtype=torch.float64, device=dev)
+    for t in range(rows):
+        g = torch._standard_gamma(conc, generator=gen) * 5.0e4
+        g[torch.rand(ld, device=dev, generator=gen) < 0.5] = 0.0
+        d_lat[t] = g
+    d_out = torch.empty((rows, ld), dtype=torch.float64, device=dev)
+    d_q = torch.zeros(n, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        plan.route_dev(rr.MODE_RAPID, d_q.data_ptr(), d_lat.data_ptr(), ld, d_out.data_ptr(), ld, rows, 1, stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    rr.launch_count(reset=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for s in range(args.steps):
+        step()
+        ev[s + 1].record()
+    barrier()
+    launches = rr.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
+    t_max = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t_max.item())
+    value = args.reaches * rows * args.steps / (total_ms_max * 1e-3)
+
+    # ---- summary outputs gathered over NVLink (outside the time loop): outlet discharge of the last step ----
+    outlets = torch.from_numpy(np.flatnonzero(local_down < 0)).to(dev)
+    summary = torch.stack([d_out[rows - 1, outlets].sum(), d_q.sum(), torch.tensor(float(n), device=dev, dtype=torch.float64)])
+    if dist is not None:
+        parts = [torch.empty_like(summary) for _ in range(world)]
+        dist.all_gather(parts, summary)
+        summary_all = torch.stack(parts).cpu().numpy()
+    else:
+        summary_all = summary.cpu().numpy()[None]
+    finite = bool(torch.isfinite(d_out[:, :n]).all().item())
+
+    # ---- end to end through the host-array API: pinned H2D + route + D2H every step ----
+    er = args.e2e_rows
+    h_lat = rr.pinned_empty((er, n))
+    h_out = rr.pinned_empty((er, n))
+    h_lat[:] = d_lat[:er, :n].cpu().numpy()
+    h_q = np.zeros(n)
+    plan.route_host(rr.MODE_RAPID, h_q, h_lat, h_out, 1)          # warm-up (allocates the staging buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        plan.route_host(rr.MODE_RAPID, h_q, h_lat, h_out, 1)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = args.reaches * er * args.e2e_steps / float(e2e_t.item())
+    # the host path must agree with the device path on the same inputs (first chunk, zero state)
+    d_chk_q = torch.zeros(n, dtype=torch.float64, device=dev)
+    d_chk = torch.empty((er, ld), dtype=torch.float64, device=dev)
+    h_q2 = np.zeros(n)
+    plan.route_host(rr.MODE_RAPID, h_q2, h_lat, h_out, 1)
+    plan.route_dev(rr.MODE_RAPID, d_chk_q.data_ptr(), d_lat.data_ptr(), ld, d_chk.data_ptr(), ld, er, 1, stream)
+    torch.cuda.synchronize()
+    host_equals_dev = bool(np.array_equal(d_chk[:, :n].cpu().numpy(), h_out))
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kernel_ms = float(np.mean(step_ms))
+        achieved = B_ALG * n * rows / (kernel_ms * 1e-3) / 1e9
+        traffic = ncu_traffic()
+        line = {
+            'metric': 'reach-timesteps/sec (RapidMuskingum, fp64)', 'value': value, 'unit': 'reach-timesteps/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms_max / args.steps,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': dict(workload_config(args, rows), reaches_rank0=n, plan={k_: int(v) for k_, v in info.items()}),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': (traffic or {}).get('dram_bytes_per_launch'),
+                         'kernel': 'rr_wavefront_kernel<RAPID>', 'kernel_ms': kernel_ms,
+                         'algorithmic_bytes_per_reach_step': B_ALG, 'peak_source': peak_src,
+                         'traffic_source': (traffic or {}).get('source')},
+            'e2e': {'value': e2e_value, 'unit': 'reach-timesteps/s', 'h2d_bytes_per_step': int(n * er * 8 + n * 8),
+                    'd2h_bytes_per_step': int(n * er * 8 + n * 8), 'rows_per_step': er, 'steps': args.e2e_steps,
+                    'api': 'Plan.route_host (pinned host arrays, chunked cudaMemcpyAsync inside rr_route_host)',
+                    'host_equals_device_path': host_equals_dev},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'checks': {'finite': finite, 'summary_per_rank[outlet_q_last_step, state_sum, reaches]': summary_all.tolist()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline(down, k, x, args.cpu_sample_reaches, rows)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -41,7 +41,7 @@ struct rr_device_state {
     int device = 0, sm_count = 0;
     // plan arrays
     int32_t *up_ptr = nullptr, *up_idx = nullptr, *slot_src = nullptr, *export_id = nullptr;
-    int32_t *dep_ptr = nullptr, *dep_idx = nullptr, *down = nullptr, *exp_off = nullptr, *exp_ring = nullptr;
+    int32_t *dep_ptr = nullptr, *dep_idx = nullptr, *down = nullptr, *exp_ro = nullptr, *edge_ro = nullptr;
     int32_t *lvl_ptr = nullptr, *lvl_blk = nullptr;
     uint8_t *skew = nullptr;
     rr_blk_meta *meta = nullptr;
@@ -131,7 +131,7 @@ void rr_device_release(rr_plan *p) {
     if (!d) return;
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {d->up_ptr, d->up_idx, d->slot_src, d->export_id, d->dep_ptr, d->dep_idx, d->down, d->exp_off, d->exp_ring,
+    void *ptrs[] = {d->up_ptr, d->up_idx, d->slot_src, d->export_id, d->dep_ptr, d->dep_idx, d->down, d->exp_ro, d->edge_ro,
                     d->lvl_ptr, d->lvl_blk, d->skew, d->meta, d->coef, d->key_start, d->raw, d->done, d->ticket,
                     d->d_lat[0], d->d_lat[1], d->d_out[0], d->d_out[1], d->d_q, d->d_qfull};
     for (void *q : ptrs)
@@ -165,7 +165,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     // tile geometry: aim for `time_tile` routing substeps per work item
     const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(T, p->opts.time_tile / K));
     const int64_t n_tiles = (T + rows - 1) / rows;
-    const int64_t pitch = ((rows * K + 2 + 3) / 4) * 4;
+    const int64_t pitch = 4 + ((rows * K + 3) / 4) * 4;   // [2] q_full carry, [3] carry, [4+s] substeps (rr_route.cu)
     const int64_t budget_rows = std::max<int64_t>(1, p->opts.raw_budget_bytes / (int64_t)(pitch * sizeof(double) * n_members));
     if (d->sched_tiles != n_tiles || d->sched_budget_rows != budget_rows) {
         if ((double)n_tiles * (double)(p->max_level + 1) > 2e9) {
@@ -183,15 +183,14 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
         }
         CK(cudaMemcpy(d->key_start, d->sched.key_start.data(), d->sched.key_start.size() * sizeof(int64_t),
                       cudaMemcpyHostToDevice));
-        const size_t ne = std::max<size_t>(d->sched.exp_ring.size(), 1);
-        if (!d->exp_off) {
-            CK(cudaMalloc((void **)&d->exp_off, ne * sizeof(int32_t)));
-            CK(cudaMalloc((void **)&d->exp_ring, ne * sizeof(int32_t)));
+        if (!d->exp_ro) {
+            CK(cudaMalloc((void **)&d->exp_ro, std::max<size_t>(d->sched.exp_ro.size(), 2) * sizeof(int32_t)));
+            CK(cudaMalloc((void **)&d->edge_ro, std::max<size_t>(d->sched.edge_ro.size(), 2) * sizeof(int32_t)));
         }
-        if (!d->sched.exp_ring.empty()) {
-            CK(cudaMemcpy(d->exp_off, d->sched.exp_off.data(), d->sched.exp_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d->exp_ring, d->sched.exp_ring.data(), d->sched.exp_ring.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        }
+        if (!d->sched.exp_ro.empty())
+            CK(cudaMemcpy(d->exp_ro, d->sched.exp_ro.data(), d->sched.exp_ro.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        if (!d->sched.edge_ro.empty())
+            CK(cudaMemcpy(d->edge_ro, d->sched.edge_ro.data(), d->sched.edge_ro.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         d->sched_tiles = n_tiles;
         d->sched_budget_rows = budget_rows;
     }
@@ -218,7 +217,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.up_ptr = d->up_ptr; P.up_idx = d->up_idx; P.slot_src = d->slot_src; P.skew = d->skew;
     P.export_id = d->export_id; P.meta = d->meta;
     P.dep_ptr = d->dep_ptr; P.dep_idx = d->dep_idx; P.down = d->down;
-    P.exp_off = d->exp_off; P.exp_ring = d->exp_ring; P.raw_rows = d->sched.raw_rows;
+    P.exp_ro = d->exp_ro; P.edge_ro = d->edge_ro; P.raw_rows = d->sched.raw_rows;
     P.lvl_ptr = d->lvl_ptr; P.lvl_blk = d->lvl_blk;
     P.c1 = d->coef; P.c2 = d->coef + p->n; P.c3 = d->coef + 2 * p->n; P.c4 = d->coef + 3 * p->n;
     P.key_start = d->key_start; P.n_keys = d->sched.n_keys; P.n_items = d->sched.n_items;

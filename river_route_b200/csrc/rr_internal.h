@@ -54,8 +54,8 @@ struct rr_schedule {
     int32_t delta = 1;
     int64_t n_keys = 0;
     std::vector<int64_t> key_start;  // [n_keys+1] prefix sum of items per key
-    std::vector<int32_t> exp_ring;   // [n_export] ring depth of each exported series
-    std::vector<int32_t> exp_off;    // [n_export] first row of the ring in the exchange buffer
+    std::vector<int32_t> exp_ro;     // [n_export][2] {first row, ring depth} of each exported series
+    std::vector<int32_t> edge_ro;    // [edges][2] the same pair for the upstream of each upstream-CSR entry
     int64_t raw_rows = 0;            // total rows (per ensemble member)
 };
 // delta = ticket-key distance between consecutive tiles of one block (0: smallest power of two whose

@@ -212,6 +212,7 @@ extern "C" int rr_plan_create(int64_t n, const int32_t *down, const rr_plan_opts
         int32_t lvl = 0;
         for (int32_t ub : tmp) lvl = std::max(lvl, p->meta[ub].level + 1);
         m.level = lvl;
+        if (m.int_mask == 0 && m.max_skew == 0 && m.max_deg <= RR_MAX_FAST_DEG) m.int_mask |= 0x40;  // fast-path eligible
         p->dep_idx.insert(p->dep_idx.end(), tmp.begin(), tmp.end());
         p->dep_ptr[b + 1] = (int32_t)p->dep_idx.size();
         p->max_level = std::max(p->max_level, lvl);
@@ -318,13 +319,19 @@ void rr_build_schedule(const rr_plan &p, int64_t n_tiles, int32_t delta, int64_t
         delta = (int32_t)std::min<int64_t>(d, (int64_t)p.max_level + 1);
     }
     s.delta = delta;
-    s.exp_ring.resize(p.n_export);
-    s.exp_off.resize(p.n_export);
+    s.exp_ro.resize(2 * (size_t)p.n_export);
     int64_t rows = 0;
     for (int64_t e = 0; e < p.n_export; ++e) {
-        s.exp_off[e] = (int32_t)rows;
-        s.exp_ring[e] = (int32_t)std::min<int64_t>(p.exp_span[e] / delta + 1, n_tiles);
-        rows += s.exp_ring[e];
+        const int64_t ring = std::min<int64_t>(p.exp_span[e] / delta + 1, n_tiles);
+        s.exp_ro[2 * e] = (int32_t)rows;
+        s.exp_ro[2 * e + 1] = (int32_t)ring;
+        rows += ring;
+    }
+    s.edge_ro.assign(2 * (size_t)p.n_edges, 0);
+    for (int64_t e = 0; e < p.n_edges; ++e) {
+        const int32_t x = p.export_id[p.up_idx[e]];
+        s.edge_ro[2 * e] = x >= 0 ? s.exp_ro[2 * (size_t)x] : -1;
+        s.edge_ro[2 * e + 1] = x >= 0 ? s.exp_ro[2 * (size_t)x + 1] : 1;
     }
     s.raw_rows = std::max<int64_t>(rows, 1);
     s.n_keys = (int64_t)p.max_level + (n_tiles - 1) * (int64_t)s.delta + 1;

@@ -17,47 +17,189 @@
 //     guarantees that every in-block upstream lane is exactly ONE step ahead, so its newest and
 //     previous discharge are fetched with warp shuffles -- no shared memory, no in-block flags.
 //   * Between blocks, a reach whose downstream lives in another block exports its raw (unclamped)
-//     substep series for the tile to the exchange buffer raw[slot][export_id][1 + s] (entry 0 is
-//     the carry-in value).  Consumers read those series; the producer publishes "tile j done" with
-//     a release store on done[b], consumers acquire it.  A reach therefore advances to tile j+1 as
-//     soon as its upstream blocks and its own tile j are done: the wavefront pipelines time through
-//     deep networks with no grid-wide barrier and one kernel launch per call.
+//     substep series for the tile into its private ring of rows in the exchange buffer.  Row layout
+//     (doubles): [2] = q_full carry-in (UNIT), [3] = carry-in, [4 + s] = value after substep s, so the
+//     four values of steps 4g..4g+3 are one aligned 32-byte sector.  The producer publishes
+//     "tile j done" with a release store on done[b]; consumers poll it and acquire.  A reach therefore
+//     advances to tile j+1 as soon as its upstream blocks and its own tile j are done: the wavefront
+//     pipelines time through deep networks with no grid-wide barrier and one launch per call.
 //   * Persistent warps take tickets from a global counter; the ticket order (rr_plan.cpp) is a
 //     linear extension of all dependencies, so the lowest unfinished ticket can always finish.
+//   * Blocks without in-block edges and with at most RR_MAX_FAST_DEG upstreams per reach (all blocks
+//     of a level-sorted network) run a register-blocked fast path: four time steps per iteration,
+//     32-byte exchange loads/stores, next iteration's operands in flight while this one computes.
 #include <cuda_runtime.h>
 
 #include "rr_route.cuh"
 
 #define FULL_MASK 0xffffffffu
 #define SLOT_NONE ((int32_t)0x80000000)
+#define RAW_QF 2      // row entry holding the q_full carry-in (UNIT)
+#define RAW_CARRY 3   // row entry holding the value before the tile's first substep
+#define RAW_S0 4      // row entry of substep 0
 
 namespace {
 
-__device__ __forceinline__ int32_t ld_acquire(const int32_t *p) {
+__device__ __forceinline__ int32_t ld_relaxed(const int32_t *p) {
     int32_t v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int32_t *p, int32_t v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Spin with relaxed loads (no L1 invalidation per poll); the caller fences once after all waits.
 __device__ __forceinline__ void wait_ge(const int32_t *flag, int32_t want) {
-    unsigned ns = 20;
-    while (ld_acquire(flag) < want) {
+    unsigned ns = 32;
+    while (ld_relaxed(flag) < want) {
         __nanosleep(ns);
-        if (ns < 640) ns <<= 1;
+        if (ns < 512) ns <<= 1;
     }
 }
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // streaming read of data that is never written during the launch
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldg(p); }
+
+struct d4 { double a, b, c, d; };
+// one aligned 32-byte sector of an exchange row (written by another SM earlier in this launch:
+// plain coherent loads, ordered after the acquire fence)
+__device__ __forceinline__ d4 ld_sector(const double *p) {
+    d4 v;
+    const double2 lo = *reinterpret_cast<const double2 *>(p);
+    const double2 hi = *reinterpret_cast<const double2 *>(p + 2);
+    v.a = lo.x; v.b = lo.y; v.c = hi.x; v.d = hi.y;
+    return v;
+}
+__device__ __forceinline__ void st_sector(double *p, double a, double b, double c, double d) {
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2(c, d);
+}
+
+struct item_ctx {
+    int m, b, j, lane;
+    int64_t i;
+    bool valid;
+    int t0, rows, TT;
+    double *raw_m;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: K == 1, no in-block edges, every reach has at most NS upstreams (all external).
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int NS>
+__device__ __forceinline__ void fast_item(const rr_route_params &P, const item_ctx &c, double c1, double c2, double c3,
+                                          double c4, int e0, int deg, int ex, double q) {
+    constexpr bool HAS_LAT = (MODE == RR_MODE_RAPID);
+    constexpr int NA = NS > 0 ? NS : 1;
+    const int j = c.j;
+    const double *up[NA];
+    bool has[NA];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        has[k] = k < deg;
+        up[k] = c.raw_m;
+        if (has[k]) {
+            const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + e0 + k);
+            up[k] = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+        }
+    }
+    double *myraw = nullptr;
+    if (ex >= 0) {
+        const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + ex);
+        myraw = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+        myraw[RAW_CARRY] = q;
+    }
+    const double *lat = HAS_LAT ? P.lateral[c.m] + (size_t)c.t0 * P.ldl + c.i : nullptr;
+    double *outp = P.out[c.m] + (size_t)c.t0 * P.ldo + c.i;
+    const int TT = c.TT;
+
+    // operands of the first group: sector 0 holds the carry in .d, sector 1 the values of steps 0..3
+    d4 cur[NA], nxt[NA];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        cur[k] = d4{0, 0, 0, 0};
+        nxt[k] = d4{0, 0, 0, 0};
+        if (has[k]) { cur[k] = ld_sector(up[k]); nxt[k] = ld_sector(up[k] + 4); }
+    }
+    double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+    if (HAS_LAT && c.valid) {
+        l0 = ld_stream(lat);
+        if (1 < TT) l1 = ld_stream(lat + P.ldl);
+        if (2 < TT) l2 = ld_stream(lat + 2 * P.ldl);
+        if (3 < TT) l3 = ld_stream(lat + 3 * P.ldl);
+    }
+    for (int s = 0; s < TT; s += 4) {
+        // ---- issue the next group's loads before computing this one ----
+        d4 fut[NA];
+        double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        const bool more = s + 4 < TT;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            fut[k] = d4{0, 0, 0, 0};
+            if (has[k] && more) fut[k] = ld_sector(up[k] + s + 8);
+        }
+        if (HAS_LAT && c.valid && more) {
+            const double *lp = lat + (size_t)(s + 4) * P.ldl;
+            n0 = ld_stream(lp);
+            if (s + 5 < TT) n1 = ld_stream(lp + P.ldl);
+            if (s + 6 < TT) n2 = ld_stream(lp + 2 * P.ldl);
+            if (s + 7 < TT) n3 = ld_stream(lp + 3 * P.ldl);
+        }
+        // ---- four substeps; old = value before the substep, new = value after it ----
+        // step s: old = cur.d, new = nxt.a;  step s+1: old = nxt.a, new = nxt.b;  ...
+        double r0, r1, r2, r3;
+        {
+            double r = c3 * q;                                       // _numba_kernels.py:27-28 / :68-69
+            if (HAS_LAT) r = fma(c4, l0, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c2, cur[k].d, r);   // :29-33 / :70-74, ascending upstream
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].a, r);   // :36-39 / :75-78 (lhs_off = -c1)
+            r0 = r;
+            r = c3 * r0;
+            if (HAS_LAT) r = fma(c4, l1, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c2, nxt[k].a, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].b, r);
+            r1 = r;
+            r = c3 * r1;
+            if (HAS_LAT) r = fma(c4, l2, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c2, nxt[k].b, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].c, r);
+            r2 = r;
+            r = c3 * r2;
+            if (HAS_LAT) r = fma(c4, l3, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c2, nxt[k].c, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].d, r);
+            r3 = r;
+        }
+        if (c.valid) {
+            // K == 1: the interval mean is the value itself; clamp as :44-46 / :82-84
+            double *o = outp + (size_t)s * P.ldo;
+            o[0] = r0 > 0.0 ? r0 : 0.0;
+            if (s + 1 < TT) o[P.ldo] = r1 > 0.0 ? r1 : 0.0;
+            if (s + 2 < TT) o[2 * P.ldo] = r2 > 0.0 ? r2 : 0.0;
+            if (s + 3 < TT) o[3 * P.ldo] = r3 > 0.0 ? r3 : 0.0;
+        }
+        if (myraw) st_sector(myraw + RAW_S0 + s, r0, r1, r2, r3);
+        q = (s + 3 < TT) ? r3 : ((s + 2 < TT) ? r2 : ((s + 1 < TT) ? r1 : r0));
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { cur[k] = nxt[k]; nxt[k] = fut[k]; }
+        l0 = n0; l1 = n1; l2 = n2; l3 = n3;
+    }
+    if (c.valid) P.q_state[c.m][c.i] = q;
+}
 
 }  // namespace
 
 template <int MODE>
-__global__ void __launch_bounds__(256) rr_wavefront_kernel(const __grid_constant__ rr_route_params P) {
+__global__ void __launch_bounds__(256, 2) rr_wavefront_kernel(const __grid_constant__ rr_route_params P) {
     constexpr bool HAS_LAT = (MODE != RR_MODE_MUSKINGUM);
     constexpr bool UNIT = (MODE == RR_MODE_UNIT);
     const int lane = threadIdx.x & 31;
@@ -98,23 +240,74 @@ __global__ void __launch_bounds__(256) rr_wavefront_kernel(const __grid_constant
         const int64_t ic = valid ? i : P.n - 1;
         const double c1 = __ldg(P.c1 + ic), c2 = __ldg(P.c2 + ic), c3 = __ldg(P.c3 + ic);
         const double c4 = HAS_LAT && !UNIT ? __ldg(P.c4 + ic) : 0.0;
-        const int d = __ldg(P.skew + ic);
         const int e0 = __ldg(P.up_ptr + ic);
         const int deg = valid ? __ldg(P.up_ptr + ic + 1) - e0 : 0;
         const int ex = valid ? __ldg(P.export_id + ic) : -1;
         const rr_blk_meta M = P.meta[b];
+
+        item_ctx c;
+        c.m = m; c.b = b; c.j = j; c.lane = lane; c.i = i; c.valid = valid;
+        c.t0 = j * P.tile_rows;
+        c.rows = min(P.tile_rows, P.T - c.t0);
+        c.TT = c.rows * K;
+        c.raw_m = P.raw + (size_t)m * (size_t)P.raw_rows * P.raw_pitch;
+        const int t0 = c.t0, rows = c.rows, TT = c.TT;
+        double *raw_m = c.raw_m;
+
+        if (HAS_LAT) {
+            // pull this item's lateral tile towards L2 while the dependency wait runs
+            const double *lt = P.lateral[m] + (size_t)t0 * P.ldl + (size_t)b * RR_BLOCK;
+            const int64_t left = P.n - (int64_t)b * RR_BLOCK;
+            const int row_bytes = (int)(left < RR_BLOCK ? left : RR_BLOCK) * 8;
+            for (int r = lane; r < rows; r += 32) {
+                const char *a = (const char *)(lt + (size_t)r * P.ldl);
+                prefetch_l2(a);
+                if (row_bytes > 128) prefetch_l2(a + 128);
+                prefetch_l2(a + row_bytes - 1);
+            }
+        }
+
+        // ---------------- dependencies ----------------
+        int32_t *done = P.done + (size_t)m * P.n_blocks;
+        if (lane == 0 && j > 0) wait_ge(done + b, j);                       // own previous tile
+        for (int e = P.dep_ptr[b] + lane; e < P.dep_ptr[b + 1]; e += 32)    // upstream blocks, this tile
+            wait_ge(done + P.dep_idx[e], j + 1);
+        if (ex >= 0) {                                                      // exchange-ring reuse
+            const int32_t ring = __ldg(P.exp_ro + 2 * ex + 1);
+            if (j >= ring) wait_ge(done + __ldg(P.down + i) / RR_BLOCK, j - ring + 1);
+        }
+        __syncwarp();
+        fence_acquire();
+
+        // ---------------- state ----------------
+        // first tile of a reference call: every member starts from the shared initial state and
+        // (UNIT) q_ch = q_full = state (UnitMuskingum.py:78-79); later tiles / chunks continue
+        // from the member's own running state.
+        const bool use_init = (j == 0) && P.first_call;
+        double qcur = 0.0;   // q_t (UNIT: q_ch)
+        if (valid) qcur = use_init ? P.q_init[i] : P.q_state[m][i];
+
+        if (!UNIT && K == 1 && (M.int_mask & 0x40)) {
+            // fast path (plan flag 0x40: no in-block edges and max in-degree <= RR_MAX_FAST_DEG)
+            switch (M.max_deg) {
+                case 0: fast_item<MODE, 0>(P, c, c1, c2, c3, c4, e0, deg, ex, qcur); break;
+                case 1: fast_item<MODE, 1>(P, c, c1, c2, c3, c4, e0, deg, ex, qcur); break;
+                case 2: fast_item<MODE, 2>(P, c, c1, c2, c3, c4, e0, deg, ex, qcur); break;
+                case 3: fast_item<MODE, 3>(P, c, c1, c2, c3, c4, e0, deg, ex, qcur); break;
+                default: fast_item<MODE, 4>(P, c, c1, c2, c3, c4, e0, deg, ex, qcur); break;
+            }
+            __syncwarp();
+            if (lane == 0) st_release(done + b, j + 1);
+            continue;
+        }
+
+        // ================= general path: systolic item with shuffles =================
+        const int d = __ldg(P.skew + ic);
         const int nfast = M.max_deg < RR_MAX_FAST_DEG ? M.max_deg : RR_MAX_FAST_DEG;
-
-        const int t0 = j * P.tile_rows;
-        const int rows = min(P.tile_rows, P.T - t0);
-        const int TT = rows * K;
-        double *raw_m = P.raw + (size_t)m * (size_t)P.raw_rows * P.raw_pitch;
-        // row of exported series e for this tile: its private ring, indexed by tile
-        auto raw_row = [&](int32_t e) -> double * {
-            const int32_t ring = __ldg(P.exp_ring + e);
-            return raw_m + ((size_t)__ldg(P.exp_off + e) + (size_t)(j % ring)) * P.raw_pitch;
+        auto raw_row = [&](int e) -> double * {   // e = entry of the upstream-CSR (an external edge)
+            const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + e);
+            return raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         };
-
         int32_t src[RR_MAX_FAST_DEG];
         const double *rp[RR_MAX_FAST_DEG];   // exported series of an external upstream
         int ilane[RR_MAX_FAST_DEG];          // lane of an in-block upstream (own lane if none)
@@ -126,45 +319,14 @@ __global__ void __launch_bounds__(256) rr_wavefront_kernel(const __grid_constant
             ilane[k] = lane;
             ug[k] = 0;
             if (src[k] != SLOT_NONE) {
-                if (src[k] >= 0) rp[k] = raw_row(src[k] & ~RR_SLOT_HW_BIT);
+                if (src[k] >= 0) rp[k] = raw_row(e0 + k);
                 else ilane[k] = (-src[k] - 1) & 31;
                 if (UNIT) ug[k] = __ldg(P.up_idx + e0 + k);
             }
         }
-        const double *lat = nullptr;
-        if (HAS_LAT) {
-            lat = P.lateral[m] + (size_t)t0 * P.ldl + (size_t)b * RR_BLOCK;
-            // pull this item's lateral tile towards L2 before the dependency wait hides the latency
-            const int64_t left = P.n - (int64_t)b * RR_BLOCK;
-            const int row_bytes = (int)(left < RR_BLOCK ? left : RR_BLOCK) * 8;
-            for (int r = lane; r < rows; r += 32) {
-                const char *a = (const char *)(lat + (size_t)r * P.ldl);
-                prefetch_l2(a);
-                if (row_bytes > 128) prefetch_l2(a + 128);
-                prefetch_l2(a + row_bytes - 1);
-            }
-            lat += lane;
-        }
+        const double *lat = HAS_LAT ? P.lateral[m] + (size_t)t0 * P.ldl + i : nullptr;
         double *outp = P.out[m] + (size_t)t0 * P.ldo + i;
 
-        // ---------------- dependencies ----------------
-        int32_t *done = P.done + (size_t)m * P.n_blocks;
-        if (lane == 0 && j > 0) wait_ge(done + b, j);                       // own previous tile
-        for (int e = P.dep_ptr[b] + lane; e < P.dep_ptr[b + 1]; e += 32)    // upstream blocks, this tile
-            wait_ge(done + P.dep_idx[e], j + 1);
-        if (ex >= 0) {                                                      // exchange-ring reuse
-            const int32_t ring = __ldg(P.exp_ring + ex);
-            if (j >= ring) wait_ge(done + __ldg(P.down + i) / RR_BLOCK, j - ring + 1);
-        }
-        __syncwarp();
-
-        // ---------------- state ----------------
-        // first tile of a reference call: every member starts from the shared initial state and
-        // (UNIT) q_ch = q_full = state (UnitMuskingum.py:78-79); later tiles / chunks continue
-        // from the member's own running state.
-        const bool use_init = (j == 0) && P.first_call;
-        double qcur = 0.0;   // q_t (UNIT: q_ch)
-        if (valid) qcur = use_init ? P.q_init[i] : P.q_state[m][i];
         double qprev = qcur;
         double qf_cur = 0.0, qf_prev = 0.0;  // UNIT: q_full and its previous value
         if (UNIT && valid) {
@@ -173,9 +335,10 @@ __global__ void __launch_bounds__(256) rr_wavefront_kernel(const __grid_constant
         }
         double *myraw = nullptr;
         if (ex >= 0) {
-            myraw = raw_row(ex);
-            myraw[0] = qcur;                               // carry-in for consumers
-            if (UNIT) myraw[P.raw_pitch - 1] = qf_cur;     // q_full carry-in
+            const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + ex);
+            myraw = raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+            myraw[RAW_CARRY] = qcur;                 // carry-in for consumers
+            if (UNIT) myraw[RAW_QF] = qf_cur;        // q_full carry-in
         }
 
         // one-step lookahead registers for the external series and the lateral row
@@ -185,8 +348,8 @@ __global__ void __launch_bounds__(256) rr_wavefront_kernel(const __grid_constant
         for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
             eo[k] = en[k] = lu[k] = lu_old[k] = 0.0;
             if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) {
-                eo[k] = UNIT ? rp[k][P.raw_pitch - 1] : rp[k][0];
-                en[k] = rp[k][1];
+                eo[k] = UNIT ? rp[k][RAW_QF] : rp[k][RAW_CARRY];
+                en[k] = rp[k][RAW_S0];
             }
         }
         double ql = 0.0, ql_nx = 0.0;
@@ -269,15 +432,15 @@ __global__ void __launch_bounds__(256) rr_wavefront_kernel(const __grid_constant
                     double v = __shfl_sync(FULL_MASK, UNIT ? qf_prev : qprev, il);
                     bool use = act && k < deg;
                     if (use && sk >= 0) {
-                        const double *q = raw_row(sk & ~RR_SLOT_HW_BIT);
+                        const double *q = raw_row(e0 + k);
                         if (UNIT) {
                             if (sk & RR_SLOT_HW_BIT) use = false;
-                            else if (s == 0) v = q[P.raw_pitch - 1];
+                            else if (s == 0) v = q[RAW_QF];
                             else {
                                 const int prow = (sub == 0) ? row - 1 : row;
-                                v = q[s] + ld_stream(P.lateral[m] + (size_t)(t0 + prow) * P.ldl + __ldg(P.up_idx + e0 + k));
+                                v = q[RAW_CARRY + s] + ld_stream(P.lateral[m] + (size_t)(t0 + prow) * P.ldl + __ldg(P.up_idx + e0 + k));
                             }
-                        } else v = q[s];
+                        } else v = q[RAW_CARRY + s];
                     } else if (use && UNIT && (((-sk - 1) >> 6) & 1)) use = false;
                     if (use) r = fma(c2, v, r);
                 }
@@ -302,7 +465,7 @@ __global__ void __launch_bounds__(256) rr_wavefront_kernel(const __grid_constant
                     bool use = act && k < deg;
                     if (use && sk >= 0) {
                         if (UNIT && (sk & RR_SLOT_HW_BIT)) use = false;
-                        else v = raw_row(sk & ~RR_SLOT_HW_BIT)[s + 1];
+                        else v = raw_row(e0 + k)[RAW_S0 + s];
                     } else if (use && UNIT && (((-sk - 1) >> 6) & 1)) use = false;
                     if (use) r = fma(c1, v, r);
                 }
@@ -319,7 +482,7 @@ __global__ void __launch_bounds__(256) rr_wavefront_kernel(const __grid_constant
                         qf_cur = r + ql;            // :165-166
                         acc += qf_cur;
                     } else acc += r;                // :41-42 / :79-80
-                    if (myraw) myraw[1 + s] = r;
+                    if (myraw) myraw[RAW_S0 + s] = r;
                 }
                 if (++sub == K) {
                     double v;
@@ -334,7 +497,7 @@ __global__ void __launch_bounds__(256) rr_wavefront_kernel(const __grid_constant
                 if (s + 1 < TT) {
 #pragma unroll
                     for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
-                        if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) { eo[k] = en[k]; en[k] = rp[k][s + 2]; }
+                        if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) { eo[k] = en[k]; en[k] = rp[k][RAW_S0 + s + 1]; }
                     }
                     if (HAS_LAT && sub == 0) ql_nx = ld_stream(lat + (size_t)row * P.ldl);
                 }

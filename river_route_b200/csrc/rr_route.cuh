@@ -35,8 +35,8 @@ struct rr_route_params {
     int32_t n_members;
     int32_t first_call;   // UNIT: 1 when q_state holds the start-of-file state (q_ch = q_full = state)
     int32_t last_call;    // UNIT: 1 when q_state must end as the recombined vector (hw: lateral, inner: q_full)
-    const int32_t *exp_off;   // [n_export] first row of each exported series' ring
-    const int32_t *exp_ring;  // [n_export] ring depth (tiles) of each exported series
+    const int32_t *exp_ro;    // [n_export][2] {first row, ring depth in tiles} of each exported series' ring
+    const int32_t *edge_ro;   // [edges][2]    the same pair for the upstream of every upstream-CSR entry
     int64_t raw_rows;     // rows of the exchange buffer per ensemble member
     int64_t ldl, ldo;
     double *raw;          // [member][raw_rows][raw_pitch]

@@ -42,6 +42,10 @@ typedef struct rr_plan_opts {
     int32_t device;         /* CUDA device ordinal (default: current device)                 */
     int32_t threads_per_cta;/* persistent CTA size, multiple of 32 (default 256)             */
     int64_t raw_budget_bytes;/* cap for the exchange buffer (default 16 GiB)                 */
+    int32_t renumber;       /* 0 auto, 1 keep the params_file order, 2 always work on reaches sorted
+                               by topological level (inputs/outputs stay in params_file order; the
+                               library permutes them on the device)                             */
+    int32_t reserved;
 } rr_plan_opts;
 
 /* Host-visible description of a built plan (for tests, DESIGN.md numbers and bench.py). */
@@ -57,6 +61,8 @@ typedef struct rr_plan_info {
     int32_t n_outlets_lo;    /* number of outlets (low 32 bits)                              */
     int64_t n_dep_edges;     /* distinct (block -> upstream block) dependencies              */
     int64_t device_bytes;    /* bytes of plan-owned device memory (after first upload)       */
+    int32_t renumbered;      /* 1 when the plan works on level-sorted reaches                */
+    int32_t reach_depth;     /* longest upstream-to-outlet path, in reaches                  */
 } rr_plan_info;
 
 const char *rr_last_error(void);
@@ -191,7 +197,8 @@ int rr_plan_get_arrays(const rr_plan *p,
                        const int32_t **blk_level,/* [n_blocks] level in the block DAG            */
                        const int32_t **dep_ptr,  /* [n_blocks+1]                                 */
                        const int32_t **dep_idx,  /* distinct upstream blocks                     */
-                       const int32_t **exp_span  /* [n_export] block-level distance producer -> consumer */);
+                       const int32_t **exp_span, /* [n_export] block-level distance producer -> consumer */
+                       const int32_t **perm      /* [n] user index of each working reach, NULL if not renumbered */);
 /* Ticket -> (block, tile) decode used by the kernel, for schedule-validity tests. */
 int rr_plan_schedule(const rr_plan *p, int64_t n_tiles, int32_t tile_stride, int64_t *n_items,
                      int32_t *item_block /* [n_blocks*n_tiles] or NULL */,

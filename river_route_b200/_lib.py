@@ -23,14 +23,15 @@ c_f64p = C.POINTER(C.c_double)
 
 class PlanOpts(C.Structure):
     _fields_ = [('time_tile', C.c_int32), ('tile_stride', C.c_int32), ('device', C.c_int32),
-                ('threads_per_cta', C.c_int32), ('raw_budget_bytes', C.c_int64)]
+                ('threads_per_cta', C.c_int32), ('raw_budget_bytes', C.c_int64), ('renumber', C.c_int32),
+                ('reserved', C.c_int32)]
 
 
 class PlanInfo(C.Structure):
     _fields_ = [('n', C.c_int64), ('n_edges', C.c_int64), ('n_blocks', C.c_int64), ('n_export', C.c_int64),
                 ('n_internal_edges', C.c_int64), ('max_skew', C.c_int32), ('max_indegree', C.c_int32),
                 ('max_block_level', C.c_int32), ('n_outlets_lo', C.c_int32), ('n_dep_edges', C.c_int64),
-                ('device_bytes', C.c_int64)]
+                ('device_bytes', C.c_int64), ('renumbered', C.c_int32), ('reach_depth', C.c_int32)]
 
 
 def _load() -> C.CDLL:
@@ -66,7 +67,7 @@ def _load() -> C.CDLL:
         'rr_host_free': (C.c_int, [vp]),
         'rr_synth_forest': (C.c_int, [i64, i64, C.c_uint64, C.c_double, i64, C.c_double, c_i32p]),
         'rr_plan_get_arrays': (C.c_int, [vp] + [C.POINTER(c_i32p), C.POINTER(c_i32p), C.POINTER(c_u8p)]
-                               + [C.POINTER(c_i32p)] * 6),
+                               + [C.POINTER(c_i32p)] * 7),
         'rr_plan_schedule': (C.c_int, [vp, i64, i32, c_i64p, c_i32p, c_i32p]),
     }
     for name, (res, args) in sig.items():

@@ -64,6 +64,10 @@ struct rr_device_state {
     double *d_lat[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
     size_t chunk_cap = 0;  // doubles per chunk buffer
     double *d_q = nullptr, *d_qfull = nullptr;
+    // renumbered plans: user -> working index and scratch in the working order
+    int32_t *inv = nullptr;
+    double *p_lat = nullptr, *p_out = nullptr, *p_q = nullptr;
+    size_t p_lat_cap = 0, p_out_cap = 0, p_q_cap = 0;
     size_t bytes = 0;
 };
 
@@ -100,6 +104,7 @@ static int ensure_device(rr_plan *p) {
         rc |= upload(&d->lvl_blk, p->lvl_blk, d->bytes);
         rc |= upload(&d->skew, p->skew, d->bytes);
         rc |= upload(&d->meta, p->meta, d->bytes);
+        if (!p->inv.empty()) rc |= upload(&d->inv, p->inv, d->bytes);
         if (rc) return rc;
         CK(cudaMalloc((void **)&d->coef, sizeof(double) * 4 * (size_t)p->n));
         d->bytes += sizeof(double) * 4 * (size_t)p->n;
@@ -133,7 +138,8 @@ void rr_device_release(rr_plan *p) {
     cudaDeviceSynchronize();
     void *ptrs[] = {d->up_ptr, d->up_idx, d->slot_src, d->export_id, d->dep_ptr, d->dep_idx, d->down, d->exp_ro, d->edge_ro,
                     d->lvl_ptr, d->lvl_blk, d->skew, d->meta, d->coef, d->key_start, d->raw, d->done, d->ticket,
-                    d->d_lat[0], d->d_lat[1], d->d_out[0], d->d_out[1], d->d_q, d->d_qfull};
+                    d->d_lat[0], d->d_lat[1], d->d_out[0], d->d_out[1], d->d_q, d->d_qfull,
+                    d->inv, d->p_lat, d->p_out, d->p_q};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     if (d->s_comp) cudaStreamDestroy(d->s_comp);
@@ -248,6 +254,103 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Renumbered plans: the caller's arrays stay in params_file order; the router works on reaches sorted
+// by level.  Both permutations walk the USER index (coalesced on the caller's side); reaches that are
+// neighbours in the working order are same-level reaches with nearby user indices, so the scattered
+// side of each copy completes whole 32-byte sectors while they are still in L2.
+// ---------------------------------------------------------------------------------------------------
+#define PERM_ROWS 8
+__global__ void __launch_bounds__(256) permute_to_working(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
+                                                          int64_t ldd, const int32_t *__restrict__ inv, int64_t n, int64_t T) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t k = __ldg(inv + i);
+    const int64_t t0 = (int64_t)blockIdx.y * PERM_ROWS;
+    double v[PERM_ROWS];
+#pragma unroll
+    for (int r = 0; r < PERM_ROWS; ++r) v[r] = (t0 + r < T) ? __ldg(src + (t0 + r) * lds + i) : 0.0;
+#pragma unroll
+    for (int r = 0; r < PERM_ROWS; ++r)
+        if (t0 + r < T) dst[(t0 + r) * ldd + k] = v[r];
+}
+__global__ void __launch_bounds__(256) permute_to_user(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
+                                                       int64_t ldd, const int32_t *__restrict__ inv, int64_t n, int64_t T) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t k = __ldg(inv + i);
+    const int64_t t0 = (int64_t)blockIdx.y * PERM_ROWS;
+    double v[PERM_ROWS];
+#pragma unroll
+    for (int r = 0; r < PERM_ROWS; ++r) v[r] = (t0 + r < T) ? src[(t0 + r) * lds + k] : 0.0;
+#pragma unroll
+    for (int r = 0; r < PERM_ROWS; ++r)
+        if (t0 + r < T) dst[(t0 + r) * ldd + i] = v[r];
+}
+static int permute(bool to_working, const double *src, int64_t lds, double *dst, int64_t ldd, const int32_t *inv,
+                   int64_t n, int64_t T, cudaStream_t stream) {
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)((T + PERM_ROWS - 1) / PERM_ROWS));
+    if (to_working) permute_to_working<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T);
+    else permute_to_user<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T);
+    CK(cudaGetLastError());
+    rr_count_launch(1);
+    return 0;
+}
+static int grow(double **buf, size_t *cap, size_t need) {
+    if (need <= *cap) return 0;
+    CK(cudaDeviceSynchronize());
+    if (*buf) CK(cudaFree(*buf));
+    *buf = nullptr; *cap = 0;
+    CK(cudaMalloc((void **)buf, need * sizeof(double)));
+    *cap = need;
+    return 0;
+}
+
+// Route with all arrays in the caller's (params_file) order, whatever order the plan works in.
+static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, const double *const *lateral,
+                     int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
+                     int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream) {
+    if (p->perm.empty())
+        return launch_route(p, mode, n_members, q_init, lateral, ldl, out, ldo, q_state, q_full, T, K, first_call,
+                            last_call, stream);
+    int rc = ensure_device(p);
+    if (rc) return rc;
+    rr_device_state *d = p->dev;
+    const int64_t n = p->n, ldp = ((n + 31) / 32) * 32;
+    const bool has_lat = mode != RR_MODE_MUSKINGUM;
+    const bool unit = mode == RR_MODE_UNIT;
+    if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
+    if (T <= 0) { rr_set_error("T must be positive"); return 100; }
+    if (has_lat && (rc = grow(&d->p_lat, &d->p_lat_cap, (size_t)n_members * T * ldp))) return rc;
+    if ((rc = grow(&d->p_out, &d->p_out_cap, (size_t)n_members * T * ldp))) return rc;
+    // state scratch: [init][member states][member q_full]
+    if ((rc = grow(&d->p_q, &d->p_q_cap, (size_t)(1 + 2 * n_members) * ldp))) return rc;
+    double *w_init = d->p_q;
+    const double *lat_w[RR_MAX_MEMBERS];
+    double *out_w[RR_MAX_MEMBERS], *qs_w[RR_MAX_MEMBERS], *qf_w[RR_MAX_MEMBERS];
+    if (first_call && (rc = permute(true, q_init, n, w_init, ldp, d->inv, n, 1, stream))) return rc;
+    for (int m = 0; m < n_members; ++m) {
+        lat_w[m] = has_lat ? d->p_lat + (size_t)m * T * ldp : nullptr;
+        out_w[m] = d->p_out + (size_t)m * T * ldp;
+        qs_w[m] = d->p_q + (size_t)(1 + m) * ldp;
+        qf_w[m] = d->p_q + (size_t)(1 + n_members + m) * ldp;
+        if (has_lat && (rc = permute(true, lateral[m], ldl, d->p_lat + (size_t)m * T * ldp, ldp, d->inv, n, T, stream))) return rc;
+        if (!first_call) {
+            if ((rc = permute(true, q_state[m], n, qs_w[m], ldp, d->inv, n, 1, stream))) return rc;
+            if (unit && (rc = permute(true, q_full[m], n, qf_w[m], ldp, d->inv, n, 1, stream))) return rc;
+        }
+    }
+    rc = launch_route(p, mode, n_members, w_init, has_lat ? lat_w : nullptr, ldp, out_w, ldp, qs_w, qf_w, T, K,
+                      first_call, last_call, stream);
+    if (rc) return rc;
+    for (int m = 0; m < n_members; ++m) {
+        if ((rc = permute(false, out_w[m], ldp, out[m], ldo, d->inv, n, T, stream))) return rc;
+        if ((rc = permute(false, qs_w[m], ldp, q_state[m], n, d->inv, n, 1, stream))) return rc;
+        if (unit && !(last_call) && (rc = permute(false, qf_w[m], ldp, q_full[m], n, d->inv, n, 1, stream))) return rc;
+    }
+    return 0;
+}
+
 extern "C" int rr_route_dev(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,
                             int64_t ldl, double *out, int64_t ldo, int64_t T, int64_t substeps, void *stream) {
     if (!p || !q_state || !out || (mode != RR_MODE_MUSKINGUM && !lateral)) { rr_set_error("null argument"); return 100; }
@@ -262,8 +365,8 @@ extern "C" int rr_route_dev(rr_plan *p, int mode, double *q_state, double *q_ful
     }
     const double *lat1[1] = {lateral};
     double *out1[1] = {out}, *qs1[1] = {q_state}, *qf1[1] = {qf};
-    return launch_route(p, mode, 1, q_state, lat1, ldl, out1, ldo, qs1, qf1, T, substeps, router_level, router_level,
-                        (cudaStream_t)stream);
+    return route_any(p, mode, 1, q_state, lat1, ldl, out1, ldo, qs1, qf1, T, substeps, router_level, router_level,
+                     (cudaStream_t)stream);
 }
 
 extern "C" int rr_route_ensemble_dev(rr_plan *p, int mode, const double *q_init, int32_t n_members,
@@ -271,8 +374,8 @@ extern "C" int rr_route_ensemble_dev(rr_plan *p, int mode, const double *q_init,
                                      double *const *q_final, int64_t T, int64_t substeps, void *stream) {
     if (!p || !q_init || !out || !q_final || (mode != RR_MODE_MUSKINGUM && !lateral)) { rr_set_error("null argument"); return 100; }
     if (mode == RR_MODE_UNIT) { rr_set_error("ensemble launch supports Muskingum / RapidMuskingum"); return 100; }
-    return launch_route(p, mode, n_members, q_init, lateral, ldl, out, ldo, q_final, nullptr, T, substeps, 1, 1,
-                        (cudaStream_t)stream);
+    return route_any(p, mode, n_members, q_init, lateral, ldl, out, ldo, q_final, nullptr, T, substeps, 1, 1,
+                     (cudaStream_t)stream);
 }
 
 // Host arrays: stream time chunks through two device buffers per direction.
@@ -332,8 +435,8 @@ extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_fu
         if (c >= 2) CK(cudaStreamWaitEvent(d->s_comp, d->ev_out[k], 0));  // out buffer drained
         const double *lat1[1] = {d->d_lat[k]};
         double *out1[1] = {d->d_out[k]}, *qs1[1] = {d->d_q}, *qf1[1] = {d->d_qfull};
-        rc = launch_route(p, mode, 1, d->d_q, lat1, ldd, out1, ldd, qs1, qf1, rows_of(c), substeps,
-                          router_level && c == 0, router_level && c == n_chunks - 1, d->s_comp);
+        rc = route_any(p, mode, 1, d->d_q, lat1, ldd, out1, ldd, qs1, qf1, rows_of(c), substeps,
+                       router_level && c == 0, router_level && c == n_chunks - 1, d->s_comp);
         if (rc) return rc;
         CK(cudaEventRecord(d->ev_comp[k], d->s_comp));
         CK(cudaStreamWaitEvent(d->s_out, d->ev_comp[k], 0));

@@ -26,7 +26,9 @@ struct rr_device_state;  // defined in rr_api.cu
 struct rr_plan {
     int64_t n = 0, n_edges = 0, n_blocks = 0, n_export = 0, n_internal = 0, n_outlets = 0;
     rr_plan_opts opts{};
-    std::vector<int32_t> down;       // [n]
+    std::vector<int32_t> down;       // [n] downstream reach in the WORKING order (user order unless renumbered)
+    std::vector<int32_t> perm, inv;  // renumbered plans: perm[working] = user index, inv[user] = working index
+    int32_t reach_depth = 0;         // longest upstream-to-outlet path, in reaches
     std::vector<int32_t> up_ptr;     // [n+1]
     std::vector<int32_t> up_idx;     // [edges] ascending upstream index per row
     std::vector<int32_t> slot_src;   // [edges] encoded source (see rr_b200.h)

@@ -120,27 +120,14 @@ extern "C" int rr_label_basins(int64_t n, const int32_t *down, int32_t *basin, i
 // ------------------------------------------------------------------------------------------
 // Plan
 // ------------------------------------------------------------------------------------------
-extern "C" int rr_plan_create(int64_t n, const int32_t *down, const rr_plan_opts *opts, rr_plan **out) {
-    if (!out) { rr_set_error("null output pointer"); return 100; }
-    *out = nullptr;
-    if (n <= 0 || n > 0x7ffffff0ll) { rr_set_error("reach count must be in [1, 2^31)"); return 100; }
-    for (int64_t i = 0; i < n; ++i) {
-        if (down[i] >= 0 && (down[i] <= i || down[i] >= n)) {
-            rr_set_error("params_file must be topologically sorted upstream to downstream");
-            return 3;
-        }
-    }
-    rr_plan *p = new rr_plan();
-    if (opts) p->opts = *opts;
-    if (p->opts.time_tile <= 0) p->opts.time_tile = 32;
-    if (p->opts.threads_per_cta <= 0) p->opts.threads_per_cta = 256;
-    p->opts.threads_per_cta = std::max(32, (p->opts.threads_per_cta / 32) * 32);
-    if (p->opts.raw_budget_bytes <= 0) p->opts.raw_budget_bytes = 16ll << 30;
-    if (!opts || opts->device < 0) p->opts.device = -1;
-    p->n = n;
-    p->n_blocks = (n + RR_BLOCK - 1) / RR_BLOCK;
+// Builds every derived structure of the plan from p->down (the working order; p->inv maps user ->
+// working index when the plan is renumbered).
+static int build_structures(rr_plan *p) {
+    const int64_t n = p->n;
+    const int32_t *down = p->down.data();
     const int64_t nb = p->n_blocks;
-    p->down.assign(down, down + n);
+    p->n_edges = p->n_export = p->n_internal = p->n_outlets = 0;
+    p->max_level = p->max_skew = p->max_deg = 0;
 
     // upstream-CSR: counting sort by downstream index keeps upstream indices ascending per row
     p->up_ptr.assign(n + 1, 0);
@@ -149,9 +136,13 @@ extern "C" int rr_plan_create(int64_t n, const int32_t *down, const rr_plan_opts
     for (int64_t i = 0; i < n; ++i) p->up_ptr[i + 1] += p->up_ptr[i];
     p->up_idx.resize(p->n_edges);
     {
+        // rows are filled in ascending USER index so that every confluence sums its inflows in the
+        // reference's order even when the plan works on renumbered reaches
         std::vector<int32_t> fill(p->up_ptr.begin(), p->up_ptr.end() - 1);
-        for (int64_t i = 0; i < n; ++i)
+        for (int64_t u = 0; u < n; ++u) {
+            const int64_t i = p->inv.empty() ? u : p->inv[u];
             if (down[i] >= 0) p->up_idx[fill[down[i]]++] = (int32_t)i;
+        }
     }
     p->is_hw.resize(n);
     for (int64_t i = 0; i < n; ++i) p->is_hw[i] = p->up_ptr[i + 1] == p->up_ptr[i];
@@ -192,7 +183,7 @@ extern "C" int rr_plan_create(int64_t n, const int32_t *down, const rr_plan_opts
         const int64_t lo = b * RR_BLOCK, hi = std::min<int64_t>(n, lo + RR_BLOCK);
         for (int64_t i = lo; i < hi; ++i) {
             const int32_t deg = p->up_ptr[i + 1] - p->up_ptr[i];
-            if (deg > 65535) { delete p; rr_set_error("in-degree above 65535 is not supported"); return 100; }
+            if (deg > 65535) { rr_set_error("in-degree above 65535 is not supported"); return 100; }
             m.max_skew = std::max(m.max_skew, p->skew[i]);
             m.max_deg = std::max<uint16_t>(m.max_deg, (uint16_t)deg);
             for (int32_t k = 0; k < deg; ++k) {
@@ -237,6 +228,66 @@ extern "C" int rr_plan_create(int64_t n, const int32_t *down, const rr_plan_opts
         std::vector<int32_t> fill(p->lvl_ptr.begin(), p->lvl_ptr.end() - 1);
         for (int64_t b = 0; b < nb; ++b) p->lvl_blk[fill[p->blk_level[b]]++] = (int32_t)b;
     }
+    return 0;
+}
+
+extern "C" int rr_plan_create(int64_t n, const int32_t *down, const rr_plan_opts *opts, rr_plan **out) {
+    if (!out) { rr_set_error("null output pointer"); return 100; }
+    *out = nullptr;
+    if (n <= 0 || n > 0x7ffffff0ll) { rr_set_error("reach count must be in [1, 2^31)"); return 100; }
+    for (int64_t i = 0; i < n; ++i) {
+        if (down[i] >= 0 && (down[i] <= i || down[i] >= n)) {
+            rr_set_error("params_file must be topologically sorted upstream to downstream");
+            return 3;
+        }
+    }
+    rr_plan *p = new rr_plan();
+    if (opts) p->opts = *opts;
+    if (p->opts.time_tile <= 0) p->opts.time_tile = 32;
+    if (p->opts.threads_per_cta <= 0) p->opts.threads_per_cta = 256;
+    p->opts.threads_per_cta = std::max(32, (p->opts.threads_per_cta / 32) * 32);
+    if (p->opts.raw_budget_bytes <= 0) p->opts.raw_budget_bytes = 16ll << 30;
+    if (!opts || opts->device < 0) p->opts.device = -1;
+    p->n = n;
+    p->n_blocks = (n + RR_BLOCK - 1) / RR_BLOCK;
+    p->down.assign(down, down + n);
+    // topological level of every reach (0 = headwater) in the user's order
+    std::vector<int32_t> lvl(n, 0);
+    int32_t depth = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (down[i] >= 0) lvl[down[i]] = std::max(lvl[down[i]], lvl[i] + 1);
+        depth = std::max(depth, lvl[i] + 1);
+    }
+    p->reach_depth = depth;
+    int rc = 0;
+    bool renumber = p->opts.renumber == 2;
+    if (p->opts.renumber != 2) {
+        rc = build_structures(p);
+        if (rc) { delete p; return rc; }
+        // Blocks of 32 consecutive reaches merge their dependencies; in an arbitrary (valid) order the
+        // block DAG can be tens of times deeper than the river network.  Sorting reaches by level
+        // makes it as shallow as the network itself.
+        if (p->opts.renumber == 0 && p->max_level > 2 * (int64_t)depth + 16) renumber = true;
+    }
+    if (renumber) {
+        // working order = stable sort by level: perm[k] = user index of working reach k
+        std::vector<int64_t> start(depth + 1, 0);
+        for (int64_t i = 0; i < n; ++i) start[lvl[i] + 1]++;
+        for (int32_t l = 0; l < depth; ++l) start[l + 1] += start[l];
+        p->perm.resize(n);
+        p->inv.resize(n);
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t k = start[lvl[i]]++;
+            p->perm[k] = (int32_t)i;
+            p->inv[i] = (int32_t)k;
+        }
+        for (int64_t k = 0; k < n; ++k) {
+            const int32_t d = down[p->perm[k]];
+            p->down[k] = d >= 0 ? p->inv[d] : -1;
+        }
+        rc = build_structures(p);
+        if (rc) { delete p; return rc; }
+    }
     *out = p;
     return 0;
 }
@@ -261,17 +312,22 @@ extern "C" int rr_plan_get_info(const rr_plan *p, rr_plan_info *info) {
     info->n_outlets_lo = (int32_t)p->n_outlets;
     info->n_dep_edges = (int64_t)p->dep_idx.size();
     info->device_bytes = 0;
+    info->renumbered = p->perm.empty() ? 0 : 1;
+    info->reach_depth = p->reach_depth;
     return 0;
 }
 
 extern "C" int rr_plan_set_coefficients(rr_plan *p, const double *c1, const double *c2, const double *c3,
                                         const double *c4_dt) {
     if (!p || !c1 || !c2 || !c3) { rr_set_error("null argument"); return 100; }
-    p->c1.assign(c1, c1 + p->n);
-    p->c2.assign(c2, c2 + p->n);
-    p->c3.assign(c3, c3 + p->n);
+    auto put = [&](std::vector<double> &dst, const double *src) {
+        dst.resize(p->n);
+        if (p->perm.empty()) std::copy(src, src + p->n, dst.begin());
+        else for (int64_t k = 0; k < p->n; ++k) dst[k] = src[p->perm[k]];
+    };
+    put(p->c1, c1); put(p->c2, c2); put(p->c3, c3);
     p->have_c4 = c4_dt != nullptr;
-    if (c4_dt) p->c4.assign(c4_dt, c4_dt + p->n); else p->c4.assign(p->n, 0.0);
+    if (c4_dt) put(p->c4, c4_dt); else p->c4.assign(p->n, 0.0);
     p->coeff_version++;
     return 0;
 }
@@ -279,7 +335,7 @@ extern "C" int rr_plan_set_coefficients(rr_plan *p, const double *c1, const doub
 extern "C" int rr_plan_get_arrays(const rr_plan *p, const int32_t **up_ptr, const int32_t **up_idx,
                                   const uint8_t **skew, const int32_t **slot_src, const int32_t **export_id,
                                   const int32_t **blk_level, const int32_t **dep_ptr, const int32_t **dep_idx,
-                                  const int32_t **exp_span) {
+                                  const int32_t **exp_span, const int32_t **perm) {
     if (!p) { rr_set_error("null plan"); return 100; }
     if (up_ptr) *up_ptr = p->up_ptr.data();
     if (up_idx) *up_idx = p->up_idx.data();
@@ -290,6 +346,7 @@ extern "C" int rr_plan_get_arrays(const rr_plan *p, const int32_t **up_ptr, cons
     if (dep_ptr) *dep_ptr = p->dep_ptr.data();
     if (dep_idx) *dep_idx = p->dep_idx.data();
     if (exp_span) *exp_span = p->exp_span.data();
+    if (perm) *perm = p->perm.empty() ? nullptr : p->perm.data();
     return 0;
 }
 

@@ -75,12 +75,15 @@ def down_from_csc(indptr, indices, n: int) -> np.ndarray:
 class Plan:
     """Owns an ``rr_plan``.  ``down`` is the int32 downstream-index vector (-1 = outlet)."""
 
+    RENUMBER = {'auto': 0, 'never': 1, 'always': 2}
+
     def __init__(self, down, time_tile: int = 0, tile_stride: int = 0, device: int = -1, threads_per_cta: int = 0,
-                 raw_budget_bytes: int = 0):
+                 raw_budget_bytes: int = 0, renumber: str = 'auto'):
         down = np.ascontiguousarray(down, dtype=np.int32)
         self.n = int(down.shape[0])
         self.down = down
-        opts = _lib.PlanOpts(int(time_tile), int(tile_stride), int(device), int(threads_per_cta), int(raw_budget_bytes))
+        opts = _lib.PlanOpts(int(time_tile), int(tile_stride), int(device), int(threads_per_cta), int(raw_budget_bytes),
+                             self.RENUMBER[renumber], 0)
         handle = C.c_void_p()
         check(lib.rr_plan_create(self.n, _lib.as_i32p(down), C.byref(opts), C.byref(handle)))
         self._h = handle
@@ -160,14 +163,25 @@ class Plan:
     # ---- introspection (tests, DESIGN.md numbers) ----
     def arrays(self) -> dict:
         inf = self.info
-        ptrs = [_lib.c_i32p(), _lib.c_i32p(), _lib.c_u8p()] + [_lib.c_i32p() for _ in range(6)]
+        ptrs = [_lib.c_i32p(), _lib.c_i32p(), _lib.c_u8p()] + [_lib.c_i32p() for _ in range(7)]
         check(lib.rr_plan_get_arrays(self._h, *[C.byref(p) for p in ptrs]))
         n, e, nb, nd = inf['n'], inf['n_edges'], inf['n_blocks'], inf['n_dep_edges']
-        sizes = [n + 1, e, n, e, n, nb, nb + 1, nd, inf['n_export']]
-        names = ['up_ptr', 'up_idx', 'skew', 'slot_src', 'export_id', 'blk_level', 'dep_ptr', 'dep_idx', 'exp_span']
+        sizes = [n + 1, e, n, e, n, nb, nb + 1, nd, inf['n_export'], n if inf['renumbered'] else 0]
+        names = ['up_ptr', 'up_idx', 'skew', 'slot_src', 'export_id', 'blk_level', 'dep_ptr', 'dep_idx', 'exp_span',
+                 'perm']
         out = {}
         for name, p, sz in zip(names, ptrs, sizes):
             out[name] = np.ctypeslib.as_array(p, shape=(sz,)).copy() if sz > 0 else np.zeros(0, dtype=np.int32)
+        # downstream index in the WORKING order (== self.down unless the plan is renumbered)
+        if inf['renumbered']:
+            perm = out['perm']
+            inv = np.empty(n, dtype=np.int64)
+            inv[perm] = np.arange(n)
+            d = self.down[perm]
+            out['down'] = np.where(d >= 0, inv[np.where(d >= 0, d, 0)], -1).astype(np.int32)
+        else:
+            out['perm'] = None
+            out['down'] = self.down
         return out
 
     def schedule(self, n_tiles: int, tile_stride: int):

@@ -23,8 +23,18 @@ def emulate(plan, mode, c1, c2, c3, c4, q0, lat, T, K, tile_substeps=32, delta=1
     UNIT = mode == 2
     HAS_LAT = mode != 0
     a = plan.arrays()
-    down = plan.down
+    down = a['down']
     n = plan.n
+    perm = a['perm']
+    if perm is not None:
+        # renumbered plan: run in the working order, hand results back in the caller's order
+        inv = np.empty(n, dtype=np.int64)
+        inv[perm] = np.arange(n)
+        c1, c2, c3 = c1[perm], c2[perm], c3[perm]
+        c4 = None if c4 is None else c4[perm]
+        q0 = np.asarray(q0)[perm]
+        lat = None if lat is None else np.ascontiguousarray(lat[:, perm])
+        qfull0 = None if qfull0 is None else np.asarray(qfull0)[perm]
     nb = (n + B - 1) // B
     rows_tile = max(1, min(T, tile_substeps // K))
     n_tiles = (T + rows_tile - 1) // rows_tile
@@ -180,4 +190,6 @@ def emulate(plan, mode, c1, c2, c3, c4, q0, lat, T, K, tile_substeps=32, delta=1
                 q_state[i] = qcur[i]
         done[b] = j + 1
     assert len(seen) == nb * n_tiles
+    if perm is not None:
+        out, q_state, q_full = out[:, inv], q_state[inv], q_full[inv]
     return out, q_state, (q_full if UNIT else None)

@@ -103,8 +103,10 @@ SYNTH = [
 ]
 
 
+@pytest.mark.parametrize('renumber', ['never', 'always'])
 @pytest.mark.parametrize('n,nbas,bias,stem,T,dt_runoff,dt_routing,opts', SYNTH)
-def test_rapid_and_muskingum_vs_oracle(n, nbas, bias, stem, T, dt_runoff, dt_routing, opts):
+def test_rapid_and_muskingum_vs_oracle(n, nbas, bias, stem, T, dt_runoff, dt_routing, opts, renumber):
+    opts = dict(opts, renumber=renumber)
     base = synth.forest(n, nbas, seed=n % 97, depth_bias=bias, main_stem=stem)
     k, x = synth.muskingum_params(n, 1)
     K = dt_runoff // dt_routing
@@ -131,8 +133,10 @@ def test_rapid_and_muskingum_vs_oracle(n, nbas, bias, stem, T, dt_runoff, dt_rou
         plan.close()
 
 
+@pytest.mark.parametrize('renumber', ['never', 'always'])
 @pytest.mark.parametrize('n,nbas,bias,stem,T,dt_runoff,dt_routing,opts', SYNTH[:5])
-def test_unit_vs_oracle(n, nbas, bias, stem, T, dt_runoff, dt_routing, opts):
+def test_unit_vs_oracle(n, nbas, bias, stem, T, dt_runoff, dt_routing, opts, renumber):
+    opts = dict(opts, renumber=renumber)
     base = synth.forest(n, nbas, seed=n % 89, depth_bias=bias, main_stem=stem)
     k, x = synth.muskingum_params(n, 2)
     K = dt_runoff // dt_routing
@@ -161,7 +165,8 @@ def test_unit_vs_oracle(n, nbas, bias, stem, T, dt_runoff, dt_routing, opts):
         plan.close()
 
 
-def test_high_indegree_confluences():
+@pytest.mark.parametrize('renumber', ['never', 'always'])
+def test_high_indegree_confluences(renumber):
     """Reaches with more upstreams than the kernel keeps in registers (slow-slot path), in- and cross-block."""
     rng = np.random.default_rng(4)
     n = 3000
@@ -181,7 +186,7 @@ def test_high_indegree_confluences():
     a = network_arrays(down, k, x, 1800, 3600)
     q0 = rng.uniform(0, 10, n)
     ql = synth.lateral_volumes(25, n, 3)
-    plan = rr.Plan(down)
+    plan = rr.Plan(down, renumber=renumber)
     plan.set_coefficients(a['c1'], a['c2'], a['c3'], a['c4_dt'])
     q_ref, ref = q0.copy(), np.zeros((25, n))
     oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q_ref, ql, ref, 2)
@@ -266,13 +271,14 @@ def test_superposition_of_unclamped_state():
 # ------------------------------------------------------------------------------------------------------
 # device-pointer API (torch tensors as plain device buffers) and ensembles
 # ------------------------------------------------------------------------------------------------------
-def test_device_api_and_ensemble():
+@pytest.mark.parametrize('renumber', ['never', 'always'])
+def test_device_api_and_ensemble(renumber):
     import torch
     n, T, M = 50000, 48, 5
     down = synth.forest(n, 6, seed=12, depth_bias=0.6)
     k, x = synth.muskingum_params(n, 12)
     a = network_arrays(down, k, x, 1800, 3600)
-    plan = rr.Plan(down)
+    plan = rr.Plan(down, renumber=renumber)
     plan.set_coefficients(a['c1'], a['c2'], a['c3'], a['c4_dt'])
     rng = np.random.default_rng(12)
     q0 = rng.uniform(0, 30, n)

@@ -105,15 +105,21 @@ def _variants(name):
 
 
 @pytest.mark.parametrize('name', list(NETWORKS))
-def test_plan_structures(name):
-    for label, down in _variants(name):
-        plan = rr.Plan(down)
+@pytest.mark.parametrize('renumber', ['never', 'always'])
+def test_plan_structures(name, renumber):
+    for label, user_down in _variants(name):
+        plan = rr.Plan(user_down, renumber=renumber)
         a, inf = plan.arrays(), plan.info
-        n = down.shape[0]
-        # upstream-CSR lists each reach's upstreams in ascending order
+        n = user_down.shape[0]
+        down = a['down']
+        assert inf['renumbered'] == (renumber == 'always') and inf['reach_depth'] == synth.depth(user_down)
+        perm = a['perm'] if a['perm'] is not None else np.arange(n)
+        assert np.array_equal(np.sort(perm), np.arange(n))
+        assert np.all(down[down >= 0] > np.flatnonzero(down >= 0))          # working order is topological too
+        # upstream-CSR lists each reach's upstreams in ascending USER index (the reference's summation order)
         for i in range(n):
             ups = a['up_idx'][a['up_ptr'][i]:a['up_ptr'][i + 1]]
-            assert np.array_equal(ups, np.flatnonzero(down == i)), label
+            assert np.array_equal(perm[ups], np.flatnonzero(user_down == perm[i])), label
         blk = np.arange(n) // 32
         has = down >= 0
         internal = has & (blk == np.where(has, down, 0) // 32)
@@ -129,10 +135,11 @@ def test_plan_structures(name):
 
 
 @pytest.mark.parametrize('delta', [1, 3, 1000])
-def test_ticket_order_is_a_linear_extension(delta):
-    down = synth.forest(**NETWORKS['deep'])
-    plan = rr.Plan(down)
+@pytest.mark.parametrize('renumber', ['never', 'always'])
+def test_ticket_order_is_a_linear_extension(delta, renumber):
+    plan = rr.Plan(synth.forest(**NETWORKS['deep']), renumber=renumber)
     a = plan.arrays()
+    down = a['down']
     n_tiles = 5
     blocks, tiles = plan.schedule(n_tiles, delta)
     nb = plan.info['n_blocks']
@@ -156,7 +163,8 @@ CASES = [  # network, variant-independent numerics: (T, K, tile_substeps, delta)
 
 
 @pytest.mark.parametrize('name,T,K,tile,delta', CASES)
-def test_emulated_dataflow_is_bit_exact(name, T, K, tile, delta):
+@pytest.mark.parametrize('renumber', ['never', 'always'])
+def test_emulated_dataflow_is_bit_exact(name, T, K, tile, delta, renumber):
     for label, down in _variants(name):
         n = down.shape[0]
         k, x = synth.muskingum_params(n, 1)
@@ -165,7 +173,7 @@ def test_emulated_dataflow_is_bit_exact(name, T, K, tile, delta):
         rng = np.random.default_rng(5)
         q0 = rng.uniform(0, 50, n)
         ql = synth.lateral_volumes(T, n, 2)
-        plan = rr.Plan(down)
+        plan = rr.Plan(down, renumber=renumber)
         # RapidMuskingum
         q, ref = q0.copy(), np.zeros((T, n))
         oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q, ql, ref, K)

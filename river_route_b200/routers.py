@@ -1,0 +1,470 @@
+"""
+Host side of the routers: the same classes, constructor arguments, config keys, lifecycle, hooks and
+errors as river_route.Muskingum / RapidMuskingum / UnitMuskingum, with ``_router`` -- the seam named in
+SURVEY.md 8b (river_route/routers/TransformMuskingum.py:150-152, Muskingum.py:262-290) -- marshalling
+arrays to librr_b200.so instead of calling the numba loops.  Everything here is plain Python host code
+(config, parquet / netCDF I/O, time bookkeeping); no arithmetic of the routing path runs on the CPU.
+"""
+from __future__ import annotations
+
+import dataclasses
+import datetime
+import json
+import logging
+import os
+import sys
+from typing import Any, Callable, Iterator
+
+import numpy as np
+import pandas as pd
+
+from .plan import MODE_MUSKINGUM, MODE_RAPID, MODE_UNIT, Plan, downstream_index
+from .runoff import runoff_to_qlateral
+from .uhkernels import UnitHydrograph
+
+__all__ = ['Configs', 'Muskingum', 'RapidMuskingum', 'UnitMuskingum', 'PROGRESS']
+
+PROGRESS = 25  # custom log level of the reference (river_route/logging.py:3-4)
+logging.addLevelName(PROGRESS, 'PROGRESS')
+
+_CHOICES = {
+    'grid_accumulation_type': ('incremental', 'cumulative'),
+    'runoff_processing_mode': ('sequential', 'ensemble'),
+    'log_level': ('DEBUG', 'INFO', 'PROGRESS', 'WARNING', 'ERROR', 'CRITICAL'),
+}
+_PATHS = ('params_file', 'discharge_dir', 'channel_state_init_file', 'channel_state_final_file', 'grid_weights_file',
+          'uh_kernel_file', 'uh_state_init_file', 'uh_state_final_file')
+_PATH_LISTS = ('discharge_files', 'qlateral_files', 'grid_runoff_files')
+_INPUT_PATHS = ('params_file', 'channel_state_init_file', 'grid_weights_file', 'uh_kernel_file', 'uh_state_init_file')
+_INPUT_LISTS = ('qlateral_files', 'grid_runoff_files')
+_OUTPUT_FILES = ('channel_state_final_file', 'uh_state_final_file')
+
+
+@dataclasses.dataclass
+class Configs:
+    """
+    The configuration surface of the reference (river_route/routers/Config.py:31-65, examples/config.yaml):
+    same keys, defaults, path normalisation (:112-130), discharge_dir resolution (:146-164), existence checks
+    (:132-183) and value checks (:87-93).
+    """
+    params_file: Any = None
+    discharge_dir: Any = None
+    discharge_files: Any = dataclasses.field(default_factory=list)
+    channel_state_init_file: Any = None
+    channel_state_final_file: Any = None
+    dt_routing: int = 0
+    dt_total: int = 0
+    dt_discharge: int = 0
+    dt_runoff: int = 0
+    start_datetime: str = '1970-01-01'
+    qlateral_files: Any = dataclasses.field(default_factory=list)
+    grid_runoff_files: Any = dataclasses.field(default_factory=list)
+    grid_weights_file: Any = None
+    grid_accumulation_type: str = 'incremental'
+    runoff_processing_mode: str = 'sequential'
+    uh_kernel_file: Any = None
+    uh_state_init_file: Any = None
+    uh_state_final_file: Any = None
+    log: bool = True
+    progress_bar: bool = True
+    log_level: str = 'PROGRESS'
+    log_stream: str = 'stdout'
+    log_format: str = '%(levelname)s - %(asctime)s - %(message)s'
+    var_river_id: str = 'river_id'
+    var_discharge: str = 'Q'
+    var_grid_runoff: str = 'ro'
+    var_x: str = 'x'
+    var_y: str = 'y'
+    var_t: str = 'time'
+
+    def __setattr__(self, name, value):
+        allowed = _CHOICES.get(name)
+        if allowed is not None and value not in allowed:
+            raise ValueError(f'{name} must be one of {sorted(allowed)}, got {value!r}')
+        object.__setattr__(self, name, value)
+
+    def __post_init__(self):
+        self.progress_bar = bool(self.log) and bool(self.progress_bar)
+        for key in _PATH_LISTS:                       # a single path means a one-element list
+            val = getattr(self, key)
+            if isinstance(val, (str, os.PathLike)) and val:
+                setattr(self, key, [str(val)])
+            elif val is None:
+                setattr(self, key, [])
+        for key in _PATHS:
+            if getattr(self, key):
+                setattr(self, key, os.path.abspath(getattr(self, key)))
+        for key in _PATH_LISTS:
+            setattr(self, key, [os.path.abspath(p) for p in getattr(self, key)])
+        # where the discharge goes: a directory (names derived from the inputs) or explicit files
+        if self.discharge_dir:
+            if self.discharge_files:
+                raise ValueError('Provide discharge_dir or discharge_files, not both')
+            inputs = self.qlateral_files or self.grid_runoff_files
+            names = [f'discharge_{os.path.basename(f)}' for f in inputs] or ['discharge.nc']
+            self.discharge_files = [os.path.join(self.discharge_dir, nm) for nm in names]
+        elif not self.discharge_files:
+            raise ValueError('Provide discharge_dir (or discharge_files for explicit output paths)')
+        for key in _INPUT_PATHS:
+            val = getattr(self, key)
+            if val and not os.path.exists(val):
+                raise FileNotFoundError(f'{key} not found: {val}')
+        for key in _INPUT_LISTS:
+            for path in getattr(self, key):
+                if not os.path.exists(path):
+                    raise FileNotFoundError(f'{key}: {path} not found')
+        outputs = [getattr(self, k) for k in _OUTPUT_FILES if getattr(self, k)] + list(self.discharge_files)
+        for path in outputs:
+            if not os.path.exists(os.path.dirname(path)):
+                raise NotADirectoryError(f'Output directory not found for specified output path: {path}')
+        if self.discharge_dir and not os.path.isdir(self.discharge_dir):
+            raise NotADirectoryError(f'Output directory not found: {self.discharge_dir}')
+        if self.params_file in (None, '', []):
+            raise ValueError('Missing required config: params_file')
+
+
+def _read_config_file(path) -> dict:
+    text = str(path)
+    if text.endswith('.json'):
+        with open(path) as f:
+            return json.load(f)
+    if text.endswith(('.yml', '.yaml')):
+        import yaml
+        with open(path) as f:
+            return yaml.load(f, Loader=yaml.FullLoader)
+    raise RuntimeError('Unrecognized simulation config file type. Must be .json or .yaml')
+
+
+class Muskingum:
+    """
+    Muskingum channel routing without lateral inflow (river_route/routers/Muskingum.py).  The solve
+    (I - c1 A) Q(t+1) = c2 A Q(t) + c3 Q(t) runs on the GPU (RR_MODE_MUSKINGUM of include/rr_b200.h).
+    """
+    _ROUTER_REQUIRED_CONFIGS = ('channel_state_init_file', 'dt_routing', 'dt_total')
+    _network_time_signature = None
+
+    def __init__(self, configs=None, **kwargs):
+        raw = _read_config_file(configs) if configs not in (None, '') and not isinstance(configs, Configs) else {}
+        if isinstance(configs, Configs):
+            raw = dataclasses.asdict(configs)
+        raw.update(kwargs)
+        raw.pop('_router', None)
+        self.cfg = Configs(**raw)
+        self.logger = logging.getLogger(f'river_route_b200.{id(self):x}')
+        self.logger.disabled = not self.cfg.log
+        self.logger.setLevel(PROGRESS if self.cfg.log_level == 'PROGRESS' else self.cfg.log_level)
+        handler = logging.StreamHandler(sys.stdout) if self.cfg.log_stream == 'stdout' \
+            else logging.FileHandler(self.cfg.log_stream)
+        handler.setFormatter(logging.Formatter(self.cfg.log_format))
+        self.logger.addHandler(handler)
+        self._writer: Callable | None = None
+        self.plan: Plan | None = None
+
+    def __repr__(self):
+        return f'{type(self).__name__}(params_file={self.cfg.params_file!r})'
+
+    # ---------------- validation ----------------
+    def _validate_configs(self):
+        for key in self._ROUTER_REQUIRED_CONFIGS:
+            if not getattr(self.cfg, key, None):
+                raise ValueError(f'{key} is required for {type(self).__name__}')
+        self._validate_router_configs()
+
+    def _validate_router_configs(self):
+        if len(self.cfg.discharge_files) != 1:
+            raise ValueError('Muskingum requires exactly one entry in discharge_files')
+
+    # ---------------- state ----------------
+    def _read_initial_state(self):
+        if hasattr(self, 'channel_state'):
+            return
+        if not self.cfg.channel_state_init_file:
+            self.logger.warning('channel_state_init_file not provided. Defaulting to zero initial conditions')
+            self.channel_state = np.zeros(self.n, dtype=np.float64)
+            return
+        self.channel_state = pd.read_parquet(self.cfg.channel_state_init_file).values.flatten() \
+            .astype(np.float64, copy=False)
+
+    def _write_final_state(self):
+        if self.cfg.channel_state_final_file:
+            pd.DataFrame({'Q': self.channel_state}).to_parquet(self.cfg.channel_state_final_file)
+
+    # ---------------- network ----------------
+    def _set_network_dependent_vectors(self):
+        """params parquet -> ids, k, x and the device plan (replaces Muskingum.py:141-169 + tools.adjacency_matrix)."""
+        df = pd.read_parquet(self.cfg.params_file, columns=[self.cfg.var_river_id, 'k', 'x', 'downstream_river_id'])
+        self.river_ids = df[self.cfg.var_river_id].to_numpy(dtype=np.int64, copy=False)
+        self.k = df['k'].to_numpy(dtype=np.float64, copy=False)
+        self.x = df['x'].to_numpy(dtype=np.float64, copy=False)
+        # duplicate ids, unknown downstream ids and topological order raise the reference's ValueErrors
+        self.down = downstream_index(self.river_ids, df['downstream_river_id'].to_numpy(dtype=np.int64, copy=False))
+        self.n = int(self.river_ids.shape[0])
+        self.plan = Plan(self.down)
+        self.logger.log(PROGRESS, f'Network: {self.n} river segments')
+
+    @property
+    def A(self):
+        """scipy CSC adjacency matrix A[downstream, upstream] = 1, built on demand (river_route/tools.py:75-109)."""
+        import scipy.sparse
+        has = self.down >= 0
+        return scipy.sparse.csc_matrix((np.ones(int(has.sum())), (self.down[has], np.flatnonzero(has))),
+                                       shape=(self.n, self.n))
+
+    def _muskingum_coefficients(self, dt_routing):
+        """c1, c2, c3 with the reference's exact expressions and check (Muskingum.py:172-185)."""
+        dt_div_k = dt_routing / self.k
+        denominator = dt_div_k + (2 * (1 - self.x))
+        _2x = 2 * self.x
+        self.c1 = (dt_div_k - _2x) / denominator
+        self.c2 = (dt_div_k + _2x) / denominator
+        self.c3 = ((2 * (1 - self.x)) - dt_div_k) / denominator
+        if not np.allclose(self.c1 + self.c2 + self.c3, 1):
+            self.logger.warning('Muskingum coefficients do not sum to 1')
+            raise ValueError('Muskingum coefficients do not sum to 1, check routing parameters and time step')
+
+    def _set_muskingum_coefficients(self, dt_routing):
+        self._muskingum_coefficients(dt_routing)
+        self.plan.set_coefficients(self.c1, self.c2, self.c3, None)
+
+    # ---------------- lifecycle ----------------
+    def route(self):
+        self.logger.log(PROGRESS, 'Beginning routing')
+        t1 = datetime.datetime.now()
+        self._validate_configs()
+        self._set_network_dependent_vectors()
+        self._read_initial_state()
+        self._hook_before_route()
+        self._execute_routing()
+        self._write_final_state()
+        self._hook_after_route()
+        self.logger.log(PROGRESS, f'Routing completed in {(datetime.datetime.now() - t1).total_seconds()} seconds')
+        return self
+
+    def _execute_routing(self):
+        self.dt_routing = self.cfg.dt_routing
+        self.dt_total = self.cfg.dt_total
+        self.dt_discharge = self.cfg.dt_discharge or self.dt_routing
+        if not (self.dt_total >= self.dt_discharge >= self.dt_routing):
+            raise ValueError('Need dt_total >= dt_discharge >= dt_routing')
+        if self.dt_total % self.dt_discharge != 0:
+            raise ValueError('dt_total must be an integer multiple of dt_discharge')
+        if self.dt_discharge % self.dt_routing != 0:
+            raise ValueError('dt_discharge must be an integer multiple of dt_routing')
+        num_output_steps = int(self.dt_total / self.dt_discharge)
+        num_routing_per_output = int(self.dt_discharge / self.dt_routing)
+        self._set_muskingum_coefficients(self.dt_routing)
+        discharge_array = self._router(num_output_steps, num_routing_per_output)
+        dates = pd.date_range(start=self.cfg.start_datetime, periods=num_output_steps,
+                              freq=pd.to_timedelta(self.dt_discharge, unit='s')).to_numpy()
+        self._write(dates, discharge_array.astype(np.float32, copy=False), self.cfg.discharge_files[0])
+
+    def _router(self, num_output_steps, num_routing_per_output):
+        """The seam of Muskingum.py:262-290: returns the fp64 (num_output_steps, n) discharge array."""
+        if not np.any(self.channel_state):
+            self.logger.warning(
+                'Initial channel state is all zeros. Muskingum routing without lateral inflow requires a '
+                'non-zero initial state to produce meaningful results. Provide channel_state_init_file.')
+        discharge_array = np.zeros((num_output_steps, self.n), dtype=np.float64)
+        q_t = self.channel_state.astype(np.float64, copy=True)
+        self.plan.route_host(MODE_MUSKINGUM, q_t, None, discharge_array, num_routing_per_output)
+        self.channel_state = q_t
+        return discharge_array
+
+    def _hook_before_route(self):
+        return
+
+    def _hook_after_route(self):
+        return
+
+    # ---------------- output ----------------
+    def set_write_discharges(self, func):
+        """Inject a writer ``func(dates, q_array, q_file, routed_file='')`` (Muskingum.py:308-317)."""
+        self._writer = func
+        return self
+
+    def _write(self, dates, q_array, q_file, routed_file=''):
+        (self._writer or self._write_discharges)(dates, q_array, q_file, routed_file)
+
+    def _write_discharges(self, dates, q_array, q_file, routed_file=''):
+        """The reference's netCDF layout (Muskingum.py:337-351): time f8, river id i4, Q f4 (time, river_id)."""
+        try:
+            import netCDF4 as nc
+        except ImportError as e:  # pragma: no cover - depends on the host environment
+            raise ImportError('netCDF4 is required to write discharge files; install it or inject a writer with '
+                              'set_write_discharges()') from e
+        with nc.Dataset(str(q_file), mode='w', format='NETCDF4') as ds:
+            ds.createDimension('time', size=q_array.shape[0])
+            ds.createDimension(self.cfg.var_river_id, size=q_array.shape[1])
+            ds.runoff_file = str(routed_file)
+            tv = ds.createVariable('time', 'f8', ('time',))
+            tv.units = f'seconds since {pd.Timestamp(dates[0]).strftime("%Y-%m-%d %H:%M:%S")}'
+            tv[:] = (dates - dates[0]).astype('timedelta64[s]').astype(np.int64)
+            iv = ds.createVariable(self.cfg.var_river_id, 'i4', self.cfg.var_river_id)
+            iv[:] = self.river_ids
+            qv = ds.createVariable(self.cfg.var_discharge, 'f4', ('time', self.cfg.var_river_id))
+            qv[:] = q_array
+            qv.long_name = 'Discharge at catchment outlet'
+            qv.standard_name = 'discharge'
+            qv.aggregation_method = 'mean'
+            qv.units = 'm3 s-1'
+
+
+class TransformMuskingum(Muskingum):
+    """Routers driven by lateral inflow files (river_route/routers/TransformMuskingum.py)."""
+    _ROUTER_REQUIRED_CONFIGS = ()
+    _as_volumes = False
+    _mode = MODE_RAPID
+
+    def _qlateral_generator(self) -> Iterator[tuple]:
+        """Yields (dates, (T, n) fp64 lateral array, input file, output file) per input file (:30-51)."""
+        if self.cfg.qlateral_files:
+            for lateral_file, discharge_file in zip(self.cfg.qlateral_files, self.cfg.discharge_files):
+                dates, array = _read_qlateral(lateral_file)
+                yield dates, array, lateral_file, discharge_file
+        elif self.cfg.grid_runoff_files and self.cfg.grid_weights_file:
+            for runoff_file, discharge_file in zip(self.cfg.grid_runoff_files, self.cfg.discharge_files):
+                ds = runoff_to_qlateral(runoff_file, grid_weights_file=self.cfg.grid_weights_file,
+                                        var_runoff=self.cfg.var_grid_runoff, var_x=self.cfg.var_x, var_y=self.cfg.var_y,
+                                        var_t=self.cfg.var_t, var_river_id=self.cfg.var_river_id,
+                                        cumulative=self.cfg.grid_accumulation_type == 'cumulative',
+                                        as_volumes=self._as_volumes)
+                yield (ds['time'].values.astype('datetime64[s]'), ds['qlateral'].values.astype(np.float64, copy=False),
+                       runoff_file, discharge_file)
+
+    def _validate_router_configs(self):
+        qlateral = self.cfg.qlateral_files
+        grids = self.cfg.grid_runoff_files and self.cfg.grid_weights_file
+        if qlateral and grids:
+            raise ValueError('Provide qlateral_files or grid_runoff_files with grid_weights_file, not both')
+        if not qlateral and not grids:
+            raise ValueError('Provide qlateral_files or grid_runoff_files with grid_weights_file')
+        if len(self.cfg.discharge_files) != len(qlateral) + len(self.cfg.grid_runoff_files or []):
+            raise ValueError('Number of resolved discharge output files must match number of input files')
+
+    def _set_network_and_time_dependent_vectors(self, dates):
+        """Time bookkeeping of TransformMuskingum.py:66-106; the device coefficients are refreshed only when the
+        (dt_total, dt_runoff, dt_discharge, dt_routing) signature changes, as the reference caches them."""
+        self.dt_runoff = self.cfg.dt_runoff or int((dates[1] - dates[0]).astype('timedelta64[s]').astype(int))
+        self.dt_discharge = self.cfg.dt_discharge or self.dt_runoff
+        self.dt_total = self.cfg.dt_total or self.dt_runoff * dates.shape[0]
+        if not self.cfg.dt_routing:
+            self.logger.warning('dt_routing was not provided or is Null/False, defaulting to dt_runoff')
+        self.dt_routing = self.cfg.dt_routing or self.dt_runoff
+        signature = (self.dt_total, self.dt_runoff, self.dt_discharge, self.dt_routing)
+        if self._network_time_signature == signature:
+            return
+        for big, small, msg in ((self.dt_total, self.dt_runoff, 'dt_total must be >= dt_runoff'),
+                                (self.dt_total, self.dt_discharge, 'dt_total must be >= dt_discharge'),
+                                (self.dt_discharge, self.dt_runoff, 'dt_discharge must be >= dt_runoff'),
+                                (self.dt_runoff, self.dt_routing, 'dt_runoff must be >= dt_routing')):
+            if big < small:
+                raise ValueError(msg)
+        for big, small, msg in ((self.dt_total, self.dt_runoff, 'dt_total must be an integer multiple of dt_runoff'),
+                                (self.dt_total, self.dt_discharge, 'dt_total must be an integer multiple of dt_discharge'),
+                                (self.dt_discharge, self.dt_runoff, 'dt_discharge must be an integer multiple of dt_runoff'),
+                                (self.dt_runoff, self.dt_routing, 'dt_runoff must be an integer multiple of dt_routing')):
+            if big % small != 0:
+                raise ValueError(msg)
+        self.num_runoff_steps = int(self.dt_total / self.dt_runoff)
+        self.num_runoff_steps_per_discharge = int(self.dt_discharge / self.dt_runoff)
+        self.num_routing_steps_per_runoff = int(self.dt_runoff / self.dt_routing)
+        self._set_muskingum_coefficients(self.dt_routing)
+        self._network_time_signature = signature
+
+    def _set_muskingum_coefficients(self, dt_routing):
+        self._muskingum_coefficients(dt_routing)
+        self.c4 = self.c1 + self.c2                                         # TransformMuskingum.py:104
+        self.plan.set_coefficients(self.c1, self.c2, self.c3, self.c4 / self.dt_runoff)   # RapidMuskingum.py:25
+
+    def _execute_routing(self):
+        self._ensemble_member_states = []
+        files = self._qlateral_generator()
+        if self.cfg.progress_bar:
+            from tqdm import tqdm
+            files = tqdm(files, total=len(self.cfg.qlateral_files or self.cfg.grid_runoff_files), desc='Files Routed')
+        for dates, qlateral, runoff_file, discharge_file in files:
+            self.logger.info(f'Routing qlateral: {runoff_file}')
+            self._set_network_and_time_dependent_vectors(dates)
+            q_t, q_array = self._router(qlateral)
+            if self.cfg.runoff_processing_mode == 'sequential':
+                self.channel_state = q_t
+            else:                                                            # every member starts from the same state
+                self._ensemble_member_states.append(q_t.copy())
+            if self.dt_discharge > self.dt_runoff:                           # :128-139
+                q_array = q_array.reshape((int(self.dt_total / self.dt_discharge),
+                                           int(self.dt_discharge / self.dt_runoff), self.n)).mean(axis=1)
+                dates = dates[::self.num_runoff_steps_per_discharge]
+            self._write(dates, q_array.astype(np.float32, copy=False), discharge_file, runoff_file)
+        if self.cfg.runoff_processing_mode == 'ensemble':
+            self.channel_state = np.array(self._ensemble_member_states).mean(axis=0)   # :145-146
+
+    def _router(self, qlateral):
+        """The seam of TransformMuskingum.py:150-152: (final state, fp64 (T, n) discharge array)."""
+        if qlateral.shape != (self.num_runoff_steps, self.n):
+            raise ValueError(f'qlateral shape {qlateral.shape} does not match (num_runoff_steps, n) = '
+                             f'{(self.num_runoff_steps, self.n)}')
+        discharge_array = np.zeros((self.num_runoff_steps, self.n), dtype=np.float64)
+        q_t = self.channel_state.astype(np.float64, copy=True)
+        self.plan.route_host(self._mode, q_t, qlateral, discharge_array, self.num_routing_steps_per_runoff)
+        return q_t, discharge_array
+
+
+class RapidMuskingum(TransformMuskingum):
+    """Muskingum routing with direct lateral inflow volumes (river_route/routers/RapidMuskingum.py)."""
+    _as_volumes = True
+    _mode = MODE_RAPID
+
+
+class UnitMuskingum(TransformMuskingum):
+    """Muskingum routing with unit-hydrograph lateral inflow (river_route/routers/UnitMuskingum.py): runoff depths
+    are convolved with the UH kernel on the GPU, headwaters pass the convolved inflow through, inner reaches are
+    routed; the headwater / inner split lives inside the device plan."""
+    _ROUTER_REQUIRED_CONFIGS = ('uh_kernel_file',)
+    _as_volumes = False
+    _mode = MODE_UNIT
+    _uh: UnitHydrograph | None = None
+
+    def _hook_before_route(self):
+        if self._uh is None:
+            self._uh = UnitHydrograph(self.cfg.uh_kernel_file)
+            if self.cfg.uh_state_init_file:
+                self._uh.set_state(self.cfg.uh_state_init_file)
+        if not hasattr(self, 'hw_idx'):
+            incoming = np.bincount(self.down[self.down >= 0], minlength=self.n)
+            self.hw_idx = np.where(incoming == 0)[0]
+            self.inner_idx = np.where(incoming != 0)[0]
+            self.logger.info(f'Headwater split: {len(self.hw_idx)} headwater, {len(self.inner_idx)} inner '
+                             f'({len(self.hw_idx) / self.n * 100:.0f}% excluded from solve)')
+
+    def _set_muskingum_coefficients(self, dt_routing):
+        self._muskingum_coefficients(dt_routing)
+        self.c4 = self.c1 + self.c2
+        self.plan.set_coefficients(self.c1, self.c2, self.c3, None)
+
+    def _router(self, qlateral):
+        convolved = self._uh.convolve(qlateral)                              # UnitMuskingum.py:75
+        return super()._router(convolved)
+
+    def _write_final_state(self):
+        super()._write_final_state()
+        if self.cfg.uh_state_final_file and self._uh is not None:
+            self._uh.write_state(self.cfg.uh_state_final_file)
+
+
+def _read_qlateral(path):
+    """qlateral netCDF: variable ``qlateral(time, river_id)`` (docs/references/io-file-schema.md:52-55)."""
+    try:
+        import xarray as xr
+        with xr.open_dataset(path) as ds:
+            return ds['time'].values.astype('datetime64[s]'), ds['qlateral'].values.astype(np.float64, copy=False)
+    except ImportError:
+        pass
+    try:
+        import netCDF4 as nc
+    except ImportError as e:  # pragma: no cover - depends on the host environment
+        raise ImportError('xarray or netCDF4 is required to read qlateral files') from e
+    with nc.Dataset(str(path)) as ds:
+        tv = ds['time']
+        dates = nc.num2date(tv[:], tv.units, only_use_cftime_datetimes=False, only_use_python_datetimes=True)
+        return (np.array(dates, dtype='datetime64[s]'),
+                np.asarray(ds['qlateral'][:], dtype=np.float64))

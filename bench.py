@@ -81,17 +81,8 @@ def coefficients(k, x, dt_routing, dt_runoff):
 
 def shard(down, n_parts, part_id):
     """Reaches of this rank's basins, in their original relative order, and the local downstream index."""
-    import river_route_b200 as rr
-    from river_route_b200 import synth
-    if n_parts == 1:
-        return np.arange(down.shape[0]), down
-    _, _, part = rr.label_basins(down, n_parts)
-    idx = np.flatnonzero(part == part_id)
-    new_of_old = np.full(down.shape[0], -1, dtype=np.int64)
-    new_of_old[idx] = np.arange(idx.shape[0])
-    d = down[idx]
-    local = np.where(d >= 0, new_of_old[np.where(d >= 0, d, 0)], -1).astype(np.int32)
-    return idx, local
+    from river_route_b200.sharding import shard_by_basin
+    return shard_by_basin(down, n_parts, part_id)
 
 
 class ClockSampler:

@@ -282,6 +282,9 @@ def main():
     if rank == 0:
         sampler.start()
     rr.launch_count(reset=True)
+    from river_route_b200.plan import timing_enable, timing_read
+    timing_enable(True)
+    timing_read(reset=True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
     for s in range(args.steps):
@@ -289,6 +292,8 @@ def main():
         ev[s + 1].record()
     barrier()
     launches = rr.launch_count()
+    ktimes = timing_read(reset=True)
+    timing_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
@@ -337,7 +342,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        kernel_ms = float(np.mean(step_ms))
+        kernel_ms = ktimes['route']['ms'] / max(ktimes['route']['launches'], 1)   # the routing kernel alone (CUDA events)
         achieved = B_ALG * n * rows / (kernel_ms * 1e-3) / 1e9
         traffic = ncu_traffic()
         line = {
@@ -348,6 +353,7 @@ def main():
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': (traffic or {}).get('dram_bytes_per_launch'),
                          'kernel': 'rr_wavefront_kernel<RAPID>', 'kernel_ms': kernel_ms,
+                         'step_ms_by_kernel': {k_: v['ms'] / args.steps for k_, v in ktimes.items()},
                          'algorithmic_bytes_per_reach_step': B_ALG, 'peak_source': peak_src,
                          'traffic_source': (traffic or {}).get('source')},
             'e2e': {'value': e2e_value, 'unit': 'reach-timesteps/s', 'h2d_bytes_per_step': int(n * er * 8 + n * 8),

@@ -36,7 +36,7 @@ enum {
 
 /* Tunables of the wavefront solve; zero / negative fields mean "choose for me". */
 typedef struct rr_plan_opts {
-    int32_t time_tile;      /* runoff/output rows advanced per work item (default 32)        */
+    int32_t time_tile;      /* routing substeps advanced per work item (default 64)          */
     int32_t tile_stride;    /* ticket-key distance between consecutive tiles of one block;
                                0 = smallest power of two whose exchange rings fit the budget */
     int32_t device;         /* CUDA device ordinal (default: current device)                 */
@@ -147,6 +147,11 @@ int rr_route_ensemble_dev(rr_plan *p, int mode, const double *q_init, int32_t n_
 /* Kernel launches issued by this library on this thread since the last reset (bench.py's
  * gpu_launches claim). */
 int64_t rr_launch_count(int reset);
+/* Optional device timing of this library's kernels with CUDA events on the launching stream:
+ * ms[0] routing kernel, ms[1] permute to working order, ms[2] permute to params order, ms[3] other;
+ * counts[] = launches per class.  rr_timing_read synchronises on the recorded events. */
+int rr_timing_enable(int on);
+int rr_timing_read(double *ms, int64_t *counts, int reset);
 
 /* ---- unit hydrograph ----------------------------------------------------------------------
  * Replaces UnitHydrograph.convolve (river_route/uhkernels/UnitHydrograph.py:77-107):

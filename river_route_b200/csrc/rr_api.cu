@@ -22,6 +22,44 @@ extern "C" int64_t rr_launch_count(int reset) {
 }
 void rr_count_launch(int64_t k) { g_launches += k; }
 
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
+struct rr_timed { int cls; cudaEvent_t a, b; };
+static thread_local bool g_timing = false;
+static thread_local std::vector<rr_timed> g_timed;
+extern "C" int rr_timing_enable(int on) { g_timing = on != 0; return 0; }
+struct rr_timer {
+    rr_timed t{};
+    bool on;
+    cudaStream_t s;
+    rr_timer(int cls, cudaStream_t stream) : on(g_timing), s(stream) {
+        if (!on) return;
+        t.cls = cls;
+        cudaEventCreate(&t.a);
+        cudaEventCreate(&t.b);
+        cudaEventRecord(t.a, s);
+    }
+    ~rr_timer() {
+        if (!on) return;
+        cudaEventRecord(t.b, s);
+        g_timed.push_back(t);
+    }
+};
+extern "C" int rr_timing_read(double *ms, int64_t *counts, int reset) {
+    for (int k = 0; k < 4; ++k) { ms[k] = 0.0; counts[k] = 0; }
+    for (auto &t : g_timed) {
+        cudaEventSynchronize(t.b);
+        float e = 0.f;
+        cudaEventElapsedTime(&e, t.a, t.b);
+        ms[t.cls & 3] += e;
+        counts[t.cls & 3]++;
+    }
+    if (reset) {
+        for (auto &t : g_timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+        g_timed.clear();
+    }
+    return 0;
+}
+
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -249,7 +287,10 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     const int64_t total_items = d->sched.n_items * n_members;
     int64_t grid = (int64_t)d->sm_count * d->occ[mode];
     grid = std::max<int64_t>(1, std::min<int64_t>(grid, (total_items + warps_per_cta - 1) / warps_per_cta));
-    CK(rr_launch_wavefront(mode, P, (int)grid, block, stream));
+    {
+        rr_timer tm(0, stream);
+        CK(rr_launch_wavefront(mode, P, (int)grid, block, stream));
+    }
     rr_count_launch(1);
     return 0;
 }
@@ -290,6 +331,7 @@ __global__ void __launch_bounds__(256) permute_to_user(const double *__restrict_
 static int permute(bool to_working, const double *src, int64_t lds, double *dst, int64_t ldd, const int32_t *inv,
                    int64_t n, int64_t T, cudaStream_t stream) {
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)((T + PERM_ROWS - 1) / PERM_ROWS));
+    rr_timer tm(to_working ? 1 : 2, stream);
     if (to_working) permute_to_working<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T);
     else permute_to_user<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T);
     CK(cudaGetLastError());

@@ -32,6 +32,9 @@
 
 #include "rr_route.cuh"
 
+#ifndef RR_MIN_CTAS
+#define RR_MIN_CTAS 2
+#endif
 #define FULL_MASK 0xffffffffu
 #define SLOT_NONE ((int32_t)0x80000000)
 #define RAW_QF 2      // row entry holding the q_full carry-in (UNIT)
@@ -45,17 +48,22 @@ __device__ __forceinline__ int32_t ld_relaxed(const int32_t *p) {
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ int32_t ld_acquire(const int32_t *p) {
+    int32_t v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release(int32_t *p, int32_t v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Spin with relaxed loads (no L1 invalidation per poll); the caller fences once after all waits.
+// Spin with relaxed loads (an acquire load invalidates the SM's L1 on every poll), then acquire once.
 __device__ __forceinline__ void wait_ge(const int32_t *flag, int32_t want) {
     unsigned ns = 32;
     while (ld_relaxed(flag) < want) {
         __nanosleep(ns);
         if (ns < 512) ns <<= 1;
     }
+    (void)ld_acquire(flag);
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // streaming read of data that is never written during the launch
@@ -199,7 +207,7 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
 }  // namespace
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) rr_wavefront_kernel(const __grid_constant__ rr_route_params P) {
+__global__ void __launch_bounds__(256, RR_MIN_CTAS) rr_wavefront_kernel(const __grid_constant__ rr_route_params P) {
     constexpr bool HAS_LAT = (MODE != RR_MODE_MUSKINGUM);
     constexpr bool UNIT = (MODE == RR_MODE_UNIT);
     const int lane = threadIdx.x & 31;
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(256, 2) rr_wavefront_kernel(const __grid_const
 
         // ---------------- dependencies ----------------
         int32_t *done = P.done + (size_t)m * P.n_blocks;
-        if (lane == 0 && j > 0) wait_ge(done + b, j);                       // own previous tile
+        if (lane == 0) wait_ge(done + b, j);                                // own previous tile (acquire)
         for (int e = P.dep_ptr[b] + lane; e < P.dep_ptr[b + 1]; e += 32)    // upstream blocks, this tile
             wait_ge(done + P.dep_idx[e], j + 1);
         if (ex >= 0) {                                                      // exchange-ring reuse
@@ -277,7 +285,6 @@ __global__ void __launch_bounds__(256, 2) rr_wavefront_kernel(const __grid_const
             if (j >= ring) wait_ge(done + __ldg(P.down + i) / RR_BLOCK, j - ring + 1);
         }
         __syncwarp();
-        fence_acquire();
 
         // ---------------- state ----------------
         // first tile of a reference call: every member starts from the shared initial state and

@@ -199,3 +199,17 @@ class Plan:
 def launch_count(reset: bool = False) -> int:
     """Kernel launches issued by the library on this thread (bench.py's gpu_launches)."""
     return int(lib.rr_launch_count(1 if reset else 0))
+
+
+def timing_enable(on: bool = True) -> None:
+    """Record CUDA events around every kernel this library launches (read with ``timing_read``)."""
+    lib.rr_timing_enable(1 if on else 0)
+
+
+def timing_read(reset: bool = True) -> dict:
+    """Accumulated device time (ms) and launch counts per kernel class since the last reset."""
+    ms = (C.c_double * 4)()
+    cnt = (C.c_int64 * 4)()
+    lib.rr_timing_read(ms, cnt, 1 if reset else 0)
+    names = ('route', 'permute_to_working', 'permute_to_user', 'other')
+    return {n: {'ms': ms[i], 'launches': cnt[i]} for i, n in enumerate(names)}

@@ -171,7 +171,7 @@ int rr_uh_convolve_host(int64_t n, int64_t n_ks, int64_t T,
  * cumulative->incremental, optional clip at 0, NaN->0, optional multiply by area[r].
  * x is the gathered grid runoff [T][ldx], float32 (x_is_f32 != 0) or float64; the product
  * is formed in fp64 as the reference's scipy call does.  Device pointers. */
-int rr_weights_transform_dev(int64_t n_rivers, int64_t T, const int32_t *indptr,
+int rr_weights_transform_dev(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr,
                              const int32_t *indices, const double *w, const void *x, int x_is_f32,
                              int64_t ldx, double *y, int64_t ldy, int cumulative, int force_positive,
                              const double *area, void *stream);

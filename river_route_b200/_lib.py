@@ -61,7 +61,7 @@ def _load() -> C.CDLL:
         'rr_timing_read': (C.c_int, [f64p, c_i64p, C.c_int]),
         'rr_uh_convolve_dev': (C.c_int, [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
         'rr_uh_convolve_host': (C.c_int, [i64, i64, i64, f64p, i64, f64p, i64, f64p, i64, f64p, i64]),
-        'rr_weights_transform_dev': (C.c_int, [i64, i64, vp, vp, vp, vp, C.c_int, i64, vp, i64, C.c_int, C.c_int,
+        'rr_weights_transform_dev': (C.c_int, [i64, i64, i64, vp, vp, vp, vp, C.c_int, i64, vp, i64, C.c_int, C.c_int,
                                                vp, vp]),
         'rr_weights_transform_host': (C.c_int, [i64, i64, i64, c_i32p, c_i32p, f64p, vp, C.c_int, i64, f64p, i64,
                                                 C.c_int, C.c_int, f64p]),

@@ -267,7 +267,13 @@ extern "C" int rr_plan_create(int64_t n, const int32_t *down, const rr_plan_opts
         // Blocks of 32 consecutive reaches merge their dependencies; in an arbitrary (valid) order the
         // block DAG can be tens of times deeper than the river network.  Sorting reaches by level
         // makes it as shallow as the network itself.
-        if (p->opts.renumber == 0 && p->max_level > 2 * (int64_t)depth + 16) renumber = true;
+        // Two reasons to work on level-sorted reaches instead (the caller's arrays stay as they are):
+        //  * the block DAG is much deeper than the network, so launches are dependency-latency bound;
+        //  * many blocks have in-block edges and miss the register-blocked fast path of the kernel.
+        int64_t fast_blocks = 0;
+        for (const rr_blk_meta &m : p->meta) fast_blocks += (m.int_mask & 0x40) ? 1 : 0;
+        if (p->opts.renumber == 0 &&
+            (p->max_level > 2 * (int64_t)depth + 16 || fast_blocks * 10 < p->n_blocks * 9)) renumber = true;
     }
     if (renumber) {
         // working order = stable sort by level: perm[k] = user index of working reach k

@@ -5,8 +5,8 @@
 // (ascending column) order -- scipy's csr_matvecs row-wise axpy order -- then cumulative ->
 // incremental, optional clip at zero, NaN -> 0 and optional multiplication by catchment area.
 // Memory-bound CSR SpMM with time as the dense dimension: one thread per river so the (T, n)
-// output rows are written as coalesced 256-byte segments; grid cells of neighbouring catchments
-// are neighbours in the grid row, which stays L2 resident (a 0.25 degree global row is 4 MB).
+// output rows are written as coalesced 256-byte segments; the runoff is transposed to (cell, time)
+// first so that each weight entry reads one full 32-byte sector (8 time steps of one cell).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -27,28 +27,55 @@ void rr_count_launch(int64_t k);
 
 namespace {
 
-constexpr int FAST_NNZ = 8;   // row entries cached in registers
-constexpr int TSTEP = 4;      // time steps in flight per thread
+constexpr int TB = 8;   // time steps per register block == one 32-byte sector of float32 runoff
 
+// Gathered grid runoff arrives time-major (T, n_points); a catchment touches a handful of scattered
+// cells, so reading it in place wastes 7/8 of every sector.  It is transposed once per call to
+// (n_points, Tp) so that the TB time steps of one cell are one contiguous sector.
 template <typename XT>
-__device__ __forceinline__ double row_dot(const XT *__restrict__ xrow, const int32_t *__restrict__ indices,
-                                          const double *__restrict__ w, int p0, int nnz, const int32_t (&col)[FAST_NNZ],
-                                          const double (&wt)[FAST_NNZ]) {
-    double acc = 0.0;
-#pragma unroll
-    for (int k = 0; k < FAST_NNZ; ++k)
-        if (k < nnz) acc = fma(wt[k], (double)__ldg(xrow + col[k]), acc);
-    for (int k = FAST_NNZ; k < nnz; ++k)
-        acc = fma(__ldg(w + p0 + k), (double)__ldg(xrow + __ldg(indices + p0 + k)), acc);
-    return acc;
+__global__ void __launch_bounds__(256) transpose_kernel(const XT *__restrict__ x, int64_t ldx, XT *__restrict__ xt,
+                                                        int64_t Tp, int64_t T, int64_t n_points) {
+    __shared__ XT tile[32][33];
+    const int64_t c0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t t = t0 + r, c = c0 + tx;
+        tile[r][tx] = (t < T && c < n_points) ? x[t * ldx + c] : XT(0);
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t c = c0 + r, t = t0 + tx;
+        if (c < n_points && t < Tp) xt[c * Tp + t] = tile[tx][r];
+    }
 }
 
+template <typename XT> struct vec8;
+template <> struct vec8<float> {
+    float v[8];
+    __device__ __forceinline__ void load(const float *p) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+template <> struct vec8<double> {
+    double v[8];
+    __device__ __forceinline__ void load(const double *p) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(p) + k);
+            v[2 * k] = a.x; v[2 * k + 1] = a.y;
+        }
+    }
+};
+
+// One thread per river, TB outputs in registers; row entries are walked in stored (ascending column)
+// order so every output accumulates in scipy's csr_matvecs order; the tail of runoff.py:309-337 is fused.
 template <typename XT>
-__global__ void __launch_bounds__(128) weights_kernel(int64_t n_rivers, int64_t T, int64_t chunk,
+__global__ void __launch_bounds__(128) weights_kernel(int64_t n_rivers, int64_t T, int64_t Tp, int64_t chunk,
                                                       const int32_t *__restrict__ indptr,
                                                       const int32_t *__restrict__ indices,
-                                                      const double *__restrict__ w, const XT *__restrict__ x,
-                                                      int64_t ldx, double *__restrict__ y, int64_t ldy,
+                                                      const double *__restrict__ w, const XT *__restrict__ xt,
+                                                      double *__restrict__ y, int64_t ldy,
                                                       int cumulative, int force_positive,
                                                       const double *__restrict__ area) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,65 +83,93 @@ __global__ void __launch_bounds__(128) weights_kernel(int64_t n_rivers, int64_t 
     const int64_t tb = (int64_t)blockIdx.y * chunk;
     const int64_t te = min(T, tb + chunk);
     const int p0 = __ldg(indptr + r);
-    const int nnz = __ldg(indptr + r + 1) - p0;
-    int32_t col[FAST_NNZ];
-    double wt[FAST_NNZ];
-#pragma unroll
-    for (int k = 0; k < FAST_NNZ; ++k) {
-        col[k] = k < nnz ? __ldg(indices + p0 + k) : 0;
-        wt[k] = k < nnz ? __ldg(w + p0 + k) : 0.0;
-    }
+    const int p1 = __ldg(indptr + r + 1);
     const double a = area ? __ldg(area + r) : 1.0;
-    // cumulative input: the chunk needs the aggregated value of the step before it (runoff.py:310-312)
-    double prev = 0.0;
-    if (cumulative && tb > 0) prev = row_dot(x + (tb - 1) * ldx, indices, w, p0, nnz, col, wt);
-    for (int64_t t = tb; t < te; t += TSTEP) {
-        double v[TSTEP];
+    double prev = 0.0;   // aggregated value of the step before this block (cumulative input, runoff.py:310-312)
+    if (cumulative && tb > 0) {
+        for (int j = p0; j < p1; ++j)
+            prev = fma(__ldg(w + j), (double)__ldg(xt + (int64_t)__ldg(indices + j) * Tp + tb - 1), prev);
+    }
+    for (int64_t t0 = tb; t0 < te; t0 += TB) {
+        double acc[TB];
 #pragma unroll
-        for (int u = 0; u < TSTEP; ++u)
-            v[u] = (t + u < te) ? row_dot(x + (t + u) * ldx, indices, w, p0, nnz, col, wt) : 0.0;
+        for (int u = 0; u < TB; ++u) acc[u] = 0.0;
+        for (int j = p0; j < p1; ++j) {
+            const double wj = __ldg(w + j);
+            vec8<XT> xv;
+            xv.load(xt + (int64_t)__ldg(indices + j) * Tp + t0);
 #pragma unroll
-        for (int u = 0; u < TSTEP; ++u) {
-            if (t + u < te) {
-                double q = v[u];
-                if (cumulative) { if (t + u > 0) q = v[u] - prev; prev = v[u]; }
+            for (int u = 0; u < TB; ++u) acc[u] = fma(wj, (double)xv.v[u], acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < TB; ++u) {
+            if (t0 + u < te) {
+                double q = acc[u];
+                if (cumulative) { if (t0 + u > 0) q = acc[u] - prev; prev = acc[u]; }
                 if (force_positive && q < 0.0) q = 0.0;   // :313-314
                 if (q != q) q = 0.0;                      // :331-333
                 if (area) q *= a;                         // :335-336
-                y[(t + u) * ldy + r] = q;
+                y[(t0 + u) * ldy + r] = q;
             }
         }
     }
 }
 
-}  // namespace
-
-extern "C" int rr_weights_transform_dev(int64_t n_rivers, int64_t T, const int32_t *indptr, const int32_t *indices,
-                                        const double *w, const void *x, int x_is_f32, int64_t ldx, double *y,
-                                        int64_t ldy, int cumulative, int force_positive, const double *area,
-                                        void *stream_) {
-    if (n_rivers <= 0 || T <= 0) { rr_set_error("n_rivers and T must be positive"); return 100; }
-    if (!indptr || !indices || !w || !x || !y) { rr_set_error("null argument"); return 100; }
-    cudaStream_t stream = (cudaStream_t)stream_;
+template <typename XT>
+int run_weights(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr, const int32_t *indices,
+                const double *w, const XT *x, int64_t ldx, double *y, int64_t ldy, int cumulative, int force_positive,
+                const double *area, cudaStream_t stream) {
+    const int64_t Tp = ((T + TB - 1) / TB) * TB;
+    XT *xt = nullptr;
+    {   // keep the stream-ordered pool's memory between calls (the default trims it at every sync)
+        static thread_local int tuned_device = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (tuned_device != dev) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            tuned_device = dev;
+        }
+    }
+    CK(cudaMallocAsync((void **)&xt, sizeof(XT) * (size_t)n_points * Tp, stream));
+    dim3 tg((unsigned)((n_points + 31) / 32), (unsigned)((Tp + 31) / 32));
+    transpose_kernel<XT><<<tg, 256, 0, stream>>>(x, ldx, xt, Tp, T, n_points);
+    CK(cudaGetLastError());
     const int threads = 128;
     const unsigned gx = (unsigned)((n_rivers + threads - 1) / threads);
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want_y = std::max<int64_t>(1, ((int64_t)sms * 16 + gx - 1) / gx);
-    int64_t chunk = std::max<int64_t>(32, (T + want_y - 1) / want_y);
-    chunk = std::min<int64_t>(((chunk + TSTEP - 1) / TSTEP) * TSTEP, std::max<int64_t>(T, 1));
+    int64_t chunk = std::max<int64_t>(64, (T + want_y - 1) / want_y);
+    chunk = std::min<int64_t>(((chunk + TB - 1) / TB) * TB, Tp);
     dim3 grid(gx, (unsigned)((T + chunk - 1) / chunk));
-    if (x_is_f32)
-        weights_kernel<float><<<grid, threads, 0, stream>>>(n_rivers, T, chunk, indptr, indices, w, (const float *)x,
-                                                            ldx, y, ldy, cumulative, force_positive, area);
-    else
-        weights_kernel<double><<<grid, threads, 0, stream>>>(n_rivers, T, chunk, indptr, indices, w,
-                                                             (const double *)x, ldx, y, ldy, cumulative,
-                                                             force_positive, area);
+    weights_kernel<XT><<<grid, threads, 0, stream>>>(n_rivers, T, Tp, chunk, indptr, indices, w, xt, y, ldy, cumulative,
+                                                     force_positive, area);
     CK(cudaGetLastError());
-    rr_count_launch(1);
+    CK(cudaFreeAsync(xt, stream));
+    rr_count_launch(2);
     return 0;
+}
+
+}  // namespace
+
+extern "C" int rr_weights_transform_dev(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr,
+                                        const int32_t *indices, const double *w, const void *x, int x_is_f32,
+                                        int64_t ldx, double *y, int64_t ldy, int cumulative, int force_positive,
+                                        const double *area, void *stream_) {
+    if (n_rivers <= 0 || T <= 0 || n_points <= 0) { rr_set_error("n_rivers, n_points and T must be positive"); return 100; }
+    if (!indptr || !indices || !w || !x || !y) { rr_set_error("null argument"); return 100; }
+    if (ldx < n_points || ldy < n_rivers) { rr_set_error("leading dimension too small"); return 100; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (x_is_f32)
+        return run_weights<float>(n_rivers, n_points, T, indptr, indices, w, (const float *)x, ldx, y, ldy, cumulative,
+                                  force_positive, area, stream);
+    return run_weights<double>(n_rivers, n_points, T, indptr, indices, w, (const double *)x, ldx, y, ldy, cumulative,
+                               force_positive, area, stream);
 }
 
 extern "C" int rr_weights_transform_host(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr,
@@ -150,8 +205,9 @@ extern "C" int rr_weights_transform_host(int64_t n_rivers, int64_t n_points, int
     fail(cudaMemcpy2D(d_x, n_points * es, x, ldx * es, n_points * es, T, cudaMemcpyHostToDevice), "H2D runoff");
     if (area) fail(cudaMemcpy(d_area, area, sizeof(double) * (size_t)n_rivers, cudaMemcpyHostToDevice), "H2D area");
     if (!rc)
-        rc = rr_weights_transform_dev(n_rivers, T, d_ptr, d_idx, d_w, d_x, x_is_f32, n_points, d_y, ldyd, cumulative,
-                                      force_positive, d_area, nullptr);
+        rc = rr_weights_transform_dev(n_rivers, n_points, T, d_ptr, d_idx, d_w, d_x, x_is_f32, n_points, d_y, ldyd,
+                                      cumulative, force_positive, d_area, nullptr);
+    if (!rc) fail(cudaStreamSynchronize(nullptr), "weights kernel");
     if (!rc) fail(cudaMemcpy2D(y, ldy * 8, d_y, ldyd * 8, n_rivers * 8, T, cudaMemcpyDeviceToHost), "D2H qlateral");
     cudaFree(d_ptr); cudaFree(d_idx); cudaFree(d_w); cudaFree(d_x); cudaFree(d_y);
     if (d_area) cudaFree(d_area);

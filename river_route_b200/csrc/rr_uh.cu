@@ -5,8 +5,9 @@
 // accumulated oldest contribution first, which is the order of the reference's exact
 // direct form convolve_incrementally (:64-75; the FFT path agrees with it to 1e-12,
 // tests/test_uhkernels.py:52-78).  Not a dense contraction: each basin has its own taps, so
-// there is nothing for tensor cores; it is a register-blocked FIR, one thread per basin,
-// all arrays (time, basin) row-major so every warp access is a coalesced 256-byte row segment.
+// there is nothing for tensor cores; it is a register-blocked FIR (8 outputs x sliding input window per
+// thread), one thread per basin, all arrays (time, basin) row-major so every warp access is a coalesced
+// 256-byte row segment.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -27,10 +28,13 @@ void rr_count_launch(int64_t k);
 
 namespace {
 
-// Taps and a circular window of the last NK inputs live in registers; the time loop is
-// unrolled NK-fold so every window index is a compile-time constant (no register moves).
-// grid.y splits time into chunks; a chunk warms its window from the NK-1 inputs before it.
-template <int NK>
+// One thread per basin, TB outputs per iteration held in registers.  Taps are walked from the oldest
+// input to the newest (tau descending), which is the accumulation order of convolve_incrementally; the
+// TB inputs that pair with one tap slide by one position per tap, so each tap costs one new input load,
+// one tap load and TB independent FMAs.  The tap loop is unrolled TB-fold with a rotating register
+// window, so no register moves are needed.  Taps beyond n_ks are zero (fma(0, x, acc) == acc).
+// grid.y splits time into chunks when there are few basins.
+template <int TB>
 __global__ void __launch_bounds__(128) uh_conv_kernel(int64_t n, int n_ks, int64_t T, int64_t chunk,
                                                       const double *__restrict__ lat, int64_t ldl,
                                                       const double *__restrict__ ker, int64_t ldk,
@@ -40,48 +44,31 @@ __global__ void __launch_bounds__(128) uh_conv_kernel(int64_t n, int n_ks, int64
     if (b >= n) return;
     const int64_t tb = (int64_t)blockIdx.y * chunk;
     const int64_t te = min(T, tb + chunk);
-    double kq[NK], win[NK];
+    const int n_groups = (n_ks + TB - 1) / TB;
+    const double *lb = lat + b;
+    auto input = [&](int64_t t) -> double { return (t >= 0 && t < T) ? __ldg(lb + t * ldl) : 0.0; };
+    for (int64_t t0 = tb; t0 < te; t0 += TB) {
+        double acc[TB], w[TB];
 #pragma unroll
-    for (int k = 0; k < NK; ++k) kq[k] = k < n_ks ? __ldg(ker + (int64_t)k * ldk + b) : 0.0;
-    // window slot u holds the input of time (tb + u) mod NK-periodic; warm-up: inputs tb-NK+1 .. tb-1
+        for (int u = 0; u < TB; ++u) {
+            const int64_t t = t0 + u;
+            acc[u] = (t < n_ks && t < te) ? state[t * lds + b] : 0.0;      // UnitHydrograph.py:100
+        }
+        int tau = n_groups * TB - 1;                                        // oldest (possibly padded) tap
 #pragma unroll
-    for (int u = 1; u < NK; ++u) {
-        const int64_t t = tb - NK + u;
-        win[u] = t >= 0 ? __ldg(lat + t * ldl + b) : 0.0;
-    }
-    win[0] = 0.0;
-    for (int64_t t = tb; t < te; t += NK) {
+        for (int u = 0; u < TB; ++u) w[u] = input(t0 + u - tau);
+        for (int g = 0; g < n_groups; ++g) {
 #pragma unroll
-        for (int u = 0; u < NK; ++u) {
-            const int64_t tt = t + u;
-            if (tt < te) {
-                win[u] = __ldg(lat + tt * ldl + b);
-                double acc = tt < n_ks ? state[tt * lds + b] : 0.0;   // UnitHydrograph.py:100
+            for (int p = 0; p < TB; ++p, --tau) {
+                const double kt = tau < n_ks ? __ldg(ker + (int64_t)tau * ldk + b) : 0.0;
 #pragma unroll
-                for (int tau = NK - 1; tau >= 0; --tau)               // oldest input first
-                    acc = fma(kq[tau], win[(u - tau + 2 * NK) % NK], acc);
-                out[tt * ldo + b] = acc;
+                for (int u = 0; u < TB; ++u) acc[u] = fma(kt, w[(u + p) % TB], acc[u]);
+                w[p % TB] = input(t0 + TB - tau);                           // newest input of the next tap
             }
         }
-    }
-}
-
-// Any kernel length: taps and inputs re-read through L1/L2.
-__global__ void __launch_bounds__(128) uh_conv_generic(int64_t n, int n_ks, int64_t T, int64_t chunk,
-                                                       const double *__restrict__ lat, int64_t ldl,
-                                                       const double *__restrict__ ker, int64_t ldk,
-                                                       const double *__restrict__ state, int64_t lds,
-                                                       double *__restrict__ out, int64_t ldo) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n) return;
-    const int64_t tb = (int64_t)blockIdx.y * chunk;
-    const int64_t te = min(T, tb + chunk);
-    for (int64_t t = tb; t < te; ++t) {
-        double acc = t < n_ks ? state[t * lds + b] : 0.0;
-        const int tau_hi = (int)(t < (int64_t)n_ks - 1 ? t : (int64_t)n_ks - 1);
-        for (int tau = tau_hi; tau >= 0; --tau)
-            acc = fma(__ldg(ker + (int64_t)tau * ldk + b), __ldg(lat + (t - tau) * ldl + b), acc);
-        out[t * ldo + b] = acc;
+#pragma unroll
+        for (int u = 0; u < TB; ++u)
+            if (t0 + u < te) out[(t0 + u) * ldo + b] = acc[u];
     }
 }
 
@@ -122,18 +109,11 @@ extern "C" int rr_uh_convolve_dev(int64_t n, int64_t n_ks, int64_t T, const doub
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int64_t want_y = std::max<int64_t>(1, ((int64_t)sms * 16 + gx - 1) / gx);
     int64_t chunk = std::max<int64_t>(std::max<int64_t>(8 * n_ks, 64), (T + want_y - 1) / want_y);
-    chunk = std::min<int64_t>(chunk, T);
+    chunk = std::min<int64_t>(((chunk + 7) / 8) * 8, std::max<int64_t>(T, 1));
     const unsigned gy = (unsigned)((T + chunk - 1) / chunk);
     dim3 grid(gx, gy);
     const int nk = (int)n_ks;
-#define RR_UH_LAUNCH(NKT) \
-    uh_conv_kernel<NKT><<<grid, threads, 0, stream>>>(n, nk, T, chunk, lateral, ldl, kernel, ldk, state, lds, out, ldo)
-    if (nk <= 8) RR_UH_LAUNCH(8);
-    else if (nk <= 16) RR_UH_LAUNCH(16);
-    else if (nk <= 24) RR_UH_LAUNCH(24);
-    else if (nk <= 32) RR_UH_LAUNCH(32);
-    else uh_conv_generic<<<grid, threads, 0, stream>>>(n, nk, T, chunk, lateral, ldl, kernel, ldk, state, lds, out, ldo);
-#undef RR_UH_LAUNCH
+    uh_conv_kernel<8><<<grid, threads, 0, stream>>>(n, nk, T, chunk, lateral, ldl, kernel, ldk, state, lds, out, ldo);
     CK(cudaGetLastError());
     uh_state_kernel<<<gx, threads, 0, stream>>>(n, nk, T, lateral, ldl, kernel, ldk, state, lds);
     CK(cudaGetLastError());

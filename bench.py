@@ -352,7 +352,7 @@ def main():
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': dict(workload_config(args, rows), reaches_rank0=n, plan={k_: int(v) for k_, v in info.items()}),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': (traffic or {}).get('dram_bytes_per_launch'),
+                         'traffic': ((traffic or {}).get('dram_bytes_per_reach_step') or 0) * n * rows or None,
                          'kernel': 'rr_wavefront_kernel<RAPID>', 'kernel_ms': kernel_ms,
                          'step_ms_by_kernel': {k_: v['ms'] / args.steps for k_, v in ktimes.items()},
                          'algorithmic_bytes_per_reach_step': B_ALG, 'peak_source': peak_src,

@@ -90,6 +90,9 @@ struct rr_device_state {
     size_t key_cap = 0;
     int64_t sched_tiles = -1, sched_budget_rows = -1;
     rr_schedule sched;
+    struct key_table { int64_t n_tiles = -1, n_keys = 0, n_items = 0; int64_t *dev = nullptr; size_t cap = 0; uint64_t used = 0; };
+    key_table keys[4];
+    uint64_t key_clock = 0;
     double *raw = nullptr;
     size_t raw_bytes = 0;
     int32_t *done = nullptr;
@@ -180,6 +183,7 @@ void rr_device_release(rr_plan *p) {
                     d->inv, d->p_lat, d->p_out, d->p_q};
     for (void *q : ptrs)
         if (q) cudaFree(q);
+    for (auto &k : d->keys) if (k.dev) cudaFree(k.dev);
     if (d->s_comp) cudaStreamDestroy(d->s_comp);
     if (d->s_in) cudaStreamDestroy(d->s_in);
     if (d->s_out) cudaStreamDestroy(d->s_out);
@@ -209,24 +213,19 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     // tile geometry: aim for `time_tile` routing substeps per work item
     const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(T, p->opts.time_tile / K));
     const int64_t n_tiles = (T + rows - 1) / rows;
-    const int64_t pitch = 4 + ((rows * K + 3) / 4) * 4;   // [2] q_full carry, [3] carry, [4+s] substeps (rr_route.cu)
+    // row pitch of the exchange buffer: [2] q_full carry, [3] carry, [4+s] substeps (rr_route.cu); sized for the
+    // plan's nominal tile so that short calls (the last chunk of a stream) reuse the same rings
+    const int64_t nominal = std::max<int64_t>(std::max<int64_t>(1, p->opts.time_tile / K) * K, rows * K);
+    const int64_t pitch = 4 + ((nominal + 3) / 4) * 4;
     const int64_t budget_rows = std::max<int64_t>(1, p->opts.raw_budget_bytes / (int64_t)(pitch * sizeof(double) * n_members));
-    if (d->sched_tiles != n_tiles || d->sched_budget_rows != budget_rows) {
-        if ((double)n_tiles * (double)(p->max_level + 1) > 2e9) {
-            rr_set_error("network too deep for the ticket scheduler at this tile size; raise time_tile");
-            return 100;
-        }
-        rr_build_schedule(*p, n_tiles, p->opts.tile_stride, budget_rows, d->sched);
-        // the previous launch may still be reading the old tables on another stream
-        CK(cudaDeviceSynchronize());
-        if (d->sched.key_start.size() > d->key_cap) {
-            if (d->key_start) CK(cudaFree(d->key_start));
-            d->key_start = nullptr; d->key_cap = 0;
-            CK(cudaMalloc((void **)&d->key_start, d->sched.key_start.size() * sizeof(int64_t)));
-            d->key_cap = d->sched.key_start.size();
-        }
-        CK(cudaMemcpy(d->key_start, d->sched.key_start.data(), d->sched.key_start.size() * sizeof(int64_t),
-                      cudaMemcpyHostToDevice));
+    if ((double)n_tiles * (double)(p->max_level + 1) > 2e9) {
+        rr_set_error("network too deep for the ticket scheduler at this tile size; raise time_tile");
+        return 100;
+    }
+    if (d->sched_budget_rows != budget_rows) {
+        // exchange rings depend on the network and the budget only; built once and kept on the device
+        rr_build_rings(*p, p->opts.tile_stride, budget_rows, d->sched);
+        CK(cudaDeviceSynchronize());   // an earlier launch may still be reading the old tables
         if (!d->exp_ro) {
             CK(cudaMalloc((void **)&d->exp_ro, std::max<size_t>(d->sched.exp_ro.size(), 2) * sizeof(int32_t)));
             CK(cudaMalloc((void **)&d->edge_ro, std::max<size_t>(d->sched.edge_ro.size(), 2) * sizeof(int32_t)));
@@ -235,9 +234,28 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
             CK(cudaMemcpy(d->exp_ro, d->sched.exp_ro.data(), d->sched.exp_ro.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         if (!d->sched.edge_ro.empty())
             CK(cudaMemcpy(d->edge_ro, d->sched.edge_ro.data(), d->sched.edge_ro.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        d->sched_tiles = n_tiles;
         d->sched_budget_rows = budget_rows;
+        for (auto &k : d->keys) k.n_tiles = -1;
     }
+    // ticket keys per call length: a few tables are cached (the streaming path alternates between the
+    // full chunk and the last, shorter one)
+    rr_device_state::key_table *kt = nullptr;
+    for (auto &k : d->keys) if (k.n_tiles == n_tiles) kt = &k;
+    if (!kt) {
+        kt = &d->keys[0];
+        for (auto &k : d->keys) if (k.used < kt->used) kt = &k;
+        rr_build_keys(*p, n_tiles, d->sched);
+        CK(cudaDeviceSynchronize());
+        if (d->sched.key_start.size() > kt->cap) {
+            if (kt->dev) CK(cudaFree(kt->dev));
+            kt->dev = nullptr; kt->cap = 0;
+            CK(cudaMalloc((void **)&kt->dev, d->sched.key_start.size() * sizeof(int64_t)));
+            kt->cap = d->sched.key_start.size();
+        }
+        CK(cudaMemcpy(kt->dev, d->sched.key_start.data(), d->sched.key_start.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        kt->n_tiles = n_tiles; kt->n_keys = d->sched.n_keys; kt->n_items = d->sched.n_items;
+    }
+    kt->used = ++d->key_clock;
     const size_t raw_need = (size_t)n_members * (size_t)d->sched.raw_rows * pitch * sizeof(double);
     if (raw_need > d->raw_bytes) {
         CK(cudaDeviceSynchronize());
@@ -264,7 +282,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.exp_ro = d->exp_ro; P.edge_ro = d->edge_ro; P.raw_rows = d->sched.raw_rows;
     P.lvl_ptr = d->lvl_ptr; P.lvl_blk = d->lvl_blk;
     P.c1 = d->coef; P.c2 = d->coef + p->n; P.c3 = d->coef + 2 * p->n; P.c4 = d->coef + 3 * p->n;
-    P.key_start = d->key_start; P.n_keys = d->sched.n_keys; P.n_items = d->sched.n_items;
+    P.key_start = kt->dev; P.n_keys = kt->n_keys; P.n_items = kt->n_items;
     P.delta = d->sched.delta; P.n_tiles = (int32_t)n_tiles;
     P.T = (int32_t)T; P.K = (int32_t)K; P.tile_rows = (int32_t)rows;
     P.raw_pitch = (int32_t)pitch; P.n_members = n_members; P.first_call = first_call; P.last_call = last_call;
@@ -284,7 +302,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
         if (d->occ[mode] <= 0) { rr_set_error("occupancy query failed for the wavefront kernel"); return 200; }
     }
     const int64_t warps_per_cta = block / 32;
-    const int64_t total_items = d->sched.n_items * n_members;
+    const int64_t total_items = kt->n_items * n_members;
     int64_t grid = (int64_t)d->sm_count * d->occ[mode];
     grid = std::max<int64_t>(1, std::min<int64_t>(grid, (total_items + warps_per_cta - 1) / warps_per_cta));
     {
@@ -434,8 +452,10 @@ extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_fu
     const int64_t n = p->n;
     const int64_t ldd = ((n + 31) / 32) * 32;  // device rows start on 256-byte boundaries
     const int64_t rows_tile = std::max<int64_t>(1, p->opts.time_tile / substeps);
-    int64_t chunk = std::max<int64_t>(1, (1ll << 30) / (ldd * 8));      // ~1 GiB per buffer
-    chunk = std::max<int64_t>(rows_tile, (chunk / rows_tile) * rows_tile);
+    // chunk: about 512 MiB per buffer so that H2D, routing and D2H of neighbouring chunks overlap; whole tiles
+    // when a chunk holds several
+    int64_t chunk = std::max<int64_t>(1, (512ll << 20) / (ldd * 8));
+    if (chunk > rows_tile) chunk = (chunk / rows_tile) * rows_tile;
     chunk = std::min<int64_t>(chunk, T);
     const size_t need = (size_t)chunk * ldd;
     if (need > d->chunk_cap) {

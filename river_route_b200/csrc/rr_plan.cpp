@@ -362,30 +362,31 @@ extern "C" int rr_plan_get_arrays(const rr_plan *p, const int32_t **up_ptr, cons
 //   upstream block, same tile      level(b') < level(b)
 //   same block, previous tile      delta >= 1
 //   exchange-ring reuse (WAR)      the series of reach u lives in a ring of depth
-//                                  R_u = span_u / delta + 1 (span_u = level(consumer) - level(producer));
+//                                  R_u = span_u / delta + 1 tiles (span_u = level(consumer) - level(producer));
 //                                  producer (b', j) overwrites what consumer (c, j - R_u) read, and
 //                                  key(c, j - R_u) < key(b', j)  <=>  span_u < R_u * delta.
 // so the warp holding the lowest unfinished ticket can always finish: no deadlock, for any grid
 // size, without a cooperative launch.  A small delta lets many tiles be in flight at once (the
 // wavefront through deep networks); the budget bounds the ring memory that costs.
 // ------------------------------------------------------------------------------------------
-static int64_t ring_rows(const rr_plan &p, int64_t n_tiles, int64_t delta) {
+static int64_t ring_rows(const rr_plan &p, int64_t delta) {
     int64_t rows = 0;
-    for (int32_t sp : p.exp_span) rows += std::min<int64_t>(sp / delta + 1, n_tiles);
+    for (int32_t sp : p.exp_span) rows += sp / delta + 1;
     return rows;
 }
 
-void rr_build_schedule(const rr_plan &p, int64_t n_tiles, int32_t delta, int64_t budget_rows, rr_schedule &s) {
+// Exchange rings: depend on the network and the memory budget only (not on the length of the call).
+void rr_build_rings(const rr_plan &p, int32_t delta, int64_t budget_rows, rr_schedule &s) {
     if (delta <= 0) {
         int64_t d = 1;
-        while (d <= p.max_level && ring_rows(p, n_tiles, d) > budget_rows) d <<= 1;
+        while (d <= p.max_level && ring_rows(p, d) > budget_rows) d <<= 1;
         delta = (int32_t)std::min<int64_t>(d, (int64_t)p.max_level + 1);
     }
     s.delta = delta;
     s.exp_ro.resize(2 * (size_t)p.n_export);
     int64_t rows = 0;
     for (int64_t e = 0; e < p.n_export; ++e) {
-        const int64_t ring = std::min<int64_t>(p.exp_span[e] / delta + 1, n_tiles);
+        const int64_t ring = p.exp_span[e] / delta + 1;
         s.exp_ro[2 * e] = (int32_t)rows;
         s.exp_ro[2 * e + 1] = (int32_t)ring;
         rows += ring;
@@ -397,6 +398,10 @@ void rr_build_schedule(const rr_plan &p, int64_t n_tiles, int32_t delta, int64_t
         s.edge_ro[2 * e + 1] = x >= 0 ? s.exp_ro[2 * (size_t)x + 1] : 1;
     }
     s.raw_rows = std::max<int64_t>(rows, 1);
+}
+
+// Ticket keys for a call of n_tiles tiles (small: max_level + n_tiles * delta entries).
+void rr_build_keys(const rr_plan &p, int64_t n_tiles, rr_schedule &s) {
     s.n_keys = (int64_t)p.max_level + (n_tiles - 1) * (int64_t)s.delta + 1;
     s.key_start.assign(s.n_keys + 1, 0);
     for (int64_t j = 0; j < n_tiles; ++j)
@@ -404,6 +409,11 @@ void rr_build_schedule(const rr_plan &p, int64_t n_tiles, int32_t delta, int64_t
             s.key_start[l + j * s.delta + 1] += p.lvl_ptr[l + 1] - p.lvl_ptr[l];
     for (int64_t k = 0; k < s.n_keys; ++k) s.key_start[k + 1] += s.key_start[k];
     s.n_items = s.key_start[s.n_keys];
+}
+
+void rr_build_schedule(const rr_plan &p, int64_t n_tiles, int32_t delta, int64_t budget_rows, rr_schedule &s) {
+    rr_build_rings(p, delta, budget_rows, s);
+    rr_build_keys(p, n_tiles, s);
 }
 
 void rr_decode_ticket(const rr_plan &p, const rr_schedule &s, int64_t n_tiles, int64_t ticket,

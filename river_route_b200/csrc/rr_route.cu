@@ -73,15 +73,13 @@ struct d4 { double a, b, c, d; };
 // one aligned 32-byte sector of an exchange row (written by another SM earlier in this launch:
 // plain coherent loads, ordered after the acquire fence)
 __device__ __forceinline__ d4 ld_sector(const double *p) {
-    d4 v;
-    const double2 lo = *reinterpret_cast<const double2 *>(p);
-    const double2 hi = *reinterpret_cast<const double2 *>(p + 2);
-    v.a = lo.x; v.b = lo.y; v.c = hi.x; v.d = hi.y;
+    d4 v;   // one 256-bit load (LDG.E.256 on sm_100a)
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p) : "memory");
     return v;
 }
+// one 256-bit store: the whole sector is written at once, so L2 never has to fill it from DRAM first
 __device__ __forceinline__ void st_sector(double *p, double a, double b, double c, double d) {
-    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
-    *reinterpret_cast<double2 *>(p + 2) = make_double2(c, d);
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
 struct item_ctx {
@@ -122,13 +120,14 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
     double *outp = P.out[c.m] + (size_t)c.t0 * P.ldo + c.i;
     const int TT = c.TT;
 
-    // operands of the first group: sector 0 holds the carry in .d, sector 1 the values of steps 0..3
-    d4 cur[NA], nxt[NA];
+    // operands of the first group: the carry-in and the sector with the values of steps 0..3
+    double old[NA];   // upstream value before the group's first substep
+    d4 nxt[NA];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-        cur[k] = d4{0, 0, 0, 0};
+        old[k] = 0.0;
         nxt[k] = d4{0, 0, 0, 0};
-        if (has[k]) { cur[k] = ld_sector(up[k]); nxt[k] = ld_sector(up[k] + 4); }
+        if (has[k]) { old[k] = up[k][RAW_CARRY]; nxt[k] = ld_sector(up[k] + RAW_S0); }
     }
     double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
     if (HAS_LAT && c.valid) {
@@ -155,13 +154,13 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
             if (s + 7 < TT) n3 = ld_stream(lp + 3 * P.ldl);
         }
         // ---- four substeps; old = value before the substep, new = value after it ----
-        // step s: old = cur.d, new = nxt.a;  step s+1: old = nxt.a, new = nxt.b;  ...
+        // step s: old = old[k], new = nxt.a;  step s+1: old = nxt.a, new = nxt.b;  ...
         double r0, r1, r2, r3;
         {
             double r = c3 * q;                                       // _numba_kernels.py:27-28 / :68-69
             if (HAS_LAT) r = fma(c4, l0, r);
 #pragma unroll
-            for (int k = 0; k < NS; ++k) r = fma(c2, cur[k].d, r);   // :29-33 / :70-74, ascending upstream
+            for (int k = 0; k < NS; ++k) r = fma(c2, old[k], r);     // :29-33 / :70-74, ascending upstream
 #pragma unroll
             for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].a, r);   // :36-39 / :75-78 (lhs_off = -c1)
             r0 = r;
@@ -198,7 +197,7 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
         if (myraw) st_sector(myraw + RAW_S0 + s, r0, r1, r2, r3);
         q = (s + 3 < TT) ? r3 : ((s + 2 < TT) ? r2 : ((s + 1 < TT) ? r1 : r0));
 #pragma unroll
-        for (int k = 0; k < NS; ++k) { cur[k] = nxt[k]; nxt[k] = fut[k]; }
+        for (int k = 0; k < NS; ++k) { old[k] = nxt[k].d; nxt[k] = fut[k]; }
         l0 = n0; l1 = n1; l2 = n2; l3 = n3;
     }
     if (c.valid) P.q_state[c.m][c.i] = q;

@@ -53,6 +53,7 @@ def parse():
     ap.add_argument('--time-tile', type=int, default=0)
     ap.add_argument('--tile-stride', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--staging', default='auto', choices=['auto', 'registers', 'registers-tiled', 'tma'])
     ap.add_argument('--order', default='growth', choices=['growth', 'level'],
                     help='reach order of the synthetic params file: generator order or sorted by topological level')
     return ap.parse_args()
@@ -248,7 +249,8 @@ def main():
     down, k, x = network(args)
     idx, local_down = shard(down, world, rank)
     n = int(idx.shape[0])
-    plan = rr.Plan(local_down, time_tile=args.time_tile, tile_stride=args.tile_stride, device=local_rank)
+    plan = rr.Plan(local_down, time_tile=args.time_tile, tile_stride=args.tile_stride, device=local_rank,
+                   staging=args.staging)
     c1, c2, c3, c4 = coefficients(k[idx], x[idx], DT, DT)
     plan.set_coefficients(c1, c2, c3, c4)
     info = plan.info

@@ -45,7 +45,9 @@ typedef struct rr_plan_opts {
     int32_t renumber;       /* 0 auto, 1 keep the params_file order, 2 always work on reaches sorted
                                by topological level (inputs/outputs stay in params_file order; the
                                library permutes them on the device)                             */
-    int32_t reserved;
+    int32_t staging;        /* renumbered plans: 0 auto (= 2), 1 register path on row-major working arrays,
+                               2 register path on tile-major working arrays, 3 bulk-async-copy (TMA)
+                               staged kernel on tile-major working arrays                            */
 } rr_plan_opts;
 
 /* Host-visible description of a built plan (for tests, DESIGN.md numbers and bench.py). */

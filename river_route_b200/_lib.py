@@ -24,7 +24,7 @@ c_f64p = C.POINTER(C.c_double)
 class PlanOpts(C.Structure):
     _fields_ = [('time_tile', C.c_int32), ('tile_stride', C.c_int32), ('device', C.c_int32),
                 ('threads_per_cta', C.c_int32), ('raw_budget_bytes', C.c_int64), ('renumber', C.c_int32),
-                ('reserved', C.c_int32)]
+                ('staging', C.c_int32)]
 
 
 class PlanInfo(C.Structure):

@@ -197,26 +197,31 @@ void rr_device_release(rr_plan *p) {
 }
 
 // One kernel launch == one reference call (or one time chunk of it).
+// Rows of one work item for a call of T rows with K substeps per row (aims at `time_tile` substeps per item).
+static int64_t tile_rows_for(const rr_plan *p, int64_t T, int64_t K) {
+    return std::max<int64_t>(1, std::min<int64_t>(T, p->opts.time_tile / K));
+}
+
 static int launch_route(rr_plan *p, int mode, int n_members, const double *q_init, const double *const *lateral,
                         int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
-                        int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream) {
+                        int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream, int tile_major = 0) {
     if (mode < 0 || mode > 2) { rr_set_error("unknown router mode"); return 100; }
     if (T <= 0 || K <= 0 || T > 0x7fffffff || K > 0x7fffffff) { rr_set_error("T and substeps must be positive"); return 100; }
     if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
     if (mode == RR_MODE_RAPID && !p->have_c4) { rr_set_error("RapidMuskingum needs c4_dt coefficients"); return 100; }
-    if (mode != RR_MODE_MUSKINGUM && ldl < p->n) { rr_set_error("lateral leading dimension smaller than n"); return 100; }
-    if (ldo < p->n) { rr_set_error("output leading dimension smaller than n"); return 100; }
+    if (!tile_major && mode != RR_MODE_MUSKINGUM && ldl < p->n) { rr_set_error("lateral leading dimension smaller than n"); return 100; }
+    if (!tile_major && ldo < p->n) { rr_set_error("output leading dimension smaller than n"); return 100; }
     int rc = ensure_device(p);
     if (rc) return rc;
     rr_device_state *d = p->dev;
 
     // tile geometry: aim for `time_tile` routing substeps per work item
-    const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(T, p->opts.time_tile / K));
+    const int64_t rows = tile_rows_for(p, T, K);
     const int64_t n_tiles = (T + rows - 1) / rows;
-    // row pitch of the exchange buffer: [2] q_full carry, [3] carry, [4+s] substeps (rr_route.cu); sized for the
+    // row pitch of the exchange buffer: [14] q_full carry, [15] carry, [16+s] substeps (rr_route.cu); sized for the
     // plan's nominal tile so that short calls (the last chunk of a stream) reuse the same rings
     const int64_t nominal = std::max<int64_t>(std::max<int64_t>(1, p->opts.time_tile / K) * K, rows * K);
-    const int64_t pitch = 4 + ((nominal + 3) / 4) * 4;
+    const int64_t pitch = 16 + ((nominal + 15) / 16) * 16;
     const int64_t budget_rows = std::max<int64_t>(1, p->opts.raw_budget_bytes / (int64_t)(pitch * sizeof(double) * n_members));
     if ((double)n_tiles * (double)(p->max_level + 1) > 2e9) {
         rr_set_error("network too deep for the ticket scheduler at this tile size; raise time_tile");
@@ -296,14 +301,27 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     }
     CK(cudaMemsetAsync(d->done, 0, done_need * sizeof(int32_t), stream));
     CK(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), stream));
-    const int block = p->opts.threads_per_cta;
+    int block = p->opts.threads_per_cta;
+    P.tile_major = tile_major;
+    if (tile_major && K == 1 && mode != RR_MODE_UNIT && p->opts.staging == 3) {
+        // TMA-staged kernel: 4 warps per CTA, each with [tile | upstream row slots | mbarrier] in shared memory
+        int max_smem = 0;
+        CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
+        const int64_t tile_bytes = rows * RR_BLOCK * 8, row_bytes = pitch * 8 + 16;
+        const int64_t slots = std::min<int64_t>(64, ((int64_t)max_smem / 4 - tile_bytes - 16 - 128) / row_bytes);
+        if (slots >= 32) {
+            P.row_slots = (int32_t)slots;
+            P.smem_region = (int32_t)(((tile_bytes + slots * row_bytes + 16 + 127) / 128) * 128);
+            block = 128;
+        }
+    }
     if (!d->occ[mode]) {
         d->occ[mode] = rr_wavefront_occupancy(mode, block);
         if (d->occ[mode] <= 0) { rr_set_error("occupancy query failed for the wavefront kernel"); return 200; }
     }
     const int64_t warps_per_cta = block / 32;
     const int64_t total_items = kt->n_items * n_members;
-    int64_t grid = (int64_t)d->sm_count * d->occ[mode];
+    int64_t grid = (int64_t)d->sm_count * (P.smem_region > 0 ? 1 : d->occ[mode]);
     grid = std::max<int64_t>(1, std::min<int64_t>(grid, (total_items + warps_per_cta - 1) / warps_per_cta));
     {
         rr_timer tm(0, stream);
@@ -320,8 +338,16 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
 // side of each copy completes whole 32-byte sectors while they are still in L2.
 // ---------------------------------------------------------------------------------------------------
 #define PERM_ROWS 8
+// Address of working element (row t, working reach k).  tile_rows == 0: row-major with leading dimension ld;
+// otherwise the tile-major layout [tile][block][row in tile][lane] the TMA-staged kernel reads with bulk copies.
+__device__ __forceinline__ int64_t working_index(int64_t t, int64_t k, int64_t ld, int64_t tile_rows, int64_t n_blocks) {
+    if (tile_rows == 0) return t * ld + k;
+    const int64_t j = t / tile_rows, r = t - j * tile_rows;
+    return ((j * n_blocks + (k >> 5)) * tile_rows + r) * RR_BLOCK + (k & 31);
+}
 __global__ void __launch_bounds__(256) permute_to_working(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
-                                                          int64_t ldd, const int32_t *__restrict__ inv, int64_t n, int64_t T) {
+                                                          int64_t ldd, const int32_t *__restrict__ inv, int64_t n, int64_t T,
+                                                          int64_t tile_rows, int64_t n_blocks) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t k = __ldg(inv + i);
@@ -331,27 +357,28 @@ __global__ void __launch_bounds__(256) permute_to_working(const double *__restri
     for (int r = 0; r < PERM_ROWS; ++r) v[r] = (t0 + r < T) ? __ldg(src + (t0 + r) * lds + i) : 0.0;
 #pragma unroll
     for (int r = 0; r < PERM_ROWS; ++r)
-        if (t0 + r < T) dst[(t0 + r) * ldd + k] = v[r];
+        if (t0 + r < T) dst[working_index(t0 + r, k, ldd, tile_rows, n_blocks)] = v[r];
 }
 __global__ void __launch_bounds__(256) permute_to_user(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
-                                                       int64_t ldd, const int32_t *__restrict__ inv, int64_t n, int64_t T) {
+                                                       int64_t ldd, const int32_t *__restrict__ inv, int64_t n, int64_t T,
+                                                       int64_t tile_rows, int64_t n_blocks) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t k = __ldg(inv + i);
     const int64_t t0 = (int64_t)blockIdx.y * PERM_ROWS;
     double v[PERM_ROWS];
 #pragma unroll
-    for (int r = 0; r < PERM_ROWS; ++r) v[r] = (t0 + r < T) ? src[(t0 + r) * lds + k] : 0.0;
+    for (int r = 0; r < PERM_ROWS; ++r) v[r] = (t0 + r < T) ? src[working_index(t0 + r, k, lds, tile_rows, n_blocks)] : 0.0;
 #pragma unroll
     for (int r = 0; r < PERM_ROWS; ++r)
         if (t0 + r < T) dst[(t0 + r) * ldd + i] = v[r];
 }
 static int permute(bool to_working, const double *src, int64_t lds, double *dst, int64_t ldd, const int32_t *inv,
-                   int64_t n, int64_t T, cudaStream_t stream) {
+                   int64_t n, int64_t T, cudaStream_t stream, int64_t tile_rows = 0, int64_t n_blocks = 0) {
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)((T + PERM_ROWS - 1) / PERM_ROWS));
     rr_timer tm(to_working ? 1 : 2, stream);
-    if (to_working) permute_to_working<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T);
-    else permute_to_user<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T);
+    if (to_working) permute_to_working<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks);
+    else permute_to_user<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks);
     CK(cudaGetLastError());
     rr_count_launch(1);
     return 0;
@@ -380,9 +407,14 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     const bool has_lat = mode != RR_MODE_MUSKINGUM;
     const bool unit = mode == RR_MODE_UNIT;
     if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
-    if (T <= 0) { rr_set_error("T must be positive"); return 100; }
-    if (has_lat && (rc = grow(&d->p_lat, &d->p_lat_cap, (size_t)n_members * T * ldp))) return rc;
-    if ((rc = grow(&d->p_out, &d->p_out_cap, (size_t)n_members * T * ldp))) return rc;
+    if (T <= 0 || K <= 0) { rr_set_error("T and substeps must be positive"); return 100; }
+    // working arrays: tile-major for the TMA-staged kernel (one substep per row, not UnitMuskingum), else row-major
+    const bool tiled = (K == 1 && !unit && p->opts.staging != 1);
+    const int64_t trows = tiled ? tile_rows_for(p, T, K) : 0;
+    const int64_t n_tiles = tiled ? (T + trows - 1) / trows : 0;
+    const size_t member_elems = tiled ? (size_t)n_tiles * p->n_blocks * trows * RR_BLOCK : (size_t)T * ldp;
+    if (has_lat && (rc = grow(&d->p_lat, &d->p_lat_cap, (size_t)n_members * member_elems))) return rc;
+    if ((rc = grow(&d->p_out, &d->p_out_cap, (size_t)n_members * member_elems))) return rc;
     // state scratch: [init][member states][member q_full]
     if ((rc = grow(&d->p_q, &d->p_q_cap, (size_t)(1 + 2 * n_members) * ldp))) return rc;
     double *w_init = d->p_q;
@@ -390,21 +422,21 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     double *out_w[RR_MAX_MEMBERS], *qs_w[RR_MAX_MEMBERS], *qf_w[RR_MAX_MEMBERS];
     if (first_call && (rc = permute(true, q_init, n, w_init, ldp, d->inv, n, 1, stream))) return rc;
     for (int m = 0; m < n_members; ++m) {
-        lat_w[m] = has_lat ? d->p_lat + (size_t)m * T * ldp : nullptr;
-        out_w[m] = d->p_out + (size_t)m * T * ldp;
+        lat_w[m] = has_lat ? d->p_lat + (size_t)m * member_elems : nullptr;
+        out_w[m] = d->p_out + (size_t)m * member_elems;
         qs_w[m] = d->p_q + (size_t)(1 + m) * ldp;
         qf_w[m] = d->p_q + (size_t)(1 + n_members + m) * ldp;
-        if (has_lat && (rc = permute(true, lateral[m], ldl, d->p_lat + (size_t)m * T * ldp, ldp, d->inv, n, T, stream))) return rc;
+        if (has_lat && (rc = permute(true, lateral[m], ldl, d->p_lat + (size_t)m * member_elems, ldp, d->inv, n, T, stream, trows, p->n_blocks))) return rc;
         if (!first_call) {
             if ((rc = permute(true, q_state[m], n, qs_w[m], ldp, d->inv, n, 1, stream))) return rc;
             if (unit && (rc = permute(true, q_full[m], n, qf_w[m], ldp, d->inv, n, 1, stream))) return rc;
         }
     }
     rc = launch_route(p, mode, n_members, w_init, has_lat ? lat_w : nullptr, ldp, out_w, ldp, qs_w, qf_w, T, K,
-                      first_call, last_call, stream);
+                      first_call, last_call, stream, tiled ? 1 : 0);
     if (rc) return rc;
     for (int m = 0; m < n_members; ++m) {
-        if ((rc = permute(false, out_w[m], ldp, out[m], ldo, d->inv, n, T, stream))) return rc;
+        if ((rc = permute(false, out_w[m], ldp, out[m], ldo, d->inv, n, T, stream, trows, p->n_blocks))) return rc;
         if ((rc = permute(false, qs_w[m], ldp, q_state[m], n, d->inv, n, 1, stream))) return rc;
         if (unit && !(last_call) && (rc = permute(false, qf_w[m], ldp, q_full[m], n, d->inv, n, 1, stream))) return rc;
     }

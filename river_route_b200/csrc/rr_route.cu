@@ -18,8 +18,8 @@
 //     previous discharge are fetched with warp shuffles -- no shared memory, no in-block flags.
 //   * Between blocks, a reach whose downstream lives in another block exports its raw (unclamped)
 //     substep series for the tile into its private ring of rows in the exchange buffer.  Row layout
-//     (doubles): [2] = q_full carry-in (UNIT), [3] = carry-in, [4 + s] = value after substep s, so the
-//     four values of steps 4g..4g+3 are one aligned 32-byte sector.  The producer publishes
+//     (doubles): [14] = q_full carry-in (UNIT), [15] = carry-in, [16 + s] = value after substep s, so the
+//     series starts on a 128-byte line and the four values of steps 4g..4g+3 are one aligned sector.  The producer publishes
 //     "tile j done" with a release store on done[b]; consumers poll it and acquire.  A reach therefore
 //     advances to tile j+1 as soon as its upstream blocks and its own tile j are done: the wavefront
 //     pipelines time through deep networks with no grid-wide barrier and one launch per call.
@@ -37,9 +37,9 @@
 #endif
 #define FULL_MASK 0xffffffffu
 #define SLOT_NONE ((int32_t)0x80000000)
-#define RAW_QF 2      // row entry holding the q_full carry-in (UNIT)
-#define RAW_CARRY 3   // row entry holding the value before the tile's first substep
-#define RAW_S0 4      // row entry of substep 0
+#define RAW_QF 14     // row entry holding the q_full carry-in (UNIT)
+#define RAW_CARRY 15  // row entry holding the value before the tile's first substep
+#define RAW_S0 16     // row entry of substep 0: the series starts on a 128-byte line
 
 namespace {
 
@@ -73,8 +73,10 @@ struct d4 { double a, b, c, d; };
 // one aligned 32-byte sector of an exchange row (written by another SM earlier in this launch:
 // plain coherent loads, ordered after the acquire fence)
 __device__ __forceinline__ d4 ld_sector(const double *p) {
-    d4 v;   // one 256-bit load (LDG.E.256 on sm_100a)
-    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p) : "memory");
+    // one 256-bit load (LDG.E.256 on sm_100a); L2 fetches the whole 128-byte line, i.e. this and the next
+    // three sectors of the series, in one DRAM burst instead of four half-used 64-byte ones
+    d4 v;
+    asm volatile("ld.global.L2::128B.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p) : "memory");
     return v;
 }
 // one 256-bit store: the whole sector is written at once, so L2 never has to fill it from DRAM first
@@ -85,17 +87,26 @@ __device__ __forceinline__ void st_sector(double *p, double a, double b, double 
 struct item_ctx {
     int m, b, j, lane;
     int64_t i;
-    bool valid;
+    bool valid, use_init;
     int t0, rows, TT;
     double *raw_m;
+    double c1, c2, c3, c4, q;   // q = state before the tile (UNIT: q_ch)
+    int e0, deg, ex;
+    rr_blk_meta M;
+    const double *lat0;          // this lane's lateral value of the tile's first row
+    int64_t lstride;             // distance between consecutive rows of the lateral tile
+    double *out0;                // this lane's discharge value of the tile's first row
+    int64_t ostride;
 };
 
 // ------------------------------------------------------------------------------------------------
 // Fast path: K == 1, no in-block edges, every reach has at most NS upstreams (all external).
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int NS>
-__device__ __forceinline__ void fast_item(const rr_route_params &P, const item_ctx &c, double c1, double c2, double c3,
-                                          double c4, int e0, int deg, int ex, double q) {
+__device__ __forceinline__ void fast_item(const rr_route_params &P, const item_ctx &c) {
+    const double c1 = c.c1, c2 = c.c2, c3 = c.c3, c4 = c.c4;
+    const int e0 = c.e0, deg = c.deg, ex = c.ex;
+    double q = c.q;
     constexpr bool HAS_LAT = (MODE == RR_MODE_RAPID);
     constexpr int NA = NS > 0 ? NS : 1;
     const int j = c.j;
@@ -116,8 +127,9 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
         myraw = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         myraw[RAW_CARRY] = q;
     }
-    const double *lat = HAS_LAT ? P.lateral[c.m] + (size_t)c.t0 * P.ldl + c.i : nullptr;
-    double *outp = P.out[c.m] + (size_t)c.t0 * P.ldo + c.i;
+    const double *lat = c.lat0;
+    double *outp = c.out0;
+    const int64_t ldl = c.lstride, ldo = c.ostride;
     const int TT = c.TT;
 
     // operands of the first group: the carry-in and the sector with the values of steps 0..3
@@ -127,14 +139,21 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
     for (int k = 0; k < NS; ++k) {
         old[k] = 0.0;
         nxt[k] = d4{0, 0, 0, 0};
-        if (has[k]) { old[k] = up[k][RAW_CARRY]; nxt[k] = ld_sector(up[k] + RAW_S0); }
+        if (has[k]) {
+            // the series is consumed line by line (16 steps = 128 B): keep two lines ahead in L2 so the
+            // register lookahead below only has to cover L2 latency, not DRAM latency
+            prefetch_l2(up[k] + RAW_S0 + 16);
+            if (TT > 32) prefetch_l2(up[k] + RAW_S0 + 32);
+            old[k] = up[k][RAW_CARRY];
+            nxt[k] = ld_sector(up[k] + RAW_S0);
+        }
     }
     double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
     if (HAS_LAT && c.valid) {
         l0 = ld_stream(lat);
-        if (1 < TT) l1 = ld_stream(lat + P.ldl);
-        if (2 < TT) l2 = ld_stream(lat + 2 * P.ldl);
-        if (3 < TT) l3 = ld_stream(lat + 3 * P.ldl);
+        if (1 < TT) l1 = ld_stream(lat + ldl);
+        if (2 < TT) l2 = ld_stream(lat + 2 * ldl);
+        if (3 < TT) l3 = ld_stream(lat + 3 * ldl);
     }
     for (int s = 0; s < TT; s += 4) {
         // ---- issue the next group's loads before computing this one ----
@@ -144,14 +163,15 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             fut[k] = d4{0, 0, 0, 0};
-            if (has[k] && more) fut[k] = ld_sector(up[k] + s + 8);
+            if (has[k] && more) fut[k] = ld_sector(up[k] + RAW_S0 + s + 4);
+            if (has[k] && (s & 15) == 0 && s + 48 < TT) prefetch_l2(up[k] + RAW_S0 + s + 48);
         }
         if (HAS_LAT && c.valid && more) {
-            const double *lp = lat + (size_t)(s + 4) * P.ldl;
+            const double *lp = lat + (size_t)(s + 4) * ldl;
             n0 = ld_stream(lp);
-            if (s + 5 < TT) n1 = ld_stream(lp + P.ldl);
-            if (s + 6 < TT) n2 = ld_stream(lp + 2 * P.ldl);
-            if (s + 7 < TT) n3 = ld_stream(lp + 3 * P.ldl);
+            if (s + 5 < TT) n1 = ld_stream(lp + ldl);
+            if (s + 6 < TT) n2 = ld_stream(lp + 2 * ldl);
+            if (s + 7 < TT) n3 = ld_stream(lp + 3 * ldl);
         }
         // ---- four substeps; old = value before the substep, new = value after it ----
         // step s: old = old[k], new = nxt.a;  step s+1: old = nxt.a, new = nxt.b;  ...
@@ -188,11 +208,11 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
         }
         if (c.valid) {
             // K == 1: the interval mean is the value itself; clamp as :44-46 / :82-84
-            double *o = outp + (size_t)s * P.ldo;
+            double *o = outp + (size_t)s * ldo;
             o[0] = r0 > 0.0 ? r0 : 0.0;
-            if (s + 1 < TT) o[P.ldo] = r1 > 0.0 ? r1 : 0.0;
-            if (s + 2 < TT) o[2 * P.ldo] = r2 > 0.0 ? r2 : 0.0;
-            if (s + 3 < TT) o[3 * P.ldo] = r3 > 0.0 ? r3 : 0.0;
+            if (s + 1 < TT) o[ldo] = r1 > 0.0 ? r1 : 0.0;
+            if (s + 2 < TT) o[2 * ldo] = r2 > 0.0 ? r2 : 0.0;
+            if (s + 3 < TT) o[3 * ldo] = r3 > 0.0 ? r3 : 0.0;
         }
         if (myraw) st_sector(myraw + RAW_S0 + s, r0, r1, r2, r3);
         q = (s + 3 < TT) ? r3 : ((s + 2 < TT) ? r2 : ((s + 1 < TT) ? r1 : r0));
@@ -203,328 +223,524 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
     if (c.valid) P.q_state[c.m][c.i] = q;
 }
 
-}  // namespace
-
+// ------------------------------------------------------------------------------------------------
+// General path: systolic item with shuffles -- any skew, any in-degree, any number of substeps,
+// UnitMuskingum.  Ends with the state write-back (the caller publishes done[b]).
+// ------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256, RR_MIN_CTAS) rr_wavefront_kernel(const __grid_constant__ rr_route_params P) {
+__device__ __noinline__ void general_item(const rr_route_params &P, const item_ctx &c) {
     constexpr bool HAS_LAT = (MODE != RR_MODE_MUSKINGUM);
     constexpr bool UNIT = (MODE == RR_MODE_UNIT);
-    const int lane = threadIdx.x & 31;
-    const int K = P.K;
+    const int lane = c.lane, m = c.m, b = c.b, j = c.j, K = P.K;
+    const int64_t i = c.i;
+    const bool valid = c.valid, use_init = c.use_init;
+    const int64_t ic = valid ? i : P.n - 1;
+    const double c1 = c.c1, c2 = c.c2, c3 = c.c3, c4 = c.c4;
+    const int e0 = c.e0, deg = c.deg, ex = c.ex;
+    const rr_blk_meta M = c.M;
+    const int t0 = c.t0, TT = c.TT;
+    double *raw_m = c.raw_m;
+    double qcur = c.q;
     const double inv_k = 1.0 / (double)K;  // _numba_kernels.py:19, :60, :104
+    (void)b;
+    const int d = __ldg(P.skew + ic);
+    const int nfast = M.max_deg < RR_MAX_FAST_DEG ? M.max_deg : RR_MAX_FAST_DEG;
+    auto raw_row = [&](int e) -> double * {   // e = entry of the upstream-CSR (an external edge)
+        const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + e);
+        return raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+    };
+    int32_t src[RR_MAX_FAST_DEG];
+    const double *rp[RR_MAX_FAST_DEG];   // exported series of an external upstream
+    int ilane[RR_MAX_FAST_DEG];          // lane of an in-block upstream (own lane if none)
+    int64_t ug[RR_MAX_FAST_DEG];         // UNIT: global index of the upstream reach
+#pragma unroll
+    for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+        src[k] = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
+        rp[k] = nullptr;
+        ilane[k] = lane;
+        ug[k] = 0;
+        if (src[k] != SLOT_NONE) {
+            if (src[k] >= 0) rp[k] = raw_row(e0 + k);
+            else ilane[k] = (-src[k] - 1) & 31;
+            if (UNIT) ug[k] = __ldg(P.up_idx + e0 + k);
+        }
+    }
+    const double *lat = c.lat0;
+    double *outp = c.out0;
 
-    for (;;) {
-        // ---------------- ticket -> (member, block, tile) ----------------
-        unsigned long long tk = 0;
-        if (lane == 0) tk = atomicAdd(P.ticket, 1ull);
-        tk = __shfl_sync(FULL_MASK, tk, 0);
-        if (tk >= (unsigned long long)P.n_items * (unsigned)P.n_members) break;
-        int m = 0;
-        int64_t ticket = (int64_t)tk;
-        if (P.n_members > 1) { m = (int)(tk % (unsigned)P.n_members); ticket = (int64_t)(tk / (unsigned)P.n_members); }
-        int b, j;
-        {
-            int64_t lo = 0, hi = P.n_keys;
-            while (hi - lo > 1) {
-                const int64_t mid = (lo + hi) >> 1;
-                if (__ldg(P.key_start + mid) <= ticket) lo = mid; else hi = mid;
+    double qprev = qcur;
+    double qf_cur = 0.0, qf_prev = 0.0;  // UNIT: q_full and its previous value
+    if (UNIT && valid) {
+        qf_cur = use_init ? qcur : P.q_full[m][i];
+        qf_prev = qf_cur;
+    }
+    double *myraw = nullptr;
+    if (ex >= 0) {
+        const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + ex);
+        myraw = raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+        myraw[RAW_CARRY] = qcur;                 // carry-in for consumers
+        if (UNIT) myraw[RAW_QF] = qf_cur;        // q_full carry-in
+    }
+
+    // one-step lookahead registers for the external series and the lateral row
+    double eo[RR_MAX_FAST_DEG], en[RR_MAX_FAST_DEG];
+    double lu[RR_MAX_FAST_DEG], lu_old[RR_MAX_FAST_DEG];   // UNIT: upstream lateral (this / previous row)
+#pragma unroll
+    for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+        eo[k] = en[k] = lu[k] = lu_old[k] = 0.0;
+        if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) {
+            eo[k] = UNIT ? rp[k][RAW_QF] : rp[k][RAW_CARRY];
+            en[k] = rp[k][RAW_S0];
+        }
+    }
+    double ql = 0.0, ql_nx = 0.0;
+    if (HAS_LAT && valid) ql_nx = ld_stream(lat);
+    double acc = 0.0, base = 0.0;
+    int sub = 0, row = 0;
+
+    const int nsteps = TT + M.max_skew;
+    for (int sig = 0; sig < nsteps; ++sig) {
+        const int s = sig - d;
+        const bool act = valid && s >= 0 && s < TT;
+        const bool row_start = act && sub == 0;
+
+        // ---- gather upstream values (shuffles are executed by every lane) ----
+        double vo[RR_MAX_FAST_DEG], vn[RR_MAX_FAST_DEG];
+#pragma unroll
+        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+            vo[k] = eo[k];
+            vn[k] = en[k];
+            if (k < nfast && (M.int_mask >> k) & 1) {
+                const double so = __shfl_sync(FULL_MASK, UNIT ? qf_prev : qprev, ilane[k]);
+                const double sn = __shfl_sync(FULL_MASK, qcur, ilane[k]);
+                if (src[k] < 0 && src[k] != SLOT_NONE) { vo[k] = so; vn[k] = sn; }
             }
-            int64_t r = ticket - __ldg(P.key_start + lo);
-            int64_t jj = lo > P.max_level ? (lo - P.max_level + P.delta - 1) / P.delta : 0;
-            for (;; ++jj) {
-                const int64_t l = lo - jj * P.delta;
-                const int32_t base = __ldg(P.lvl_ptr + l);
-                const int64_t w = __ldg(P.lvl_ptr + l + 1) - base;
-                if (r < w) { b = __ldg(P.lvl_blk + base + r); break; }
-                r -= w;
-            }
-            j = (int)jj;
         }
 
-        // ---------------- per-lane constants ----------------
-        const int64_t i = (int64_t)b * RR_BLOCK + lane;
-        const bool valid = i < P.n;
-        const int64_t ic = valid ? i : P.n - 1;
-        const double c1 = __ldg(P.c1 + ic), c2 = __ldg(P.c2 + ic), c3 = __ldg(P.c3 + ic);
-        const double c4 = HAS_LAT && !UNIT ? __ldg(P.c4 + ic) : 0.0;
-        const int e0 = __ldg(P.up_ptr + ic);
-        const int deg = valid ? __ldg(P.up_ptr + ic + 1) - e0 : 0;
-        const int ex = valid ? __ldg(P.export_id + ic) : -1;
-        const rr_blk_meta M = P.meta[b];
+        double r = 0.0;
+        if (UNIT) {
+            if (row_start) {
+                // _numba_kernels.py:116-143: lateral gathers, A_inner@ql and A_hw@ql in ascending
+                // column order, c1*(a_inner + a_hw); rhs base = c1_A_ql + c2*a_hw (:151)
+                ql = ql_nx;
+                double a_in = 0.0, a_hw = 0.0;
+#pragma unroll
+                for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+                    if (k < deg) {
+                        lu_old[k] = lu[k];
+                        lu[k] = ld_stream(P.lateral[m] + (size_t)(t0 + row) * P.ldl + ug[k]);
+                        const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
+                        if (hw) a_hw += lu[k]; else a_in += lu[k];
+                    }
+                }
+                for (int k = RR_MAX_FAST_DEG; k < deg; ++k) {
+                    const int32_t sk = __ldg(P.slot_src + e0 + k);
+                    const double l = ld_stream(P.lateral[m] + (size_t)(t0 + row) * P.ldl + __ldg(P.up_idx + e0 + k));
+                    const bool hw = sk >= 0 ? (sk & RR_SLOT_HW_BIT) != 0 : (((-sk - 1) >> 6) & 1) != 0;
+                    if (hw) a_hw += l; else a_in += l;
+                }
+                base = c1 * (a_in + a_hw) + c2 * a_hw;
+            }
+            r = base + c3 * qcur;
+        } else {
+            if (row_start) ql = ql_nx;
+            r = c3 * qcur;                      // :27-28 / :68-69
+            if (HAS_LAT) r = fma(c4, ql, r);
+        }
 
-        item_ctx c;
-        c.m = m; c.b = b; c.j = j; c.lane = lane; c.i = i; c.valid = valid;
-        c.t0 = j * P.tile_rows;
-        c.rows = min(P.tile_rows, P.T - c.t0);
-        c.TT = c.rows * K;
-        c.raw_m = P.raw + (size_t)m * (size_t)P.raw_rows * P.raw_pitch;
-        const int t0 = c.t0, rows = c.rows, TT = c.TT;
-        double *raw_m = c.raw_m;
+        // ---- pass A: c2 * (previous-substep discharge of each upstream), ascending ----
+#pragma unroll
+        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+            if (k < deg) {
+                if (UNIT) {
+                    const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
+                    if (!hw) {
+                        // external inner upstream: q_full_old = q_ch_old + lateral of the row that substep
+                        // belonged to; at s == 0 the exported carry already is q_full
+                        double qfo = vo[k];
+                        if (src[k] >= 0 && s > 0) qfo = vo[k] + (sub == 0 ? lu_old[k] : lu[k]);
+                        r = fma(c2, qfo, r);
+                    }
+                } else {
+                    r = fma(c2, vo[k], r);
+                }
+            }
+        }
+        if (M.max_deg > RR_MAX_FAST_DEG) {
+            for (int k = RR_MAX_FAST_DEG; k < M.max_deg; ++k) {
+                const int32_t sk = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
+                const int il = (sk < 0 && sk != SLOT_NONE) ? ((-sk - 1) & 31) : lane;
+                double v = __shfl_sync(FULL_MASK, UNIT ? qf_prev : qprev, il);
+                bool use = act && k < deg;
+                if (use && sk >= 0) {
+                    const double *q = raw_row(e0 + k);
+                    if (UNIT) {
+                        if (sk & RR_SLOT_HW_BIT) use = false;
+                        else if (s == 0) v = q[RAW_QF];
+                        else {
+                            const int prow = (sub == 0) ? row - 1 : row;
+                            v = q[RAW_CARRY + s] + ld_stream(P.lateral[m] + (size_t)(t0 + prow) * P.ldl + __ldg(P.up_idx + e0 + k));
+                        }
+                    } else v = q[RAW_CARRY + s];
+                } else if (use && UNIT && (((-sk - 1) >> 6) & 1)) use = false;
+                if (use) r = fma(c2, v, r);
+            }
+        }
+        // ---- pass B: c1 * (this-substep discharge of each upstream), ascending ----
+#pragma unroll
+        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+            if (k < deg) {
+                if (UNIT) {
+                    const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
+                    if (!hw) r = fma(c1, vn[k], r);
+                } else {
+                    r = fma(c1, vn[k], r);      // rhs -= lhs_off * q_new with lhs_off = -c1 (:36-39)
+                }
+            }
+        }
+        if (M.max_deg > RR_MAX_FAST_DEG) {
+            for (int k = RR_MAX_FAST_DEG; k < M.max_deg; ++k) {
+                const int32_t sk = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
+                const int il = (sk < 0 && sk != SLOT_NONE) ? ((-sk - 1) & 31) : lane;
+                double v = __shfl_sync(FULL_MASK, qcur, il);
+                bool use = act && k < deg;
+                if (use && sk >= 0) {
+                    if (UNIT && (sk & RR_SLOT_HW_BIT)) use = false;
+                    else v = raw_row(e0 + k)[RAW_S0 + s];
+                } else if (use && UNIT && (((-sk - 1) >> 6) & 1)) use = false;
+                if (use) r = fma(c1, v, r);
+            }
+        }
 
-        if (HAS_LAT) {
-            // pull this item's lateral tile towards L2 while the dependency wait runs
-            const double *lt = P.lateral[m] + (size_t)t0 * P.ldl + (size_t)b * RR_BLOCK;
+        // ---- commit ----
+        if (act) {
+            const bool inner = !UNIT || deg > 0;
+            if (inner) {
+                qprev = qcur;
+                qcur = r;
+                if (UNIT) {
+                    qf_prev = qf_cur;
+                    qf_cur = r + ql;            // :165-166
+                    acc += qf_cur;
+                } else acc += r;                // :41-42 / :79-80
+                if (myraw) myraw[RAW_S0 + s] = r;
+            }
+            if (++sub == K) {
+                double v;
+                if (UNIT && !inner) v = ql;     // headwater: lateral inflow, unclamped (:122-123)
+                else { v = acc * inv_k; v = v > 0.0 ? v : 0.0; }   // :44-46 / :82-84 / :169-171
+                outp[(size_t)row * c.ostride] = v;
+                acc = 0.0;
+                sub = 0;
+                ++row;
+            }
+            // lookahead for the next step of this lane
+            if (s + 1 < TT) {
+#pragma unroll
+                for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+                    if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) { eo[k] = en[k]; en[k] = rp[k][RAW_S0 + s + 1]; }
+                }
+                if (HAS_LAT && sub == 0) ql_nx = ld_stream(lat + (size_t)row * c.lstride);
+            }
+        }
+    }
+
+    // ---------------- publish ----------------
+    if (valid) {
+        const bool last = (j == P.n_tiles - 1);
+        if (UNIT) {
+            if (last && P.last_call) P.q_state[m][i] = deg > 0 ? qf_cur : ql;   // UnitMuskingum.py:94-98
+            else { P.q_state[m][i] = qcur; P.q_full[m][i] = qf_cur; }
+        } else P.q_state[m][i] = qcur;
+    }
+}
+
+// ticket -> (member, block, tile); false when the tickets are exhausted
+__device__ __forceinline__ bool next_item(const rr_route_params &P, int lane, int &m, int &b, int &j) {
+    unsigned long long tk = 0;
+    if (lane == 0) tk = atomicAdd(P.ticket, 1ull);
+    tk = __shfl_sync(FULL_MASK, tk, 0);
+    if (tk >= (unsigned long long)P.n_items * (unsigned)P.n_members) return false;
+    m = 0;
+    int64_t ticket = (int64_t)tk;
+    if (P.n_members > 1) { m = (int)(tk % (unsigned)P.n_members); ticket = (int64_t)(tk / (unsigned)P.n_members); }
+    int64_t lo = 0, hi = P.n_keys;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(P.key_start + mid) <= ticket) lo = mid; else hi = mid;
+    }
+    int64_t r = ticket - __ldg(P.key_start + lo);
+    int64_t jj = lo > P.max_level ? (lo - P.max_level + P.delta - 1) / P.delta : 0;
+    for (;; ++jj) {
+        const int64_t l = lo - jj * P.delta;
+        const int32_t base = __ldg(P.lvl_ptr + l);
+        const int64_t w = __ldg(P.lvl_ptr + l + 1) - base;
+        if (r < w) { b = __ldg(P.lvl_blk + base + r); break; }
+        r -= w;
+    }
+    j = (int)jj;
+    return true;
+}
+
+// per-lane constants of an item, lateral prefetch, dependency waits, initial state
+template <int MODE>
+__device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c, int lane, int m, int b, int j) {
+    constexpr bool HAS_LAT = (MODE != RR_MODE_MUSKINGUM);
+    constexpr bool UNIT = (MODE == RR_MODE_UNIT);
+    const int64_t i = (int64_t)b * RR_BLOCK + lane;
+    const bool valid = i < P.n;
+    const int64_t ic = valid ? i : P.n - 1;
+    c.m = m; c.b = b; c.j = j; c.lane = lane; c.i = i; c.valid = valid;
+    c.c1 = __ldg(P.c1 + ic); c.c2 = __ldg(P.c2 + ic); c.c3 = __ldg(P.c3 + ic);
+    c.c4 = HAS_LAT && !UNIT ? __ldg(P.c4 + ic) : 0.0;
+    c.e0 = __ldg(P.up_ptr + ic);
+    c.deg = valid ? __ldg(P.up_ptr + ic + 1) - c.e0 : 0;
+    c.ex = valid ? __ldg(P.export_id + ic) : -1;
+    c.M = P.meta[b];
+    c.t0 = j * P.tile_rows;
+    c.rows = min(P.tile_rows, P.T - c.t0);
+    c.TT = c.rows * P.K;
+    c.raw_m = P.raw + (size_t)m * (size_t)P.raw_rows * P.raw_pitch;
+    if (P.tile_major) {
+        // working arrays stored tile by tile: [tile][block][row][lane] -- an item's rows are contiguous
+        const size_t tile = ((size_t)j * P.n_blocks + b) * (size_t)P.tile_rows * RR_BLOCK + lane;
+        c.lat0 = HAS_LAT ? P.lateral[m] + tile : nullptr;
+        c.out0 = P.out[m] + tile;
+        c.lstride = c.ostride = RR_BLOCK;
+    } else {
+        c.lat0 = HAS_LAT ? P.lateral[m] + (size_t)c.t0 * P.ldl + i : nullptr;
+        c.out0 = P.out[m] + (size_t)c.t0 * P.ldo + i;
+        c.lstride = P.ldl;
+        c.ostride = P.ldo;
+    }
+    if (HAS_LAT) {
+        // pull this item's lateral tile towards L2 while the dependency wait runs
+        if (P.tile_major) {
+            const char *t = (const char *)(c.lat0 - lane);
+            for (int l = lane; l < c.rows * 2; l += 32) prefetch_l2(t + (size_t)l * 128);
+        } else {
+            const double *lt = c.lat0 - lane;
             const int64_t left = P.n - (int64_t)b * RR_BLOCK;
             const int row_bytes = (int)(left < RR_BLOCK ? left : RR_BLOCK) * 8;
-            for (int r = lane; r < rows; r += 32) {
-                const char *a = (const char *)(lt + (size_t)r * P.ldl);
+            for (int r = lane; r < c.rows; r += 32) {
+                const char *a = (const char *)(lt + (size_t)r * c.lstride);
                 prefetch_l2(a);
                 if (row_bytes > 128) prefetch_l2(a + 128);
                 prefetch_l2(a + row_bytes - 1);
             }
         }
-
-        // ---------------- dependencies ----------------
-        int32_t *done = P.done + (size_t)m * P.n_blocks;
-        if (lane == 0) wait_ge(done + b, j);                                // own previous tile (acquire)
-        for (int e = P.dep_ptr[b] + lane; e < P.dep_ptr[b + 1]; e += 32)    // upstream blocks, this tile
-            wait_ge(done + P.dep_idx[e], j + 1);
-        if (ex >= 0) {                                                      // exchange-ring reuse
-            const int32_t ring = __ldg(P.exp_ro + 2 * ex + 1);
-            if (j >= ring) wait_ge(done + __ldg(P.down + i) / RR_BLOCK, j - ring + 1);
-        }
-        __syncwarp();
-
-        // ---------------- state ----------------
-        // first tile of a reference call: every member starts from the shared initial state and
-        // (UNIT) q_ch = q_full = state (UnitMuskingum.py:78-79); later tiles / chunks continue
-        // from the member's own running state.
-        const bool use_init = (j == 0) && P.first_call;
-        double qcur = 0.0;   // q_t (UNIT: q_ch)
-        if (valid) qcur = use_init ? P.q_init[i] : P.q_state[m][i];
-
-        if (!UNIT && K == 1 && (M.int_mask & 0x40)) {
-            // fast path (plan flag 0x40: no in-block edges and max in-degree <= RR_MAX_FAST_DEG)
-            switch (M.max_deg) {
-                case 0: fast_item<MODE, 0>(P, c, c1, c2, c3, c4, e0, deg, ex, qcur); break;
-                case 1: fast_item<MODE, 1>(P, c, c1, c2, c3, c4, e0, deg, ex, qcur); break;
-                case 2: fast_item<MODE, 2>(P, c, c1, c2, c3, c4, e0, deg, ex, qcur); break;
-                case 3: fast_item<MODE, 3>(P, c, c1, c2, c3, c4, e0, deg, ex, qcur); break;
-                default: fast_item<MODE, 4>(P, c, c1, c2, c3, c4, e0, deg, ex, qcur); break;
-            }
-            __syncwarp();
-            if (lane == 0) st_release(done + b, j + 1);
-            continue;
-        }
-
-        // ================= general path: systolic item with shuffles =================
-        const int d = __ldg(P.skew + ic);
-        const int nfast = M.max_deg < RR_MAX_FAST_DEG ? M.max_deg : RR_MAX_FAST_DEG;
-        auto raw_row = [&](int e) -> double * {   // e = entry of the upstream-CSR (an external edge)
-            const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + e);
-            return raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
-        };
-        int32_t src[RR_MAX_FAST_DEG];
-        const double *rp[RR_MAX_FAST_DEG];   // exported series of an external upstream
-        int ilane[RR_MAX_FAST_DEG];          // lane of an in-block upstream (own lane if none)
-        int64_t ug[RR_MAX_FAST_DEG];         // UNIT: global index of the upstream reach
-#pragma unroll
-        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
-            src[k] = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
-            rp[k] = nullptr;
-            ilane[k] = lane;
-            ug[k] = 0;
-            if (src[k] != SLOT_NONE) {
-                if (src[k] >= 0) rp[k] = raw_row(e0 + k);
-                else ilane[k] = (-src[k] - 1) & 31;
-                if (UNIT) ug[k] = __ldg(P.up_idx + e0 + k);
-            }
-        }
-        const double *lat = HAS_LAT ? P.lateral[m] + (size_t)t0 * P.ldl + i : nullptr;
-        double *outp = P.out[m] + (size_t)t0 * P.ldo + i;
-
-        double qprev = qcur;
-        double qf_cur = 0.0, qf_prev = 0.0;  // UNIT: q_full and its previous value
-        if (UNIT && valid) {
-            qf_cur = use_init ? qcur : P.q_full[m][i];
-            qf_prev = qf_cur;
-        }
-        double *myraw = nullptr;
-        if (ex >= 0) {
-            const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + ex);
-            myraw = raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
-            myraw[RAW_CARRY] = qcur;                 // carry-in for consumers
-            if (UNIT) myraw[RAW_QF] = qf_cur;        // q_full carry-in
-        }
-
-        // one-step lookahead registers for the external series and the lateral row
-        double eo[RR_MAX_FAST_DEG], en[RR_MAX_FAST_DEG];
-        double lu[RR_MAX_FAST_DEG], lu_old[RR_MAX_FAST_DEG];   // UNIT: upstream lateral (this / previous row)
-#pragma unroll
-        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
-            eo[k] = en[k] = lu[k] = lu_old[k] = 0.0;
-            if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) {
-                eo[k] = UNIT ? rp[k][RAW_QF] : rp[k][RAW_CARRY];
-                en[k] = rp[k][RAW_S0];
-            }
-        }
-        double ql = 0.0, ql_nx = 0.0;
-        if (HAS_LAT && valid) ql_nx = ld_stream(lat);
-        double acc = 0.0, base = 0.0;
-        int sub = 0, row = 0;
-
-        const int nsteps = TT + M.max_skew;
-        for (int sig = 0; sig < nsteps; ++sig) {
-            const int s = sig - d;
-            const bool act = valid && s >= 0 && s < TT;
-            const bool row_start = act && sub == 0;
-
-            // ---- gather upstream values (shuffles are executed by every lane) ----
-            double vo[RR_MAX_FAST_DEG], vn[RR_MAX_FAST_DEG];
-#pragma unroll
-            for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
-                vo[k] = eo[k];
-                vn[k] = en[k];
-                if (k < nfast && (M.int_mask >> k) & 1) {
-                    const double so = __shfl_sync(FULL_MASK, UNIT ? qf_prev : qprev, ilane[k]);
-                    const double sn = __shfl_sync(FULL_MASK, qcur, ilane[k]);
-                    if (src[k] < 0 && src[k] != SLOT_NONE) { vo[k] = so; vn[k] = sn; }
-                }
-            }
-
-            double r = 0.0;
-            if (UNIT) {
-                if (row_start) {
-                    // _numba_kernels.py:116-143: lateral gathers, A_inner@ql and A_hw@ql in ascending
-                    // column order, c1*(a_inner + a_hw); rhs base = c1_A_ql + c2*a_hw (:151)
-                    ql = ql_nx;
-                    double a_in = 0.0, a_hw = 0.0;
-#pragma unroll
-                    for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
-                        if (k < deg) {
-                            lu_old[k] = lu[k];
-                            lu[k] = ld_stream(P.lateral[m] + (size_t)(t0 + row) * P.ldl + ug[k]);
-                            const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
-                            if (hw) a_hw += lu[k]; else a_in += lu[k];
-                        }
-                    }
-                    for (int k = RR_MAX_FAST_DEG; k < deg; ++k) {
-                        const int32_t sk = __ldg(P.slot_src + e0 + k);
-                        const double l = ld_stream(P.lateral[m] + (size_t)(t0 + row) * P.ldl + __ldg(P.up_idx + e0 + k));
-                        const bool hw = sk >= 0 ? (sk & RR_SLOT_HW_BIT) != 0 : (((-sk - 1) >> 6) & 1) != 0;
-                        if (hw) a_hw += l; else a_in += l;
-                    }
-                    base = c1 * (a_in + a_hw) + c2 * a_hw;
-                }
-                r = base + c3 * qcur;
-            } else {
-                if (row_start) ql = ql_nx;
-                r = c3 * qcur;                      // :27-28 / :68-69
-                if (HAS_LAT) r = fma(c4, ql, r);
-            }
-
-            // ---- pass A: c2 * (previous-substep discharge of each upstream), ascending ----
-#pragma unroll
-            for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
-                if (k < deg) {
-                    if (UNIT) {
-                        const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
-                        if (!hw) {
-                            // external inner upstream: q_full_old = q_ch_old + lateral of the row that substep
-                            // belonged to; at s == 0 the exported carry already is q_full
-                            double qfo = vo[k];
-                            if (src[k] >= 0 && s > 0) qfo = vo[k] + (sub == 0 ? lu_old[k] : lu[k]);
-                            r = fma(c2, qfo, r);
-                        }
-                    } else {
-                        r = fma(c2, vo[k], r);
-                    }
-                }
-            }
-            if (M.max_deg > RR_MAX_FAST_DEG) {
-                for (int k = RR_MAX_FAST_DEG; k < M.max_deg; ++k) {
-                    const int32_t sk = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
-                    const int il = (sk < 0 && sk != SLOT_NONE) ? ((-sk - 1) & 31) : lane;
-                    double v = __shfl_sync(FULL_MASK, UNIT ? qf_prev : qprev, il);
-                    bool use = act && k < deg;
-                    if (use && sk >= 0) {
-                        const double *q = raw_row(e0 + k);
-                        if (UNIT) {
-                            if (sk & RR_SLOT_HW_BIT) use = false;
-                            else if (s == 0) v = q[RAW_QF];
-                            else {
-                                const int prow = (sub == 0) ? row - 1 : row;
-                                v = q[RAW_CARRY + s] + ld_stream(P.lateral[m] + (size_t)(t0 + prow) * P.ldl + __ldg(P.up_idx + e0 + k));
-                            }
-                        } else v = q[RAW_CARRY + s];
-                    } else if (use && UNIT && (((-sk - 1) >> 6) & 1)) use = false;
-                    if (use) r = fma(c2, v, r);
-                }
-            }
-            // ---- pass B: c1 * (this-substep discharge of each upstream), ascending ----
-#pragma unroll
-            for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
-                if (k < deg) {
-                    if (UNIT) {
-                        const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
-                        if (!hw) r = fma(c1, vn[k], r);
-                    } else {
-                        r = fma(c1, vn[k], r);      // rhs -= lhs_off * q_new with lhs_off = -c1 (:36-39)
-                    }
-                }
-            }
-            if (M.max_deg > RR_MAX_FAST_DEG) {
-                for (int k = RR_MAX_FAST_DEG; k < M.max_deg; ++k) {
-                    const int32_t sk = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
-                    const int il = (sk < 0 && sk != SLOT_NONE) ? ((-sk - 1) & 31) : lane;
-                    double v = __shfl_sync(FULL_MASK, qcur, il);
-                    bool use = act && k < deg;
-                    if (use && sk >= 0) {
-                        if (UNIT && (sk & RR_SLOT_HW_BIT)) use = false;
-                        else v = raw_row(e0 + k)[RAW_S0 + s];
-                    } else if (use && UNIT && (((-sk - 1) >> 6) & 1)) use = false;
-                    if (use) r = fma(c1, v, r);
-                }
-            }
-
-            // ---- commit ----
-            if (act) {
-                const bool inner = !UNIT || deg > 0;
-                if (inner) {
-                    qprev = qcur;
-                    qcur = r;
-                    if (UNIT) {
-                        qf_prev = qf_cur;
-                        qf_cur = r + ql;            // :165-166
-                        acc += qf_cur;
-                    } else acc += r;                // :41-42 / :79-80
-                    if (myraw) myraw[RAW_S0 + s] = r;
-                }
-                if (++sub == K) {
-                    double v;
-                    if (UNIT && !inner) v = ql;     // headwater: lateral inflow, unclamped (:122-123)
-                    else { v = acc * inv_k; v = v > 0.0 ? v : 0.0; }   // :44-46 / :82-84 / :169-171
-                    outp[(size_t)row * P.ldo] = v;
-                    acc = 0.0;
-                    sub = 0;
-                    ++row;
-                }
-                // lookahead for the next step of this lane
-                if (s + 1 < TT) {
-#pragma unroll
-                    for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
-                        if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) { eo[k] = en[k]; en[k] = rp[k][RAW_S0 + s + 1]; }
-                    }
-                    if (HAS_LAT && sub == 0) ql_nx = ld_stream(lat + (size_t)row * P.ldl);
-                }
-            }
-        }
-
-        // ---------------- publish ----------------
-        if (valid) {
-            const bool last = (j == P.n_tiles - 1);
-            if (UNIT) {
-                if (last && P.last_call) P.q_state[m][i] = deg > 0 ? qf_cur : ql;   // UnitMuskingum.py:94-98
-                else { P.q_state[m][i] = qcur; P.q_full[m][i] = qf_cur; }
-            } else P.q_state[m][i] = qcur;
-        }
-        __syncwarp();
-        if (lane == 0) st_release(done + b, j + 1);
     }
+    // ---- dependencies ----
+    int32_t *done = P.done + (size_t)m * P.n_blocks;
+    if (lane == 0) wait_ge(done + b, j);                                // own previous tile (acquire)
+    for (int e = P.dep_ptr[b] + lane; e < P.dep_ptr[b + 1]; e += 32)    // upstream blocks, this tile
+        wait_ge(done + P.dep_idx[e], j + 1);
+    if (c.ex >= 0) {                                                    // exchange-ring reuse
+        const int32_t ring = __ldg(P.exp_ro + 2 * c.ex + 1);
+        if (j >= ring) wait_ge(done + __ldg(P.down + i) / RR_BLOCK, j - ring + 1);
+    }
+    __syncwarp();
+    // first tile of a reference call: every member starts from the shared initial state and
+    // (UNIT) q_ch = q_full = state (UnitMuskingum.py:78-79); later tiles / chunks continue
+    // from the member's own running state.
+    c.use_init = (j == 0) && P.first_call;
+    c.q = 0.0;
+    if (valid) c.q = c.use_init ? P.q_init[i] : P.q_state[m][i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged fast path (tile-major working arrays, K == 1, no in-block edges).
+// One bulk async copy (cp.async.bulk, the 1-D TMA engine) brings the item's whole lateral tile
+// [rows][32] -- contiguous in the tile-major layout -- into shared memory, and one more per upstream
+// reach brings that reach's exchange row; all complete on one mbarrier per warp.  The time loop then
+// runs out of shared memory, writes the clamped discharge over the lateral tile in place, and a bulk
+// copy stores the tile back.  DRAM sees 16 KB / 640 B contiguous bursts instead of 32-byte sectors.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// returns false when the block needs more upstream row slots than the warp's shared-memory region has
+template <int MODE>
+__device__ __forceinline__ bool tma_item(const rr_route_params &P, const item_ctx &c, unsigned char *region,
+                                         uint32_t &phase, bool &store_pending) {
+    constexpr bool HAS_LAT = (MODE == RR_MODE_RAPID);
+    const int lane = c.lane, j = c.j, TT = c.TT;
+    const int cnt = c.deg;                         // every upstream is in another block
+    int pre = cnt;                                 // inclusive warp scan of the slot counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL_MASK, pre, o);
+        if (lane >= o) pre += v;
+    }
+    const int total = __shfl_sync(FULL_MASK, pre, 31);
+    if (total > P.row_slots) return false;
+    pre -= cnt;
+
+    double *tile = reinterpret_cast<double *>(region);
+    const int row_stride = P.raw_pitch + 2;        // doubles; +16 bytes keeps the lanes' rows on different banks
+    double *rows = tile + (size_t)P.tile_rows * RR_BLOCK;
+    const uint32_t bar = smem_u32(region + P.smem_region - 16);
+    const uint32_t tile_bytes = (uint32_t)c.rows * RR_BLOCK * 8;
+
+    if (store_pending) {                           // the previous item's tile store must have read the tile
+        if (lane == 0) bulk_wait_read();
+        store_pending = false;
+    }
+    __syncwarp();
+    fence_async_smem();                            // generic-proxy accesses of the last item before new async writes
+    const uint32_t my_bytes = (uint32_t)cnt * P.raw_pitch * 8 + ((HAS_LAT && lane == 0) ? tile_bytes : 0u);
+    mbar_arrive_expect_tx(bar, my_bytes);
+    if (HAS_LAT && lane == 0) bulk_load(smem_u32(tile), c.lat0, tile_bytes, bar);
+    const double *rowp[RR_MAX_FAST_DEG];
+#pragma unroll
+    for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+        rowp[k] = rows;
+        if (k < cnt) {
+            const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + c.e0 + k);
+            const double *src = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+            double *dst = rows + (size_t)(pre + k) * row_stride;
+            bulk_load(smem_u32(dst), src, (uint32_t)P.raw_pitch * 8, bar);
+            rowp[k] = dst;
+        }
+    }
+    double q = c.q;
+    double *myraw = nullptr;
+    if (c.ex >= 0) {
+        const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + c.ex);
+        myraw = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+        myraw[RAW_CARRY] = q;
+    }
+    const double c1 = c.c1, c2 = c.c2, c3 = c.c3, c4 = c.c4;
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+
+    double *col = tile + lane;
+    for (int s = 0; s < TT; s += 4) {
+        double r4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = RAW_CARRY + s + u;       // row entry before substep s+u; e + 1 is the entry after it
+            double r = c3 * q;                                        // _numba_kernels.py:27-28 / :68-69
+            if (HAS_LAT) r = fma(c4, col[(s + u) * RR_BLOCK], r);
+#pragma unroll
+            for (int k = 0; k < RR_MAX_FAST_DEG; ++k)
+                if (k < cnt) r = fma(c2, rowp[k][e], r);              // :29-33 / :70-74, ascending upstream
+#pragma unroll
+            for (int k = 0; k < RR_MAX_FAST_DEG; ++k)
+                if (k < cnt) r = fma(c1, rowp[k][e + 1], r);          // :36-39 / :75-78 (lhs_off = -c1)
+            r4[u] = r;
+            if (s + u < TT) {
+                col[(s + u) * RR_BLOCK] = r > 0.0 ? r : 0.0;          // K == 1: mean == value; clamp :44-46 / :82-84
+                q = r;
+            }
+        }
+        if (myraw) st_sector(myraw + RAW_S0 + s, r4[0], r4[1], r4[2], r4[3]);
+    }
+    if (c.valid) P.q_state[c.m][c.i] = q;
+    fence_async_smem();                            // make the tile visible to the async proxy
+    __syncwarp();
+    if (lane == 0) bulk_store(c.out0, smem_u32(tile), tile_bytes);
+    store_pending = true;
+    return true;
+}
+
+template <int MODE>
+__device__ __forceinline__ void register_fast_item(const rr_route_params &P, const item_ctx &c) {
+    switch (c.M.max_deg) {
+        case 0: fast_item<MODE, 0>(P, c); break;
+        case 1: fast_item<MODE, 1>(P, c); break;
+        case 2: fast_item<MODE, 2>(P, c); break;
+        case 3: fast_item<MODE, 3>(P, c); break;
+        default: fast_item<MODE, 4>(P, c); break;
+    }
+}
+
+}  // namespace
+
+template <int MODE>
+__global__ void __launch_bounds__(256, RR_MIN_CTAS) rr_wavefront_kernel(const __grid_constant__ rr_route_params P) {
+    constexpr bool UNIT = (MODE == RR_MODE_UNIT);
+    const int lane = threadIdx.x & 31;
+    int m, b, j;
+    while (next_item(P, lane, m, b, j)) {
+        item_ctx c;
+        open_item<MODE>(P, c, lane, m, b, j);
+        // plan flag 0x40: no in-block edges and max in-degree <= RR_MAX_FAST_DEG
+        if (!UNIT && P.K == 1 && (c.M.int_mask & 0x40)) register_fast_item<MODE>(P, c);
+        else general_item<MODE>(P, c);
+        __syncwarp();
+        if (lane == 0) st_release(P.done + (size_t)m * P.n_blocks + b, j + 1);
+    }
+}
+
+// Persistent kernel of the TMA-staged path: 4 warps per CTA, one CTA per SM, each warp owns a private
+// shared-memory region (tile + upstream row slots + its mbarrier).
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) rr_wavefront_tma_kernel(const __grid_constant__ rr_route_params P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *region = smem + (size_t)warp * P.smem_region;
+    if (lane == 0) mbar_init(smem_u32(region + P.smem_region - 16), 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+    __syncthreads();
+    uint32_t phase = 0;
+    bool store_pending = false;
+    int m, b, j;
+    while (next_item(P, lane, m, b, j)) {
+        item_ctx c;
+        open_item<MODE>(P, c, lane, m, b, j);
+        bool done_item = false;
+        if (c.M.int_mask & 0x40) {
+            done_item = tma_item<MODE>(P, c, region, phase, store_pending);
+            if (!done_item) { register_fast_item<MODE>(P, c); done_item = true; }
+        }
+        if (!done_item) general_item<MODE>(P, c);
+        __syncwarp();
+        if (lane == 0) st_release(P.done + (size_t)m * P.n_blocks + b, j + 1);
+    }
+    if (lane == 0) bulk_wait_all();
 }
 
 // Host-callable launcher (used by rr_api.cu).
 cudaError_t rr_launch_wavefront(int mode, const rr_route_params &P, int grid, int block, cudaStream_t stream) {
+    if (P.smem_region > 0) {   // TMA-staged path (tile-major working arrays, one substep per row)
+        const size_t smem = (size_t)P.smem_region * 4;
+        cudaError_t e;
+        if (mode == RR_MODE_MUSKINGUM) {
+            e = cudaFuncSetAttribute(rr_wavefront_tma_kernel<RR_MODE_MUSKINGUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            rr_wavefront_tma_kernel<RR_MODE_MUSKINGUM><<<grid, 128, smem, stream>>>(P);
+        } else if (mode == RR_MODE_RAPID) {
+            e = cudaFuncSetAttribute(rr_wavefront_tma_kernel<RR_MODE_RAPID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            rr_wavefront_tma_kernel<RR_MODE_RAPID><<<grid, 128, smem, stream>>>(P);
+        } else return cudaErrorInvalidValue;
+        return cudaGetLastError();
+    }
     switch (mode) {
         case RR_MODE_MUSKINGUM: rr_wavefront_kernel<RR_MODE_MUSKINGUM><<<grid, block, 0, stream>>>(P); break;
         case RR_MODE_RAPID: rr_wavefront_kernel<RR_MODE_RAPID><<<grid, block, 0, stream>>>(P); break;

@@ -33,6 +33,9 @@ struct rr_route_params {
     int32_t tile_rows;    // rows per work item
     int32_t raw_pitch;    // doubles per exported series (1 carry + tile_rows*K, padded to 4)
     int32_t n_members;
+    int32_t tile_major;   // 1: lateral / out are the library's working arrays stored [tile][block][row][lane]
+    int32_t smem_region;  // > 0: TMA-staged kernel; bytes of shared memory per warp (tile + row slots + mbarrier)
+    int32_t row_slots;    // upstream exchange rows a warp's region can hold
     int32_t first_call;   // UNIT: 1 when q_state holds the start-of-file state (q_ch = q_full = state)
     int32_t last_call;    // UNIT: 1 when q_state must end as the recombined vector (hw: lateral, inner: q_full)
     const int32_t *exp_ro;    // [n_export][2] {first row, ring depth in tiles} of each exported series' ring

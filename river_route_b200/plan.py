@@ -78,12 +78,12 @@ class Plan:
     RENUMBER = {'auto': 0, 'never': 1, 'always': 2}
 
     def __init__(self, down, time_tile: int = 0, tile_stride: int = 0, device: int = -1, threads_per_cta: int = 0,
-                 raw_budget_bytes: int = 0, renumber: str = 'auto'):
+                 raw_budget_bytes: int = 0, renumber: str = 'auto', staging: str = 'auto'):
         down = np.ascontiguousarray(down, dtype=np.int32)
         self.n = int(down.shape[0])
         self.down = down
         opts = _lib.PlanOpts(int(time_tile), int(tile_stride), int(device), int(threads_per_cta), int(raw_budget_bytes),
-                             self.RENUMBER[renumber], 0)
+                             self.RENUMBER[renumber], {'auto': 0, 'registers': 1, 'registers-tiled': 2, 'tma': 3}[staging])
         handle = C.c_void_p()
         check(lib.rr_plan_create(self.n, _lib.as_i32p(down), C.byref(opts), C.byref(handle)))
         self._h = handle

@@ -204,7 +204,8 @@ static int64_t tile_rows_for(const rr_plan *p, int64_t T, int64_t K) {
 
 static int launch_route(rr_plan *p, int mode, int n_members, const double *q_init, const double *const *lateral,
                         int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
-                        int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream, int tile_major = 0) {
+                        int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream, int tile_major = 0,
+                        int out_layout = 0) {
     if (mode < 0 || mode > 2) { rr_set_error("unknown router mode"); return 100; }
     if (T <= 0 || K <= 0 || T > 0x7fffffff || K > 0x7fffffff) { rr_set_error("T and substeps must be positive"); return 100; }
     if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
@@ -261,7 +262,8 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
         kt->n_tiles = n_tiles; kt->n_keys = d->sched.n_keys; kt->n_items = d->sched.n_items;
     }
     kt->used = ++d->key_clock;
-    const size_t raw_need = (size_t)n_members * (size_t)d->sched.raw_rows * pitch * sizeof(double);
+    // one spare row: the kernel prefetches a few lines past the row it is reading
+    const size_t raw_need = ((size_t)n_members * (size_t)d->sched.raw_rows + 1) * pitch * sizeof(double);
     if (raw_need > d->raw_bytes) {
         CK(cudaDeviceSynchronize());
         if (d->raw) CK(cudaFree(d->raw));
@@ -303,7 +305,9 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     CK(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), stream));
     int block = p->opts.threads_per_cta;
     P.tile_major = tile_major;
-    if (tile_major && K == 1 && mode != RR_MODE_UNIT && p->opts.staging == 3) {
+    P.out_layout = out_layout;
+    P.tile_pitch = (int32_t)((rows + 3) & ~(int64_t)3);
+    if (tile_major == 1 && K == 1 && mode != RR_MODE_UNIT) {
         // TMA-staged kernel: 4 warps per CTA, each with [tile | upstream row slots | mbarrier] in shared memory
         int max_smem = 0;
         CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
@@ -340,14 +344,23 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
 #define PERM_ROWS 8
 // Address of working element (row t, working reach k).  tile_rows == 0: row-major with leading dimension ld;
 // otherwise the tile-major layout [tile][block][row in tile][lane] the TMA-staged kernel reads with bulk copies.
-__device__ __forceinline__ int64_t working_index(int64_t t, int64_t k, int64_t ld, int64_t tile_rows, int64_t n_blocks) {
-    if (tile_rows == 0) return t * ld + k;
+__device__ __forceinline__ int64_t working_index(int64_t t, int64_t k, int64_t ld, int64_t tile_rows, int64_t n_blocks,
+                                                 int layout) {
+    if (layout == 0) return t * ld + k;
     const int64_t j = t / tile_rows, r = t - j * tile_rows;
-    return ((j * n_blocks + (k >> 5)) * tile_rows + r) * RR_BLOCK + (k & 31);
+    if (layout == 1) return ((j * n_blocks + (k >> 5)) * tile_rows + r) * RR_BLOCK + (k & 31);
+    const int64_t pitch = (tile_rows + 3) & ~(int64_t)3;
+    return ((j * n_blocks + (k >> 5)) * RR_BLOCK + (k & 31)) * pitch + r;
+}
+__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld256(const double *p, double &a, double &b, double &c, double &d) {
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
 }
 __global__ void __launch_bounds__(256) permute_to_working(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
                                                           int64_t ldd, const int32_t *__restrict__ inv, int64_t n, int64_t T,
-                                                          int64_t tile_rows, int64_t n_blocks) {
+                                                          int64_t tile_rows, int64_t n_blocks, int layout) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t k = __ldg(inv + i);
@@ -355,30 +368,44 @@ __global__ void __launch_bounds__(256) permute_to_working(const double *__restri
     double v[PERM_ROWS];
 #pragma unroll
     for (int r = 0; r < PERM_ROWS; ++r) v[r] = (t0 + r < T) ? __ldg(src + (t0 + r) * lds + i) : 0.0;
+    if (layout == 2 && (tile_rows & 7) == 0) {
+        // the 8 rows of this reach are 64 contiguous bytes of its tile: two whole-sector stores
+        double *q = dst + working_index(t0, k, ldd, tile_rows, n_blocks, 2);
+        st256(q, v[0], v[1], v[2], v[3]);
+        st256(q + 4, v[4], v[5], v[6], v[7]);
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < PERM_ROWS; ++r)
-        if (t0 + r < T) dst[working_index(t0 + r, k, ldd, tile_rows, n_blocks)] = v[r];
+        if (t0 + r < T) dst[working_index(t0 + r, k, ldd, tile_rows, n_blocks, layout)] = v[r];
 }
 __global__ void __launch_bounds__(256) permute_to_user(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
                                                        int64_t ldd, const int32_t *__restrict__ inv, int64_t n, int64_t T,
-                                                       int64_t tile_rows, int64_t n_blocks) {
+                                                       int64_t tile_rows, int64_t n_blocks, int layout) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t k = __ldg(inv + i);
     const int64_t t0 = (int64_t)blockIdx.y * PERM_ROWS;
     double v[PERM_ROWS];
+    if (layout == 2 && (tile_rows & 7) == 0) {
+        const double *q = src + working_index(t0, k, lds, tile_rows, n_blocks, 2);
+        ld256(q, v[0], v[1], v[2], v[3]);
+        ld256(q + 4, v[4], v[5], v[6], v[7]);
+    } else {
 #pragma unroll
-    for (int r = 0; r < PERM_ROWS; ++r) v[r] = (t0 + r < T) ? src[working_index(t0 + r, k, lds, tile_rows, n_blocks)] : 0.0;
+        for (int r = 0; r < PERM_ROWS; ++r)
+            v[r] = (t0 + r < T) ? src[working_index(t0 + r, k, lds, tile_rows, n_blocks, layout)] : 0.0;
+    }
 #pragma unroll
     for (int r = 0; r < PERM_ROWS; ++r)
         if (t0 + r < T) dst[(t0 + r) * ldd + i] = v[r];
 }
 static int permute(bool to_working, const double *src, int64_t lds, double *dst, int64_t ldd, const int32_t *inv,
-                   int64_t n, int64_t T, cudaStream_t stream, int64_t tile_rows = 0, int64_t n_blocks = 0) {
+                   int64_t n, int64_t T, cudaStream_t stream, int64_t tile_rows = 0, int64_t n_blocks = 0, int layout = 0) {
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)((T + PERM_ROWS - 1) / PERM_ROWS));
     rr_timer tm(to_working ? 1 : 2, stream);
-    if (to_working) permute_to_working<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks);
-    else permute_to_user<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks);
+    if (to_working) permute_to_working<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
+    else permute_to_user<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
     CK(cudaGetLastError());
     rr_count_launch(1);
     return 0;
@@ -409,12 +436,19 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
     if (T <= 0 || K <= 0) { rr_set_error("T and substeps must be positive"); return 100; }
     // working arrays: tile-major for the TMA-staged kernel (one substep per row, not UnitMuskingum), else row-major
+    // working arrays: row-major (staging 1, substeps, UnitMuskingum), [tile][block][row][lane] for the TMA-staged
+    // kernel (3), [tile][block][lane][row] otherwise (register path: whole-sector accesses everywhere)
     const bool tiled = (K == 1 && !unit && p->opts.staging != 1);
+    // lateral: reach-major tiles (whole-sector scatter in the permute, 256-bit loads in the kernel); discharge:
+    // row-major tiles (coalesced row stores in the kernel, sector-sharing gathers in the permute) -- measured best
+    const int layout = !tiled ? 0 : (p->opts.staging == 3 ? 1 : 2);
+    const int out_layout = !tiled ? 0 : 1;
     const int64_t trows = tiled ? tile_rows_for(p, T, K) : 0;
+    const int64_t tpitch = ((trows + 3) & ~(int64_t)3);
     const int64_t n_tiles = tiled ? (T + trows - 1) / trows : 0;
-    const size_t member_elems = tiled ? (size_t)n_tiles * p->n_blocks * trows * RR_BLOCK : (size_t)T * ldp;
-    if (has_lat && (rc = grow(&d->p_lat, &d->p_lat_cap, (size_t)n_members * member_elems))) return rc;
-    if ((rc = grow(&d->p_out, &d->p_out_cap, (size_t)n_members * member_elems))) return rc;
+    const size_t member_elems = tiled ? (size_t)n_tiles * p->n_blocks * tpitch * RR_BLOCK : (size_t)T * ldp;
+    if (has_lat && (rc = grow(&d->p_lat, &d->p_lat_cap, (size_t)n_members * member_elems + 64))) return rc;
+    if ((rc = grow(&d->p_out, &d->p_out_cap, (size_t)n_members * member_elems + 64))) return rc;
     // state scratch: [init][member states][member q_full]
     if ((rc = grow(&d->p_q, &d->p_q_cap, (size_t)(1 + 2 * n_members) * ldp))) return rc;
     double *w_init = d->p_q;
@@ -426,17 +460,17 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
         out_w[m] = d->p_out + (size_t)m * member_elems;
         qs_w[m] = d->p_q + (size_t)(1 + m) * ldp;
         qf_w[m] = d->p_q + (size_t)(1 + n_members + m) * ldp;
-        if (has_lat && (rc = permute(true, lateral[m], ldl, d->p_lat + (size_t)m * member_elems, ldp, d->inv, n, T, stream, trows, p->n_blocks))) return rc;
+        if (has_lat && (rc = permute(true, lateral[m], ldl, d->p_lat + (size_t)m * member_elems, ldp, d->inv, n, T, stream, trows, p->n_blocks, layout))) return rc;
         if (!first_call) {
             if ((rc = permute(true, q_state[m], n, qs_w[m], ldp, d->inv, n, 1, stream))) return rc;
             if (unit && (rc = permute(true, q_full[m], n, qf_w[m], ldp, d->inv, n, 1, stream))) return rc;
         }
     }
     rc = launch_route(p, mode, n_members, w_init, has_lat ? lat_w : nullptr, ldp, out_w, ldp, qs_w, qf_w, T, K,
-                      first_call, last_call, stream, tiled ? 1 : 0);
+                      first_call, last_call, stream, layout, out_layout);
     if (rc) return rc;
     for (int m = 0; m < n_members; ++m) {
-        if ((rc = permute(false, out_w[m], ldp, out[m], ldo, d->inv, n, T, stream, trows, p->n_blocks))) return rc;
+        if ((rc = permute(false, out_w[m], ldp, out[m], ldo, d->inv, n, T, stream, trows, p->n_blocks, out_layout))) return rc;
         if ((rc = permute(false, qs_w[m], ldp, q_state[m], n, d->inv, n, 1, stream))) return rc;
         if (unit && !(last_call) && (rc = permute(false, qf_w[m], ldp, q_full[m], n, d->inv, n, 1, stream))) return rc;
     }

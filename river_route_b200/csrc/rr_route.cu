@@ -79,6 +79,12 @@ __device__ __forceinline__ d4 ld_sector(const double *p) {
     asm volatile("ld.global.L2::128B.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p) : "memory");
     return v;
 }
+// read-only data (never written during the launch): non-coherent path
+__device__ __forceinline__ d4 ld_sector_ro(const double *p) {
+    d4 v;
+    asm volatile("ld.global.nc.L2::128B.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+    return v;
+}
 // one 256-bit store: the whole sector is written at once, so L2 never has to fill it from DRAM first
 __device__ __forceinline__ void st_sector(double *p, double a, double b, double c, double d) {
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
@@ -102,7 +108,7 @@ struct item_ctx {
 // ------------------------------------------------------------------------------------------------
 // Fast path: K == 1, no in-block edges, every reach has at most NS upstreams (all external).
 // ------------------------------------------------------------------------------------------------
-template <int MODE, int NS>
+template <int MODE, int NS, bool VEC>
 __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_ctx &c) {
     const double c1 = c.c1, c2 = c.c2, c3 = c.c3, c4 = c.c4;
     const int e0 = c.e0, deg = c.deg, ex = c.ex;
@@ -150,10 +156,16 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
     }
     double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
     if (HAS_LAT && c.valid) {
-        l0 = ld_stream(lat);
-        if (1 < TT) l1 = ld_stream(lat + ldl);
-        if (2 < TT) l2 = ld_stream(lat + 2 * ldl);
-        if (3 < TT) l3 = ld_stream(lat + 3 * ldl);
+        if (VEC) {   // rows of this reach are contiguous (and padded to a multiple of 4): one 256-bit load
+            prefetch_l2(lat + 16);
+            const d4 v = ld_sector_ro(lat);
+            l0 = v.a; l1 = v.b; l2 = v.c; l3 = v.d;
+        } else {
+            l0 = ld_stream(lat);
+            if (1 < TT) l1 = ld_stream(lat + ldl);
+            if (2 < TT) l2 = ld_stream(lat + 2 * ldl);
+            if (3 < TT) l3 = ld_stream(lat + 3 * ldl);
+        }
     }
     for (int s = 0; s < TT; s += 4) {
         // ---- issue the next group's loads before computing this one ----
@@ -166,7 +178,16 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
             if (has[k] && more) fut[k] = ld_sector(up[k] + RAW_S0 + s + 4);
             if (has[k] && (s & 15) == 0 && s + 48 < TT) prefetch_l2(up[k] + RAW_S0 + s + 48);
         }
-        if (HAS_LAT && c.valid && more) {
+        if (HAS_LAT && VEC) {
+            if (c.valid && (s & 15) == 0 && s + 32 < TT) prefetch_l2(lat + s + 32);
+            if (c.valid && more) { const d4 v = ld_sector_ro(lat + s + 4); n0 = v.a; n1 = v.b; n2 = v.c; n3 = v.d; }
+        }
+        if (HAS_LAT && !VEC && (s & 7) == 0 && c.lane < 16) {
+            // rows s+16 .. s+23, two 128-byte lines each, one line per lane
+            const int r = s + 16 + (c.lane >> 1);
+            if (r < TT) prefetch_l2((const char *)(lat - c.lane + (size_t)r * ldl) + (c.lane & 1) * 128);
+        }
+        if (HAS_LAT && !VEC && c.valid && more) {
             const double *lp = lat + (size_t)(s + 4) * ldl;
             n0 = ld_stream(lp);
             if (s + 5 < TT) n1 = ld_stream(lp + ldl);
@@ -206,7 +227,9 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
             for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].d, r);
             r3 = r;
         }
-        if (c.valid) {
+        if (c.valid && ldo == 1) {   // this reach's rows are contiguous in the working discharge array
+            st_sector(outp + s, r0 > 0.0 ? r0 : 0.0, r1 > 0.0 ? r1 : 0.0, r2 > 0.0 ? r2 : 0.0, r3 > 0.0 ? r3 : 0.0);
+        } else if (c.valid) {
             // K == 1: the interval mean is the value itself; clamp as :44-46 / :82-84
             double *o = outp + (size_t)s * ldo;
             o[0] = r0 > 0.0 ? r0 : 0.0;
@@ -501,28 +524,36 @@ __device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c,
     c.rows = min(P.tile_rows, P.T - c.t0);
     c.TT = c.rows * P.K;
     c.raw_m = P.raw + (size_t)m * (size_t)P.raw_rows * P.raw_pitch;
-    if (P.tile_major) {
-        // working arrays stored tile by tile: [tile][block][row][lane] -- an item's rows are contiguous
-        const size_t tile = ((size_t)j * P.n_blocks + b) * (size_t)P.tile_rows * RR_BLOCK + lane;
-        c.lat0 = HAS_LAT ? P.lateral[m] + tile : nullptr;
-        c.out0 = P.out[m] + tile;
-        c.lstride = c.ostride = RR_BLOCK;
-    } else {
-        c.lat0 = HAS_LAT ? P.lateral[m] + (size_t)c.t0 * P.ldl + i : nullptr;
-        c.out0 = P.out[m] + (size_t)c.t0 * P.ldo + i;
-        c.lstride = P.ldl;
-        c.ostride = P.ldo;
-    }
+    // Working-array layouts (renumbered plans; the caller's arrays are permuted into them on the device):
+    //   0 row-major (T, ld)   1 [tile][block][row][lane]   2 [tile][block][lane][row] (tile_pitch doubles per reach)
+    auto place = [&](int layout, const double *base, int64_t ld, const double *&p0, int64_t &stride) {
+        if (layout == 2) { p0 = base + (((size_t)j * P.n_blocks + b) * RR_BLOCK + lane) * (size_t)P.tile_pitch; stride = 1; }
+        else if (layout == 1) { p0 = base + ((size_t)j * P.n_blocks + b) * (size_t)P.tile_rows * RR_BLOCK + lane; stride = RR_BLOCK; }
+        else { p0 = base + (size_t)c.t0 * ld + i; stride = ld; }
+    };
+    c.lat0 = nullptr;
+    c.lstride = 1;
+    if (HAS_LAT) place(P.tile_major, P.lateral[m], P.ldl, c.lat0, c.lstride);
+    const double *o0 = nullptr;
+    place(P.out_layout, P.out[m], P.ldo, o0, c.ostride);
+    c.out0 = const_cast<double *>(o0);
     if (HAS_LAT) {
-        // pull this item's lateral tile towards L2 while the dependency wait runs
-        if (P.tile_major) {
+        // pull the first 16 rows of this item's lateral tile towards L2 while the dependency wait runs; the
+        // fast path keeps prefetching 16 rows ahead of its time loop (a whole tile per warp up front would
+        // not survive in L2 until it is used: the chip streams ~L2-size bytes during one item)
+        const bool fast = (c.M.int_mask & 0x40) && P.K == 1 && MODE != RR_MODE_UNIT;
+        const int pf_rows = fast ? min(c.rows, 16) : c.rows;
+        if (P.tile_major == 2) {
+            prefetch_l2(c.lat0);                                   // this lane's first line (16 rows)
+            if (!fast) for (int r = 16; r < c.rows; r += 16) prefetch_l2(c.lat0 + r);
+        } else if (P.tile_major) {
             const char *t = (const char *)(c.lat0 - lane);
-            for (int l = lane; l < c.rows * 2; l += 32) prefetch_l2(t + (size_t)l * 128);
+            for (int l = lane; l < pf_rows * 2; l += 32) prefetch_l2(t + (size_t)l * 128);
         } else {
             const double *lt = c.lat0 - lane;
             const int64_t left = P.n - (int64_t)b * RR_BLOCK;
             const int row_bytes = (int)(left < RR_BLOCK ? left : RR_BLOCK) * 8;
-            for (int r = lane; r < c.rows; r += 32) {
+            for (int r = lane; r < pf_rows; r += 32) {
                 const char *a = (const char *)(lt + (size_t)r * c.lstride);
                 prefetch_l2(a);
                 if (row_bytes > 128) prefetch_l2(a + 128);
@@ -669,12 +700,22 @@ __device__ __forceinline__ bool tma_item(const rr_route_params &P, const item_ct
 
 template <int MODE>
 __device__ __forceinline__ void register_fast_item(const rr_route_params &P, const item_ctx &c) {
-    switch (c.M.max_deg) {
-        case 0: fast_item<MODE, 0>(P, c); break;
-        case 1: fast_item<MODE, 1>(P, c); break;
-        case 2: fast_item<MODE, 2>(P, c); break;
-        case 3: fast_item<MODE, 3>(P, c); break;
-        default: fast_item<MODE, 4>(P, c); break;
+    if (P.tile_major == 2) {
+        switch (c.M.max_deg) {
+            case 0: fast_item<MODE, 0, true>(P, c); break;
+            case 1: fast_item<MODE, 1, true>(P, c); break;
+            case 2: fast_item<MODE, 2, true>(P, c); break;
+            case 3: fast_item<MODE, 3, true>(P, c); break;
+            default: fast_item<MODE, 4, true>(P, c); break;
+        }
+    } else {
+        switch (c.M.max_deg) {
+            case 0: fast_item<MODE, 0, false>(P, c); break;
+            case 1: fast_item<MODE, 1, false>(P, c); break;
+            case 2: fast_item<MODE, 2, false>(P, c); break;
+            case 3: fast_item<MODE, 3, false>(P, c); break;
+            default: fast_item<MODE, 4, false>(P, c); break;
+        }
     }
 }
 

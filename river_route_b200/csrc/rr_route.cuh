@@ -33,7 +33,10 @@ struct rr_route_params {
     int32_t tile_rows;    // rows per work item
     int32_t raw_pitch;    // doubles per exported series (1 carry + tile_rows*K, padded to 4)
     int32_t n_members;
-    int32_t tile_major;   // 1: lateral / out are the library's working arrays stored [tile][block][row][lane]
+    int32_t tile_major;   // working-array layout of lateral / out: 0 row-major (T, ld); 1 [tile][block][row][lane];
+                          // 2 [tile][block][lane][row] with tile_pitch doubles per reach
+    int32_t out_layout;   // layout of out (same codes); tile_major is the layout of lateral
+    int32_t tile_pitch;   // layout 2: tile_rows rounded up to a multiple of 4
     int32_t smem_region;  // > 0: TMA-staged kernel; bytes of shared memory per warp (tile + row slots + mbarrier)
     int32_t row_slots;    // upstream exchange rows a warp's region can hold
     int32_t first_call;   // UNIT: 1 when q_state holds the start-of-file state (q_ch = q_full = state)

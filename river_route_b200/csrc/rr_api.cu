@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -198,8 +199,24 @@ void rr_device_release(rr_plan *p) {
 
 // One kernel launch == one reference call (or one time chunk of it).
 // Rows of one work item for a call of T rows with K substeps per row (aims at `time_tile` substeps per item).
+// With an automatic tile the length is chosen per call from a two-term cost model: streaming time of the call
+// (longer tiles amortise the per-item setup) against the dependency critical path of one launch,
+// (block levels + tiles) x item latency (shorter tiles shorten every hop).  Small per-GPU networks -- strong
+// scaling over many GPUs -- are latency bound and get shorter tiles.
 static int64_t tile_rows_for(const rr_plan *p, int64_t T, int64_t K) {
-    return std::max<int64_t>(1, std::min<int64_t>(T, p->opts.time_tile / K));
+    int64_t tile = p->opts.time_tile;
+    if (p->auto_tile) {
+        double best = 1e300;
+        for (int64_t cand : {64, 32, 16}) {
+            const double overhead = cand == 64 ? 1.0 : (cand == 32 ? 1.18 : 1.6);
+            const double stream_us = (double)p->n * (double)T * (double)K * 33.0 / 4.6e6 * overhead;   // bytes / (B/us)
+            const double n_tiles = std::ceil((double)T * K / (double)cand);
+            const double critical_us = ((double)p->max_level + n_tiles) * (5.0 + 0.4 * (double)cand);
+            const double est = std::max(stream_us, critical_us) + 0.3 * std::min(stream_us, critical_us);
+            if (est < best) { best = est; tile = cand; }
+        }
+    }
+    return std::max<int64_t>(1, std::min<int64_t>(T, tile / K));
 }
 
 static int launch_route(rr_plan *p, int mode, int n_members, const double *q_init, const double *const *lateral,
@@ -517,7 +534,7 @@ extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_fu
     rr_device_state *d = p->dev;
     const int64_t n = p->n;
     const int64_t ldd = ((n + 31) / 32) * 32;  // device rows start on 256-byte boundaries
-    const int64_t rows_tile = std::max<int64_t>(1, p->opts.time_tile / substeps);
+    const int64_t rows_tile = std::max<int64_t>(1, p->opts.time_tile / substeps);   // largest tile: chunk granularity
     // chunk: about 512 MiB per buffer so that H2D, routing and D2H of neighbouring chunks overlap; whole tiles
     // when a chunk holds several
     int64_t chunk = std::max<int64_t>(1, (512ll << 20) / (ldd * 8));

@@ -29,6 +29,7 @@ struct rr_plan {
     std::vector<int32_t> down;       // [n] downstream reach in the WORKING order (user order unless renumbered)
     std::vector<int32_t> perm, inv;  // renumbered plans: perm[working] = user index, inv[user] = working index
     int32_t reach_depth = 0;         // longest upstream-to-outlet path, in reaches
+    bool auto_tile = true;           // choose the tile length per call (opts.time_tile is then the largest one)
     std::vector<int32_t> up_ptr;     // [n+1]
     std::vector<int32_t> up_idx;     // [edges] ascending upstream index per row
     std::vector<int32_t> slot_src;   // [edges] encoded source (see rr_b200.h)

@@ -243,7 +243,8 @@ extern "C" int rr_plan_create(int64_t n, const int32_t *down, const rr_plan_opts
     }
     rr_plan *p = new rr_plan();
     if (opts) p->opts = *opts;
-    if (p->opts.time_tile <= 0) p->opts.time_tile = 64;
+    p->auto_tile = p->opts.time_tile <= 0;
+    if (p->auto_tile) p->opts.time_tile = 64;
     if (p->opts.threads_per_cta <= 0) p->opts.threads_per_cta = 256;
     p->opts.threads_per_cta = std::max(32, (p->opts.threads_per_cta / 32) * 32);
     if (p->opts.raw_budget_bytes <= 0) p->opts.raw_budget_bytes = 16ll << 30;

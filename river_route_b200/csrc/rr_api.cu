@@ -375,25 +375,26 @@ __device__ __forceinline__ void st256(double *p, double a, double b, double c, d
 __device__ __forceinline__ void ld256(const double *p, double &a, double &b, double &c, double &d) {
     asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
 }
+template <int ROWS>
 __global__ void __launch_bounds__(256) permute_to_working(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
                                                           int64_t ldd, const int32_t *__restrict__ inv, int64_t n, int64_t T,
                                                           int64_t tile_rows, int64_t n_blocks, int layout) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t k = __ldg(inv + i);
-    const int64_t t0 = (int64_t)blockIdx.y * PERM_ROWS;
-    double v[PERM_ROWS];
+    const int64_t t0 = (int64_t)blockIdx.y * ROWS;
+    double v[ROWS];
 #pragma unroll
-    for (int r = 0; r < PERM_ROWS; ++r) v[r] = (t0 + r < T) ? __ldg(src + (t0 + r) * lds + i) : 0.0;
-    if (layout == 2 && (tile_rows & 7) == 0) {
-        // the 8 rows of this reach are 64 contiguous bytes of its tile: two whole-sector stores
+    for (int r = 0; r < ROWS; ++r) v[r] = (t0 + r < T) ? __ldg(src + (t0 + r) * lds + i) : 0.0;
+    if (layout == 2 && (tile_rows % ROWS) == 0) {
+        // the ROWS rows of this reach are contiguous in its tile: whole-sector (ROWS = 16: whole-line) stores
         double *q = dst + working_index(t0, k, ldd, tile_rows, n_blocks, 2);
-        st256(q, v[0], v[1], v[2], v[3]);
-        st256(q + 4, v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int r = 0; r < ROWS; r += 4) st256(q + r, v[r], v[r + 1], v[r + 2], v[r + 3]);
         return;
     }
 #pragma unroll
-    for (int r = 0; r < PERM_ROWS; ++r)
+    for (int r = 0; r < ROWS; ++r)
         if (t0 + r < T) dst[working_index(t0 + r, k, ldd, tile_rows, n_blocks, layout)] = v[r];
 }
 __global__ void __launch_bounds__(256) permute_to_user(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
@@ -419,10 +420,18 @@ __global__ void __launch_bounds__(256) permute_to_user(const double *__restrict_
 }
 static int permute(bool to_working, const double *src, int64_t lds, double *dst, int64_t ldd, const int32_t *inv,
                    int64_t n, int64_t T, cudaStream_t stream, int64_t tile_rows = 0, int64_t n_blocks = 0, int layout = 0) {
-    dim3 grid((unsigned)((n + 255) / 256), (unsigned)((T + PERM_ROWS - 1) / PERM_ROWS));
     rr_timer tm(to_working ? 1 : 2, stream);
-    if (to_working) permute_to_working<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
-    else permute_to_user<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
+    const unsigned gx = (unsigned)((n + 255) / 256);
+    if (to_working && layout == 2 && (tile_rows % 16) == 0) {
+        dim3 grid(gx, (unsigned)((T + 15) / 16));
+        permute_to_working<16><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
+    } else if (to_working) {
+        dim3 grid(gx, (unsigned)((T + PERM_ROWS - 1) / PERM_ROWS));
+        permute_to_working<PERM_ROWS><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
+    } else {
+        dim3 grid(gx, (unsigned)((T + PERM_ROWS - 1) / PERM_ROWS));
+        permute_to_user<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
+    }
     CK(cudaGetLastError());
     rr_count_launch(1);
     return 0;

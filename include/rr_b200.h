@@ -47,7 +47,8 @@ typedef struct rr_plan_opts {
                                library permutes them on the device)                             */
     int32_t staging;        /* renumbered plans: 0 auto (= 2), 1 register path on row-major working arrays,
                                2 register path on tile-major working arrays, 3 bulk-async-copy (TMA)
-                               staged kernel on tile-major working arrays                            */
+                               staged kernel on tile-major working arrays, 4 as 2 with reach-major
+                               discharge tiles (experiments; 0 is the measured best)               */
 } rr_plan_opts;
 
 /* Host-visible description of a built plan (for tests, DESIGN.md numbers and bench.py). */

@@ -397,25 +397,26 @@ __global__ void __launch_bounds__(256) permute_to_working(const double *__restri
     for (int r = 0; r < ROWS; ++r)
         if (t0 + r < T) dst[working_index(t0 + r, k, ldd, tile_rows, n_blocks, layout)] = v[r];
 }
+template <int ROWS>
 __global__ void __launch_bounds__(256) permute_to_user(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
                                                        int64_t ldd, const int32_t *__restrict__ inv, int64_t n, int64_t T,
                                                        int64_t tile_rows, int64_t n_blocks, int layout) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t k = __ldg(inv + i);
-    const int64_t t0 = (int64_t)blockIdx.y * PERM_ROWS;
-    double v[PERM_ROWS];
-    if (layout == 2 && (tile_rows & 7) == 0) {
+    const int64_t t0 = (int64_t)blockIdx.y * ROWS;
+    double v[ROWS];
+    if (layout == 2 && (tile_rows % ROWS) == 0) {
         const double *q = src + working_index(t0, k, lds, tile_rows, n_blocks, 2);
-        ld256(q, v[0], v[1], v[2], v[3]);
-        ld256(q + 4, v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int r = 0; r < ROWS; r += 4) ld256(q + r, v[r], v[r + 1], v[r + 2], v[r + 3]);
     } else {
 #pragma unroll
-        for (int r = 0; r < PERM_ROWS; ++r)
+        for (int r = 0; r < ROWS; ++r)
             v[r] = (t0 + r < T) ? src[working_index(t0 + r, k, lds, tile_rows, n_blocks, layout)] : 0.0;
     }
 #pragma unroll
-    for (int r = 0; r < PERM_ROWS; ++r)
+    for (int r = 0; r < ROWS; ++r)
         if (t0 + r < T) dst[(t0 + r) * ldd + i] = v[r];
 }
 static int permute(bool to_working, const double *src, int64_t lds, double *dst, int64_t ldd, const int32_t *inv,
@@ -428,9 +429,12 @@ static int permute(bool to_working, const double *src, int64_t lds, double *dst,
     } else if (to_working) {
         dim3 grid(gx, (unsigned)((T + PERM_ROWS - 1) / PERM_ROWS));
         permute_to_working<PERM_ROWS><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
+    } else if (layout == 2 && (tile_rows % 16) == 0) {
+        dim3 grid(gx, (unsigned)((T + 15) / 16));
+        permute_to_user<16><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
     } else {
         dim3 grid(gx, (unsigned)((T + PERM_ROWS - 1) / PERM_ROWS));
-        permute_to_user<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
+        permute_to_user<PERM_ROWS><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
     }
     CK(cudaGetLastError());
     rr_count_launch(1);
@@ -468,7 +472,7 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     // lateral: reach-major tiles (whole-sector scatter in the permute, 256-bit loads in the kernel); discharge:
     // row-major tiles (coalesced row stores in the kernel, sector-sharing gathers in the permute) -- measured best
     const int layout = !tiled ? 0 : (p->opts.staging == 3 ? 1 : 2);
-    const int out_layout = !tiled ? 0 : 1;
+    const int out_layout = !tiled ? 0 : (p->opts.staging == 4 ? 2 : 1);
     const int64_t trows = tiled ? tile_rows_for(p, T, K) : 0;
     const int64_t tpitch = ((trows + 3) & ~(int64_t)3);
     const int64_t n_tiles = tiled ? (T + trows - 1) / trows : 0;

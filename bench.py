@@ -322,7 +322,8 @@ def main():
     h_lat = rr.pinned_empty((er, n))
     h_out = rr.pinned_empty((er, n))
     h_lat[:] = d_lat[:er, :n].cpu().numpy()
-    h_q = np.zeros(n)
+    h_q = rr.pinned_empty((n,))
+    h_q[:] = 0.0
     plan.route_host(rr.MODE_RAPID, h_q, h_lat, h_out, 1)          # warm-up (allocates the staging buffers)
     barrier()
     t0 = time.perf_counter()
@@ -337,7 +338,8 @@ def main():
     # the host path must agree with the device path on the same inputs (first chunk, zero state)
     d_chk_q = torch.zeros(n, dtype=torch.float64, device=dev)
     d_chk = torch.empty((er, ld), dtype=torch.float64, device=dev)
-    h_q2 = np.zeros(n)
+    h_q2 = rr.pinned_empty((n,))
+    h_q2[:] = 0.0
     plan.route_host(rr.MODE_RAPID, h_q2, h_lat, h_out, 1)
     plan.route_dev(rr.MODE_RAPID, d_chk_q.data_ptr(), d_lat.data_ptr(), ld, d_chk.data_ptr(), ld, er, 1, stream)
     torch.cuda.synchronize()

@@ -87,41 +87,77 @@ def shard(down, n_parts, part_id):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every few
+    milliseconds from a thread (the timed region is only a few hundred ms); nvidia-smi as a fallback."""
+    SMI_Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.samples, self.stop_flag, self.thread, self.proc = index, [], False, None, None
+        self.max_mhz = None
+
+    def _visible_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            try:
+                return int(vis.split(',')[self.index])
+            except Exception:
+                pass
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons = {'hw_slowdown': pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                       'hw_thermal_slowdown': pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                       'sw_thermal_slowdown': pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                       'sw_power_cap': pynvml.nvmlClocksThrottleReasonSwPowerCap}
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.samples.append((mhz, [k for k, bit in reasons.items() if mask & bit]))
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.SMI_Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self._visible_index()), '-lms', '50'], stdout=subprocess.PIPE, text=True)
+
+            def read():
+                names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+                for line in self.proc.stdout:
+                    f = [x.strip() for x in line.split(',')]
+                    try:
+                        self.max_mhz = float(f[2])
+                        self.samples.append((float(f[1]), [nm for nm, v in zip(names, f[5:9]) if v.lower().startswith('active')]))
+                    except Exception:
+                        continue
+            threading.Thread(target=read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.1)
             self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for l in self.lines:
-            f = [s.strip() for s in l.split(',')]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx = max(mx, float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+        sm = [x[0] for x in self.samples]
+        reasons = sorted({r for x in self.samples for r in x[1]})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.max_mhz, 'reasons': reasons,
                 'samples': len(sm)}
 
 

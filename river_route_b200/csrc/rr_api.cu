@@ -548,9 +548,9 @@ extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_fu
     const int64_t n = p->n;
     const int64_t ldd = ((n + 31) / 32) * 32;  // device rows start on 256-byte boundaries
     const int64_t rows_tile = std::max<int64_t>(1, p->opts.time_tile / substeps);   // largest tile: chunk granularity
-    // chunk: about 512 MiB per buffer so that H2D, routing and D2H of neighbouring chunks overlap; whole tiles
-    // when a chunk holds several
-    int64_t chunk = std::max<int64_t>(1, (512ll << 20) / (ldd * 8));
+    // chunk: about 256 MiB per buffer so that H2D, routing and D2H of neighbouring chunks overlap with little
+    // fill / drain; whole tiles when a chunk holds several
+    int64_t chunk = std::max<int64_t>(1, (256ll << 20) / (ldd * 8));
     if (chunk > rows_tile) chunk = (chunk / rows_tile) * rows_tile;
     chunk = std::min<int64_t>(chunk, T);
     const size_t need = (size_t)chunk * ldd;

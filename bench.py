@@ -332,6 +332,7 @@ def main():
     barrier()
     launches = rr.launch_count()
     ktimes = timing_read(reset=True)
+    prof = plan.read_profile()
     timing_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
@@ -401,7 +402,7 @@ def main():
                     'd2h_bytes_per_step': int(n * er * 8 + n * 8), 'rows_per_step': er, 'steps': args.e2e_steps,
                     'api': 'Plan.route_host (pinned host arrays, chunked cudaMemcpyAsync inside rr_route_host)',
                     'host_equals_device_path': host_equals_dev},
-            'gpu_launches': int(launches),
+            'gpu_launches': int(launches), 'kernel_phase_cycles': prof,
             'clocks': clocks,
             'checks': {'finite': finite, 'summary_per_rank[outlet_q_last_step, state_sum, reaches]': summary_all.tolist()},
         }

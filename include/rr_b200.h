@@ -183,6 +183,10 @@ int rr_weights_transform_host(int64_t n_rivers, int64_t n_points, int64_t T, con
                               int64_t ldx, double *y, int64_t ldy, int cumulative, int force_positive,
                               const double *area);
 
+/* Diagnostic cycle counters of the routing kernel (builds with -DRR_PROFILE; zeros otherwise), summed over warps:
+ * [0] ticket + decode, [1] per-item constants + dependency waits, [2] item body, [3] publish.  Resets on read. */
+int rr_plan_read_profile(rr_plan *p, uint64_t *out8);
+
 /* ---- pinned host memory for the streaming path ---------------------------------------------- */
 int rr_host_alloc(void **ptr, int64_t bytes);
 int rr_host_free(void *ptr);

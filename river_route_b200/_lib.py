@@ -65,6 +65,7 @@ def _load() -> C.CDLL:
                                                vp, vp]),
         'rr_weights_transform_host': (C.c_int, [i64, i64, i64, c_i32p, c_i32p, f64p, vp, C.c_int, i64, f64p, i64,
                                                 C.c_int, C.c_int, f64p]),
+        'rr_plan_read_profile': (C.c_int, [vp, C.POINTER(C.c_uint64)]),
         'rr_host_alloc': (C.c_int, [C.POINTER(vp), i64]),
         'rr_host_free': (C.c_int, [vp]),
         'rr_synth_forest': (C.c_int, [i64, i64, C.c_uint64, C.c_double, i64, C.c_double, c_i32p]),
@@ -84,7 +85,7 @@ EXPORTED_SYMBOLS = (
     'rr_last_error', 'rr_version', 'rr_cuda_available', 'rr_downstream_index', 'rr_label_basins',
     'rr_plan_create', 'rr_plan_destroy', 'rr_plan_get_info', 'rr_plan_set_coefficients', 'rr_route_dev',
     'rr_route_host', 'rr_route_ensemble_dev', 'rr_launch_count', 'rr_timing_enable', 'rr_timing_read', 'rr_uh_convolve_dev', 'rr_uh_convolve_host',
-    'rr_weights_transform_dev', 'rr_weights_transform_host', 'rr_host_alloc', 'rr_host_free', 'rr_synth_forest',
+    'rr_weights_transform_dev', 'rr_weights_transform_host', 'rr_plan_read_profile', 'rr_host_alloc', 'rr_host_free', 'rr_synth_forest',
     'rr_plan_get_arrays', 'rr_plan_schedule',
 )
 

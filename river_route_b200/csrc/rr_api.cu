@@ -98,7 +98,7 @@ struct rr_device_state {
     size_t raw_bytes = 0;
     int32_t *done = nullptr;
     size_t done_cap = 0;
-    unsigned long long *ticket = nullptr;
+    unsigned long long *ticket = nullptr, *prof = nullptr;
     int occ[3] = {0, 0, 0};
     // host streaming path
     cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
@@ -151,6 +151,8 @@ static int ensure_device(rr_plan *p) {
         CK(cudaMalloc((void **)&d->coef, sizeof(double) * 4 * (size_t)p->n));
         d->bytes += sizeof(double) * 4 * (size_t)p->n;
         CK(cudaMalloc((void **)&d->ticket, sizeof(unsigned long long)));
+        CK(cudaMalloc((void **)&d->prof, 8 * sizeof(unsigned long long)));
+        CK(cudaMemset(d->prof, 0, 8 * sizeof(unsigned long long)));
         CK(cudaStreamCreateWithFlags(&d->s_comp, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
@@ -179,7 +181,7 @@ void rr_device_release(rr_plan *p) {
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {d->up_ptr, d->up_idx, d->slot_src, d->export_id, d->dep_ptr, d->dep_idx, d->down, d->exp_ro, d->edge_ro,
-                    d->lvl_ptr, d->lvl_blk, d->skew, d->meta, d->coef, d->key_start, d->raw, d->done, d->ticket,
+                    d->lvl_ptr, d->lvl_blk, d->skew, d->meta, d->coef, d->key_start, d->raw, d->done, d->ticket, d->prof,
                     d->d_lat[0], d->d_lat[1], d->d_out[0], d->d_out[1], d->d_q, d->d_qfull,
                     d->inv, d->p_lat, d->p_out, d->p_q};
     for (void *q : ptrs)
@@ -311,7 +313,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.T = (int32_t)T; P.K = (int32_t)K; P.tile_rows = (int32_t)rows;
     P.raw_pitch = (int32_t)pitch; P.n_members = n_members; P.first_call = first_call; P.last_call = last_call;
     P.ldl = ldl; P.ldo = ldo;
-    P.raw = d->raw; P.done = d->done; P.ticket = d->ticket; P.q_init = q_init;
+    P.raw = d->raw; P.done = d->done; P.ticket = d->ticket; P.prof = d->prof; P.q_init = q_init;
     for (int m = 0; m < n_members; ++m) {
         P.lateral[m] = lateral ? lateral[m] : nullptr;
         P.out[m] = out[m];
@@ -608,6 +610,16 @@ extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_fu
     CK(cudaStreamSynchronize(d->s_comp));
     CK(cudaStreamSynchronize(d->s_out));
     CK(cudaStreamSynchronize(d->s_in));
+    return 0;
+}
+
+// Cycle counters of RR_PROFILE builds (zero otherwise): [0] ticket + decode, [1] constants + dependency waits,
+// [2] item body, [3] release; summed over warps.  Resets after reading.
+extern "C" int rr_plan_read_profile(rr_plan *p, uint64_t *out8) {
+    if (!p || !p->dev || !out8) { rr_set_error("no device state"); return 100; }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out8, p->dev->prof, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(p->dev->prof, 0, 8 * sizeof(uint64_t)));
     return 0;
 }
 

@@ -41,6 +41,16 @@
 #define RAW_CARRY 15  // row entry holding the value before the tile's first substep
 #define RAW_S0 16     // row entry of substep 0: the series starts on a 128-byte line
 
+#ifdef RR_PROFILE
+#define PROF_DECL long long prof_t = clock64(); unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_MARK(k) { const long long n_ = clock64(); prof_acc[k] += (unsigned long long)(n_ - prof_t); prof_t = n_; }
+#define PROF_FLUSH if ((threadIdx.x & 31) == 0 && P.prof) { for (int k_ = 0; k_ < 8; ++k_) atomicAdd(P.prof + k_, prof_acc[k_]); }
+#else
+#define PROF_DECL
+#define PROF_MARK(k)
+#define PROF_FLUSH
+#endif
+
 namespace {
 
 __device__ __forceinline__ int32_t ld_relaxed(const int32_t *p) {
@@ -58,6 +68,7 @@ __device__ __forceinline__ void st_release(int32_t *p, int32_t v) {
 }
 // Spin with relaxed loads (an acquire load invalidates the SM's L1 on every poll), then acquire once.
 __device__ __forceinline__ void wait_ge(const int32_t *flag, int32_t want) {
+    if (ld_acquire(flag) >= want) return;          // the common case: one round trip
     unsigned ns = 32;
     while (ld_relaxed(flag) < want) {
         __nanosleep(ns);
@@ -65,6 +76,8 @@ __device__ __forceinline__ void wait_ge(const int32_t *flag, int32_t want) {
     }
     (void)ld_acquire(flag);
 }
+// latency mode (narrow levels of the block DAG, where the launch is dependency bound rather than bandwidth bound)
+__device__ __forceinline__ void prefetch_l2_now(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // L2 prefetch hints are compiled out by default: measured on B200 the kernel is limited by L2 transaction
 // throughput (~2.4 L2 bytes per DRAM byte), and every prefetched line crosses L2 twice (-7% with them on).
 #ifdef RR_L2_PREFETCH
@@ -100,6 +113,10 @@ struct item_ctx {
     int m, b, j, lane;
     int64_t i;
     bool valid, use_init;
+    bool narrow;                 // the block's level has few blocks: optimise the item for latency, not bandwidth
+#ifdef RR_PROFILE
+    mutable unsigned long long prof_wait, prof_setup;
+#endif
     int t0, rows, TT;
     double *raw_m;
     double c1, c2, c3, c4, q;   // q = state before the tile (UNIT: q_ch)
@@ -116,6 +133,9 @@ struct item_ctx {
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int NS, bool VEC>
 __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_ctx &c) {
+#ifdef RR_PROFILE
+    const long long s0_ = clock64();
+#endif
     const double c1 = c.c1, c2 = c.c2, c3 = c.c3, c4 = c.c4;
     const int e0 = c.e0, deg = c.deg, ex = c.ex;
     double q = c.q;
@@ -144,89 +164,72 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
     const int64_t ldl = c.lstride, ldo = c.ostride;
     const int TT = c.TT;
 
-    // operands of the first group: the carry-in and the sector with the values of steps 0..3
+    // Software pipeline, two groups (8 time steps) deep: while group g is computed, the loads of groups g+1 and
+    // g+2 are in flight.  Under load one memory round trip takes ~2500 cycles, a group ~600 cycles of arithmetic.
+    auto lat_group = [&](int s0) -> d4 {
+        d4 v{0, 0, 0, 0};
+        if (!(HAS_LAT && c.valid) || s0 >= TT) return v;
+        if (VEC) return ld_sector_ro(lat + s0);    // this reach's rows are contiguous (padded to a multiple of 4)
+        const double *lp = lat + (size_t)s0 * ldl;
+        v.a = ld_stream(lp);
+        if (s0 + 1 < TT) v.b = ld_stream(lp + ldl);
+        if (s0 + 2 < TT) v.c = ld_stream(lp + 2 * ldl);
+        if (s0 + 3 < TT) v.d = ld_stream(lp + 3 * ldl);
+        return v;
+    };
     double old[NA];   // upstream value before the group's first substep
-    d4 nxt[NA];
+    d4 nxt[NA], fut[NA];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         old[k] = 0.0;
-        nxt[k] = d4{0, 0, 0, 0};
+        nxt[k] = fut[k] = d4{0, 0, 0, 0};
         if (has[k]) {
-            // the series is consumed line by line (16 steps = 128 B): keep two lines ahead in L2 so the
-            // register lookahead below only has to cover L2 latency, not DRAM latency
-            prefetch_l2(up[k] + RAW_S0 + 16);
-            if (TT > 32) prefetch_l2(up[k] + RAW_S0 + 32);
             old[k] = up[k][RAW_CARRY];
             nxt[k] = ld_sector(up[k] + RAW_S0);
+            if (4 < TT) fut[k] = ld_sector(up[k] + RAW_S0 + 4);
         }
     }
-    double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
-    if (HAS_LAT && c.valid) {
-        if (VEC) {   // rows of this reach are contiguous (and padded to a multiple of 4): one 256-bit load
-            prefetch_l2(lat + 16);
-            const d4 v = ld_sector_ro(lat);
-            l0 = v.a; l1 = v.b; l2 = v.c; l3 = v.d;
-        } else {
-            l0 = ld_stream(lat);
-            if (1 < TT) l1 = ld_stream(lat + ldl);
-            if (2 < TT) l2 = ld_stream(lat + 2 * ldl);
-            if (3 < TT) l3 = ld_stream(lat + 3 * ldl);
-        }
-    }
+    d4 lcur = lat_group(0), lnxt = lat_group(4);
+#ifdef RR_PROFILE
+    __syncwarp();
+    c.prof_setup = (unsigned long long)(clock64() - s0_);
+#endif
     for (int s = 0; s < TT; s += 4) {
-        // ---- issue the next group's loads before computing this one ----
-        d4 fut[NA];
-        double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-        const bool more = s + 4 < TT;
+        // ---- issue the loads of group g+2 ----
+        d4 far[NA];
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            fut[k] = d4{0, 0, 0, 0};
-            if (has[k] && more) fut[k] = ld_sector(up[k] + RAW_S0 + s + 4);
-            if (has[k] && (s & 15) == 0 && s + 48 < TT) prefetch_l2(up[k] + RAW_S0 + s + 48);
+            far[k] = d4{0, 0, 0, 0};
+            if (has[k] && s + 8 < TT) far[k] = ld_sector(up[k] + RAW_S0 + s + 8);
         }
-        if (HAS_LAT && VEC) {
-            if (c.valid && (s & 15) == 0 && s + 32 < TT) prefetch_l2(lat + s + 32);
-            if (c.valid && more) { const d4 v = ld_sector_ro(lat + s + 4); n0 = v.a; n1 = v.b; n2 = v.c; n3 = v.d; }
-        }
-        if (HAS_LAT && !VEC && (s & 7) == 0 && c.lane < 16) {
-            // rows s+16 .. s+23, two 128-byte lines each, one line per lane
-            const int r = s + 16 + (c.lane >> 1);
-            if (r < TT) prefetch_l2((const char *)(lat - c.lane + (size_t)r * ldl) + (c.lane & 1) * 128);
-        }
-        if (HAS_LAT && !VEC && c.valid && more) {
-            const double *lp = lat + (size_t)(s + 4) * ldl;
-            n0 = ld_stream(lp);
-            if (s + 5 < TT) n1 = ld_stream(lp + ldl);
-            if (s + 6 < TT) n2 = ld_stream(lp + 2 * ldl);
-            if (s + 7 < TT) n3 = ld_stream(lp + 3 * ldl);
-        }
+        const d4 lfar = lat_group(s + 8);
         // ---- four substeps; old = value before the substep, new = value after it ----
         // step s: old = old[k], new = nxt.a;  step s+1: old = nxt.a, new = nxt.b;  ...
         double r0, r1, r2, r3;
         {
             double r = c3 * q;                                       // _numba_kernels.py:27-28 / :68-69
-            if (HAS_LAT) r = fma(c4, l0, r);
+            if (HAS_LAT) r = fma(c4, lcur.a, r);
 #pragma unroll
             for (int k = 0; k < NS; ++k) r = fma(c2, old[k], r);     // :29-33 / :70-74, ascending upstream
 #pragma unroll
             for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].a, r);   // :36-39 / :75-78 (lhs_off = -c1)
             r0 = r;
             r = c3 * r0;
-            if (HAS_LAT) r = fma(c4, l1, r);
+            if (HAS_LAT) r = fma(c4, lcur.b, r);
 #pragma unroll
             for (int k = 0; k < NS; ++k) r = fma(c2, nxt[k].a, r);
 #pragma unroll
             for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].b, r);
             r1 = r;
             r = c3 * r1;
-            if (HAS_LAT) r = fma(c4, l2, r);
+            if (HAS_LAT) r = fma(c4, lcur.c, r);
 #pragma unroll
             for (int k = 0; k < NS; ++k) r = fma(c2, nxt[k].b, r);
 #pragma unroll
             for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].c, r);
             r2 = r;
             r = c3 * r2;
-            if (HAS_LAT) r = fma(c4, l3, r);
+            if (HAS_LAT) r = fma(c4, lcur.d, r);
 #pragma unroll
             for (int k = 0; k < NS; ++k) r = fma(c2, nxt[k].c, r);
 #pragma unroll
@@ -246,8 +249,9 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
         if (myraw) st_sector(myraw + RAW_S0 + s, r0, r1, r2, r3);
         q = (s + 3 < TT) ? r3 : ((s + 2 < TT) ? r2 : ((s + 1 < TT) ? r1 : r0));
 #pragma unroll
-        for (int k = 0; k < NS; ++k) { old[k] = nxt[k].d; nxt[k] = fut[k]; }
-        l0 = n0; l1 = n1; l2 = n2; l3 = n3;
+        for (int k = 0; k < NS; ++k) { old[k] = nxt[k].d; nxt[k] = fut[k]; fut[k] = far[k]; }
+        lcur = lnxt;
+        lnxt = lfar;
     }
     if (c.valid) P.q_state[c.m][c.i] = q;
 }
@@ -526,6 +530,7 @@ __device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c,
     c.deg = valid ? __ldg(P.up_ptr + ic + 1) - c.e0 : 0;
     c.ex = valid ? __ldg(P.export_id + ic) : -1;
     c.M = P.meta[b];
+    c.narrow = false;
     c.t0 = j * P.tile_rows;
     c.rows = min(P.tile_rows, P.T - c.t0);
     c.TT = c.rows * P.K;
@@ -568,8 +573,11 @@ __device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c,
         }
     }
     // ---- dependencies ----
+#ifdef RR_PROFILE
+    const long long w0_ = clock64();
+#endif
     int32_t *done = P.done + (size_t)m * P.n_blocks;
-    if (lane == 0) wait_ge(done + b, j);                                // own previous tile (acquire)
+    if (lane == 0 && j > 0) wait_ge(done + b, j);                       // own previous tile (acquire)
     for (int e = P.dep_ptr[b] + lane; e < P.dep_ptr[b + 1]; e += 32)    // upstream blocks, this tile
         wait_ge(done + P.dep_idx[e], j + 1);
     if (c.ex >= 0) {                                                    // exchange-ring reuse
@@ -577,6 +585,10 @@ __device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c,
         if (j >= ring) wait_ge(done + __ldg(P.down + i) / RR_BLOCK, j - ring + 1);
     }
     __syncwarp();
+#ifdef RR_PROFILE
+    c.prof_wait = (unsigned long long)(clock64() - w0_);
+    c.prof_setup = 0;
+#endif
     // first tile of a reference call: every member starts from the shared initial state and
     // (UNIT) q_ch = q_full = state (UnitMuskingum.py:78-79); later tiles / chunks continue
     // from the member's own running state.
@@ -732,15 +744,27 @@ __global__ void __launch_bounds__(256, RR_MIN_CTAS) rr_wavefront_kernel(const __
     constexpr bool UNIT = (MODE == RR_MODE_UNIT);
     const int lane = threadIdx.x & 31;
     int m, b, j;
-    while (next_item(P, lane, m, b, j)) {
+    PROF_DECL
+    for (;;) {
+        const bool more = next_item(P, lane, m, b, j);
+        PROF_MARK(0)
+        if (!more) break;
         item_ctx c;
         open_item<MODE>(P, c, lane, m, b, j);
+        PROF_MARK(1)
         // plan flag 0x40: no in-block edges and max in-degree <= RR_MAX_FAST_DEG
         if (!UNIT && P.K == 1 && (c.M.int_mask & 0x40)) register_fast_item<MODE>(P, c);
         else general_item<MODE>(P, c);
         __syncwarp();
+        PROF_MARK(2)
+#ifdef RR_PROFILE
+        prof_acc[4] += c.prof_wait; prof_acc[5] += c.prof_setup; prof_acc[6] += 1;
+#endif
         if (lane == 0) st_release(P.done + (size_t)m * P.n_blocks + b, j + 1);
+        __syncwarp();
+        PROF_MARK(3)
     }
+    PROF_FLUSH
 }
 
 // Persistent kernel of the TMA-staged path: 4 warps per CTA, one CTA per SM, each warp owns a private

@@ -48,6 +48,7 @@ struct rr_route_params {
     double *raw;          // [member][raw_rows][raw_pitch]
     int32_t *done;        // [member][n_blocks] tiles completed
     unsigned long long *ticket;
+    unsigned long long *prof;   // optional [8] cycle counters (RR_PROFILE builds), else nullptr
     const double *q_init;                       // shared initial state
     const double *lateral[RR_MAX_MEMBERS];
     double *out[RR_MAX_MEMBERS];

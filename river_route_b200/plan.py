@@ -160,6 +160,12 @@ class Plan:
                                         int(ldo), arr(*q_final_ptrs), int(T), int(substeps),
                                         C.c_void_p(stream or None)))
 
+    def read_profile(self):
+        """Cycle counters of -DRR_PROFILE builds: ticket/decode, constants+waits, item body, publish (summed over warps)."""
+        out = (C.c_uint64 * 8)()
+        check(lib.rr_plan_read_profile(self._h, out))
+        return list(out)
+
     # ---- introspection (tests, DESIGN.md numbers) ----
     def arrays(self) -> dict:
         inf = self.info

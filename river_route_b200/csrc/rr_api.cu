@@ -468,9 +468,9 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
     if (T <= 0 || K <= 0) { rr_set_error("T and substeps must be positive"); return 100; }
     // working arrays: tile-major for the TMA-staged kernel (one substep per row, not UnitMuskingum), else row-major
-    // working arrays: row-major (staging 1, substeps, UnitMuskingum), [tile][block][row][lane] for the TMA-staged
+    // working arrays: row-major (staging 1, substeps), [tile][block][row][lane] for the TMA-staged
     // kernel (3), [tile][block][lane][row] otherwise (register path: whole-sector accesses everywhere)
-    const bool tiled = (K == 1 && !unit && p->opts.staging != 1);
+    const bool tiled = (K == 1 && p->opts.staging != 1 && !(unit && p->opts.staging == 3));
     // lateral: reach-major tiles (whole-sector scatter in the permute, 256-bit loads in the kernel); discharge:
     // row-major tiles (coalesced row stores in the kernel, sector-sharing gathers in the permute) -- measured best
     const int layout = !tiled ? 0 : (p->opts.staging == 3 ? 1 : 2);

@@ -109,6 +109,15 @@ __device__ __forceinline__ void st_sector(double *p, double a, double b, double 
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
+// Lateral inflow of working reach u at row `row` of tile j (UnitMuskingum reads its upstreams' laterals).
+__device__ __forceinline__ const double *lat_ptr(const rr_route_params &P, int m, int j, int t0, int64_t u, int row) {
+    if (P.tile_major == 2)
+        return P.lateral[m] + (((size_t)j * P.n_blocks + (size_t)(u >> 5)) * RR_BLOCK + (size_t)(u & 31)) * (size_t)P.tile_pitch + row;
+    if (P.tile_major == 1)
+        return P.lateral[m] + (((size_t)j * P.n_blocks + (size_t)(u >> 5)) * (size_t)P.tile_rows + row) * RR_BLOCK + (u & 31);
+    return P.lateral[m] + (size_t)(t0 + row) * P.ldl + u;
+}
+
 struct item_ctx {
     int m, b, j, lane;
     int64_t i;
@@ -257,6 +266,139 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// UnitMuskingum fast path: K == 1, no in-block edges, at most NS upstreams per reach.
+// Headwater lanes copy their lateral inflow to the output (unclamped, _numba_kernels.py:122-123); inner
+// lanes read, per upstream, its lateral series (from the lateral working array) and -- for inner upstreams --
+// its exported q_ch series; q_full_old of an upstream is q_ch_old + its lateral of the previous step (:165).
+// ------------------------------------------------------------------------------------------------
+template <int NS, bool VEC>
+__device__ __forceinline__ void unit_fast_item(const rr_route_params &P, const item_ctx &c) {
+    constexpr int NA = NS > 0 ? NS : 1;
+    const double c1 = c.c1, c2 = c.c2, c3 = c.c3;
+    const int e0 = c.e0, deg = c.deg, ex = c.ex, j = c.j, m = c.m, TT = c.TT;
+    const bool inner = deg > 0;
+    const double *lat = c.lat0;
+    double *outp = c.out0;
+    const int64_t ldl = c.lstride, ldo = c.ostride;
+    double q = c.q;                                                      // q_ch
+    double qf = c.use_init ? q : (c.valid ? P.q_full[m][c.i] : 0.0);     // q_full (UnitMuskingum.py:78-79)
+    const double *ex_row[NA];      // exported q_ch series of an inner upstream (nullptr: headwater upstream)
+    const double *lu_row[NA];      // lateral series of the upstream
+    int64_t lu_stride = 1;
+    bool has[NA], hw[NA];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        has[k] = k < deg;
+        hw[k] = false;
+        ex_row[k] = nullptr;
+        lu_row[k] = c.raw_m;
+        if (has[k]) {
+            const int32_t sk = __ldg(P.slot_src + e0 + k);
+            hw[k] = (sk & RR_SLOT_HW_BIT) != 0;
+            const int64_t u = __ldg(P.up_idx + e0 + k);
+            lu_row[k] = lat_ptr(P, m, j, c.t0, u, 0);
+            if (!hw[k]) {
+                const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + e0 + k);
+                ex_row[k] = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+            }
+        }
+    }
+    if (P.tile_major == 1) lu_stride = RR_BLOCK; else if (P.tile_major == 0) lu_stride = P.ldl;
+    double *myraw = nullptr;
+    if (ex >= 0 && inner) {
+        const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + ex);
+        myraw = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+        myraw[RAW_CARRY] = q;
+        myraw[RAW_QF] = qf;
+    }
+    auto group = [&](const double *p, int64_t stride, int s0, bool on, bool vec) -> d4 {
+        d4 v{0, 0, 0, 0};
+        if (!on || s0 >= TT) return v;
+        if (vec) return ld_sector_ro(p + s0);
+        const double *lp = p + (size_t)s0 * stride;
+        v.a = ld_stream(lp);
+        if (s0 + 1 < TT) v.b = ld_stream(lp + stride);
+        if (s0 + 2 < TT) v.c = ld_stream(lp + 2 * stride);
+        if (s0 + 3 < TT) v.d = ld_stream(lp + 3 * stride);
+        return v;
+    };
+    const bool uvec = P.tile_major == 2;
+    // state carried between groups: per inner upstream its q_full before the group's first substep
+    double qfo[NA];
+    d4 exn[NA], lun[NA];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        qfo[k] = 0.0;
+        exn[k] = d4{0, 0, 0, 0};
+        if (has[k] && !hw[k]) { qfo[k] = ex_row[k][RAW_QF]; exn[k] = ld_sector(ex_row[k] + RAW_S0); }
+        lun[k] = group(lu_row[k], lu_stride, 0, has[k], uvec);
+    }
+    d4 lcur = group(lat, ldl, 0, c.valid, VEC);
+    double l_last = 0.0;
+    for (int s = 0; s < TT; s += 4) {
+        d4 exf[NA], luf[NA];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            exf[k] = d4{0, 0, 0, 0};
+            if (has[k] && !hw[k] && s + 4 < TT) exf[k] = ld_sector(ex_row[k] + RAW_S0 + s + 4);
+            luf[k] = group(lu_row[k], lu_stride, s + 4, has[k], uvec);
+        }
+        const d4 lnxt = group(lat, ldl, s + 4, c.valid, VEC);
+        const double lv[4] = {lcur.a, lcur.b, lcur.c, lcur.d};
+        double r4[4], o4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double a_in = 0.0, a_hw = 0.0;                               // :126-139, ascending upstream per class
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const double l = u == 0 ? lun[k].a : (u == 1 ? lun[k].b : (u == 2 ? lun[k].c : lun[k].d));
+                if (has[k]) { if (hw[k]) a_hw += l; else a_in += l; }
+            }
+            double r = c1 * (a_in + a_hw) + c2 * a_hw;                   // :142-143, :151
+            r = r + c3 * q;
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (has[k] && !hw[k]) r = fma(c2, qfo[k], r);            // :152-156  c2 * q_full_old[upstream]
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const double qn = u == 0 ? exn[k].a : (u == 1 ? exn[k].b : (u == 2 ? exn[k].c : exn[k].d));
+                if (has[k] && !hw[k]) r = fma(c1, qn, r);                // :159-162  lhs_off = -c1
+            }
+            // upstream q_full after this substep = its q_ch + its lateral (:165-166), used by the next substep
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const double qn = u == 0 ? exn[k].a : (u == 1 ? exn[k].b : (u == 2 ? exn[k].c : exn[k].d));
+                const double l = u == 0 ? lun[k].a : (u == 1 ? lun[k].b : (u == 2 ? lun[k].c : lun[k].d));
+                qfo[k] = qn + l;
+            }
+            r4[u] = r;
+            if (s + u < TT) {
+                l_last = lv[u];
+                if (inner) { q = r; qf = r + lv[u]; o4[u] = qf > 0.0 ? qf : 0.0; }   // :165-171 (K == 1: mean == value)
+                else o4[u] = lv[u];                                                    // :122-123
+            } else o4[u] = 0.0;
+        }
+        if (c.valid && ldo == 1) st_sector(outp + s, o4[0], o4[1], o4[2], o4[3]);
+        else if (c.valid) {
+            double *o = outp + (size_t)s * ldo;
+            o[0] = o4[0];
+            if (s + 1 < TT) o[ldo] = o4[1];
+            if (s + 2 < TT) o[2 * ldo] = o4[2];
+            if (s + 3 < TT) o[3 * ldo] = o4[3];
+        }
+        if (myraw) st_sector(myraw + RAW_S0 + s, r4[0], r4[1], r4[2], r4[3]);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { exn[k] = exf[k]; lun[k] = luf[k]; }
+        lcur = lnxt;
+    }
+    if (c.valid) {
+        const bool last = (j == P.n_tiles - 1);
+        if (last && P.last_call) P.q_state[m][c.i] = inner ? qf : l_last;    // UnitMuskingum.py:94-98
+        else { P.q_state[m][c.i] = q; P.q_full[m][c.i] = qf; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // General path: systolic item with shuffles -- any skew, any in-degree, any number of substeps,
 // UnitMuskingum.  Ends with the state write-back (the caller publishes done[b]).
 // ------------------------------------------------------------------------------------------------
@@ -361,14 +503,14 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
                 for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
                     if (k < deg) {
                         lu_old[k] = lu[k];
-                        lu[k] = ld_stream(P.lateral[m] + (size_t)(t0 + row) * P.ldl + ug[k]);
+                        lu[k] = ld_stream(lat_ptr(P, m, j, t0, ug[k], row));
                         const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
                         if (hw) a_hw += lu[k]; else a_in += lu[k];
                     }
                 }
                 for (int k = RR_MAX_FAST_DEG; k < deg; ++k) {
                     const int32_t sk = __ldg(P.slot_src + e0 + k);
-                    const double l = ld_stream(P.lateral[m] + (size_t)(t0 + row) * P.ldl + __ldg(P.up_idx + e0 + k));
+                    const double l = ld_stream(lat_ptr(P, m, j, t0, __ldg(P.up_idx + e0 + k), row));
                     const bool hw = sk >= 0 ? (sk & RR_SLOT_HW_BIT) != 0 : (((-sk - 1) >> 6) & 1) != 0;
                     if (hw) a_hw += l; else a_in += l;
                 }
@@ -412,7 +554,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
                         else if (s == 0) v = q[RAW_QF];
                         else {
                             const int prow = (sub == 0) ? row - 1 : row;
-                            v = q[RAW_CARRY + s] + ld_stream(P.lateral[m] + (size_t)(t0 + prow) * P.ldl + __ldg(P.up_idx + e0 + k));
+                            v = q[RAW_CARRY + s] + ld_stream(lat_ptr(P, m, j, t0, __ldg(P.up_idx + e0 + k), prow));
                         }
                     } else v = q[RAW_CARRY + s];
                 } else if (use && UNIT && (((-sk - 1) >> 6) & 1)) use = false;
@@ -754,7 +896,14 @@ __global__ void __launch_bounds__(256, RR_MIN_CTAS) rr_wavefront_kernel(const __
         PROF_MARK(1)
         // plan flag 0x40: no in-block edges and max in-degree <= RR_MAX_FAST_DEG
         if (!UNIT && P.K == 1 && (c.M.int_mask & 0x40)) register_fast_item<MODE>(P, c);
-        else general_item<MODE>(P, c);
+        else if (UNIT && P.K == 1 && (c.M.int_mask & 0x40) && c.M.max_deg <= 2) {
+            const bool vec = P.tile_major == 2;
+            switch (c.M.max_deg) {
+                case 0: if (vec) unit_fast_item<0, true>(P, c); else unit_fast_item<0, false>(P, c); break;
+                case 1: if (vec) unit_fast_item<1, true>(P, c); else unit_fast_item<1, false>(P, c); break;
+                default: if (vec) unit_fast_item<2, true>(P, c); else unit_fast_item<2, false>(P, c); break;
+            }
+        } else general_item<MODE>(P, c);
         __syncwarp();
         PROF_MARK(2)
 #ifdef RR_PROFILE

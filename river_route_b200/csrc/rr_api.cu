@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -212,8 +213,10 @@ static int64_t tile_rows_for(const rr_plan *p, int64_t T, int64_t K) {
         for (int64_t cand : {64, 32, 16}) {
             const double overhead = cand == 64 ? 1.0 : (cand == 32 ? 1.18 : 1.6);
             const double stream_us = (double)p->n * (double)T * (double)K * 33.0 / 4.6e6 * overhead;   // bytes / (B/us)
-            const double n_tiles = std::ceil((double)T * K / (double)cand);
-            const double critical_us = ((double)p->max_level + n_tiles) * (5.0 + 0.4 * (double)cand);
+            const double rows = (double)std::max<int64_t>(1, cand / K);
+            const double n_tiles = std::ceil((double)T / rows);
+            // measured with the kernel's cycle counters: ~12 us of per-item setup + ~0.35 us per substep
+            const double critical_us = ((double)p->max_level + n_tiles) * (12.0 + 0.35 * rows * (double)K);
             const double est = std::max(stream_us, critical_us) + 0.3 * std::min(stream_us, critical_us);
             if (est < best) { best = est; tile = cand; }
         }
@@ -319,6 +322,11 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
         P.out[m] = out[m];
         P.q_state[m] = q_state[m];
         P.q_full[m] = q_full ? q_full[m] : nullptr;
+    }
+    {   // ticket batching: large launches are limited by the single-address atomic rate, small ones by latency
+        const char *env = getenv("RR_TICKET_BATCH");
+        const int64_t resident_warps = (int64_t)d->sm_count * 16;
+        P.ticket_batch = env ? std::max(1, atoi(env)) : 1;   // measured: batching hurts (neighbouring blocks should run concurrently)
     }
     CK(cudaMemsetAsync(d->done, 0, done_need * sizeof(int32_t), stream));
     CK(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), stream));

@@ -32,6 +32,12 @@
 
 #include "rr_route.cuh"
 
+#ifndef RR_SPIN_NS0
+#define RR_SPIN_NS0 64
+#endif
+#ifndef RR_SPIN_NSMAX
+#define RR_SPIN_NSMAX 4096
+#endif
 #ifndef RR_MIN_CTAS
 #define RR_MIN_CTAS 2
 #endif
@@ -69,10 +75,10 @@ __device__ __forceinline__ void st_release(int32_t *p, int32_t v) {
 // Spin with relaxed loads (an acquire load invalidates the SM's L1 on every poll), then acquire once.
 __device__ __forceinline__ void wait_ge(const int32_t *flag, int32_t want) {
     if (ld_acquire(flag) >= want) return;          // the common case: one round trip
-    unsigned ns = 32;
+    unsigned ns = RR_SPIN_NS0;
     while (ld_relaxed(flag) < want) {
         __nanosleep(ns);
-        if (ns < 512) ns <<= 1;
+        if (ns < RR_SPIN_NSMAX) ns <<= 1;
     }
     (void)ld_acquire(flag);
 }
@@ -266,6 +272,97 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast path for K > 1 routing substeps per row (dt_routing < dt_runoff): same register blocking over
+// substeps; the lateral value changes and the interval mean is written every K substeps
+// (_numba_kernels.py:60-84 / :19-46).
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int NS>
+__device__ __forceinline__ void fast_item_k(const rr_route_params &P, const item_ctx &c) {
+    constexpr bool HAS_LAT = (MODE == RR_MODE_RAPID);
+    constexpr int NA = NS > 0 ? NS : 1;
+    const double c1 = c.c1, c2 = c.c2, c3 = c.c3, c4 = c.c4;
+    const int e0 = c.e0, deg = c.deg, ex = c.ex, j = c.j, K = P.K, TT = c.TT;
+    const double inv_k = 1.0 / (double)K;
+    double q = c.q;
+    const double *up[NA];
+    bool has[NA];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        has[k] = k < deg;
+        up[k] = c.raw_m;
+        if (has[k]) {
+            const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + e0 + k);
+            up[k] = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+        }
+    }
+    double *myraw = nullptr;
+    if (ex >= 0) {
+        const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + ex);
+        myraw = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+        myraw[RAW_CARRY] = q;
+    }
+    const double *lat = c.lat0;
+    double *outp = c.out0;
+    const int64_t ldl = c.lstride, ldo = c.ostride;
+    double old[NA];
+    d4 nxt[NA];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        old[k] = 0.0;
+        nxt[k] = d4{0, 0, 0, 0};
+        if (has[k]) { old[k] = up[k][RAW_CARRY]; nxt[k] = ld_sector(up[k] + RAW_S0); }
+    }
+    double ql = 0.0, ql_next = 0.0, acc = 0.0;
+    int sub = 0, row = 0;
+    if (HAS_LAT && c.valid) {
+        ql = ld_stream(lat);
+        if (1 < c.rows) ql_next = ld_stream(lat + ldl);
+    }
+    for (int s = 0; s < TT; s += 4) {
+        d4 fut[NA];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            fut[k] = d4{0, 0, 0, 0};
+            if (has[k] && s + 4 < TT) fut[k] = ld_sector(up[k] + RAW_S0 + s + 4);
+        }
+        double r4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double r = c3 * q;                                        // :27-28 / :68-69
+            if (HAS_LAT) r = fma(c4, ql, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const double vo = u == 0 ? old[k] : (u == 1 ? nxt[k].a : (u == 2 ? nxt[k].b : nxt[k].c));
+                r = fma(c2, vo, r);                                   // :29-33 / :70-74
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const double vn = u == 0 ? nxt[k].a : (u == 1 ? nxt[k].b : (u == 2 ? nxt[k].c : nxt[k].d));
+                r = fma(c1, vn, r);                                   // :36-39 / :75-78
+            }
+            r4[u] = r;
+            if (s + u < TT) {
+                q = r;
+                acc += r;                                             // :41-42 / :79-80
+                if (++sub == K) {
+                    const double v = acc * inv_k;                     // :44-46 / :82-84
+                    if (c.valid) outp[(size_t)row * ldo] = v > 0.0 ? v : 0.0;
+                    acc = 0.0;
+                    sub = 0;
+                    ++row;
+                    ql = ql_next;
+                    if (HAS_LAT && c.valid && row + 1 < c.rows) ql_next = ld_stream(lat + (size_t)(row + 1) * ldl);
+                }
+            }
+        }
+        if (myraw) st_sector(myraw + RAW_S0 + s, r4[0], r4[1], r4[2], r4[3]);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { old[k] = nxt[k].d; nxt[k] = fut[k]; }
+    }
+    if (c.valid) P.q_state[c.m][c.i] = q;
+}
+
+// ------------------------------------------------------------------------------------------------
 // UnitMuskingum fast path: K == 1, no in-block edges, at most NS upstreams per reach.
 // Headwater lanes copy their lateral inflow to the output (unclamped, _numba_kernels.py:122-123); inner
 // lanes read, per upstream, its lateral series (from the lateral working array) and -- for inner upstreams --
@@ -402,6 +499,10 @@ __device__ __forceinline__ void unit_fast_item(const rr_route_params &P, const i
 // General path: systolic item with shuffles -- any skew, any in-degree, any number of substeps,
 // UnitMuskingum.  Ends with the state write-back (the caller publishes done[b]).
 // ------------------------------------------------------------------------------------------------
+// GEN_SLOTS upstream slots are kept in registers (2: every reach of a binary network); further upstreams go
+// through the slow loops.  Four register slots made this function spill, and its spill reloads miss L1 whenever
+// another warp of the SM executes an acquire (L1 invalidate): ~3000 cycles per step on the critical path.
+#define GEN_SLOTS 2
 template <int MODE>
 __device__ __noinline__ void general_item(const rr_route_params &P, const item_ctx &c) {
     constexpr bool HAS_LAT = (MODE != RR_MODE_MUSKINGUM);
@@ -419,24 +520,28 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
     const double inv_k = 1.0 / (double)K;  // _numba_kernels.py:19, :60, :104
     (void)b;
     const int d = __ldg(P.skew + ic);
-    const int nfast = M.max_deg < RR_MAX_FAST_DEG ? M.max_deg : RR_MAX_FAST_DEG;
+    const int nfast = M.max_deg < GEN_SLOTS ? M.max_deg : GEN_SLOTS;
     auto raw_row = [&](int e) -> double * {   // e = entry of the upstream-CSR (an external edge)
         const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + e);
         return raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
     };
-    int32_t src[RR_MAX_FAST_DEG];
-    const double *rp[RR_MAX_FAST_DEG];   // exported series of an external upstream
-    int ilane[RR_MAX_FAST_DEG];          // lane of an in-block upstream (own lane if none)
-    int64_t ug[RR_MAX_FAST_DEG];         // UNIT: global index of the upstream reach
+    int32_t src[GEN_SLOTS];
+    const double *rp[GEN_SLOTS];   // exported series of an external upstream
+    int ilane[GEN_SLOTS];          // lane of an in-block upstream (own lane if none)
+    int64_t ug[GEN_SLOTS];         // UNIT: global index of the upstream reach
 #pragma unroll
-    for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+    for (int k = 0; k < GEN_SLOTS; ++k) {
         src[k] = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
         rp[k] = nullptr;
         ilane[k] = lane;
         ug[k] = 0;
         if (src[k] != SLOT_NONE) {
-            if (src[k] >= 0) rp[k] = raw_row(e0 + k);
-            else ilane[k] = (-src[k] - 1) & 31;
+            if (src[k] >= 0) {
+                rp[k] = raw_row(e0 + k);
+                // items on this path sit on the critical path of deep networks (chains inside a block): get the
+                // whole upstream series moving towards L2 now, the loop then only pays L1 / L2 hits
+                for (int e = 0; e < TT; e += 16) prefetch_l2_now(rp[k] + RAW_S0 + e);
+            } else ilane[k] = (-src[k] - 1) & 31;
             if (UNIT) ug[k] = __ldg(P.up_idx + e0 + k);
         }
     }
@@ -458,10 +563,10 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
     }
 
     // one-step lookahead registers for the external series and the lateral row
-    double eo[RR_MAX_FAST_DEG], en[RR_MAX_FAST_DEG];
-    double lu[RR_MAX_FAST_DEG], lu_old[RR_MAX_FAST_DEG];   // UNIT: upstream lateral (this / previous row)
+    double eo[GEN_SLOTS], en[GEN_SLOTS];
+    double lu[GEN_SLOTS], lu_old[GEN_SLOTS];   // UNIT: upstream lateral (this / previous row)
 #pragma unroll
-    for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+    for (int k = 0; k < GEN_SLOTS; ++k) {
         eo[k] = en[k] = lu[k] = lu_old[k] = 0.0;
         if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) {
             eo[k] = UNIT ? rp[k][RAW_QF] : rp[k][RAW_CARRY];
@@ -480,9 +585,9 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
         const bool row_start = act && sub == 0;
 
         // ---- gather upstream values (shuffles are executed by every lane) ----
-        double vo[RR_MAX_FAST_DEG], vn[RR_MAX_FAST_DEG];
+        double vo[GEN_SLOTS], vn[GEN_SLOTS];
 #pragma unroll
-        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+        for (int k = 0; k < GEN_SLOTS; ++k) {
             vo[k] = eo[k];
             vn[k] = en[k];
             if (k < nfast && (M.int_mask >> k) & 1) {
@@ -500,7 +605,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
                 ql = ql_nx;
                 double a_in = 0.0, a_hw = 0.0;
 #pragma unroll
-                for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+                for (int k = 0; k < GEN_SLOTS; ++k) {
                     if (k < deg) {
                         lu_old[k] = lu[k];
                         lu[k] = ld_stream(lat_ptr(P, m, j, t0, ug[k], row));
@@ -508,7 +613,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
                         if (hw) a_hw += lu[k]; else a_in += lu[k];
                     }
                 }
-                for (int k = RR_MAX_FAST_DEG; k < deg; ++k) {
+                for (int k = GEN_SLOTS; k < deg; ++k) {
                     const int32_t sk = __ldg(P.slot_src + e0 + k);
                     const double l = ld_stream(lat_ptr(P, m, j, t0, __ldg(P.up_idx + e0 + k), row));
                     const bool hw = sk >= 0 ? (sk & RR_SLOT_HW_BIT) != 0 : (((-sk - 1) >> 6) & 1) != 0;
@@ -525,7 +630,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
 
         // ---- pass A: c2 * (previous-substep discharge of each upstream), ascending ----
 #pragma unroll
-        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+        for (int k = 0; k < GEN_SLOTS; ++k) {
             if (k < deg) {
                 if (UNIT) {
                     const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
@@ -541,8 +646,8 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
                 }
             }
         }
-        if (M.max_deg > RR_MAX_FAST_DEG) {
-            for (int k = RR_MAX_FAST_DEG; k < M.max_deg; ++k) {
+        if (M.max_deg > GEN_SLOTS) {
+            for (int k = GEN_SLOTS; k < M.max_deg; ++k) {
                 const int32_t sk = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
                 const int il = (sk < 0 && sk != SLOT_NONE) ? ((-sk - 1) & 31) : lane;
                 double v = __shfl_sync(FULL_MASK, UNIT ? qf_prev : qprev, il);
@@ -563,7 +668,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
         }
         // ---- pass B: c1 * (this-substep discharge of each upstream), ascending ----
 #pragma unroll
-        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+        for (int k = 0; k < GEN_SLOTS; ++k) {
             if (k < deg) {
                 if (UNIT) {
                     const bool hw = src[k] >= 0 ? (src[k] & RR_SLOT_HW_BIT) != 0 : (((-src[k] - 1) >> 6) & 1) != 0;
@@ -573,8 +678,8 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
                 }
             }
         }
-        if (M.max_deg > RR_MAX_FAST_DEG) {
-            for (int k = RR_MAX_FAST_DEG; k < M.max_deg; ++k) {
+        if (M.max_deg > GEN_SLOTS) {
+            for (int k = GEN_SLOTS; k < M.max_deg; ++k) {
                 const int32_t sk = (k < deg) ? __ldg(P.slot_src + e0 + k) : SLOT_NONE;
                 const int il = (sk < 0 && sk != SLOT_NONE) ? ((-sk - 1) & 31) : lane;
                 double v = __shfl_sync(FULL_MASK, qcur, il);
@@ -612,7 +717,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
             // lookahead for the next step of this lane
             if (s + 1 < TT) {
 #pragma unroll
-                for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+                for (int k = 0; k < GEN_SLOTS; ++k) {
                     if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) { eo[k] = en[k]; en[k] = rp[k][RAW_S0 + s + 1]; }
                 }
                 if (HAS_LAT && sub == 0) ql_nx = ld_stream(lat + (size_t)row * c.lstride);
@@ -631,10 +736,18 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
 }
 
 // ticket -> (member, block, tile); false when the tickets are exhausted
-__device__ __forceinline__ bool next_item(const rr_route_params &P, int lane, int &m, int &b, int &j) {
-    unsigned long long tk = 0;
-    if (lane == 0) tk = atomicAdd(P.ticket, 1ull);
-    tk = __shfl_sync(FULL_MASK, tk, 0);
+// Tickets are drawn in batches of P.ticket_batch consecutive tickets per warp: one global atomic per batch keeps
+// the single-address atomic rate (an L2 atomic unit serialises them) off the critical path of large launches.
+// A warp works through its batch in order, so the lowest unfinished ticket is still always being processed.
+__device__ __forceinline__ bool next_item(const rr_route_params &P, int lane, int &m, int &b, int &j,
+                                          unsigned long long &tk_next, unsigned long long &tk_end) {
+    if (tk_next >= tk_end) {
+        unsigned long long t0 = 0;
+        if (lane == 0) t0 = atomicAdd(P.ticket, (unsigned long long)P.ticket_batch);
+        tk_next = __shfl_sync(FULL_MASK, t0, 0);
+        tk_end = tk_next + (unsigned long long)P.ticket_batch;
+    }
+    const unsigned long long tk = tk_next++;
     if (tk >= (unsigned long long)P.n_items * (unsigned)P.n_members) return false;
     m = 0;
     int64_t ticket = (int64_t)tk;
@@ -886,9 +999,10 @@ __global__ void __launch_bounds__(256, RR_MIN_CTAS) rr_wavefront_kernel(const __
     constexpr bool UNIT = (MODE == RR_MODE_UNIT);
     const int lane = threadIdx.x & 31;
     int m, b, j;
+    unsigned long long tk_next = 0, tk_end = 0;
     PROF_DECL
     for (;;) {
-        const bool more = next_item(P, lane, m, b, j);
+        const bool more = next_item(P, lane, m, b, j, tk_next, tk_end);
         PROF_MARK(0)
         if (!more) break;
         item_ctx c;
@@ -896,7 +1010,13 @@ __global__ void __launch_bounds__(256, RR_MIN_CTAS) rr_wavefront_kernel(const __
         PROF_MARK(1)
         // plan flag 0x40: no in-block edges and max in-degree <= RR_MAX_FAST_DEG
         if (!UNIT && P.K == 1 && (c.M.int_mask & 0x40)) register_fast_item<MODE>(P, c);
-        else if (UNIT && P.K == 1 && (c.M.int_mask & 0x40) && c.M.max_deg <= 2) {
+        else if (!UNIT && (c.M.int_mask & 0x40) && c.M.max_deg <= 2) {
+            switch (c.M.max_deg) {
+                case 0: fast_item_k<MODE, 0>(P, c); break;
+                case 1: fast_item_k<MODE, 1>(P, c); break;
+                default: fast_item_k<MODE, 2>(P, c); break;
+            }
+        } else if (UNIT && P.K == 1 && (c.M.int_mask & 0x40) && c.M.max_deg <= 2) {
             const bool vec = P.tile_major == 2;
             switch (c.M.max_deg) {
                 case 0: if (vec) unit_fast_item<0, true>(P, c); else unit_fast_item<0, false>(P, c); break;
@@ -905,9 +1025,12 @@ __global__ void __launch_bounds__(256, RR_MIN_CTAS) rr_wavefront_kernel(const __
             }
         } else general_item<MODE>(P, c);
         __syncwarp();
+#ifdef RR_PROFILE
+        if (!(c.M.int_mask & 0x40)) { prof_acc[7] += (unsigned long long)(clock64() - prof_t); prof_acc[5] += 1; }   // general-path items
+#endif
         PROF_MARK(2)
 #ifdef RR_PROFILE
-        prof_acc[4] += c.prof_wait; prof_acc[5] += c.prof_setup; prof_acc[6] += 1;
+        prof_acc[4] += c.prof_wait; prof_acc[6] += 1;
 #endif
         if (lane == 0) st_release(P.done + (size_t)m * P.n_blocks + b, j + 1);
         __syncwarp();
@@ -930,7 +1053,8 @@ __global__ void __launch_bounds__(128, 1) rr_wavefront_tma_kernel(const __grid_c
     uint32_t phase = 0;
     bool store_pending = false;
     int m, b, j;
-    while (next_item(P, lane, m, b, j)) {
+    unsigned long long tk_next = 0, tk_end = 0;
+    while (next_item(P, lane, m, b, j, tk_next, tk_end)) {
         item_ctx c;
         open_item<MODE>(P, c, lane, m, b, j);
         bool done_item = false;

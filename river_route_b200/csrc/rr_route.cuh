@@ -33,6 +33,7 @@ struct rr_route_params {
     int32_t tile_rows;    // rows per work item
     int32_t raw_pitch;    // doubles per exported series (1 carry + tile_rows*K, padded to 4)
     int32_t n_members;
+    int32_t ticket_batch; // consecutive tickets a warp draws per global atomic
     int32_t tile_major;   // working-array layout of lateral / out: 0 row-major (T, ld); 1 [tile][block][row][lane];
                           // 2 [tile][block][lane][row] with tile_pitch doubles per reach
     int32_t out_layout;   // layout of out (same codes); tile_major is the layout of lateral

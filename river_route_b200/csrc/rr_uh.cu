@@ -72,6 +72,49 @@ __global__ void __launch_bounds__(128) uh_conv_kernel(int64_t n, int n_ks, int64
     }
 }
 
+// Same algorithm with the taps held in registers (NG groups of TB taps, n_ks <= NG * TB): the tap loop is fully
+// unrolled, so the only loads in the inner loop are the sliding inputs.
+template <int TB, int NG>
+__global__ void __launch_bounds__(128) uh_conv_kernel_reg(int64_t n, int n_ks, int64_t T, int64_t chunk,
+                                                          const double *__restrict__ lat, int64_t ldl,
+                                                          const double *__restrict__ ker, int64_t ldk,
+                                                          const double *__restrict__ state, int64_t lds,
+                                                          double *__restrict__ out, int64_t ldo) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const int64_t tb = (int64_t)blockIdx.y * chunk;
+    const int64_t te = min(T, tb + chunk);
+    constexpr int NT = NG * TB;
+    double kq[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) kq[k] = k < n_ks ? __ldg(ker + (int64_t)k * ldk + b) : 0.0;
+    const double *lb = lat + b;
+    auto input = [&](int64_t t) -> double { return (t >= 0 && t < T) ? __ldg(lb + t * ldl) : 0.0; };
+    for (int64_t t0 = tb; t0 < te; t0 += TB) {
+        double acc[TB], w[TB];
+#pragma unroll
+        for (int u = 0; u < TB; ++u) {
+            const int64_t t = t0 + u;
+            acc[u] = (t < n_ks && t < te) ? state[t * lds + b] : 0.0;      // UnitHydrograph.py:100
+        }
+#pragma unroll
+        for (int u = 0; u < TB; ++u) w[u] = input(t0 + u - (NT - 1));
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+#pragma unroll
+            for (int p = 0; p < TB; ++p) {
+                const int tau = NT - 1 - (g * TB + p);                      // oldest tap first
+#pragma unroll
+                for (int u = 0; u < TB; ++u) acc[u] = fma(kq[tau], w[(u + p) % TB], acc[u]);
+                w[p % TB] = input(t0 + TB - tau);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TB; ++u)
+            if (t0 + u < te) out[(t0 + u) * ldo + b] = acc[u];
+    }
+}
+
 // Carry-over state: rows 0..n_ks-2 = the full convolution at times T..T+n_ks-2, last row = 0
 // (UnitHydrograph.py:103-105).  Reads of the old state run ahead of the writes (row T+j > j).
 __global__ void __launch_bounds__(128) uh_state_kernel(int64_t n, int n_ks, int64_t T,
@@ -113,7 +156,17 @@ extern "C" int rr_uh_convolve_dev(int64_t n, int64_t n_ks, int64_t T, const doub
     const unsigned gy = (unsigned)((T + chunk - 1) / chunk);
     dim3 grid(gx, gy);
     const int nk = (int)n_ks;
-    uh_conv_kernel<8><<<grid, threads, 0, stream>>>(n, nk, T, chunk, lateral, ldl, kernel, ldk, state, lds, out, ldo);
+#define RR_UH_REG(NG) uh_conv_kernel_reg<8, NG><<<grid, threads, 0, stream>>>(n, nk, T, chunk, lateral, ldl, kernel, ldk, state, lds, out, ldo)
+    switch ((nk + 7) / 8) {
+        case 1: RR_UH_REG(1); break;
+        case 2: RR_UH_REG(2); break;
+        case 3: RR_UH_REG(3); break;
+        case 4: RR_UH_REG(4); break;
+        case 5: RR_UH_REG(5); break;
+        case 6: RR_UH_REG(6); break;
+        default: uh_conv_kernel<8><<<grid, threads, 0, stream>>>(n, nk, T, chunk, lateral, ldl, kernel, ldk, state, lds, out, ldo);
+    }
+#undef RR_UH_REG
     CK(cudaGetLastError());
     uh_state_kernel<<<gx, threads, 0, stream>>>(n, nk, T, lateral, ldl, kernel, ldk, state, lds);
     CK(cudaGetLastError());

@@ -7,14 +7,17 @@ a synthetic 7M-reach forest in 5000 independent basins (SURVEY.md 8d generator, 
 lateral inflow volumes, dt_routing = dt_runoff = 3600 s, fp64.  One "step" routes one resident chunk
 of `--rows` hourly time steps over the whole network, chained in time through the channel state
 (a 1-year run is 8760/rows such steps).  The 7M-reach network fits one B200, so it is the N=1
-workload; with N GPUs the basins are bin-packed over the ranks (no collective in the time loop) and
-the total work stays the same ("scaling": "strong").
+workload; with N GPUs the basins of the same network are bin-packed over the ranks (no collective in the
+time loop) and every step routes N x `--rows` time steps, so the bytes each GPU streams per step stay fixed
+("scaling": "weak"; `--scaling strong` keeps the rows, and so the total work, fixed instead).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N ...            # the reference's CPU algorithm (oracle port)
 
 Prints ONE JSON line on rank 0.  `value` is timed with CUDA events around device-resident launches;
-`e2e` is the same metric through the host-array API (pinned H2D + D2H inside the timed region).
+`e2e` is the same metric through the host-array API the router classes call (pinned fp64 lateral inflows in,
+float32 discharge out as the reference hands it to its writer; H2D + D2H inside the timed region); `e2e.variants`
+adds the kernel-level fp64-out call and the gridded-runoff -> discharge residency.
 """
 from __future__ import annotations
 
@@ -45,7 +48,10 @@ def parse():
     ap.add_argument('--reaches', type=int, default=7_000_000)
     ap.add_argument('--basins', type=int, default=5000)
     ap.add_argument('--rows', type=int, default=240, help='hourly time steps resident per step')
-    ap.add_argument('--e2e-rows', type=int, default=48, help='time steps per end-to-end (host array) step')
+    ap.add_argument('--e2e-rows', type=int, default=96, help='time steps per end-to-end (host array) step, per GPU')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: N x rows time steps per step on N GPUs (bytes per GPU fixed); strong: rows fixed')
+    ap.add_argument('--no-e2e-variants', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--ref-rows', type=int, default=24, help='time steps per step of the CPU reference arm')
     ap.add_argument('--cpu-sample-reaches', type=int, default=1_000_000)
@@ -239,7 +245,7 @@ def run_reference(args):
     line = {
         'impl': 'reference', 'metric': 'reach-timesteps/sec (RapidMuskingum, fp64)', 'value': value,
         'unit': 'reach-timesteps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args, rows),
         'cpu_baseline': {'value': value, 'unit': 'reach-timesteps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
@@ -251,6 +257,8 @@ def run_reference(args):
 
 def workload_config(args, rows):
     return {'workload': 'C4', 'router': 'RapidMuskingum', 'reaches': args.reaches, 'basins': args.basins,
+            'scaling_rule': (f'weak: rows_per_step = {args.rows} x n_gpus on the same {args.reaches}-reach network'
+                             if args.scaling == 'weak' else 'strong: rows_per_step fixed'),
             'network': f'synthetic forest seed 4 depth_bias {args.depth_bias} (SURVEY.md 8d), reach order: {args.order}',
             'rows_per_step': rows, 'dt_runoff_s': DT, 'dt_routing_s': DT, 'substeps': 1,
             'parallelism': f'basin-sharded x{args.gpus}, no collective in the time loop',
@@ -292,7 +300,7 @@ def main():
     info = plan.info
 
     # ---- device-resident inputs (synthetic lateral volumes: gamma(0.3, 5e4 m3), half zeros) ----
-    rows = args.rows
+    rows = args.rows * (world if args.scaling == 'weak' else 1)
     ld = ((n + 31) // 32) * 32
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -355,32 +363,68 @@ def main():
     finite = bool(torch.isfinite(d_out[:, :n]).all().item())
 
     # ---- end to end through the host-array API: pinned H2D + route + D2H every step ----
-    er = args.e2e_rows
+    er = min(args.e2e_rows * (world if args.scaling == 'weak' else 1), rows)
     h_lat = rr.pinned_empty((er, n))
-    h_out = rr.pinned_empty((er, n))
     h_lat[:] = d_lat[:er, :n].cpu().numpy()
     h_q = rr.pinned_empty((n,))
-    h_q[:] = 0.0
-    plan.route_host(rr.MODE_RAPID, h_q, h_lat, h_out, 1)          # warm-up (allocates the staging buffers)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        plan.route_host(rr.MODE_RAPID, h_q, h_lat, h_out, 1)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = args.reaches * er * args.e2e_steps / float(e2e_t.item())
-    # the host path must agree with the device path on the same inputs (first chunk, zero state)
+
+    def timed_host(call):
+        """max over ranks of the wall time of `e2e_steps` host-array calls (state chained between them)."""
+        h_q[:] = 0.0
+        call()                                                          # warm-up (allocates the staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            call()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return args.reaches * er * args.e2e_steps / float(t.item())
+
+    # headline: what RapidMuskingum.route() does between reading a qlateral file and handing the float32 array to
+    # the writer (routers.TransformMuskingum._route_lateral -> rr_route_host_ex)
+    h_out32 = rr.pinned_empty((er, n), dtype=np.float32)
+    e2e_value = timed_host(lambda: plan.route_host(rr.MODE_RAPID, h_q, h_lat, h_out32, 1))
+    # the host path must agree with the device path on the same inputs (zero state)
     d_chk_q = torch.zeros(n, dtype=torch.float64, device=dev)
     d_chk = torch.empty((er, ld), dtype=torch.float64, device=dev)
-    h_q2 = rr.pinned_empty((n,))
-    h_q2[:] = 0.0
-    plan.route_host(rr.MODE_RAPID, h_q2, h_lat, h_out, 1)
+    h_q[:] = 0.0
+    plan.route_host(rr.MODE_RAPID, h_q, h_lat, h_out32, 1)
     plan.route_dev(rr.MODE_RAPID, d_chk_q.data_ptr(), d_lat.data_ptr(), ld, d_chk.data_ptr(), ld, er, 1, stream)
     torch.cuda.synchronize()
-    host_equals_dev = bool(np.array_equal(d_chk[:, :n].cpu().numpy(), h_out))
+    host_equals_dev = bool(np.array_equal(d_chk[:, :n].cpu().numpy().astype(np.float32), h_out32))
+    del d_chk
+    variants = {}
+    if not args.no_e2e_variants:
+        # (a) the reference kernel's own contract: fp64 discharge array back to the host (rapid_route drop-in)
+        h_out64 = rr.pinned_empty((er, n))
+        variants['kernel_level_f64_out'] = {
+            'value': timed_host(lambda: plan.route_host(rr.MODE_RAPID, h_q, h_lat, h_out64, 1)),
+            'h2d_bytes_per_step': int(n * er * 8 + n * 8), 'd2h_bytes_per_step': int(n * er * 8 + n * 8),
+            'api': 'Plan.route_host -> rr_route_host (kernels.rapid_route signature)'}
+        del h_out64
+        # (b) gridded runoff in (float32, ERA5 0.25 degree grid), float32 discharge out: weight table -> route in
+        #     one device residency (routers.TransformMuskingum._route_runoff -> rr_runoff_route_host)
+        from river_route_b200.transforms import Transform
+        n_cells = 721 * 1440
+        rng = np.random.default_rng(77 + rank)
+        per = rng.integers(4, 9, n)
+        indptr = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum(per, out=indptr[1:])
+        first = rng.integers(0, n_cells - 8, n)
+        indices = (np.repeat(first, per) + (np.arange(indptr[-1]) - np.repeat(indptr[:-1], per))).astype(np.int32)
+        w = rng.random(indptr[-1])
+        w /= np.repeat(np.add.reduceat(w, indptr[:-1]), per)
+        tf = Transform(indptr, indices, w, n_cells, area=rng.uniform(1e5, 5e8, n), device=local_rank)
+        h_grid = rr.pinned_empty((er, n_cells), dtype=np.float32)
+        h_grid[:] = (rng.gamma(0.3, 2e-3, (er, n_cells)) * (rng.random((er, n_cells)) < 0.4)).astype(np.float32)
+        variants['grid_runoff_to_discharge_f32'] = {
+            'value': timed_host(lambda: plan.runoff_route_host(tf, rr.MODE_RAPID, h_q, h_grid, h_out32, 1, as_volumes=True)),
+            'h2d_bytes_per_step': int(n_cells * er * 4 + n * 8), 'd2h_bytes_per_step': int(n * er * 4 + n * 8),
+            'api': 'Plan.runoff_route_host -> rr_runoff_route_host (weights SpMM + route + float32 cast on the device)',
+            'weight_table': f'{int(indptr[-1])} entries, 4-8 cells per river, {n_cells} grid cells'}
+        tf.close()
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -390,7 +434,7 @@ def main():
         line = {
             'metric': 'reach-timesteps/sec (RapidMuskingum, fp64)', 'value': value, 'unit': 'reach-timesteps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms_max / args.steps,
-            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': dict(workload_config(args, rows), reaches_rank0=n, plan={k_: int(v) for k_, v in info.items()}),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': ((traffic or {}).get('dram_bytes_per_reach_step') or 0) * n * rows or None,
@@ -399,9 +443,11 @@ def main():
                          'algorithmic_bytes_per_reach_step': B_ALG, 'peak_source': peak_src,
                          'traffic_source': (traffic or {}).get('source')},
             'e2e': {'value': e2e_value, 'unit': 'reach-timesteps/s', 'h2d_bytes_per_step': int(n * er * 8 + n * 8),
-                    'd2h_bytes_per_step': int(n * er * 8 + n * 8), 'rows_per_step': er, 'steps': args.e2e_steps,
-                    'api': 'Plan.route_host (pinned host arrays, chunked cudaMemcpyAsync inside rr_route_host)',
-                    'host_equals_device_path': host_equals_dev},
+                    'd2h_bytes_per_step': int(n * er * 4 + n * 8), 'rows_per_step': er, 'steps': args.e2e_steps,
+                    'api': 'Plan.route_host with a float32 output array -> rr_route_host_ex: pinned fp64 lateral inflows '
+                           'in, route, float32 cast on the device (TransformMuskingum.py:146), float32 discharge out; '
+                           'chunked cudaMemcpyAsync on three streams',
+                    'host_equals_device_path': host_equals_dev, 'variants': variants},
             'gpu_launches': int(launches), 'kernel_phase_cycles': prof,
             'clocks': clocks,
             'checks': {'finite': finite, 'summary_per_rank[outlet_q_last_step, state_sum, reaches]': summary_all.tolist()},

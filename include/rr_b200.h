@@ -140,6 +140,16 @@ int rr_route_dev(rr_plan *p, int mode, double *q_state, double *q_full, const do
 int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,
                   int64_t ldl, double *out, int64_t ldo, int64_t T, int64_t substeps);
 
+/* Host variant with the output tail of the reference's router loop done on the device before the copy back:
+ * `resample` >= 1 consecutive rows are averaged (q_array.reshape(T/k, k, n).mean(axis=1),
+ * routers/TransformMuskingum.py:128-139; rows added in order, then divided by k) and, with out_f32 != 0, the result
+ * is cast to float32 exactly as the reference's `astype(np.float32)` before the writer (:146, Muskingum.py:259).
+ * out is [T / resample][ldo] of float64 or float32; T must be a multiple of resample.  Halves (or more) the
+ * device-to-host traffic of a run; results are bit-identical to doing both steps in numpy on the fp64 array. */
+int rr_route_host_ex(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,
+                     int64_t ldl, void *out, int64_t ldo, int64_t T, int64_t substeps, int out_f32,
+                     int64_t resample);
+
 /* Ensemble: n_members independent lateral arrays routed from the SAME initial state in one
  * launch (TransformMuskingum._execute_routing 'ensemble' mode, TransformMuskingum.py:121-126).
  * lateral[m], out[m], q_final[m] are device pointers per member; q_init [n] is shared. */
@@ -182,6 +192,32 @@ int rr_weights_transform_host(int64_t n_rivers, int64_t n_points, int64_t T, con
                               const int32_t *indices, const double *w, const void *x, int x_is_f32,
                               int64_t ldx, double *y, int64_t ldy, int cumulative, int force_positive,
                               const double *area);
+
+/* ---- gridded runoff -> discharge in one residency -----------------------------------------------
+ * The whole per-file chain of TransformMuskingum.route() with grid inputs (routers/TransformMuskingum.py:38-51,
+ * :108-148) without the lateral inflows ever leaving the device:
+ *   gathered grid runoff (host, float32 or float64, [T][ldx] in unique-cell order, runoff.py:267-280)
+ *   -> weight SpMM + tail (runoff.py:292-337)  [-> UnitHydrograph.convolve, RR_MODE_UNIT, UnitMuskingum.py:75]
+ *   -> route -> optional resample / float32 (as rr_route_host_ex) -> host.
+ * An rr_transform is the device-resident weight table in CSR form over the plan's river order (row r = river r of
+ * the params file; the reference assumes, runoff.py:265, that the table lists rivers in that order), built on the
+ * host exactly as scipy builds W (duplicates summed, columns ascending); area may be NULL when as_volumes is never
+ * used.  rr_transform_set_uh attaches the (n_ks, n) unit-hydrograph kernel and carry-over state
+ * (uhkernels/UnitHydrograph.py:27-62); the state lives on the device across calls like UnitHydrograph.state does
+ * across files and is read back with rr_transform_get_uh_state. */
+typedef struct rr_transform rr_transform;
+int  rr_transform_create(int64_t n_rivers, int64_t n_points, const int32_t *indptr, const int32_t *indices,
+                         const double *w, const double *area, int32_t device, rr_transform **out);
+int  rr_transform_set_uh(rr_transform *t, int64_t n_ks, const double *kernel, int64_t ldk,
+                         const double *state /* NULL = zeros */, int64_t lds);
+int  rr_transform_get_uh_state(rr_transform *t, double *state, int64_t lds);
+void rr_transform_destroy(rr_transform *t);
+/* mode: RR_MODE_RAPID (as_volumes as RapidMuskingum sets it) or RR_MODE_UNIT (depths -> unit hydrograph).
+ * cumulative / force_positive are runoff_to_qlateral's options (runoff.py:309-314). */
+int rr_runoff_route_host(rr_plan *p, rr_transform *t, int mode, double *q_state, const void *runoff,
+                         int x_is_f32, int64_t ldx, int64_t T, int cumulative, int force_positive,
+                         int as_volumes, void *out, int64_t ldo, int64_t substeps, int out_f32,
+                         int64_t resample);
 
 /* Diagnostic cycle counters of the routing kernel (builds with -DRR_PROFILE; zeros otherwise), summed over warps:
  * [0] ticket + decode, [1] per-item constants + dependency waits, [2] item body, [3] publish.  Resets on read. */

@@ -104,8 +104,10 @@ struct rr_device_state {
     // host streaming path
     cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    double *d_lat[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
-    size_t chunk_cap = 0;  // doubles per chunk buffer
+    void *s_inb[2] = {nullptr, nullptr}, *s_outb[2] = {nullptr, nullptr};   // double-buffered chunk input / output
+    size_t s_inb_cap[2] = {0, 0}, s_outb_cap[2] = {0, 0};                     // bytes
+    double *s_lat = nullptr, *s_conv = nullptr, *s_route = nullptr;           // compute-stream scratch of one chunk
+    size_t s_lat_cap = 0, s_conv_cap = 0, s_route_cap = 0;
     double *d_q = nullptr, *d_qfull = nullptr;
     // renumbered plans: user -> working index and scratch in the working order
     int32_t *inv = nullptr;
@@ -183,7 +185,7 @@ void rr_device_release(rr_plan *p) {
     cudaDeviceSynchronize();
     void *ptrs[] = {d->up_ptr, d->up_idx, d->slot_src, d->export_id, d->dep_ptr, d->dep_idx, d->down, d->exp_ro, d->edge_ro,
                     d->lvl_ptr, d->lvl_blk, d->skew, d->meta, d->coef, d->key_start, d->raw, d->done, d->ticket, d->prof,
-                    d->d_lat[0], d->d_lat[1], d->d_out[0], d->d_out[1], d->d_q, d->d_qfull,
+                    d->s_inb[0], d->s_inb[1], d->s_outb[0], d->s_outb[1], d->s_lat, d->s_conv, d->s_route, d->d_q, d->d_qfull,
                     d->inv, d->p_lat, d->p_out, d->p_q};
     for (void *q : ptrs)
         if (q) cudaFree(q);
@@ -544,39 +546,181 @@ extern "C" int rr_route_ensemble_dev(rr_plan *p, int mode, const double *q_init,
                      (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Device-resident weight table (+ optional unit hydrograph) of the grid-runoff path.
+// ---------------------------------------------------------------------------------------------------
+struct rr_transform {
+    int device = 0;
+    int64_t n_rivers = 0, n_points = 0, nnz = 0;
+    int32_t *indptr = nullptr, *indices = nullptr;
+    double *w = nullptr, *area = nullptr;
+    int64_t n_ks = 0, ld_uh = 0;
+    double *uh_kernel = nullptr, *uh_state = nullptr;
+};
+
+extern "C" void rr_transform_destroy(rr_transform *t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaDeviceSynchronize();
+    void *ptrs[] = {t->indptr, t->indices, t->w, t->area, t->uh_kernel, t->uh_state};
+    for (void *q : ptrs)
+        if (q) cudaFree(q);
+    delete t;
+}
+
+extern "C" int rr_transform_create(int64_t n_rivers, int64_t n_points, const int32_t *indptr, const int32_t *indices,
+                                   const double *w, const double *area, int32_t device, rr_transform **out) {
+    if (!out) { rr_set_error("null argument"); return 100; }
+    *out = nullptr;
+    if (n_rivers <= 0 || n_points <= 0 || !indptr || !indices || !w) { rr_set_error("bad weight table"); return 100; }
+    if (indptr[0] != 0) { rr_set_error("weight table: indptr[0] must be 0"); return 100; }
+    for (int64_t r = 0; r < n_rivers; ++r)
+        if (indptr[r + 1] < indptr[r]) { rr_set_error("weight table: indptr must be non-decreasing"); return 100; }
+    const int64_t nnz = indptr[n_rivers];
+    for (int64_t j = 0; j < nnz; ++j)
+        if (indices[j] < 0 || indices[j] >= n_points) {
+            rr_set_error("weight table refers to grid cells outside the gathered runoff array");
+            return 100;
+        }
+    if (!rr_cuda_available()) { rr_set_error("no CUDA device available: librr_b200 has no CPU fallback"); return 201; }
+    rr_transform *t = new rr_transform();
+    auto fail = [&](int rc) { rr_transform_destroy(t); return rc; };
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { rr_set_error("cudaSetDevice failed"); return fail(200); }
+    cudaGetDevice(&t->device);
+    t->n_rivers = n_rivers; t->n_points = n_points; t->nnz = nnz;
+    auto up = [&](void **dst, const void *src, size_t bytes) -> bool {
+        if (cudaMalloc(dst, std::max<size_t>(bytes, 8)) != cudaSuccess) return false;
+        return bytes == 0 || cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    bool ok = up((void **)&t->indptr, indptr, sizeof(int32_t) * (size_t)(n_rivers + 1)) &&
+              up((void **)&t->indices, indices, sizeof(int32_t) * (size_t)nnz) &&
+              up((void **)&t->w, w, sizeof(double) * (size_t)nnz) &&
+              (!area || up((void **)&t->area, area, sizeof(double) * (size_t)n_rivers));
+    if (!ok) { rr_set_error(std::string("weight table upload: ") + cudaGetErrorString(cudaGetLastError())); return fail(200); }
+    *out = t;
+    return 0;
+}
+
+extern "C" int rr_transform_set_uh(rr_transform *t, int64_t n_ks, const double *kernel, int64_t ldk,
+                                   const double *state, int64_t lds) {
+    if (!t || !kernel || n_ks <= 0 || ldk < t->n_rivers || (state && lds < t->n_rivers)) { rr_set_error("bad unit hydrograph"); return 100; }
+    CK(cudaSetDevice(t->device));
+    const int64_t ld = ((t->n_rivers + 31) / 32) * 32;
+    if (t->n_ks != n_ks) {
+        if (t->uh_kernel) CK(cudaFree(t->uh_kernel));
+        if (t->uh_state) CK(cudaFree(t->uh_state));
+        t->uh_kernel = t->uh_state = nullptr;
+        t->n_ks = 0;
+        CK(cudaMalloc((void **)&t->uh_kernel, sizeof(double) * (size_t)n_ks * ld));
+        CK(cudaMalloc((void **)&t->uh_state, sizeof(double) * (size_t)n_ks * ld));
+        t->n_ks = n_ks; t->ld_uh = ld;
+    }
+    CK(cudaMemcpy2D(t->uh_kernel, ld * 8, kernel, ldk * 8, t->n_rivers * 8, n_ks, cudaMemcpyHostToDevice));
+    if (state) CK(cudaMemcpy2D(t->uh_state, ld * 8, state, lds * 8, t->n_rivers * 8, n_ks, cudaMemcpyHostToDevice));
+    else CK(cudaMemset(t->uh_state, 0, sizeof(double) * (size_t)n_ks * ld));
+    return 0;
+}
+
+extern "C" int rr_transform_get_uh_state(rr_transform *t, double *state, int64_t lds) {
+    if (!t || !state || !t->uh_state || lds < t->n_rivers) { rr_set_error("no unit hydrograph state"); return 100; }
+    CK(cudaSetDevice(t->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy2D(state, lds * 8, t->uh_state, t->ld_uh * 8, t->n_rivers * 8, t->n_ks, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Output tail of TransformMuskingum._execute_routing on the device: mean over `k` consecutive rows
+// (reshape(T/k, k, n).mean(axis=1): rows added one after the other, then divided by k; TransformMuskingum.py:128-139)
+// and the cast to float32 the writer receives (:146 / Muskingum.py:259, round to nearest even like numpy's astype).
+template <typename OT>
+__global__ void __launch_bounds__(256) finish_output(const double *__restrict__ src, int64_t lds, OT *__restrict__ dst,
+                                                     int64_t ldd, int64_t n, int k) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *p = src + (int64_t)blockIdx.y * k * lds + i;
+    double acc = __ldg(p);
+    for (int r = 1; r < k; ++r) acc += __ldg(p + (int64_t)r * lds);
+    if (k > 1) acc = acc / (double)k;
+    dst[(int64_t)blockIdx.y * ldd + i] = (OT)acc;
+}
+
+int rr_weights_run(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr, const int32_t *indices,
+                   const double *w, const void *x, int x_is_f32, int64_t ldx, double *y, int64_t ldy, int cumulative,
+                   int force_positive, const double *area, int64_t t_skip, cudaStream_t stream);
+
+// What feeds the router, chunk by chunk: host lateral inflows (qlateral files) or gathered grid runoff that the
+// weight table (and, for UnitMuskingum, the unit hydrograph) turns into lateral inflows on the device.
+struct rr_stream_source {
+    const double *lateral = nullptr;
+    int64_t ldl = 0;
+    rr_transform *tf = nullptr;
+    const void *runoff = nullptr;
+    int x_is_f32 = 0, cumulative = 0, force_positive = 0, as_volumes = 0;
+    int64_t ldx = 0;
+};
+
 // Host arrays: stream time chunks through two device buffers per direction.
 //   s_in : H2D of chunk c+1        (cudaMemcpy2DAsync, pinned source gives full PCIe rate)
-//   s_comp: route chunk c          (one wavefront launch, state carried on the device)
+//   s_comp: [weights -> unit hydrograph ->] route chunk c [-> resample / float32]   (state carried on the device)
 //   s_out: D2H of chunk c-1
-extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,
-                             int64_t ldl, double *out, int64_t ldo, int64_t T, int64_t substeps) {
-    if (!p || !q_state || !out || (mode != RR_MODE_MUSKINGUM && !lateral)) { rr_set_error("null argument"); return 100; }
+static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, const rr_stream_source &src, void *out,
+                        int64_t ldo, int64_t T, int64_t substeps, int out_f32, int64_t resample) {
+    if (!p || !q_state || !out) { rr_set_error("null argument"); return 100; }
     if (T <= 0 || substeps <= 0) { rr_set_error("T and substeps must be positive"); return 100; }
+    if (resample < 1 || T % resample != 0) { rr_set_error("T must be a multiple of the output resampling factor"); return 100; }
+    const bool grid = src.tf != nullptr;
+    const bool has_lat = mode != RR_MODE_MUSKINGUM;
+    if (has_lat && !grid && !src.lateral) { rr_set_error("null argument"); return 100; }
+    if (grid) {
+        if (!has_lat) { rr_set_error("Muskingum (channel only) takes no runoff"); return 100; }
+        if (!src.runoff || src.ldx < src.tf->n_points) { rr_set_error("bad runoff array"); return 100; }
+        if (src.tf->n_rivers != p->n) { rr_set_error("weight table rows do not match the number of river segments"); return 100; }
+        if (mode == RR_MODE_UNIT && src.tf->n_ks <= 0) { rr_set_error("UnitMuskingum needs a unit hydrograph (rr_transform_set_uh)"); return 100; }
+        if (src.as_volumes && !src.tf->area) { rr_set_error("as_volumes needs catchment areas in the weight table"); return 100; }
+    }
+    if (ldo < p->n) { rr_set_error("output leading dimension smaller than n"); return 100; }
     int rc = ensure_device(p);
     if (rc) return rc;
     rr_device_state *d = p->dev;
+    if (grid && src.tf->device != d->device) { rr_set_error("weight table and plan live on different devices"); return 100; }
     const int64_t n = p->n;
     const int64_t ldd = ((n + 31) / 32) * 32;  // device rows start on 256-byte boundaries
-    const int64_t rows_tile = std::max<int64_t>(1, p->opts.time_tile / substeps);   // largest tile: chunk granularity
-    // chunk: about 256 MiB per buffer so that H2D, routing and D2H of neighbouring chunks overlap with little
-    // fill / drain; whole tiles when a chunk holds several
-    int64_t chunk = std::max<int64_t>(1, (256ll << 20) / (ldd * 8));
-    if (chunk > rows_tile) chunk = (chunk / rows_tile) * rows_tile;
+    const bool post = out_f32 || resample > 1;
+    const bool uh = grid && mode == RR_MODE_UNIT;
+    // Chunk length.  Short chunks keep the fill / drain of the three-stage pipeline small (aim: 1/16 of the call),
+    // but every chunk is one wavefront launch whose dependency pipeline has to fill again (~20 us per level of the
+    // block DAG), so a chunk must carry enough bytes to hide that: at least 64 MiB and 2 MB per level.  At most
+    // ~1 GiB of fp64 rows per buffer unless the depth rule asks for more; whole 8-row groups and whole output rows.
+    const int64_t row_bytes = ldd * 8;
+    const int64_t min_bytes = std::max<int64_t>(64ll << 20, (int64_t)p->max_level * (2ll << 20));
+    const int64_t min_rows = (min_bytes + row_bytes - 1) / row_bytes;
+    const int64_t cap_rows = std::max<int64_t>(min_rows, (1ll << 30) / row_bytes);
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(T / 16, min_rows), cap_rows));
+    if (const char *env = getenv("RR_STREAM_CHUNK_ROWS")) chunk = std::max(1, atoi(env));   // tests: force many chunks
+    if (chunk >= 8) chunk = (chunk / 8) * 8;
+    chunk = std::max<int64_t>(resample, (chunk / resample) * resample);
     chunk = std::min<int64_t>(chunk, T);
-    const size_t need = (size_t)chunk * ldd;
-    if (need > d->chunk_cap) {
-        for (int k = 0; k < 2; ++k) {
-            if (d->d_lat[k]) CK(cudaFree(d->d_lat[k]));
-            if (d->d_out[k]) CK(cudaFree(d->d_out[k]));
-            d->d_lat[k] = d->d_out[k] = nullptr;
-        }
-        d->chunk_cap = 0;
-        for (int k = 0; k < 2; ++k) {
-            CK(cudaMalloc((void **)&d->d_lat[k], need * sizeof(double)));
-            CK(cudaMalloc((void **)&d->d_out[k], need * sizeof(double)));
-        }
-        d->chunk_cap = need;
+    const size_t es_in = grid ? (src.x_is_f32 ? 4 : 8) : 8, es_out = out_f32 ? 4 : 8;
+    const int64_t ld_in = grid ? ((src.tf->n_points + 31) / 32) * 32 : ldd;
+    const size_t need_in = has_lat ? (size_t)(chunk + (grid ? 1 : 0)) * ld_in * es_in : 0;
+    const size_t need_out = (size_t)(chunk / resample) * ldd * es_out;
+    auto grow_bytes = [&](void **buf, size_t *cap, size_t need) -> int {
+        if (need <= *cap) return 0;
+        CK(cudaDeviceSynchronize());
+        if (*buf) CK(cudaFree(*buf));
+        *buf = nullptr; *cap = 0;
+        CK(cudaMalloc(buf, need));
+        *cap = need;
+        return 0;
+    };
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = grow_bytes(&d->s_inb[k], &d->s_inb_cap[k], need_in))) return rc;
+        if ((rc = grow_bytes(&d->s_outb[k], &d->s_outb_cap[k], need_out))) return rc;
     }
+    const size_t need_f64 = (size_t)chunk * ldd * 8;
+    if (grid && (rc = grow_bytes((void **)&d->s_lat, &d->s_lat_cap, need_f64))) return rc;
+    if (uh && (rc = grow_bytes((void **)&d->s_conv, &d->s_conv_cap, need_f64))) return rc;
+    if (post && (rc = grow_bytes((void **)&d->s_route, &d->s_route_cap, need_f64))) return rc;
     if (!d->d_q) CK(cudaMalloc((void **)&d->d_q, sizeof(double) * (size_t)n));
     if (mode == RR_MODE_UNIT && !d->d_qfull) CK(cudaMalloc((void **)&d->d_qfull, sizeof(double) * (size_t)n));
     CK(cudaMemcpyAsync(d->d_q, q_state, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, d->s_comp));
@@ -586,30 +730,69 @@ extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_fu
 
     const int64_t n_chunks = (T + chunk - 1) / chunk;
     auto rows_of = [&](int64_t c) { return std::min<int64_t>(chunk, T - c * chunk); };
+    // a cumulative grid chunk starts with the last row of the previous chunk (its aggregate is the value to subtract)
+    auto lead_of = [&](int64_t c) -> int64_t { return (grid && src.cumulative && c > 0) ? 1 : 0; };
     auto copy_in = [&](int64_t c) -> int {
-        if (mode == RR_MODE_MUSKINGUM) return 0;
+        if (!has_lat) return 0;
         const int k = (int)(c & 1);
         if (c >= 2) CK(cudaStreamWaitEvent(d->s_in, d->ev_comp[k], 0));  // buffer free once chunk c-2 was routed
-        CK(cudaMemcpy2DAsync(d->d_lat[k], ldd * 8, lateral + (size_t)c * chunk * ldl, ldl * 8, n * 8, rows_of(c),
-                             cudaMemcpyHostToDevice, d->s_in));
+        if (grid) {
+            const int64_t lead = lead_of(c);
+            const char *h = (const char *)src.runoff + (size_t)(c * chunk - lead) * src.ldx * es_in;
+            CK(cudaMemcpy2DAsync(d->s_inb[k], ld_in * es_in, h, src.ldx * es_in, src.tf->n_points * es_in,
+                                 rows_of(c) + lead, cudaMemcpyHostToDevice, d->s_in));
+        } else {
+            CK(cudaMemcpy2DAsync(d->s_inb[k], ldd * 8, src.lateral + (size_t)c * chunk * src.ldl, src.ldl * 8, n * 8,
+                                 rows_of(c), cudaMemcpyHostToDevice, d->s_in));
+        }
         CK(cudaEventRecord(d->ev_in[k], d->s_in));
         return 0;
     };
     if ((rc = copy_in(0))) return rc;
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int k = (int)(c & 1);
+        const int64_t rows = rows_of(c);
         if (c + 1 < n_chunks && (rc = copy_in(c + 1))) return rc;
-        if (mode != RR_MODE_MUSKINGUM) CK(cudaStreamWaitEvent(d->s_comp, d->ev_in[k], 0));
+        if (has_lat) CK(cudaStreamWaitEvent(d->s_comp, d->ev_in[k], 0));
         if (c >= 2) CK(cudaStreamWaitEvent(d->s_comp, d->ev_out[k], 0));  // out buffer drained
-        const double *lat1[1] = {d->d_lat[k]};
-        double *out1[1] = {d->d_out[k]}, *qs1[1] = {d->d_q}, *qf1[1] = {d->d_qfull};
-        rc = route_any(p, mode, 1, d->d_q, lat1, ldd, out1, ldd, qs1, qf1, rows_of(c), substeps,
+        const double *lat = (const double *)d->s_inb[k];
+        if (grid) {
+            const rr_transform *t = src.tf;
+            {
+                rr_timer tm(3, d->s_comp);
+                rc = rr_weights_run(n, t->n_points, rows + lead_of(c), t->indptr, t->indices, t->w, d->s_inb[k],
+                                    src.x_is_f32, ld_in, d->s_lat, ldd, src.cumulative, src.force_positive,
+                                    (src.as_volumes && !uh) ? t->area : nullptr, lead_of(c), d->s_comp);
+            }
+            if (rc) return rc;
+            lat = d->s_lat;
+            if (uh) {
+                rr_timer tm(3, d->s_comp);
+                rc = rr_uh_convolve_dev(n, t->n_ks, rows, d->s_lat, ldd, t->uh_kernel, t->ld_uh, t->uh_state, t->ld_uh,
+                                        d->s_conv, ldd, d->s_comp);
+                if (rc) return rc;
+                lat = d->s_conv;
+            }
+        }
+        double *route_out = post ? d->s_route : (double *)d->s_outb[k];
+        const double *lat1[1] = {lat};
+        double *out1[1] = {route_out}, *qs1[1] = {d->d_q}, *qf1[1] = {d->d_qfull};
+        rc = route_any(p, mode, 1, d->d_q, lat1, ldd, out1, ldd, qs1, qf1, rows, substeps,
                        router_level && c == 0, router_level && c == n_chunks - 1, d->s_comp);
         if (rc) return rc;
+        const int64_t rows_out = rows / resample;
+        if (post) {
+            rr_timer tm(3, d->s_comp);
+            dim3 g((unsigned)((n + 255) / 256), (unsigned)rows_out);
+            if (out_f32) finish_output<float><<<g, 256, 0, d->s_comp>>>(d->s_route, ldd, (float *)d->s_outb[k], ldd, n, (int)resample);
+            else finish_output<double><<<g, 256, 0, d->s_comp>>>(d->s_route, ldd, (double *)d->s_outb[k], ldd, n, (int)resample);
+            CK(cudaGetLastError());
+            rr_count_launch(1);
+        }
         CK(cudaEventRecord(d->ev_comp[k], d->s_comp));
         CK(cudaStreamWaitEvent(d->s_out, d->ev_comp[k], 0));
-        CK(cudaMemcpy2DAsync(out + (size_t)c * chunk * ldo, ldo * 8, d->d_out[k], ldd * 8, n * 8, rows_of(c),
-                             cudaMemcpyDeviceToHost, d->s_out));
+        CK(cudaMemcpy2DAsync((char *)out + (size_t)c * (chunk / resample) * ldo * es_out, ldo * es_out, d->s_outb[k],
+                             ldd * es_out, n * es_out, rows_out, cudaMemcpyDeviceToHost, d->s_out));
         CK(cudaEventRecord(d->ev_out[k], d->s_out));
     }
     CK(cudaMemcpyAsync(q_state, d->d_q, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, d->s_comp));
@@ -619,6 +802,32 @@ extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_fu
     CK(cudaStreamSynchronize(d->s_out));
     CK(cudaStreamSynchronize(d->s_in));
     return 0;
+}
+
+extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,
+                             int64_t ldl, double *out, int64_t ldo, int64_t T, int64_t substeps) {
+    rr_stream_source src;
+    src.lateral = lateral; src.ldl = ldl;
+    return stream_route(p, mode, q_state, q_full, src, out, ldo, T, substeps, 0, 1);
+}
+
+extern "C" int rr_route_host_ex(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,
+                                int64_t ldl, void *out, int64_t ldo, int64_t T, int64_t substeps, int out_f32,
+                                int64_t resample) {
+    rr_stream_source src;
+    src.lateral = lateral; src.ldl = ldl;
+    return stream_route(p, mode, q_state, q_full, src, out, ldo, T, substeps, out_f32, resample);
+}
+
+extern "C" int rr_runoff_route_host(rr_plan *p, rr_transform *t, int mode, double *q_state, const void *runoff,
+                                    int x_is_f32, int64_t ldx, int64_t T, int cumulative, int force_positive,
+                                    int as_volumes, void *out, int64_t ldo, int64_t substeps, int out_f32,
+                                    int64_t resample) {
+    if (!t) { rr_set_error("null argument"); return 100; }
+    rr_stream_source src;
+    src.tf = t; src.runoff = runoff; src.x_is_f32 = x_is_f32; src.ldx = ldx;
+    src.cumulative = cumulative; src.force_positive = force_positive; src.as_volumes = as_volumes;
+    return stream_route(p, mode, q_state, nullptr, src, out, ldo, T, substeps, out_f32, resample);
 }
 
 // Cycle counters of RR_PROFILE builds (zero otherwise): [0] ticket + decode, [1] constants + dependency waits,

@@ -50,21 +50,20 @@ __global__ void __launch_bounds__(256) transpose_kernel(const XT *__restrict__ x
 }
 
 template <typename XT> struct vec8;
+// 8 consecutive time steps of one cell: one 256-bit load (float) or two (double).  The L2::128B hint makes L2
+// fetch the whole line -- the next three time blocks of this cell -- in one DRAM burst.
 template <> struct vec8<float> {
     float v[8];
     __device__ __forceinline__ void load(const float *p) {
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        asm volatile("ld.global.nc.L2::128B.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
     }
 };
 template <> struct vec8<double> {
     double v[8];
     __device__ __forceinline__ void load(const double *p) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double2 a = __ldg(reinterpret_cast<const double2 *>(p) + k);
-            v[2 * k] = a.x; v[2 * k + 1] = a.y;
-        }
+        asm volatile("ld.global.nc.L2::128B.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+        asm volatile("ld.global.nc.L2::128B.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]) : "l"(p + 4));
     }
 };
 
@@ -77,7 +76,7 @@ __global__ void __launch_bounds__(128) weights_kernel(int64_t n_rivers, int64_t 
                                                       const double *__restrict__ w, const XT *__restrict__ xt,
                                                       double *__restrict__ y, int64_t ldy,
                                                       int cumulative, int force_positive,
-                                                      const double *__restrict__ area) {
+                                                      const double *__restrict__ area, int64_t t_skip) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rivers) return;
     const int64_t tb = (int64_t)blockIdx.y * chunk;
@@ -103,14 +102,14 @@ __global__ void __launch_bounds__(128) weights_kernel(int64_t n_rivers, int64_t 
         }
 #pragma unroll
         for (int u = 0; u < TB; ++u) {
-            if (t0 + u < te) {
+            if (t0 + u < te && t0 + u >= t_skip) {   // rows before t_skip only seed `prev` (streamed chunks)
                 double q = acc[u];
                 if (cumulative) { if (t0 + u > 0) q = acc[u] - prev; prev = acc[u]; }
                 if (force_positive && q < 0.0) q = 0.0;   // :313-314
                 if (q != q) q = 0.0;                      // :331-333
                 if (area) q *= a;                         // :335-336
-                y[(t0 + u) * ldy + r] = q;
-            }
+                y[(t0 + u - t_skip) * ldy + r] = q;
+            } else if (cumulative && t0 + u < te) prev = acc[u];
         }
     }
 }
@@ -118,7 +117,7 @@ __global__ void __launch_bounds__(128) weights_kernel(int64_t n_rivers, int64_t 
 template <typename XT>
 int run_weights(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr, const int32_t *indices,
                 const double *w, const XT *x, int64_t ldx, double *y, int64_t ldy, int cumulative, int force_positive,
-                const double *area, cudaStream_t stream) {
+                const double *area, int64_t t_skip, cudaStream_t stream) {
     const int64_t Tp = ((T + TB - 1) / TB) * TB;
     XT *xt = nullptr;
     {   // keep the stream-ordered pool's memory between calls (the default trims it at every sync)
@@ -148,7 +147,7 @@ int run_weights(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *in
     chunk = std::min<int64_t>(((chunk + TB - 1) / TB) * TB, Tp);
     dim3 grid(gx, (unsigned)((T + chunk - 1) / chunk));
     weights_kernel<XT><<<grid, threads, 0, stream>>>(n_rivers, T, Tp, chunk, indptr, indices, w, xt, y, ldy, cumulative,
-                                                     force_positive, area);
+                                                     force_positive, area, t_skip);
     CK(cudaGetLastError());
     CK(cudaFreeAsync(xt, stream));
     rr_count_launch(2);
@@ -157,19 +156,27 @@ int run_weights(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *in
 
 }  // namespace
 
+// Internal form used by the streaming pipeline (rr_api.cu): x has T rows of which the first t_skip (0 or 1) only
+// provide the previous cumulative value of a streamed time chunk; y receives T - t_skip rows.
+int rr_weights_run(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr, const int32_t *indices,
+                   const double *w, const void *x, int x_is_f32, int64_t ldx, double *y, int64_t ldy, int cumulative,
+                   int force_positive, const double *area, int64_t t_skip, cudaStream_t stream) {
+    if (n_rivers <= 0 || T <= t_skip || n_points <= 0) { rr_set_error("n_rivers, n_points and T must be positive"); return 100; }
+    if (!indptr || !indices || !w || !x || !y) { rr_set_error("null argument"); return 100; }
+    if (ldx < n_points || ldy < n_rivers) { rr_set_error("leading dimension too small"); return 100; }
+    if (x_is_f32)
+        return run_weights<float>(n_rivers, n_points, T, indptr, indices, w, (const float *)x, ldx, y, ldy, cumulative,
+                                  force_positive, area, t_skip, stream);
+    return run_weights<double>(n_rivers, n_points, T, indptr, indices, w, (const double *)x, ldx, y, ldy, cumulative,
+                               force_positive, area, t_skip, stream);
+}
+
 extern "C" int rr_weights_transform_dev(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr,
                                         const int32_t *indices, const double *w, const void *x, int x_is_f32,
                                         int64_t ldx, double *y, int64_t ldy, int cumulative, int force_positive,
                                         const double *area, void *stream_) {
-    if (n_rivers <= 0 || T <= 0 || n_points <= 0) { rr_set_error("n_rivers, n_points and T must be positive"); return 100; }
-    if (!indptr || !indices || !w || !x || !y) { rr_set_error("null argument"); return 100; }
-    if (ldx < n_points || ldy < n_rivers) { rr_set_error("leading dimension too small"); return 100; }
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (x_is_f32)
-        return run_weights<float>(n_rivers, n_points, T, indptr, indices, w, (const float *)x, ldx, y, ldy, cumulative,
-                                  force_positive, area, stream);
-    return run_weights<double>(n_rivers, n_points, T, indptr, indices, w, (const double *)x, ldx, y, ldy, cumulative,
-                               force_positive, area, stream);
+    return rr_weights_run(n_rivers, n_points, T, indptr, indices, w, x, x_is_f32, ldx, y, ldy, cumulative, force_positive,
+                          area, 0, (cudaStream_t)stream_);
 }
 
 extern "C" int rr_weights_transform_host(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr,

@@ -116,20 +116,28 @@ class Plan:
                                            _lib.as_f64p(c4) if c4 is not None else None))
 
     # ---- host arrays (numpy) : H2D / route / D2H streamed inside the library ----
-    def route_host(self, mode: int, q_state: np.ndarray, lateral, out: np.ndarray, substeps: int, q_full=None):
+    def route_host(self, mode: int, q_state: np.ndarray, lateral, out: np.ndarray, substeps: int, q_full=None,
+                   resample: int = 1):
         """
         One reference kernel call on host arrays.  ``q_state`` (n,) is updated in place with the final state,
-        ``out`` (T, n) is overwritten.  ``lateral`` is (T, n) or None for MODE_MUSKINGUM.
+        ``out`` is overwritten.  ``lateral`` is (T, n) or None for MODE_MUSKINGUM.
+
+        ``out`` is (T, n) float64 -- the reference kernel's contract -- or, for the router-level tail done on the
+        device, (T / resample, n) float64 or float32: ``resample`` consecutive rows are averaged
+        (TransformMuskingum.py:128-139) and a float32 ``out`` receives ``astype(np.float32)`` of that (:146).
         """
         if q_state.dtype != np.float64 or not q_state.flags.c_contiguous or q_state.shape != (self.n,):
             raise ValueError('q_state must be a contiguous float64 vector with one value per river segment')
-        if out.dtype != np.float64 or out.ndim != 2 or out.shape[1] != self.n:
-            raise ValueError('discharge array must be float64 with shape (T, n)')
-        T = out.shape[0]
+        if out.dtype not in (np.float64, np.float32) or out.ndim != 2 or out.shape[1] != self.n:
+            raise ValueError('discharge array must be float64 (or float32) with shape (T, n)')
+        resample = int(resample)
+        if resample < 1:
+            raise ValueError('resample must be a positive integer')
+        T = out.shape[0] * resample
         ldo = _lib.rows_ld(out)
         p_lat, ldl = None, self.n
         if mode != MODE_MUSKINGUM:
-            if lateral.shape != (T, self.n):
+            if lateral.ndim != 2 or lateral.shape[1] != self.n or lateral.shape[0] != T:
                 raise ValueError(f'lateral inflow shape {lateral.shape} does not match (T, n) = {(T, self.n)}')
             if lateral.dtype != np.float64 or (self.n > 1 and lateral.strides[1] != 8):
                 # the reference's grid path hands over an F-ordered transposed view (runoff.py:298)
@@ -141,8 +149,43 @@ class Plan:
             if q_full.dtype != np.float64 or not q_full.flags.c_contiguous or q_full.shape != (self.n,):
                 raise ValueError('q_full must be a contiguous float64 vector with one value per river segment')
             p_qf = _lib.as_f64p(q_full)
-        check(lib.rr_route_host(self._h, int(mode), _lib.as_f64p(q_state), p_qf, p_lat, ldl, _lib.as_f64p(out), ldo,
-                                T, int(substeps)))
+        if out.dtype == np.float64 and resample == 1:
+            check(lib.rr_route_host(self._h, int(mode), _lib.as_f64p(q_state), p_qf, p_lat, ldl, _lib.as_f64p(out),
+                                    ldo, T, int(substeps)))
+        else:
+            check(lib.rr_route_host_ex(self._h, int(mode), _lib.as_f64p(q_state), p_qf, p_lat, ldl,
+                                       out.ctypes.data_as(C.c_void_p), ldo, T, int(substeps),
+                                       int(out.dtype == np.float32), resample))
+
+    def runoff_route_host(self, transform, mode: int, q_state: np.ndarray, runoff: np.ndarray, out: np.ndarray,
+                          substeps: int, cumulative: bool = False, force_positive: bool = False,
+                          as_volumes: bool = False, resample: int = 1):
+        """
+        Gathered grid runoff (T, n_points), float32 or float64, -> discharge in one device residency
+        (``rr_runoff_route_host``): weight table [-> unit hydrograph] -> route -> resample / float32.
+        ``transform`` is a :class:`river_route_b200.transforms.Transform` built for this plan's river order.
+        """
+        if q_state.dtype != np.float64 or not q_state.flags.c_contiguous or q_state.shape != (self.n,):
+            raise ValueError('q_state must be a contiguous float64 vector with one value per river segment')
+        if out.dtype not in (np.float64, np.float32) or out.ndim != 2 or out.shape[1] != self.n:
+            raise ValueError('discharge array must be float64 (or float32) with shape (T, n)')
+        if transform.n_rivers != self.n:
+            raise ValueError('weight table rows do not match the number of river segments')
+        resample = int(resample)
+        if resample < 1:
+            raise ValueError('resample must be a positive integer')
+        T = out.shape[0] * resample
+        if runoff.dtype not in (np.float32, np.float64):
+            runoff = runoff.astype(np.float64)
+        if runoff.ndim != 2 or runoff.shape != (T, transform.n_points):
+            raise ValueError(f'runoff shape {runoff.shape} does not match (T, n_points) = {(T, transform.n_points)}')
+        if transform.n_points > 1 and runoff.strides[1] != runoff.itemsize:
+            runoff = np.ascontiguousarray(runoff)
+        check(lib.rr_runoff_route_host(self._h, transform._h, int(mode), _lib.as_f64p(q_state),
+                                       runoff.ctypes.data_as(C.c_void_p), int(runoff.dtype == np.float32),
+                                       _lib.rows_ld(runoff), T, int(cumulative), int(force_positive), int(as_volumes),
+                                       out.ctypes.data_as(C.c_void_p), _lib.rows_ld(out), int(substeps),
+                                       int(out.dtype == np.float32), resample))
 
     # ---- device pointers (torch tensors used purely as device buffers) ----
     def route_dev(self, mode: int, q_state_ptr: int, lateral_ptr: int, ldl: int, out_ptr: int, ldo: int, T: int,

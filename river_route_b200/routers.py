@@ -253,22 +253,29 @@ class Muskingum:
         num_output_steps = int(self.dt_total / self.dt_discharge)
         num_routing_per_output = int(self.dt_discharge / self.dt_routing)
         self._set_muskingum_coefficients(self.dt_routing)
-        discharge_array = self._router(num_output_steps, num_routing_per_output)
         dates = pd.date_range(start=self.cfg.start_datetime, periods=num_output_steps,
                               freq=pd.to_timedelta(self.dt_discharge, unit='s')).to_numpy()
-        self._write(dates, discharge_array.astype(np.float32, copy=False), self.cfg.discharge_files[0])
+        if _is_stock(self, '_router', Muskingum):
+            # the writer receives float32 (Muskingum.py:259): cast on the device, copy back half the bytes
+            q32 = np.empty((num_output_steps, self.n), dtype=np.float32)
+            self._route_channel(q32, num_routing_per_output)
+        else:
+            q32 = self._router(num_output_steps, num_routing_per_output).astype(np.float32, copy=False)
+        self._write(dates, q32, self.cfg.discharge_files[0])
 
-    def _router(self, num_output_steps, num_routing_per_output):
-        """The seam of Muskingum.py:262-290: returns the fp64 (num_output_steps, n) discharge array."""
+    def _route_channel(self, discharge_array, num_routing_per_output):
         if not np.any(self.channel_state):
             self.logger.warning(
                 'Initial channel state is all zeros. Muskingum routing without lateral inflow requires a '
                 'non-zero initial state to produce meaningful results. Provide channel_state_init_file.')
-        discharge_array = np.zeros((num_output_steps, self.n), dtype=np.float64)
         q_t = self.channel_state.astype(np.float64, copy=True)
         self.plan.route_host(MODE_MUSKINGUM, q_t, None, discharge_array, num_routing_per_output)
         self.channel_state = q_t
         return discharge_array
+
+    def _router(self, num_output_steps, num_routing_per_output):
+        """The seam of Muskingum.py:262-290: returns the fp64 (num_output_steps, n) discharge array."""
+        return self._route_channel(np.zeros((num_output_steps, self.n), dtype=np.float64), num_routing_per_output)
 
     def _hook_before_route(self):
         return
@@ -287,20 +294,16 @@ class Muskingum:
 
     def _write_discharges(self, dates, q_array, q_file, routed_file=''):
         """The reference's netCDF layout (Muskingum.py:337-351): time f8, river id i4, Q f4 (time, river_id)."""
-        try:
-            import netCDF4 as nc
-        except ImportError as e:  # pragma: no cover - depends on the host environment
-            raise ImportError('netCDF4 is required to write discharge files; install it or inject a writer with '
-                              'set_write_discharges()') from e
-        with nc.Dataset(str(q_file), mode='w', format='NETCDF4') as ds:
-            ds.createDimension('time', size=q_array.shape[0])
-            ds.createDimension(self.cfg.var_river_id, size=q_array.shape[1])
+        from . import ncio
+        with ncio.open_nc(q_file, 'w') as ds:
+            ds.createDimension('time', q_array.shape[0])
+            ds.createDimension(self.cfg.var_river_id, q_array.shape[1])
             ds.runoff_file = str(routed_file)
             tv = ds.createVariable('time', 'f8', ('time',))
             tv.units = f'seconds since {pd.Timestamp(dates[0]).strftime("%Y-%m-%d %H:%M:%S")}'
             tv[:] = (dates - dates[0]).astype('timedelta64[s]').astype(np.int64)
-            iv = ds.createVariable(self.cfg.var_river_id, 'i4', self.cfg.var_river_id)
-            iv[:] = self.river_ids
+            iv = ds.createVariable(self.cfg.var_river_id, 'i4', (self.cfg.var_river_id,))
+            iv[:] = self.river_ids.astype(np.int32)
             qv = ds.createVariable(self.cfg.var_discharge, 'f4', ('time', self.cfg.var_river_id))
             qv[:] = q_array
             qv.long_name = 'Discharge at catchment outlet'
@@ -377,36 +380,134 @@ class TransformMuskingum(Muskingum):
         self.plan.set_coefficients(self.c1, self.c2, self.c3, self.c4 / self.dt_runoff)   # RapidMuskingum.py:25
 
     def _execute_routing(self):
+        """
+        The per-file loop of TransformMuskingum.py:108-148.  With the stock ``_router`` the tail of the loop
+        (``dt_discharge`` resample :128-139 and the float32 cast :146) runs on the device, so only float32 output
+        rows cross PCIe; with the stock generator and grid inputs the weight table (and unit hydrograph) also run
+        there and the lateral inflows never leave the GPU.  A subclass that overrides ``_router`` or
+        ``_qlateral_generator`` gets the reference's sequence on fp64 host arrays instead.
+        """
         self._ensemble_member_states = []
-        files = self._qlateral_generator()
+        device_tail = _is_stock(self, '_router', TransformMuskingum)
+        fused_grid = (device_tail and not self.cfg.qlateral_files and self.cfg.grid_runoff_files
+                      and self.cfg.grid_weights_file and _is_stock(self, '_qlateral_generator', TransformMuskingum))
+        files = self._gathered_runoff_generator() if fused_grid else self._qlateral_generator()
         if self.cfg.progress_bar:
             from tqdm import tqdm
             files = tqdm(files, total=len(self.cfg.qlateral_files or self.cfg.grid_runoff_files), desc='Files Routed')
-        for dates, qlateral, runoff_file, discharge_file in files:
+        for dates, data, runoff_file, discharge_file, *kind in files:
             self.logger.info(f'Routing qlateral: {runoff_file}')
             self._set_network_and_time_dependent_vectors(dates)
-            q_t, q_array = self._router(qlateral)
+            k = self.num_runoff_steps_per_discharge if self.dt_discharge > self.dt_runoff else 1
+            if device_tail:
+                q32 = np.empty((self.num_runoff_steps // k, self.n), dtype=np.float32)
+                q_t = self._route_runoff(data, q32, k) if kind == ['runoff'] else self._route_lateral(data, q32, k)
+            else:
+                q_t, q_array = self._router(data)
+                if k > 1:                                                    # :128-139
+                    q_array = q_array.reshape((int(self.dt_total / self.dt_discharge),
+                                               int(self.dt_discharge / self.dt_runoff), self.n)).mean(axis=1)
+                q32 = q_array.astype(np.float32, copy=False)
             if self.cfg.runoff_processing_mode == 'sequential':
                 self.channel_state = q_t
             else:                                                            # every member starts from the same state
                 self._ensemble_member_states.append(q_t.copy())
-            if self.dt_discharge > self.dt_runoff:                           # :128-139
-                q_array = q_array.reshape((int(self.dt_total / self.dt_discharge),
-                                           int(self.dt_discharge / self.dt_runoff), self.n)).mean(axis=1)
+            if k > 1:
                 dates = dates[::self.num_runoff_steps_per_discharge]
-            self._write(dates, q_array.astype(np.float32, copy=False), discharge_file, runoff_file)
+            self._write(dates, q32, discharge_file, runoff_file)
         if self.cfg.runoff_processing_mode == 'ensemble':
             self.channel_state = np.array(self._ensemble_member_states).mean(axis=0)   # :145-146
 
+    def _check_lateral_shape(self, shape, width):
+        if tuple(shape) != (self.num_runoff_steps, width):
+            raise ValueError(f'qlateral shape {tuple(shape)} does not match (num_runoff_steps, n) = '
+                             f'{(self.num_runoff_steps, width)}')
+
+    def _route_lateral(self, qlateral, out, resample=1):
+        """Lateral inflows (T, n) on the host -> ``out`` (fp64 or float32, resampled); returns the final state."""
+        self._check_lateral_shape(qlateral.shape, self.n)
+        q_t = self.channel_state.astype(np.float64, copy=True)
+        self.plan.route_host(self._mode, q_t, qlateral, out, self.num_routing_steps_per_runoff, resample=resample)
+        return q_t
+
+    def _route_runoff(self, runoff_raw, out, resample=1):
+        """Gathered grid runoff (T, n_points) -> ``out`` in one device residency; returns the final state."""
+        self._check_lateral_shape(runoff_raw.shape, self._transform.n_points)
+        q_t = self.channel_state.astype(np.float64, copy=True)
+        self.plan.runoff_route_host(self._transform, self._mode, q_t, runoff_raw, out,
+                                    self.num_routing_steps_per_runoff,
+                                    cumulative=self.cfg.grid_accumulation_type == 'cumulative',
+                                    as_volumes=self._as_volumes, resample=resample)
+        return q_t
+
+    _transform = None
+    _transform_factor = None
+    _weight_table = None
+
+    def _ensure_transform(self, factor):
+        """Weight table netCDF -> device-resident CSR over the params-file river order (runoff.py:255-295), with the
+        unit conversion factor folded into the weights before duplicates are summed, as the reference does (:292-293)."""
+        from .runoff import build_weight_csr, read_weight_table
+        from .transforms import Transform
+        if self._transform is not None and factor == self._transform_factor:
+            return
+        if self._weight_table is None:
+            self._weight_table = read_weight_table(self.cfg.grid_weights_file, self.cfg.var_river_id)
+        tb = self._weight_table
+        indptr, indices, data, cx, cy, rivers, area = build_weight_csr(
+            tb['river_id'], tb['x_index'], tb['y_index'], tb['proportion'], tb['area_sqm'], factor)
+        # the reference assumes this order (runoff.py:265) and would silently route the wrong catchments otherwise
+        if rivers.shape[0] != self.n or not np.array_equal(np.asarray(rivers).astype(np.int64), self.river_ids):
+            raise ValueError('grid_weights_file must list the river segments of params_file in the same order')
+        self._detach_transform()
+        self._transform = Transform(indptr, indices, data, len(cx), area=area)
+        self._transform_factor = factor
+        self._cells = (cx, cy)
+        self._attach_unit_hydrograph()
+
+    def _attach_unit_hydrograph(self):
+        return
+
+    def _detach_transform(self):
+        if self._transform is not None:
+            self._transform.close()
+            self._transform = None
+
+    def _gathered_runoff_generator(self) -> Iterator[tuple]:
+        """Yields (dates, gathered runoff (T, n_points) in the file's dtype, input file, output file) per grid file:
+        the pointwise ``isel`` of runoff.py:267-280; everything after it happens on the device."""
+        from .runoff import _conversion_factor, gather_grid_runoff, grid_runoff_unit
+        for runoff_file, discharge_file in zip(self.cfg.grid_runoff_files, self.cfg.discharge_files):
+            self._ensure_transform(_conversion_factor(grid_runoff_unit(runoff_file, self.cfg.var_grid_runoff)))
+            cx, cy = self._cells
+            dates, raw = gather_grid_runoff(runoff_file, cx, cy, var_runoff=self.cfg.var_grid_runoff,
+                                            var_x=self.cfg.var_x, var_y=self.cfg.var_y, var_t=self.cfg.var_t)
+            if len(dates) > 2 and not np.all(np.diff(dates) == dates[1] - dates[0]):
+                # irregular time axis: the reference resamples the lateral inflows on the host (runoff.py:316-329)
+                ds = runoff_to_qlateral(runoff_file, grid_weights_file=self.cfg.grid_weights_file,
+                                        var_runoff=self.cfg.var_grid_runoff, var_x=self.cfg.var_x, var_y=self.cfg.var_y,
+                                        var_t=self.cfg.var_t, var_river_id=self.cfg.var_river_id,
+                                        cumulative=self.cfg.grid_accumulation_type == 'cumulative',
+                                        as_volumes=self._as_volumes)
+                yield (ds['time'].values.astype('datetime64[s]'), ds['qlateral'].values.astype(np.float64, copy=False),
+                       runoff_file, discharge_file, 'lateral')
+                continue
+            yield dates, raw, runoff_file, discharge_file, 'runoff'
+
     def _router(self, qlateral):
         """The seam of TransformMuskingum.py:150-152: (final state, fp64 (T, n) discharge array)."""
-        if qlateral.shape != (self.num_runoff_steps, self.n):
-            raise ValueError(f'qlateral shape {qlateral.shape} does not match (num_runoff_steps, n) = '
-                             f'{(self.num_runoff_steps, self.n)}')
         discharge_array = np.zeros((self.num_runoff_steps, self.n), dtype=np.float64)
-        q_t = self.channel_state.astype(np.float64, copy=True)
-        self.plan.route_host(self._mode, q_t, qlateral, discharge_array, self.num_routing_steps_per_runoff)
+        q_t = self._route_lateral(qlateral, discharge_array)
         return q_t, discharge_array
+
+
+def _is_stock(obj, name, *owners) -> bool:
+    """True when ``obj.<name>`` is still the implementation of one of ``owners`` (not overridden by a subclass or
+    patched on the instance): only then may the host-visible fp64 intermediate be skipped."""
+    if name in vars(obj):
+        return False
+    impl = getattr(type(obj), name, None)
+    return any(impl is vars(o).get(name) for o in owners)
 
 
 class RapidMuskingum(TransformMuskingum):
@@ -441,11 +542,28 @@ class UnitMuskingum(TransformMuskingum):
         self.c4 = self.c1 + self.c2
         self.plan.set_coefficients(self.c1, self.c2, self.c3, None)
 
-    def _router(self, qlateral):
-        convolved = self._uh.convolve(qlateral)                              # UnitMuskingum.py:75
-        return super()._router(convolved)
+    def _route_lateral(self, qlateral, out, resample=1):
+        self._check_lateral_shape(qlateral.shape, self.n)
+        self._sync_uh_state()                       # a device-resident carry-over (grid files routed earlier) comes home
+        convolved = self._uh.convolve(qlateral)     # UnitMuskingum.py:75
+        if self._transform is not None and self._transform.n_ks:
+            self._attach_unit_hydrograph()
+        return super()._route_lateral(convolved, out, resample)
+
+    def _attach_unit_hydrograph(self):
+        # the carry-over state moves to the device and stays there between files (UnitHydrograph.py:100-105)
+        self._transform.set_unit_hydrograph(self._uh.kernel, self._uh.state)
+
+    def _detach_transform(self):
+        self._sync_uh_state()
+        super()._detach_transform()
+
+    def _sync_uh_state(self):
+        if self._transform is not None and self._transform.n_ks and self._uh is not None:
+            self._uh.state = self._transform.uh_state()
 
     def _write_final_state(self):
+        self._sync_uh_state()
         super()._write_final_state()
         if self.cfg.uh_state_final_file and self._uh is not None:
             self._uh.write_state(self.cfg.uh_state_final_file)
@@ -453,18 +571,12 @@ class UnitMuskingum(TransformMuskingum):
 
 def _read_qlateral(path):
     """qlateral netCDF: variable ``qlateral(time, river_id)`` (docs/references/io-file-schema.md:52-55)."""
-    try:
-        import xarray as xr
-        with xr.open_dataset(path) as ds:
-            return ds['time'].values.astype('datetime64[s]'), ds['qlateral'].values.astype(np.float64, copy=False)
-    except ImportError:
-        pass
-    try:
-        import netCDF4 as nc
-    except ImportError as e:  # pragma: no cover - depends on the host environment
-        raise ImportError('xarray or netCDF4 is required to read qlateral files') from e
-    with nc.Dataset(str(path)) as ds:
-        tv = ds['time']
-        dates = nc.num2date(tv[:], tv.units, only_use_cftime_datetimes=False, only_use_python_datetimes=True)
-        return (np.array(dates, dtype='datetime64[s]'),
-                np.asarray(ds['qlateral'][:], dtype=np.float64))
+    from . import ncio
+    with ncio.open_nc(path) as ds:
+        tv = ds.variables['time']
+        dates = ncio.decode_time(ncio.read_array(tv), ncio.attrs_of(tv).get('units', ''))
+        var = ds.variables['qlateral']
+        array = ncio.read_array(var)
+        if tuple(var.dimensions)[0] != 'time':
+            array = array.T
+    return dates, array.astype(np.float64, copy=False)

@@ -15,7 +15,8 @@ from .transforms import weights_transform
 
 logger = logging.getLogger(__name__)
 
-__all__ = ['runoff_to_qlateral', 'weights_to_qlateral', 'build_weight_csr']
+__all__ = ['runoff_to_qlateral', 'weights_to_qlateral', 'build_weight_csr', 'read_weight_table', 'gather_grid_runoff',
+           'grid_runoff_unit', 'QlateralDataset']
 
 
 def _conversion_factor(unit):
@@ -76,24 +77,104 @@ def weights_to_qlateral(weight_table: dict, runoff_raw_or_grid: np.ndarray, *, r
     return ql, rivers
 
 
+def read_weight_table(grid_weights_file, var_river_id='river_id') -> dict:
+    """Columns of the weight table netCDF (docs/references/io-file-schema.md:76-84) in file (index) order."""
+    from . import ncio
+    with ncio.open_nc(grid_weights_file) as ds:
+        cols = {}
+        for key, name in (('river_id', var_river_id), ('x_index', 'x_index'), ('y_index', 'y_index'),
+                          ('proportion', 'proportion'), ('area_sqm', 'area_sqm')):
+            if name not in ds.variables:
+                raise KeyError(f'{name} not found in weight table {grid_weights_file}')
+            cols[key] = ncio.read_array(ds.variables[name])
+    return cols
+
+
+def _as_list(runoff_data):
+    import os
+    return [runoff_data] if isinstance(runoff_data, (str, os.PathLike)) else list(runoff_data)
+
+
+def grid_runoff_unit(runoff_data, var_runoff='ro'):
+    """``units`` attribute of the runoff variable; 'm' when the file has none (runoff.py:268)."""
+    from . import ncio
+    with ncio.open_nc(_as_list(runoff_data)[0]) as ds:
+        return ncio.attrs_of(ds.variables[var_runoff]).get('units', 'm')
+
+
+def gather_grid_runoff(runoff_data, cells_x, cells_y, *, var_runoff='ro', var_x='lon', var_y='lat', var_t='time',
+                       slab_rows=64):
+    """
+    The pointwise gather of runoff.py:267-280: (time axis as datetime64[s], (T, n_points) runoff in the file's dtype)
+    for the unique cells (x_index, y_index) of the weight table.  Files are concatenated along time like
+    ``xr.open_mfdataset`` does for consecutive files; the grid is read in slabs of time steps.
+    """
+    from . import ncio
+    dates, parts = [], []
+    for path in _as_list(runoff_data):
+        with ncio.open_nc(path) as ds:
+            var = ds.variables[var_runoff]
+            dims = tuple(var.dimensions)
+            if sorted(dims) != sorted((var_t, var_y, var_x)):
+                raise ValueError(f'{var_runoff} must have dimensions ({var_t}, {var_y}, {var_x}), found {dims}')
+            at, ay, ax = dims.index(var_t), dims.index(var_y), dims.index(var_x)
+            tv = ds.variables[var_t]
+            dates.append(ncio.decode_time(ncio.read_array(tv), ncio.attrs_of(tv).get('units', '')))
+            T = var.shape[at]
+            for t0 in range(0, T, slab_rows):
+                sel = [slice(None)] * 3
+                sel[at] = slice(t0, min(T, t0 + slab_rows))
+                slab = np.moveaxis(np.asarray(var[tuple(sel)]), (at, ay, ax), (0, 1, 2))
+                if isinstance(slab, np.ma.MaskedArray):
+                    slab = slab.filled(np.nan)
+                g = slab[:, cells_y, cells_x]
+                parts.append(np.ascontiguousarray(g, dtype=g.dtype.newbyteorder('=')))
+    return np.concatenate(dates), np.concatenate(parts, axis=0)
+
+
+class QlateralDataset(dict):
+    """What ``runoff_to_qlateral`` returns when xarray is not installed: ``ds['qlateral'].values``,
+    ``ds['time'].values``, ``ds['river_id'].values`` and ``to_netcdf`` with the reference's layout
+    (docs/references/io-file-schema.md:52-55)."""
+
+    class _Var:
+        def __init__(self, values, attrs=None):
+            self.values, self.attrs = values, dict(attrs or {})
+
+        def to_numpy(self):
+            return self.values
+
+    def __init__(self, ql, rivers, time_index, units):
+        super().__init__(qlateral=self._Var(ql, {'units': units}), river_id=self._Var(np.asarray(rivers).astype(np.int64)),
+                         time=self._Var(np.asarray(time_index)))
+
+    def to_netcdf(self, path):
+        from . import ncio
+        t = self['time'].values.astype('datetime64[s]')
+        with ncio.open_nc(path, 'w') as ds:
+            ds.createDimension('time', t.shape[0])
+            ds.createDimension('river_id', self['river_id'].values.shape[0])
+            tv = ds.createVariable('time', 'f8', ('time',))
+            tv.units = f'seconds since {pd.Timestamp(t[0]).strftime("%Y-%m-%d %H:%M:%S")}'
+            tv[:] = (t - t[0]).astype('timedelta64[s]').astype(np.float64)
+            rv = ds.createVariable('river_id', 'i4', ('river_id',))
+            rv[:] = self['river_id'].values.astype(np.int32)
+            qv = ds.createVariable('qlateral', 'f8', ('time', 'river_id'))
+            qv.units = self['qlateral'].attrs.get('units', 'm')
+            qv[:] = self['qlateral'].values
+
+
 def runoff_to_qlateral(runoff_data, grid_weights_file, *, var_runoff='ro', var_x='lon', var_y='lat', var_t='time',
                        var_river_id='river_id', runoff_depth_unit=None, cumulative=False, force_positive_runoff=False,
                        force_uniform_timesteps=True, as_volumes=False):
-    """File-level entry point with the reference's signature; returns an xarray.Dataset like the reference."""
-    try:
-        import xarray as xr
-    except ImportError as e:  # pragma: no cover - depends on the host environment
-        raise ImportError('xarray is required for runoff_to_qlateral on files; use weights_to_qlateral for arrays') from e
-    with xr.open_dataset(grid_weights_file) as ds:
-        wdf = ds[[var_river_id, 'x_index', 'y_index', 'proportion', 'area_sqm']].to_dataframe()
-    with xr.open_mfdataset(runoff_data) as ds:
-        unit = runoff_depth_unit or ds[var_runoff].attrs.get('units', 'm')
-        indptr, indices, data, cx, cy, rivers, area = build_weight_csr(
-            wdf[var_river_id].values, wdf['x_index'].values, wdf['y_index'].values, wdf['proportion'].values,
-            wdf['area_sqm'].values, _conversion_factor(unit))
-        raw = (ds[var_runoff].isel({var_x: xr.DataArray(cx, dims='points'), var_y: xr.DataArray(cy, dims='points')})
-               .transpose(var_t, 'points').values)
-        time_index = ds[var_t].to_numpy()
+    """File-level entry point with the reference's signature (runoff.py:218-378).  Returns an ``xarray.Dataset``
+    like the reference when xarray is installed, else a :class:`QlateralDataset` with the same variables."""
+    table = read_weight_table(grid_weights_file, var_river_id)
+    unit = runoff_depth_unit or grid_runoff_unit(runoff_data, var_runoff)
+    indptr, indices, data, cx, cy, rivers, area = build_weight_csr(
+        table['river_id'], table['x_index'], table['y_index'], table['proportion'], table['area_sqm'],
+        _conversion_factor(unit))
+    time_index, raw = gather_grid_runoff(runoff_data, cx, cy, var_runoff=var_runoff, var_x=var_x, var_y=var_y, var_t=var_t)
     uniform = np.all(np.diff(time_index) == time_index[1] - time_index[0]) if len(time_index) > 1 else True
     resample = (not uniform) and force_uniform_timesteps
     # the non-uniform-time resample (runoff.py:316-329, rare) works on incremental depths before NaN / area handling
@@ -109,6 +190,10 @@ def runoff_to_qlateral(runoff_data, grid_weights_file, *, var_runoff='ro', var_x
         if as_volumes:
             ql *= area[np.newaxis, :]
     units = 'm3' if as_volumes else 'm'
+    try:
+        import xarray as xr
+    except ImportError:
+        return QlateralDataset(ql, rivers, time_index, units)
     return xr.Dataset(
         {'qlateral': xr.DataArray(ql, dims=('time', 'river_id'), attrs={'units': units})},
         coords={'river_id': xr.DataArray(np.asarray(rivers).astype(np.int64), dims=('river_id',)),

@@ -3,6 +3,9 @@ Array-level entry points of the two transforms that feed the router, both execut
 
 * ``uh_convolve``       -- UnitHydrograph.convolve (river_route/uhkernels/UnitHydrograph.py:77-107)
 * ``weights_transform`` -- the SpMM core + in-place tail of runoff_to_qlateral (river_route/runoff.py:292-337)
+* ``Transform``         -- the same two, kept resident on the device in front of the router
+                           (``Plan.runoff_route_host``: grid runoff -> discharge without the lateral inflows
+                           leaving the GPU)
 """
 from __future__ import annotations
 
@@ -59,3 +62,60 @@ def weights_transform(indptr, indices, data, runoff_raw: np.ndarray, cumulative:
                                         n_points, _lib.as_f64p(y), n_rivers, int(cumulative), int(force_positive),
                                         _lib.as_f64p(a) if a is not None else None))
     return y
+
+
+class Transform:
+    """
+    Device-resident weight table (CSR over the plan's river order; scipy layout as ``build_weight_csr`` returns it)
+    and, optionally, the unit-hydrograph kernel with its carry-over state (``rr_transform`` of include/rr_b200.h).
+    """
+
+    def __init__(self, indptr, indices, data, n_points: int, area=None, device: int = -1):
+        indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        if indptr.ndim != 1 or indptr.shape[0] < 2 or indices.shape != data.shape:
+            raise ValueError('indptr / indices / data are not a CSR matrix')
+        self.n_rivers = int(indptr.shape[0] - 1)
+        self.n_points = int(n_points)
+        self.n_ks = 0
+        a = None if area is None else np.ascontiguousarray(area, dtype=np.float64)
+        if a is not None and a.shape != (self.n_rivers,):
+            raise ValueError('area must have one value per river segment')
+        self._h = None
+        handle = C.c_void_p()
+        check(lib.rr_transform_create(self.n_rivers, self.n_points, _lib.as_i32p(indptr), _lib.as_i32p(indices),
+                                      _lib.as_f64p(data), _lib.as_f64p(a) if a is not None else None, int(device),
+                                      C.byref(handle)))
+        self._h = handle
+
+    def set_unit_hydrograph(self, kernel: np.ndarray, state: np.ndarray | None = None):
+        kernel = np.ascontiguousarray(kernel, dtype=np.float64)
+        if kernel.ndim != 2 or kernel.shape[1] != self.n_rivers:
+            raise ValueError('kernel must have shape (n_kernel_steps, n_basins)')
+        st = None
+        if state is not None:
+            st = np.ascontiguousarray(state, dtype=np.float64)
+            if st.shape != kernel.shape:
+                raise ValueError(f'state shape {st.shape} does not match kernel shape {kernel.shape}')
+        check(lib.rr_transform_set_uh(self._h, kernel.shape[0], _lib.as_f64p(kernel), self.n_rivers,
+                                      _lib.as_f64p(st) if st is not None else None, self.n_rivers))
+        self.n_ks = int(kernel.shape[0])
+        return self
+
+    def uh_state(self) -> np.ndarray:
+        """Carry-over state (n_kernel_steps, n_basins) as UnitHydrograph.state holds it."""
+        st = np.empty((self.n_ks, self.n_rivers), dtype=np.float64)
+        check(lib.rr_transform_get_uh_state(self._h, _lib.as_f64p(st), self.n_rivers))
+        return st
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib.rr_transform_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -180,3 +180,145 @@ def test_weights_to_qlateral_and_unit_hydrograph_classes():
         with tempfile.TemporaryDirectory() as d:
             pd.DataFrame(np.zeros((2, 2))).to_parquet(os.path.join(d, 's.parquet'))
             full.set_state(os.path.join(d, 's.parquet'))
+
+
+# ------------------------------------------------------------------------------------------------------
+# file level: YAML config -> params parquet + grid runoff netCDF + weight table netCDF -> discharge netCDF
+# ------------------------------------------------------------------------------------------------------
+def _grid_case(tmp_path, n=3000, T=30, ny=15, nx=22, cumulative=False, units='m'):
+    from river_route_b200 import synth
+    from tests.test_io_cpu import synthetic_table, write_grid, write_weight_table
+    down = synth.forest(n, 3, seed=21, depth_bias=0.6)
+    k, x = synth.muskingum_params(n, 21)
+    ids = np.arange(n, dtype=np.int64) * 3 + 100
+    params = str(tmp_path / 'params.parquet')
+    pd.DataFrame({'river_id': ids, 'downstream_river_id': np.where(down >= 0, ids[np.where(down >= 0, down, 0)], -1),
+                  'k': k, 'x': x}).to_parquet(params)
+    rng = np.random.default_rng(5)
+    q0 = rng.uniform(0, 20, n)
+    state = str(tmp_path / 'state.parquet')
+    pd.DataFrame({'Q': q0}).to_parquet(state)
+    table = synthetic_table(n, ny, nx, seed=7, ids=ids)
+    write_weight_table(str(tmp_path / 'weights.nc'), table)
+    grids = []
+    for f in range(2):
+        ro = (rng.gamma(0.3, 2e-3, (T, ny, nx)) * (rng.random((T, ny, nx)) < 0.5)).astype(np.float32)
+        if units == 'mm':
+            ro *= 1000
+        if cumulative:
+            ro = np.cumsum(ro, axis=0, dtype=np.float32)
+        path = str(tmp_path / f'runoff_{f}.nc')
+        write_grid(path, ro, t0=f'2020-01-0{1 + f} 00:00:00', dt_hours=1, units=units)
+        grids.append((path, ro))
+    return dict(down=down, k=k, x=x, ids=ids, q0=q0, table=table, grids=grids, params=params, state=state, n=n, T=T)
+
+
+def _oracle_grid_chain(c, dt, cumulative, units, unit_hydrograph=None):
+    """The reference's sequence on the CPU oracle: runoff_to_qlateral -> [UH] -> route, file after file."""
+    from oracle import oracle
+    from river_route_b200.runoff import build_weight_csr
+    from tests.helpers import network_arrays
+    a = network_arrays(c['down'], c['k'], c['x'], dt, dt)
+    t = c['table']
+    indptr, indices, data, cx, cy, rivers, area = build_weight_csr(t['river_id'], t['x_index'], t['y_index'],
+                                                                   t['proportion'], t['area_sqm'], 0.001 if units == 'mm' else 1)
+    q, outs = c['q0'].copy(), []
+    for _, ro in c['grids']:
+        raw = ro[:, cy, cx]
+        if unit_hydrograph is None:
+            ql = oracle.weights_transform(indptr, indices, data, raw, cumulative=cumulative, area=area)
+            out = np.zeros((c['T'], c['n']))
+            oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q, ql, out, 1)
+        else:
+            ker, st = unit_hydrograph
+            conv = oracle.uh_convolve(oracle.weights_transform(indptr, indices, data, raw, cumulative=cumulative), ker, st)
+            sp = oracle.unit_split(c['down'].astype(np.int64))
+            inner, hw, ai, ah = sp['inner_idx'], sp['hw_idx'], sp['a_inner'], sp['a_hw']
+            c1i, c2i, c3i = a['c1'][inner], a['c2'][inner], a['c3'][inner]
+            q_ch = q[inner].copy()
+            q_full = q_ch.copy()
+            out = np.zeros((c['T'], c['n']))
+            oracle.unit_route(ai[0], ai[1], -c1i[ai[1]], ai[0], ai[1], ai[2], ah[0], ah[1], ah[2], c1i, c2i, c3i, hw,
+                              inner, q_ch, q_full, conv, out, 1)
+            q = np.empty(c['n'])
+            q[hw] = conv[-1][hw]
+            q[inner] = q_full
+        outs.append(out)
+    return outs, q
+
+
+@pytest.mark.parametrize('cumulative,units', [(False, 'm'), (True, 'mm')])
+def test_rapid_muskingum_from_grid_files_yaml_config(tmp_path, cumulative, units):
+    """The fused device path behind the unchanged config surface (examples/config.yaml keys): nothing is injected."""
+    import yaml
+    from river_route_b200 import ncio
+    c = _grid_case(tmp_path, cumulative=cumulative, units=units)
+    out_dir = tmp_path / 'out'
+    out_dir.mkdir()
+    cfg = dict(params_file=c['params'], grid_runoff_files=[g[0] for g in c['grids']], grid_weights_file=str(tmp_path / 'weights.nc'),
+               discharge_dir=str(out_dir), channel_state_init_file=c['state'], channel_state_final_file=str(tmp_path / 'final.parquet'),
+               grid_accumulation_type='cumulative' if cumulative else 'incremental', var_x='lon', var_y='lat', log=False)
+    with open(tmp_path / 'config.yaml', 'w') as f:
+        yaml.safe_dump(cfg, f)
+    r = rr.RapidMuskingum(str(tmp_path / 'config.yaml'))
+    before = rr.launch_count()
+    r.route()
+    assert rr.launch_count() > before and r._transform is not None      # the device-resident path ran
+    outs, q_final = _oracle_grid_chain(c, 3600, cumulative, units)
+    for f, ref in enumerate(outs):
+        with ncio.open_nc(out_dir / f'discharge_runoff_{f}.nc') as ds:
+            Q = ncio.read_array(ds.variables['Q'])
+            assert np.array_equal(ncio.read_array(ds.variables['river_id']), c['ids'].astype(np.int32))
+            tv = ds.variables['time']
+            dates = ncio.decode_time(ncio.read_array(tv), ncio.attrs_of(tv)['units'])
+            assert dates[0] == np.datetime64(f'2020-01-0{1 + f}T00:00:00') and dates.shape[0] == c['T']
+        assert Q.dtype == np.float32 and Q.shape == ref.shape
+        np.testing.assert_allclose(Q, ref.astype(np.float32), rtol=2e-6, atol=2e-6 * ref.max())
+    assert parity_error(pd.read_parquet(tmp_path / 'final.parquet')['Q'].values, q_final) < TOL
+    # the unfused sequence (override the seam -> fp64 host arrays, as the reference does it) writes the same bytes
+    class Seam(rr.RapidMuskingum):
+        def _router(self, qlateral):
+            return super()._router(qlateral)
+    cap = Capture()
+    Seam(**dict(cfg, channel_state_final_file=None)).set_write_discharges(cap).route()
+    for f in range(2):
+        with ncio.open_nc(out_dir / f'discharge_runoff_{f}.nc') as ds:
+            assert np.array_equal(ncio.read_array(ds.variables['Q']), cap.calls[f][1])
+
+
+def test_unit_muskingum_from_grid_files(tmp_path):
+    c = _grid_case(tmp_path, n=2500, T=20)
+    rng = np.random.default_rng(9)
+    ker = rng.uniform(0, 1, (7, c['n'])) * (rng.random((7, c['n'])) < 0.7)
+    kfile = str(tmp_path / 'uh.npz')
+    scipy.sparse.save_npz(kfile, scipy.sparse.csr_matrix(ker))
+    cap = Capture()
+    uh1 = str(tmp_path / 'uh1.parquet')
+    r = rr.UnitMuskingum(params_file=c['params'], grid_runoff_files=[g[0] for g in c['grids']],
+                         grid_weights_file=str(tmp_path / 'weights.nc'), discharge_dir=str(tmp_path),
+                         channel_state_init_file=c['state'], uh_kernel_file=kfile, uh_state_final_file=uh1,
+                         var_x='lon', var_y='lat', dt_discharge=7200, log=False)
+    r.set_write_discharges(cap).route()
+    st = np.zeros_like(ker)
+    outs, q_final = _oracle_grid_chain(c, 3600, False, 'm', unit_hydrograph=(ker, st))
+    for (dates, q, _, _), ref in zip(cap.calls, outs):
+        ref2 = ref.reshape(c['T'] // 2, 2, -1).mean(axis=1)
+        assert q.shape == ref2.shape and dates.shape[0] == c['T'] // 2 and dates[1] - dates[0] == np.timedelta64(7200, 's')
+        np.testing.assert_allclose(q, ref2.astype(np.float32), rtol=2e-6, atol=2e-6 * ref2.max())
+    assert parity_error(r.channel_state, q_final) < TOL
+    col = np.max(np.abs(st), axis=0) + 1e-300
+    assert parity_error(pd.read_parquet(uh1).T.to_numpy(), st, col) < TOL
+
+
+def test_qlateral_files_on_disk(route_golden, tmp_path):
+    """qlateral netCDF in, discharge netCDF out -- the reference's basic RapidMuskingum run (test_rapid_muskingum.py)."""
+    from river_route_b200 import ncio
+    from river_route_b200.runoff import QlateralDataset
+    g = route_golden
+    params, state = _files(g, tmp_path)
+    QlateralDataset(g['ql'], g['river_ids'], _dates(g['ql'].shape[0], g['dt_runoff']), 'm3').to_netcdf(str(tmp_path / 'ql.nc'))
+    rr.RapidMuskingum(params_file=params, qlateral_files=str(tmp_path / 'ql.nc'), discharge_dir=str(tmp_path),
+                      channel_state_init_file=state, dt_routing=int(g['dt_routing']), log=False).route()
+    with ncio.open_nc(tmp_path / 'discharge_ql.nc') as ds:
+        Q = ncio.read_array(ds.variables['Q'])
+    np.testing.assert_allclose(Q, g['rapid_out'].astype(np.float32), rtol=1e-6, atol=1e-6 * g['rapid_out'].max())

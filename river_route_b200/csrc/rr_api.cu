@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rr_route.cuh"
@@ -106,6 +107,8 @@ struct rr_device_state {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     void *s_inb[2] = {nullptr, nullptr}, *s_outb[2] = {nullptr, nullptr};   // double-buffered chunk input / output
     size_t s_inb_cap[2] = {0, 0}, s_outb_cap[2] = {0, 0};                     // bytes
+    void *h_inb[2] = {nullptr, nullptr}, *h_outb[2] = {nullptr, nullptr};   // pinned bounce buffers for pageable callers
+    size_t h_inb_cap[2] = {0, 0}, h_outb_cap[2] = {0, 0};
     double *s_lat = nullptr, *s_conv = nullptr, *s_route = nullptr;           // compute-stream scratch of one chunk
     size_t s_lat_cap = 0, s_conv_cap = 0, s_route_cap = 0;
     double *d_q = nullptr, *d_qfull = nullptr;
@@ -190,6 +193,10 @@ void rr_device_release(rr_plan *p) {
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (auto &k : d->keys) if (k.dev) cudaFree(k.dev);
+    for (int k = 0; k < 2; ++k) {
+        if (d->h_inb[k]) cudaFreeHost(d->h_inb[k]);
+        if (d->h_outb[k]) cudaFreeHost(d->h_outb[k]);
+    }
     if (d->s_comp) cudaStreamDestroy(d->s_comp);
     if (d->s_in) cudaStreamDestroy(d->s_in);
     if (d->s_out) cudaStreamDestroy(d->s_out);
@@ -648,6 +655,44 @@ int rr_weights_run(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t 
                    const double *w, const void *x, int x_is_f32, int64_t ldx, double *y, int64_t ldy, int cumulative,
                    int force_positive, const double *area, int64_t t_skip, cudaStream_t stream);
 
+// ---- pageable callers ------------------------------------------------------------------------------
+// numpy arrays are ordinary pageable memory: cudaMemcpyAsync on them is staged by the driver at a few GB/s and
+// does not overlap with anything (measured: 6-10x slower end to end than pinned arrays).  The streamed path
+// therefore bounces such arrays through its own pinned buffers with a few host threads doing the memcpy
+// (first-touch page faults of a fresh output array included) while the GPU and the DMA engines work on the
+// neighbouring chunks.  Pinned / registered arrays (rr_host_alloc, cudaHostRegister) are used in place.
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+static int copy_threads() {
+    if (const char *env = getenv("RR_COPY_THREADS")) return std::max(1, atoi(env));
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(8u, hw / 2));
+}
+// rows x row_bytes region copy, split evenly (by bytes) over the threads
+static void parallel_copy_2d(char *dst, size_t dst_pitch, const char *src, size_t src_pitch, size_t row_bytes, int64_t rows) {
+    const size_t total = row_bytes * (size_t)rows;
+    if (total == 0) return;
+    const int nt = (int)std::min<size_t>((size_t)copy_threads(), std::max<size_t>(1, total >> 20));
+    auto work = [=](int i) {
+        size_t a = total * (size_t)i / nt, b = total * (size_t)(i + 1) / nt;
+        while (a < b) {
+            const size_t r = a / row_bytes, o = a - r * row_bytes;
+            const size_t len = std::min(b - a, row_bytes - o);
+            std::memcpy(dst + r * dst_pitch + o, src + r * src_pitch + o, len);
+            a += len;
+        }
+    };
+    if (nt == 1) { work(0); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    for (int i = 1; i < nt; ++i) th.emplace_back(work, i);
+    work(0);
+    for (auto &t : th) t.join();
+}
+
 // What feeds the router, chunk by chunk: host lateral inflows (qlateral files) or gathered grid runoff that the
 // weight table (and, for UnitMuskingum, the unit hydrograph) turns into lateral inflows on the device.
 struct rr_stream_source {
@@ -693,7 +738,9 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
     // ~1 GiB of fp64 rows per buffer unless the depth rule asks for more; whole 8-row groups and whole output rows.
     const int64_t row_bytes = ldd * 8;
     const int64_t min_bytes = std::max<int64_t>(64ll << 20, (int64_t)p->max_level * (2ll << 20));
-    const int64_t min_rows = (min_bytes + row_bytes - 1) / row_bytes;
+    int64_t min_rows = (min_bytes + row_bytes - 1) / row_bytes;
+    // every chunk of a unit-hydrograph run also recomputes the n_ks - 1 rows of carry-over state
+    if (uh) min_rows = std::max<int64_t>(min_rows, 2 * src.tf->n_ks);
     const int64_t cap_rows = std::max<int64_t>(min_rows, (1ll << 30) / row_bytes);
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(T / 16, min_rows), cap_rows));
     if (const char *env = getenv("RR_STREAM_CHUNK_ROWS")) chunk = std::max(1, atoi(env));   // tests: force many chunks
@@ -717,6 +764,21 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
         if ((rc = grow_bytes(&d->s_inb[k], &d->s_inb_cap[k], need_in))) return rc;
         if ((rc = grow_bytes(&d->s_outb[k], &d->s_outb_cap[k], need_out))) return rc;
     }
+    const void *h_src = grid ? src.runoff : (const void *)src.lateral;
+    const bool in_bounce = has_lat && !host_is_pinned(h_src), out_bounce = !host_is_pinned(out);
+    auto grow_pinned = [&](void **buf, size_t *cap, size_t need) -> int {
+        if (need <= *cap) return 0;
+        CK(cudaDeviceSynchronize());
+        if (*buf) CK(cudaFreeHost(*buf));
+        *buf = nullptr; *cap = 0;
+        CK(cudaHostAlloc(buf, need, cudaHostAllocDefault));
+        *cap = need;
+        return 0;
+    };
+    for (int k = 0; k < 2; ++k) {
+        if (in_bounce && (rc = grow_pinned(&d->h_inb[k], &d->h_inb_cap[k], need_in))) return rc;
+        if (out_bounce && (rc = grow_pinned(&d->h_outb[k], &d->h_outb_cap[k], need_out))) return rc;
+    }
     const size_t need_f64 = (size_t)chunk * ldd * 8;
     if (grid && (rc = grow_bytes((void **)&d->s_lat, &d->s_lat_cap, need_f64))) return rc;
     if (uh && (rc = grow_bytes((void **)&d->s_conv, &d->s_conv_cap, need_f64))) return rc;
@@ -735,24 +797,35 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
     auto copy_in = [&](int64_t c) -> int {
         if (!has_lat) return 0;
         const int k = (int)(c & 1);
-        if (c >= 2) CK(cudaStreamWaitEvent(d->s_in, d->ev_comp[k], 0));  // buffer free once chunk c-2 was routed
-        if (grid) {
-            const int64_t lead = lead_of(c);
-            const char *h = (const char *)src.runoff + (size_t)(c * chunk - lead) * src.ldx * es_in;
-            CK(cudaMemcpy2DAsync(d->s_inb[k], ld_in * es_in, h, src.ldx * es_in, src.tf->n_points * es_in,
-                                 rows_of(c) + lead, cudaMemcpyHostToDevice, d->s_in));
-        } else {
-            CK(cudaMemcpy2DAsync(d->s_inb[k], ldd * 8, src.lateral + (size_t)c * chunk * src.ldl, src.ldl * 8, n * 8,
-                                 rows_of(c), cudaMemcpyHostToDevice, d->s_in));
+        const int64_t lead = lead_of(c), nrows = rows_of(c) + lead;
+        const size_t width = grid ? (size_t)src.tf->n_points * es_in : (size_t)n * 8;
+        const size_t h_pitch = grid ? (size_t)src.ldx * es_in : (size_t)src.ldl * 8, d_pitch = (size_t)ld_in * es_in;
+        const char *h = (const char *)h_src + (size_t)(c * chunk - lead) * h_pitch;
+        size_t pitch = h_pitch;
+        if (in_bounce) {
+            if (c >= 2) CK(cudaEventSynchronize(d->ev_in[k]));           // H2D of chunk c-2 has left the bounce buffer
+            parallel_copy_2d((char *)d->h_inb[k], d_pitch, h, h_pitch, width, nrows);
+            h = (const char *)d->h_inb[k];
+            pitch = d_pitch;
         }
+        if (c >= 2) CK(cudaStreamWaitEvent(d->s_in, d->ev_comp[k], 0));  // buffer free once chunk c-2 was routed
+        CK(cudaMemcpy2DAsync(d->s_inb[k], d_pitch, h, pitch, width, nrows, cudaMemcpyHostToDevice, d->s_in));
         CK(cudaEventRecord(d->ev_in[k], d->s_in));
+        return 0;
+    };
+    // pageable output: chunk c leaves its bounce buffer once its D2H has finished
+    auto drain = [&](int64_t c) -> int {
+        if (!out_bounce || c < 0) return 0;
+        const int k = (int)(c & 1);
+        CK(cudaEventSynchronize(d->ev_out[k]));
+        parallel_copy_2d((char *)out + (size_t)c * (chunk / resample) * ldo * es_out, (size_t)ldo * es_out,
+                         (const char *)d->h_outb[k], (size_t)ldd * es_out, (size_t)n * es_out, rows_of(c) / resample);
         return 0;
     };
     if ((rc = copy_in(0))) return rc;
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int k = (int)(c & 1);
         const int64_t rows = rows_of(c);
-        if (c + 1 < n_chunks && (rc = copy_in(c + 1))) return rc;
         if (has_lat) CK(cudaStreamWaitEvent(d->s_comp, d->ev_in[k], 0));
         if (c >= 2) CK(cudaStreamWaitEvent(d->s_comp, d->ev_out[k], 0));  // out buffer drained
         const double *lat = (const double *)d->s_inb[k];
@@ -791,10 +864,17 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
         }
         CK(cudaEventRecord(d->ev_comp[k], d->s_comp));
         CK(cudaStreamWaitEvent(d->s_out, d->ev_comp[k], 0));
-        CK(cudaMemcpy2DAsync((char *)out + (size_t)c * (chunk / resample) * ldo * es_out, ldo * es_out, d->s_outb[k],
-                             ldd * es_out, n * es_out, rows_out, cudaMemcpyDeviceToHost, d->s_out));
+        if (out_bounce)
+            CK(cudaMemcpyAsync(d->h_outb[k], d->s_outb[k], (size_t)rows_out * ldd * es_out, cudaMemcpyDeviceToHost, d->s_out));
+        else
+            CK(cudaMemcpy2DAsync((char *)out + (size_t)c * (chunk / resample) * ldo * es_out, ldo * es_out, d->s_outb[k],
+                                 ldd * es_out, n * es_out, rows_out, cudaMemcpyDeviceToHost, d->s_out));
         CK(cudaEventRecord(d->ev_out[k], d->s_out));
+        // host work of the neighbouring chunks while the device is busy with this one
+        if (c + 1 < n_chunks && (rc = copy_in(c + 1))) return rc;
+        if ((rc = drain(c - 1))) return rc;
     }
+    if ((rc = drain(n_chunks - 1))) return rc;
     CK(cudaMemcpyAsync(q_state, d->d_q, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, d->s_comp));
     if (!router_level)
         CK(cudaMemcpyAsync(q_full, d->d_qfull, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, d->s_comp));

@@ -196,3 +196,29 @@ def test_argument_errors():
                                    out.ctypes.data_as(C.c_void_p), n, 7, 1, 1, 3))
     tf.close()
     plan.close()
+
+
+@pytest.mark.parametrize('rows', [0, 4])
+def test_pinned_and_pageable_callers_agree(rows, chunk_rows):
+    """Pinned arrays (rr.pinned_empty) are copied in place; ordinary numpy arrays go through the library's pinned
+    bounce buffers with threaded host copies.  Same bits either way, also with padded row strides."""
+    n, T = 5000 + 7, 22
+    down, a = _network(n, 3, 4, 3600, 3600)
+    plan = rr.Plan(down)
+    plan.set_coefficients(a['c1'], a['c2'], a['c3'], a['c4_dt'])
+    ql = synth.lateral_volumes(T, n, 11)
+    q0 = np.random.default_rng(3).uniform(0, 10, n)
+    chunk_rows(rows)
+    q_a, out_a = q0.copy(), np.empty((T, n))
+    plan.route_host(rr.MODE_RAPID, q_a, ql, out_a, 1)
+    p_ql, p_out = rr.pinned_empty((T, n)), rr.pinned_empty((T, n), dtype=np.float32)
+    p_ql[:] = ql
+    q_b = q0.copy()
+    plan.route_host(rr.MODE_RAPID, q_b, p_ql, p_out, 1)
+    assert np.array_equal(p_out, out_a.astype(np.float32)) and np.array_equal(q_a, q_b)
+    wide_in, wide_out = np.full((T, n + 9), np.nan), np.full((T, n + 5), -1.0)
+    wide_in[:, :n] = ql
+    q_c = q0.copy()
+    plan.route_host(rr.MODE_RAPID, q_c, wide_in[:, :n], wide_out[:, :n], 1)
+    assert np.array_equal(wide_out[:, :n], out_a) and np.all(wide_out[:, n:] == -1.0) and np.array_equal(q_c, q_a)
+    plan.close()

@@ -1,9 +1,15 @@
 #!/usr/bin/env python
 """
-Times and parity-checks the BASELINE.json configurations C1-C3 at full size on one GPU (C4 is bench.py):
+Times and parity-checks the BASELINE.json configurations at full size on one GPU (the C4 bench line is bench.py):
   C1 RapidMuskingum 50k reaches, 1 year 3-hourly (dt_routing = dt_runoff and the 12-substep variant)
   C2 Muskingum channel-only, 500k reaches, main stem 3000, 15 days at 900 s (1440 steps), Q0 = 10
-  C3 UnitMuskingum 1M reaches: grid weights SpMM + unit-hydrograph convolution + routing, T = 744
+  C3 UnitMuskingum 1M reaches: grid weights SpMM + unit-hydrograph convolution + routing, T = 744, stage by stage
+     and as the single host call the router makes (rr_runoff_route_host: float32 grid in, float32 discharge out)
+  C4 RapidMuskingum 7M reaches / 5000 basins: parity of a 240-step resident chunk against the oracle on whole
+     basins (the oracle at full size would take minutes), then a full year (8760 hourly steps) streamed from
+     pinned host memory through the router-level call, state chained from chunk to chunk
+  C5 ensemble: 51 members x 360 hourly steps on the 7M-reach network, every member from the same initial state
+     (TransformMuskingum.py:121-126), final state = member mean; parity of members on whole basins
 Each stage is compared with the CPU oracle (full size where that takes seconds, a basin subset otherwise)
 with the parity measure of SURVEY.md 8d.  Writes one JSON object per line.
 """
@@ -202,7 +208,181 @@ def c3():
          cpu_reach_steps_per_s=n * T / cpu_s, parity=parity_error(out, ref))
 
 
+def c3_pipeline():
+    """C3 the way UnitMuskingum.route() runs it on grid files: one rr_runoff_route_host call per file."""
+    from river_route_b200.transforms import Transform
+    n, T, dt = 1_000_000, 744, 3600
+    down = synth.forest(n, 400, seed=2, depth_bias=0.5)
+    k, x = synth.muskingum_params(n, 2)
+    rng = np.random.default_rng(2)
+    a = network_arrays(down, k, x, dt, dt)
+    ny, nx = 721, 1440
+    ncell = rng.integers(4, 9, n)
+    river_idx = np.repeat(np.arange(n), ncell)
+    base = rng.integers(0, ny * nx - 3000, n)
+    cells = np.repeat(base, ncell) + rng.integers(0, 3000, river_idx.shape[0])
+    prop = rng.random(river_idx.shape[0]) + 0.05
+    prop /= np.repeat(np.add.reduceat(prop, np.concatenate([[0], np.cumsum(ncell)[:-1]])), ncell)
+    uniq, point_idx = np.unique(cells, return_inverse=True)
+    indptr, indices, data = oracle.weights_csr(river_idx, point_idx, prop, n, uniq.shape[0])
+    area = rng.uniform(1e5, 5e8, n)
+    ker = triangular_uh(k, area, float(dt))
+    grid = rr.pinned_empty((T, uniq.shape[0]), dtype=np.float32)
+    grid[:] = rng.gamma(0.3, 2e-3, grid.shape).astype(np.float32)
+    grid[rng.random(grid.shape) < 0.6] = 0.0
+    q0 = rng.uniform(0, 20, n)
+    plan = rr.Plan(down)
+    plan.set_coefficients(a['c1'], a['c2'], a['c3'], None)
+    tf = Transform(indptr, indices, data, uniq.shape[0], area=area).set_unit_hydrograph(ker)
+    out = rr.pinned_empty((T, n), dtype=np.float32)
+    q = q0.copy()
+    plan.runoff_route_host(tf, rr.MODE_UNIT, q, grid, out, 1)                 # warm-up: allocations, plan upload
+    times = []
+    for _ in range(3):
+        tf.set_unit_hydrograph(ker)
+        q = q0.copy()
+        timing_enable(True); timing_read(reset=True)
+        t = time.perf_counter()
+        plan.runoff_route_host(tf, rr.MODE_UNIT, q, grid, out, 1)
+        times.append(time.perf_counter() - t)
+        kt = timing_read(reset=True); timing_enable(False)
+    # parity on whole basins (basins are contiguous index ranges in the generator's order)
+    m = first_basins(down, 60_000)
+    sub = slice(0, m)
+    dep = oracle.weights_transform(indptr[:m + 1], indices[:indptr[m]], data[:indptr[m]], np.asarray(grid))
+    st = np.zeros((ker.shape[0], m))
+    conv = oracle.uh_convolve(dep, ker[:, sub], st)
+    sd = down[sub]
+    sa = network_arrays(sd, k[sub], x[sub], dt, dt)
+    sp = oracle.unit_split(sd.astype(np.int64))
+    inner, hw, ai, ah = sp['inner_idx'], sp['hw_idx'], sp['a_inner'], sp['a_hw']
+    c1i, c2i, c3i = sa['c1'][inner], sa['c2'][inner], sa['c3'][inner]
+    q_ch = q0[sub][inner].copy(); q_full = q_ch.copy(); ref = np.zeros((T, m))
+    oracle.unit_route(ai[0], ai[1], -c1i[ai[1]], ai[0], ai[1], ai[2], ah[0], ah[1], ah[2], c1i, c2i, c3i, hw, inner, q_ch,
+                      q_full, conv, ref, 1)
+    ref32 = ref.astype(np.float32)
+    got = out[:, sub]
+    rel = np.abs(got - ref32) / (np.abs(ref32) + np.abs(ref32).max(axis=0, keepdims=True) + 1e-30)
+    s = float(np.median(times))
+    emit(config='C3', stage='grid_to_discharge_one_call', api='rr_runoff_route_host (UNIT)', reaches=n, steps=T,
+         cells=int(uniq.shape[0]), n_ks=int(ker.shape[0]), wall_s=s, reach_steps_per_s=n * T / s,
+         h2d_bytes=int(grid.nbytes), d2h_bytes=int(out.nbytes), device_ms_by_class={k_: v['ms'] for k_, v in kt.items()},
+         parity_reaches=m, float32_max_rel_diff=float(rel.max()), float32_ulp_ok=bool(rel.max() < 2e-7))
+    tf.close(); plan.close()
+
+
+def c4_network():
+    n = 7_000_000
+    down = synth.forest(n, 5000, seed=4, depth_bias=0.5)
+    k, x = synth.muskingum_params(n, 4)
+    return n, down, k, x
+
+
+def first_basins(down, target):
+    """Number of reaches in the first whole basins holding at least `target` reaches (basins are contiguous ranges)."""
+    outlets = np.flatnonzero(down < 0)
+    return int(outlets[min(np.searchsorted(outlets, target), outlets.shape[0] - 1)]) + 1
+
+
+def subset_parity(down, k, x, m, lat_rows, out_rows, q0, q_after, dt=3600):
+    """RapidMuskingum parity of the first m reaches (whole basins) against the oracle; arrays are already cut to m."""
+    a = network_arrays(down[:m], k[:m], x[:m], dt, dt)
+    q_ref, ref = np.ascontiguousarray(q0, dtype=np.float64).copy(), np.zeros((lat_rows.shape[0], m))
+    oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q_ref,
+                       np.ascontiguousarray(lat_rows), ref, 1)
+    return parity_error(out_rows, ref), parity_error(q_after, q_ref)
+
+
+def c4():
+    n, down, k, x = c4_network()
+    a1 = bench_coefficients(k, x)
+    plan = rr.Plan(down)
+    plan.set_coefficients(*a1)
+    rows = 240
+    lat = rr.pinned_empty((rows, n))
+    synth.lateral_volumes(48, n, 5, out=lat[:48])                              # 48 distinct rows, repeated with a trend
+    for r in range(48, rows, 48):
+        np.multiply(lat[:48], 1.0 + 0.1 * (r // 48), out=lat[r:r + 48])
+    q0 = np.zeros(n)
+    ms, out, q = dev_route(plan, rr.MODE_RAPID, q0, lat, rows, 1, n, reps=3)
+    m = first_basins(down, 300_000)
+    p_out, p_q = subset_parity(down, k, x, m, lat[:, :m], out[:, :m], q0[:m], q[:m])
+    emit(config='C4', stage='resident_chunk', reaches=n, steps=rows, gpu_ms=ms, reach_steps_per_s=n * rows / (ms * 1e-3),
+         parity_reaches=m, parity=p_out, parity_state=p_q, checksum_out=float(out.sum()), checksum_state=float(q.sum()))
+    del out
+    # ---- a full year, streamed: 8760 hourly steps = 91.25 chunks of 96 rows cycled from one pinned buffer ----
+    er, year = 96, 8760
+    out32 = rr.pinned_empty((er, n), dtype=np.float32)
+    qy = np.zeros(n)
+    plan.route_host(rr.MODE_RAPID, qy, lat[:er], out32, 1)                     # warm-up
+    qy[:] = 0.0
+    t = time.perf_counter()
+    done = 0
+    while done < year:
+        r = min(er, year - done)
+        plan.route_host(rr.MODE_RAPID, qy, lat[:r], out32[:r], 1)
+        done += r
+    s = time.perf_counter() - t
+    emit(config='C4', stage='one_year_streamed', api='Plan.route_host -> rr_route_host_ex (float32 out)', reaches=n,
+         steps=year, wall_s=s, reach_steps_per_s=n * year / s, h2d_GB=n * year * 8 / 1e9, d2h_GB=n * year * 4 / 1e9,
+         state_finite=bool(np.isfinite(qy).all()), state_sum=float(qy.sum()))
+    plan.close()
+
+
+def bench_coefficients(k, x, dt=3600):
+    dt_div_k = dt / k
+    den = dt_div_k + (2 * (1 - x))
+    _2x = 2 * x
+    c1 = (dt_div_k - _2x) / den
+    c2 = (dt_div_k + _2x) / den
+    c3 = ((2 * (1 - x)) - dt_div_k) / den
+    return c1, c2, c3, (c1 + c2) / dt
+
+
+def c5():
+    """51 members x 360 steps, device resident: members are routed one after the other from the same initial state
+    (time tiling already amortises the parameters, which is what batching members as columns was for in a
+    per-timestep formulation).  Member inputs = one base series x lognormal(0, 0.3) per member."""
+    n, down, k, x = c4_network()
+    plan = rr.Plan(down)
+    plan.set_coefficients(*bench_coefficients(k, x))
+    T, M = 360, 51
+    ld = n
+    base = torch.from_numpy(synth.lateral_volumes(24, n, 6)).to(dev)
+    d_lat = torch.empty((T, ld), dtype=torch.float64, device=dev)
+    d_out = torch.empty((T, ld), dtype=torch.float64, device=dev)
+    q_init = np.random.default_rng(6).uniform(0, 30, n)
+    d_q0 = torch.from_numpy(q_init).to(dev)
+    d_mean = torch.zeros(n, dtype=torch.float64, device=dev)
+    scale = np.random.default_rng(7).lognormal(0, 0.3, M)
+    stream = torch.cuda.current_stream().cuda_stream
+    checks = []
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    route_ms = 0.0
+    for mbr in range(M):
+        for r in range(0, T, 24):
+            d_lat[r:r + 24] = base * float(scale[mbr]) * (1.0 + 0.01 * (r // 24))
+        d_q = d_q0.clone()
+        e0.record()
+        plan.route_dev(rr.MODE_RAPID, d_q.data_ptr(), d_lat.data_ptr(), ld, d_out.data_ptr(), ld, T, 1, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        route_ms += e0.elapsed_time(e1)
+        d_mean += d_q                                                         # member-order sum, then / M (:145-146)
+        if mbr in (0, M - 1):
+            m = first_basins(down, 60_000)
+            p_out, p_q = subset_parity(down, k, x, m, d_lat[:, :m].cpu().numpy(), d_out[:, :m].cpu().numpy(),
+                                       q_init[:m], d_q[:m].cpu().numpy())
+            checks.append(dict(member=mbr, parity_reaches=m, parity=p_out, parity_state=p_q))
+    d_mean /= M
+    emit(config='C5', stage='ensemble', members=M, reaches=n, steps=T, route_ms_total=route_ms,
+         reach_steps_members_per_s=n * T * M / (route_ms * 1e-3), checks=checks,
+         mean_state_finite=bool(torch.isfinite(d_mean).all().item()), mean_state_sum=float(d_mean.sum().item()))
+    plan.close()
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['c1', 'c2', 'c3']
+    which = sys.argv[1:] or ['c1', 'c2', 'c3', 'c3_pipeline', 'c4', 'c5']
     for w in which:
-        {'c1': c1, 'c2': c2, 'c3': c3}[w]()
+        {'c1': c1, 'c2': c2, 'c3': c3, 'c3_pipeline': c3_pipeline, 'c4': c4, 'c5': c5}[w]()

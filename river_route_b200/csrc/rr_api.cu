@@ -93,7 +93,7 @@ struct rr_device_state {
     size_t key_cap = 0;
     int64_t sched_tiles = -1, sched_budget_rows = -1;
     rr_schedule sched;
-    struct key_table { int64_t n_tiles = -1, n_keys = 0, n_items = 0; int64_t *dev = nullptr; size_t cap = 0; uint64_t used = 0; };
+    struct key_table { int64_t n_tiles = -1, n_items = 0; int32_t *dev = nullptr; size_t cap = 0; uint64_t used = 0; };   // ticket -> (block, tile)
     key_table keys[4];
     uint64_t key_clock = 0;
     double *raw = nullptr;
@@ -282,15 +282,17 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
         kt = &d->keys[0];
         for (auto &k : d->keys) if (k.used < kt->used) kt = &k;
         rr_build_keys(*p, n_tiles, d->sched);
+        std::vector<int32_t> items;
+        rr_build_items(*p, n_tiles, d->sched, items);
         CK(cudaDeviceSynchronize());
-        if (d->sched.key_start.size() > kt->cap) {
+        if (items.size() > kt->cap) {
             if (kt->dev) CK(cudaFree(kt->dev));
             kt->dev = nullptr; kt->cap = 0;
-            CK(cudaMalloc((void **)&kt->dev, d->sched.key_start.size() * sizeof(int64_t)));
-            kt->cap = d->sched.key_start.size();
+            CK(cudaMalloc((void **)&kt->dev, std::max<size_t>(items.size(), 2) * sizeof(int32_t)));
+            kt->cap = items.size();
         }
-        CK(cudaMemcpy(kt->dev, d->sched.key_start.data(), d->sched.key_start.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-        kt->n_tiles = n_tiles; kt->n_keys = d->sched.n_keys; kt->n_items = d->sched.n_items;
+        CK(cudaMemcpy(kt->dev, items.data(), items.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        kt->n_tiles = n_tiles; kt->n_items = d->sched.n_items;
     }
     kt->used = ++d->key_clock;
     // one spare row: the kernel prefetches a few lines past the row it is reading
@@ -320,7 +322,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.exp_ro = d->exp_ro; P.edge_ro = d->edge_ro; P.raw_rows = d->sched.raw_rows;
     P.lvl_ptr = d->lvl_ptr; P.lvl_blk = d->lvl_blk;
     P.c1 = d->coef; P.c2 = d->coef + p->n; P.c3 = d->coef + 2 * p->n; P.c4 = d->coef + 3 * p->n;
-    P.key_start = kt->dev; P.n_keys = kt->n_keys; P.n_items = kt->n_items;
+    P.items = reinterpret_cast<const int2 *>(kt->dev); P.n_items = kt->n_items;
     P.delta = d->sched.delta; P.n_tiles = (int32_t)n_tiles;
     P.T = (int32_t)T; P.K = (int32_t)K; P.tile_rows = (int32_t)rows;
     P.raw_pitch = (int32_t)pitch; P.n_members = n_members; P.first_call = first_call; P.last_call = last_call;

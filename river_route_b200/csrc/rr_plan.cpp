@@ -412,6 +412,26 @@ void rr_build_keys(const rr_plan &p, int64_t n_tiles, rr_schedule &s) {
     s.n_items = s.key_start[s.n_keys];
 }
 
+// Ticket table: (block, tile) of every ticket in ticket order -- keys ascending, within a key tiles ascending,
+// within a (key, tile) the blocks of that level in (level, id) order.  One 8-byte load decodes a ticket on the
+// device (the search over key_start that rr_decode_ticket does costs a dozen dependent loads per work item).
+void rr_build_items(const rr_plan &p, int64_t n_tiles, const rr_schedule &s, std::vector<int32_t> &items) {
+    items.resize(2 * (size_t)s.n_items);
+    size_t t = 0;
+    for (int64_t key = 0; key < s.n_keys; ++key) {
+        int64_t j = key > p.max_level ? (key - p.max_level + s.delta - 1) / s.delta : 0;
+        const int64_t jhi = std::min<int64_t>(n_tiles - 1, key / s.delta);
+        for (; j <= jhi; ++j) {
+            const int64_t l = key - j * s.delta;
+            for (int32_t r = p.lvl_ptr[l]; r < p.lvl_ptr[l + 1]; ++r) {
+                items[2 * t] = p.lvl_blk[r];
+                items[2 * t + 1] = (int32_t)j;
+                ++t;
+            }
+        }
+    }
+}
+
 void rr_build_schedule(const rr_plan &p, int64_t n_tiles, int32_t delta, int64_t budget_rows, rr_schedule &s) {
     rr_build_rings(p, delta, budget_rows, s);
     rr_build_keys(p, n_tiles, s);
@@ -442,8 +462,18 @@ extern "C" int rr_plan_schedule(const rr_plan *p, int64_t n_tiles, int32_t tile_
     rr_schedule s;
     rr_build_schedule(*p, n_tiles, tile_stride, INT64_MAX, s);
     if (n_items) *n_items = s.n_items;
-    if (item_block && item_tile)
-        for (int64_t t = 0; t < s.n_items; ++t) rr_decode_ticket(*p, s, n_tiles, t, item_block + t, item_tile + t);
+    if (item_block && item_tile) {
+        // the table the kernel reads, cross-checked against the one-ticket-at-a-time decode
+        std::vector<int32_t> items;
+        rr_build_items(*p, n_tiles, s, items);
+        for (int64_t t = 0; t < s.n_items; ++t) {
+            item_block[t] = items[2 * (size_t)t];
+            item_tile[t] = items[2 * (size_t)t + 1];
+            int32_t b = -1, j = -1;
+            rr_decode_ticket(*p, s, n_tiles, t, &b, &j);
+            if (b != item_block[t] || j != item_tile[t]) { rr_set_error("ticket table disagrees with the ticket decode"); return 101; }
+        }
+    }
     return 0;
 }
 

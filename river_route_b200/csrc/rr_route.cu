@@ -752,21 +752,9 @@ __device__ __forceinline__ bool next_item(const rr_route_params &P, int lane, in
     m = 0;
     int64_t ticket = (int64_t)tk;
     if (P.n_members > 1) { m = (int)(tk % (unsigned)P.n_members); ticket = (int64_t)(tk / (unsigned)P.n_members); }
-    int64_t lo = 0, hi = P.n_keys;
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(P.key_start + mid) <= ticket) lo = mid; else hi = mid;
-    }
-    int64_t r = ticket - __ldg(P.key_start + lo);
-    int64_t jj = lo > P.max_level ? (lo - P.max_level + P.delta - 1) / P.delta : 0;
-    for (;; ++jj) {
-        const int64_t l = lo - jj * P.delta;
-        const int32_t base = __ldg(P.lvl_ptr + l);
-        const int64_t w = __ldg(P.lvl_ptr + l + 1) - base;
-        if (r < w) { b = __ldg(P.lvl_blk + base + r); break; }
-        r -= w;
-    }
-    j = (int)jj;
+    const int2 bj = __ldg(P.items + ticket);
+    b = bj.x;
+    j = bj.y;
     return true;
 }
 

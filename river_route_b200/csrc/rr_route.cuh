@@ -22,8 +22,7 @@ struct rr_route_params {
     const int32_t *lvl_ptr, *lvl_blk;
     const double *c1, *c2, *c3, *c4;
     // ---- ticket schedule ----
-    const int64_t *key_start;
-    int64_t n_keys;
+    const int2 *items;    // [n_items] (block, tile) of every ticket, in ticket order
     int64_t n_items;      // per member
     int32_t delta;
     int32_t n_tiles;

@@ -5,11 +5,13 @@
 // (ascending column) order -- scipy's csr_matvecs row-wise axpy order -- then cumulative ->
 // incremental, optional clip at zero, NaN -> 0 and optional multiplication by catchment area.
 // Memory-bound CSR SpMM with time as the dense dimension: one thread per river so the (T, n)
-// output rows are written as coalesced 256-byte segments; the runoff is transposed to (cell, time)
-// first so that each weight entry reads one full 32-byte sector (8 time steps of one cell).
+// output rows are written as coalesced 256-byte segments; the runoff is first re-laid as
+// [time block][cell][8 steps] so that each weight entry reads one full 32-byte sector and one launch per
+// time block gathers from an L2-resident slab.
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "rr_internal.h"
@@ -30,8 +32,10 @@ namespace {
 constexpr int TB = 8;   // time steps per register block == one 32-byte sector of float32 runoff
 
 // Gathered grid runoff arrives time-major (T, n_points); a catchment touches a handful of scattered
-// cells, so reading it in place wastes 7/8 of every sector.  It is transposed once per call to
-// (n_points, Tp) so that the TB time steps of one cell are one contiguous sector.
+// cells, so reading it in place wastes 7/8 of every sector.  It is re-laid once per call as
+// [time block][cell][TB steps]: the TB time steps of one cell are one 32-byte sector (float32), and all the
+// sectors of one time block are contiguous -- n_points x 32 bytes, small enough to stay in L2 while one
+// launch gathers from it (each cell is read by several catchments, in no particular order).
 template <typename XT>
 __global__ void __launch_bounds__(256) transpose_kernel(const XT *__restrict__ x, int64_t ldx, XT *__restrict__ xt,
                                                         int64_t Tp, int64_t T, int64_t n_points) {
@@ -45,58 +49,64 @@ __global__ void __launch_bounds__(256) transpose_kernel(const XT *__restrict__ x
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         const int64_t c = c0 + r, t = t0 + tx;
-        if (c < n_points && t < Tp) xt[c * Tp + t] = tile[tx][r];
+        if (c < n_points && t < Tp) xt[((t / TB) * n_points + c) * TB + (t % TB)] = tile[tx][r];
     }
 }
 
 template <typename XT> struct vec8;
-// 8 consecutive time steps of one cell: one 256-bit load (float) or two (double).  The L2::128B hint makes L2
-// fetch the whole line -- the next three time blocks of this cell -- in one DRAM burst.
+// 8 consecutive time steps of one cell: one 256-bit load (float) or two (double)
 template <> struct vec8<float> {
     float v[8];
     __device__ __forceinline__ void load(const float *p) {
-        asm volatile("ld.global.nc.L2::128B.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
     }
 };
 template <> struct vec8<double> {
     double v[8];
     __device__ __forceinline__ void load(const double *p) {
-        asm volatile("ld.global.nc.L2::128B.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-        asm volatile("ld.global.nc.L2::128B.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]) : "l"(p + 4));
+        asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+        asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]) : "l"(p + 4));
     }
 };
 
 // One thread per river, TB outputs in registers; row entries are walked in stored (ascending column)
 // order so every output accumulates in scipy's csr_matvecs order; the tail of runoff.py:309-337 is fused.
+// One launch covers the time steps [t_begin, t_end); grid.y splits them further when there are few rivers.
+// `carry` holds the aggregated value of the last step of the previous launch (cumulative input).
 template <typename XT>
-__global__ void __launch_bounds__(128) weights_kernel(int64_t n_rivers, int64_t T, int64_t Tp, int64_t chunk,
+__global__ void __launch_bounds__(128) weights_kernel(int64_t n_rivers, int64_t n_points, int64_t t_begin, int64_t t_end,
+                                                      int64_t chunk,
                                                       const int32_t *__restrict__ indptr,
                                                       const int32_t *__restrict__ indices,
                                                       const double *__restrict__ w, const XT *__restrict__ xt,
                                                       double *__restrict__ y, int64_t ldy,
                                                       int cumulative, int force_positive,
-                                                      const double *__restrict__ area, int64_t t_skip) {
+                                                      const double *__restrict__ area, int64_t t_skip,
+                                                      double *__restrict__ carry) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rivers) return;
-    const int64_t tb = (int64_t)blockIdx.y * chunk;
-    const int64_t te = min(T, tb + chunk);
+    const int64_t tb = t_begin + (int64_t)blockIdx.y * chunk;
+    const int64_t te = min(t_end, tb + chunk);
     const int p0 = __ldg(indptr + r);
     const int p1 = __ldg(indptr + r + 1);
     const double a = area ? __ldg(area + r) : 1.0;
     double prev = 0.0;   // aggregated value of the step before this block (cumulative input, runoff.py:310-312)
     if (cumulative && tb > 0) {
-        for (int j = p0; j < p1; ++j)
-            prev = fma(__ldg(w + j), (double)__ldg(xt + (int64_t)__ldg(indices + j) * Tp + tb - 1), prev);
+        if (tb == t_begin) prev = carry[r];
+        else
+            for (int j = p0; j < p1; ++j)
+                prev = fma(__ldg(w + j), (double)__ldg(xt + (((tb - 1) / TB) * n_points + __ldg(indices + j)) * TB + (tb - 1) % TB), prev);
     }
     for (int64_t t0 = tb; t0 < te; t0 += TB) {
         double acc[TB];
 #pragma unroll
         for (int u = 0; u < TB; ++u) acc[u] = 0.0;
+        const XT *blk = xt + (t0 / TB) * n_points * TB;
         for (int j = p0; j < p1; ++j) {
             const double wj = __ldg(w + j);
             vec8<XT> xv;
-            xv.load(xt + (int64_t)__ldg(indices + j) * Tp + t0);
+            xv.load(blk + (int64_t)__ldg(indices + j) * TB);
 #pragma unroll
             for (int u = 0; u < TB; ++u) acc[u] = fma(wj, (double)xv.v[u], acc[u]);
         }
@@ -112,6 +122,7 @@ __global__ void __launch_bounds__(128) weights_kernel(int64_t n_rivers, int64_t 
             } else if (cumulative && t0 + u < te) prev = acc[u];
         }
     }
+    if (cumulative && te == t_end) carry[r] = prev;
 }
 
 template <typename XT>
@@ -120,6 +131,7 @@ int run_weights(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *in
                 const double *area, int64_t t_skip, cudaStream_t stream) {
     const int64_t Tp = ((T + TB - 1) / TB) * TB;
     XT *xt = nullptr;
+    double *carry = nullptr;
     {   // keep the stream-ordered pool's memory between calls (the default trims it at every sync)
         static thread_local int tuned_device = -1;
         int dev = 0;
@@ -134,6 +146,7 @@ int run_weights(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *in
         }
     }
     CK(cudaMallocAsync((void **)&xt, sizeof(XT) * (size_t)n_points * Tp, stream));
+    if (cumulative) CK(cudaMallocAsync((void **)&carry, sizeof(double) * (size_t)n_rivers, stream));
     dim3 tg((unsigned)((n_points + 31) / 32), (unsigned)((Tp + 31) / 32));
     transpose_kernel<XT><<<tg, 256, 0, stream>>>(x, ldx, xt, Tp, T, n_points);
     CK(cudaGetLastError());
@@ -142,15 +155,28 @@ int run_weights(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *in
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t want_y = std::max<int64_t>(1, ((int64_t)sms * 16 + gx - 1) / gx);
-    int64_t chunk = std::max<int64_t>(64, (T + want_y - 1) / want_y);
-    chunk = std::min<int64_t>(((chunk + TB - 1) / TB) * TB, Tp);
-    dim3 grid(gx, (unsigned)((T + chunk - 1) / chunk));
-    weights_kernel<XT><<<grid, threads, 0, stream>>>(n_rivers, T, Tp, chunk, indptr, indices, w, xt, y, ldy, cumulative,
-                                                     force_positive, area, t_skip);
-    CK(cudaGetLastError());
+    // time steps per launch: the gathered cells of those steps (n_points x steps x element) should stay in L2
+    // (126 MB on B200, shared with the output stream): about 32 MB; everything at once when it is that small
+    int64_t l2_mb = 32;
+    if (const char *env = getenv("RR_WEIGHTS_L2_MB")) l2_mb = std::max(1, atoi(env));
+    int64_t span = std::max<int64_t>(TB, (((l2_mb << 20) / (int64_t)(n_points * sizeof(XT))) / TB) * TB);
+    span = std::min<int64_t>(span, Tp);
+    int64_t launches = 0;
+    for (int64_t t_begin = 0; t_begin < T; t_begin += span) {
+        const int64_t t_end = std::min<int64_t>(T, t_begin + span), len = t_end - t_begin;
+        // few rivers: split the span over grid.y so that the machine is filled
+        const int64_t want_y = std::max<int64_t>(1, ((int64_t)sms * 16 + gx - 1) / gx);
+        int64_t chunk = std::max<int64_t>(64, (len + want_y - 1) / want_y);
+        chunk = std::min<int64_t>(((chunk + TB - 1) / TB) * TB, span);
+        dim3 grid(gx, (unsigned)((len + chunk - 1) / chunk));
+        weights_kernel<XT><<<grid, threads, 0, stream>>>(n_rivers, n_points, t_begin, t_end, chunk, indptr, indices, w, xt, y,
+                                                         ldy, cumulative, force_positive, area, t_skip, carry);
+        CK(cudaGetLastError());
+        ++launches;
+    }
     CK(cudaFreeAsync(xt, stream));
-    rr_count_launch(2);
+    if (carry) CK(cudaFreeAsync(carry, stream));
+    rr_count_launch(1 + launches);
     return 0;
 }
 

@@ -134,6 +134,40 @@ __global__ void __launch_bounds__(128) uh_state_kernel(int64_t n, int n_ks, int6
     state[(int64_t)(n_ks - 1) * lds + b] = 0.0;
 }
 
+// The same with the taps and the last NT - 1 inputs in registers (n_ks <= NT = NG * 8): every kernel row and every
+// input row is read once instead of once per (state row, tap) pair.  Same accumulation order: old state first,
+// then inputs from the oldest to the newest.
+template <int NG>
+__global__ void __launch_bounds__(128) uh_state_kernel_reg(int64_t n, int n_ks, int64_t T,
+                                                           const double *__restrict__ lat, int64_t ldl,
+                                                           const double *__restrict__ ker, int64_t ldk,
+                                                           double *state, int64_t lds) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    constexpr int NT = NG * 8;
+    double kq[NT], x[NT];   // x[i] = input at time T - NT + i (zero before the call started)
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+        kq[k] = k < n_ks ? __ldg(ker + (int64_t)k * ldk + b) : 0.0;
+        const int64_t t = T - NT + k;
+        x[k] = t >= 0 ? __ldg(lat + t * ldl + b) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < NT - 1; ++j) {
+        if (j < n_ks - 1) {
+            // an old state row that is still ahead of the call's end (only when T < n_ks); row T + j is overwritten
+            // later than it is read here because T >= 1
+            const int64_t t = T + j;
+            double acc = t < n_ks ? state[t * lds + b] : 0.0;
+            // inputs s = T - NT + i, tap = T + j - s = NT + j - i; taps >= n_ks are zero (kq padded), taps <= NT - 1
+#pragma unroll
+            for (int i = j + 1; i < NT; ++i) acc = fma(kq[NT + j - i], x[i], acc);
+            state[(int64_t)j * lds + b] = acc;
+        }
+    }
+    state[(int64_t)(n_ks - 1) * lds + b] = 0.0;
+}
+
 }  // namespace
 
 extern "C" int rr_uh_convolve_dev(int64_t n, int64_t n_ks, int64_t T, const double *lateral, int64_t ldl,
@@ -168,7 +202,17 @@ extern "C" int rr_uh_convolve_dev(int64_t n, int64_t n_ks, int64_t T, const doub
     }
 #undef RR_UH_REG
     CK(cudaGetLastError());
-    uh_state_kernel<<<gx, threads, 0, stream>>>(n, nk, T, lateral, ldl, kernel, ldk, state, lds);
+#define RR_UH_STATE(NG) uh_state_kernel_reg<NG><<<gx, threads, 0, stream>>>(n, nk, T, lateral, ldl, kernel, ldk, state, lds)
+    switch ((nk + 7) / 8) {
+        case 1: RR_UH_STATE(1); break;
+        case 2: RR_UH_STATE(2); break;
+        case 3: RR_UH_STATE(3); break;
+        case 4: RR_UH_STATE(4); break;
+        case 5: RR_UH_STATE(5); break;
+        case 6: RR_UH_STATE(6); break;
+        default: uh_state_kernel<<<gx, threads, 0, stream>>>(n, nk, T, lateral, ldl, kernel, ldk, state, lds);
+    }
+#undef RR_UH_STATE
     CK(cudaGetLastError());
     rr_count_launch(2);
     return 0;

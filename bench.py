@@ -396,7 +396,7 @@ def main():
     host_equals_dev = bool(np.array_equal(d_chk[:, :n].cpu().numpy().astype(np.float32), h_out32))
     del d_chk
     variants = {}
-    if not args.no_e2e_variants:
+    if not args.no_e2e_variants and world == 1:                        # extra pinned host memory: one GPU only
         # (a) the reference kernel's own contract: fp64 discharge array back to the host (rapid_route drop-in)
         h_out64 = rr.pinned_empty((er, n))
         variants['kernel_level_f64_out'] = {

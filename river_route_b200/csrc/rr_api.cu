@@ -288,7 +288,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
         if (items.size() > kt->cap) {
             if (kt->dev) CK(cudaFree(kt->dev));
             kt->dev = nullptr; kt->cap = 0;
-            CK(cudaMalloc((void **)&kt->dev, std::max<size_t>(items.size(), 2) * sizeof(int32_t)));
+            CK(cudaMalloc((void **)&kt->dev, std::max<size_t>(items.size(), 4) * sizeof(int32_t)));
             kt->cap = items.size();
         }
         CK(cudaMemcpy(kt->dev, items.data(), items.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -322,7 +322,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.exp_ro = d->exp_ro; P.edge_ro = d->edge_ro; P.raw_rows = d->sched.raw_rows;
     P.lvl_ptr = d->lvl_ptr; P.lvl_blk = d->lvl_blk;
     P.c1 = d->coef; P.c2 = d->coef + p->n; P.c3 = d->coef + 2 * p->n; P.c4 = d->coef + 3 * p->n;
-    P.items = reinterpret_cast<const int2 *>(kt->dev); P.n_items = kt->n_items;
+    P.items = reinterpret_cast<const int4 *>(kt->dev); P.n_items = kt->n_items;
     P.delta = d->sched.delta; P.n_tiles = (int32_t)n_tiles;
     P.T = (int32_t)T; P.K = (int32_t)K; P.tile_rows = (int32_t)rows;
     P.raw_pitch = (int32_t)pitch; P.n_members = n_members; P.first_call = first_call; P.last_call = last_call;

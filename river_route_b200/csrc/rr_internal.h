@@ -66,7 +66,7 @@ struct rr_schedule {
 void rr_build_schedule(const rr_plan &p, int64_t n_tiles, int32_t delta, int64_t budget_rows, rr_schedule &s);
 void rr_build_rings(const rr_plan &p, int32_t delta, int64_t budget_rows, rr_schedule &s);
 void rr_build_keys(const rr_plan &p, int64_t n_tiles, rr_schedule &s);
-void rr_build_items(const rr_plan &p, int64_t n_tiles, const rr_schedule &s, std::vector<int32_t> &items);  // [n_items][2] block, tile
+void rr_build_items(const rr_plan &p, int64_t n_tiles, const rr_schedule &s, std::vector<int32_t> &items);  // [n_items][4] block, tile, dep range
 // Host mirror of the kernel's ticket decode.
 void rr_decode_ticket(const rr_plan &p, const rr_schedule &s, int64_t n_tiles, int64_t ticket,
                       int32_t *block, int32_t *tile);

@@ -412,11 +412,11 @@ void rr_build_keys(const rr_plan &p, int64_t n_tiles, rr_schedule &s) {
     s.n_items = s.key_start[s.n_keys];
 }
 
-// Ticket table: (block, tile) of every ticket in ticket order -- keys ascending, within a key tiles ascending,
-// within a (key, tile) the blocks of that level in (level, id) order.  One 8-byte load decodes a ticket on the
+// Ticket table: {block, tile, dep_ptr[block], dep_ptr[block + 1]} of every ticket in ticket order -- keys ascending, within a key tiles ascending,
+// within a (key, tile) the blocks of that level in (level, id) order.  One 16-byte load decodes a ticket on the
 // device (the search over key_start that rr_decode_ticket does costs a dozen dependent loads per work item).
 void rr_build_items(const rr_plan &p, int64_t n_tiles, const rr_schedule &s, std::vector<int32_t> &items) {
-    items.resize(2 * (size_t)s.n_items);
+    items.resize(4 * (size_t)s.n_items);
     size_t t = 0;
     for (int64_t key = 0; key < s.n_keys; ++key) {
         int64_t j = key > p.max_level ? (key - p.max_level + s.delta - 1) / s.delta : 0;
@@ -424,8 +424,11 @@ void rr_build_items(const rr_plan &p, int64_t n_tiles, const rr_schedule &s, std
         for (; j <= jhi; ++j) {
             const int64_t l = key - j * s.delta;
             for (int32_t r = p.lvl_ptr[l]; r < p.lvl_ptr[l + 1]; ++r) {
-                items[2 * t] = p.lvl_blk[r];
-                items[2 * t + 1] = (int32_t)j;
+                const int32_t blk = p.lvl_blk[r];
+                items[4 * t] = blk;
+                items[4 * t + 1] = (int32_t)j;
+                items[4 * t + 2] = p.dep_ptr[blk];        // the block's upstream-block list, so that the kernel can
+                items[4 * t + 3] = p.dep_ptr[blk + 1];    // fetch it without first loading dep_ptr
                 ++t;
             }
         }
@@ -467,8 +470,8 @@ extern "C" int rr_plan_schedule(const rr_plan *p, int64_t n_tiles, int32_t tile_
         std::vector<int32_t> items;
         rr_build_items(*p, n_tiles, s, items);
         for (int64_t t = 0; t < s.n_items; ++t) {
-            item_block[t] = items[2 * (size_t)t];
-            item_tile[t] = items[2 * (size_t)t + 1];
+            item_block[t] = items[4 * (size_t)t];
+            item_tile[t] = items[4 * (size_t)t + 1];
             int32_t b = -1, j = -1;
             rr_decode_ticket(*p, s, n_tiles, t, &b, &j);
             if (b != item_block[t] || j != item_tile[t]) { rr_set_error("ticket table disagrees with the ticket decode"); return 101; }

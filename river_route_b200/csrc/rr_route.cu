@@ -137,6 +137,9 @@ struct item_ctx {
     double c1, c2, c3, c4, q;   // q = state before the tile (UNIT: q_ch)
     int e0, deg, ex;
     rr_blk_meta M;
+    int2 ro_me;                  // {first row, ring depth} of this lane's exported series (valid when ex >= 0)
+    int2 ro_up[RR_MAX_FAST_DEG]; // the same pair for the first upstream slots (fast-path blocks)
+    int dep_lo, dep_hi;          // this block's range in dep_idx (from the ticket table)
     const double *lat0;          // this lane's lateral value of the tile's first row
     int64_t lstride;             // distance between consecutive rows of the lateral tile
     double *out0;                // this lane's discharge value of the tile's first row
@@ -164,13 +167,13 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
         has[k] = k < deg;
         up[k] = c.raw_m;
         if (has[k]) {
-            const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + e0 + k);
+            const int2 ro = c.ro_up[k];
             up[k] = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         }
     }
     double *myraw = nullptr;
     if (ex >= 0) {
-        const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + ex);
+        const int2 ro = c.ro_me;
         myraw = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         myraw[RAW_CARRY] = q;
     }
@@ -291,13 +294,13 @@ __device__ __forceinline__ void fast_item_k(const rr_route_params &P, const item
         has[k] = k < deg;
         up[k] = c.raw_m;
         if (has[k]) {
-            const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + e0 + k);
+            const int2 ro = c.ro_up[k];
             up[k] = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         }
     }
     double *myraw = nullptr;
     if (ex >= 0) {
-        const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + ex);
+        const int2 ro = c.ro_me;
         myraw = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         myraw[RAW_CARRY] = q;
     }
@@ -395,7 +398,7 @@ __device__ __forceinline__ void unit_fast_item(const rr_route_params &P, const i
             const int64_t u = __ldg(P.up_idx + e0 + k);
             lu_row[k] = lat_ptr(P, m, j, c.t0, u, 0);
             if (!hw[k]) {
-                const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + e0 + k);
+                const int2 ro = c.ro_up[k];
                 ex_row[k] = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
             }
         }
@@ -403,7 +406,7 @@ __device__ __forceinline__ void unit_fast_item(const rr_route_params &P, const i
     if (P.tile_major == 1) lu_stride = RR_BLOCK; else if (P.tile_major == 0) lu_stride = P.ldl;
     double *myraw = nullptr;
     if (ex >= 0 && inner) {
-        const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + ex);
+        const int2 ro = c.ro_me;
         myraw = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         myraw[RAW_CARRY] = q;
         myraw[RAW_QF] = qf;
@@ -556,7 +559,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
     }
     double *myraw = nullptr;
     if (ex >= 0) {
-        const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + ex);
+        const int2 ro = c.ro_me;
         myraw = raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         myraw[RAW_CARRY] = qcur;                 // carry-in for consumers
         if (UNIT) myraw[RAW_QF] = qf_cur;        // q_full carry-in
@@ -739,7 +742,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
 // Tickets are drawn in batches of P.ticket_batch consecutive tickets per warp: one global atomic per batch keeps
 // the single-address atomic rate (an L2 atomic unit serialises them) off the critical path of large launches.
 // A warp works through its batch in order, so the lowest unfinished ticket is still always being processed.
-__device__ __forceinline__ bool next_item(const rr_route_params &P, int lane, int &m, int &b, int &j,
+__device__ __forceinline__ bool next_item(const rr_route_params &P, int lane, int &m, int &b, int &j, int &dep_lo, int &dep_hi,
                                           unsigned long long &tk_next, unsigned long long &tk_end) {
     if (tk_next >= tk_end) {
         unsigned long long t0 = 0;
@@ -752,15 +755,18 @@ __device__ __forceinline__ bool next_item(const rr_route_params &P, int lane, in
     m = 0;
     int64_t ticket = (int64_t)tk;
     if (P.n_members > 1) { m = (int)(tk % (unsigned)P.n_members); ticket = (int64_t)(tk / (unsigned)P.n_members); }
-    const int2 bj = __ldg(P.items + ticket);
-    b = bj.x;
-    j = bj.y;
+    const int4 it = __ldg(P.items + ticket);   // {block, tile, first and one-past-last entry of the block in dep_idx}
+    b = it.x;
+    j = it.y;
+    dep_lo = it.z;
+    dep_hi = it.w;
     return true;
 }
 
 // per-lane constants of an item, lateral prefetch, dependency waits, initial state
 template <int MODE>
-__device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c, int lane, int m, int b, int j) {
+__device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c, int lane, int m, int b, int j, int dep_lo,
+                                          int dep_hi) {
     constexpr bool HAS_LAT = (MODE != RR_MODE_MUSKINGUM);
     constexpr bool UNIT = (MODE == RR_MODE_UNIT);
     const int64_t i = (int64_t)b * RR_BLOCK + lane;
@@ -819,14 +825,28 @@ __device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c,
 #ifdef RR_PROFILE
     const long long w0_ = clock64();
 #endif
+    // Everything the waits and the item need from the plan is requested BEFORE the first wait (the waits are
+    // ordered asm statements: loads written after them cannot start earlier): the ids of the upstream blocks, this
+    // lane's downstream block (ring reuse) and the ring rows of its own and its upstreams' exported series.
+    c.dep_lo = dep_lo; c.dep_hi = dep_hi;
+    int32_t dep_blk = -1;
+    if (dep_lo + lane < dep_hi) dep_blk = __ldg(P.dep_idx + dep_lo + lane);
+    int32_t down_blk = -1;
+    c.ro_me = make_int2(0, 1);
+    if (c.ex >= 0) {
+        c.ro_me = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + c.ex);
+        down_blk = __ldg(P.down + i) / RR_BLOCK;
+    }
+#pragma unroll
+    for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
+        c.ro_up[k] = make_int2(0, 1);
+        if ((c.M.int_mask & 0x40) && k < c.deg) c.ro_up[k] = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + c.e0 + k);
+    }
     int32_t *done = P.done + (size_t)m * P.n_blocks;
     if (lane == 0 && j > 0) wait_ge(done + b, j);                       // own previous tile (acquire)
-    for (int e = P.dep_ptr[b] + lane; e < P.dep_ptr[b + 1]; e += 32)    // upstream blocks, this tile
-        wait_ge(done + P.dep_idx[e], j + 1);
-    if (c.ex >= 0) {                                                    // exchange-ring reuse
-        const int32_t ring = __ldg(P.exp_ro + 2 * c.ex + 1);
-        if (j >= ring) wait_ge(done + __ldg(P.down + i) / RR_BLOCK, j - ring + 1);
-    }
+    if (dep_blk >= 0) wait_ge(done + dep_blk, j + 1);                   // upstream blocks, this tile
+    for (int e = dep_lo + 32 + lane; e < dep_hi; e += 32) wait_ge(done + __ldg(P.dep_idx + e), j + 1);
+    if (c.ex >= 0 && j >= c.ro_me.y) wait_ge(done + down_blk, j - c.ro_me.y + 1);   // exchange-ring reuse
     __syncwarp();
 #ifdef RR_PROFILE
     c.prof_wait = (unsigned long long)(clock64() - w0_);
@@ -911,7 +931,7 @@ __device__ __forceinline__ bool tma_item(const rr_route_params &P, const item_ct
     for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
         rowp[k] = rows;
         if (k < cnt) {
-            const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + c.e0 + k);
+            const int2 ro = c.ro_up[k];
             const double *src = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
             double *dst = rows + (size_t)(pre + k) * row_stride;
             bulk_load(smem_u32(dst), src, (uint32_t)P.raw_pitch * 8, bar);
@@ -921,7 +941,7 @@ __device__ __forceinline__ bool tma_item(const rr_route_params &P, const item_ct
     double q = c.q;
     double *myraw = nullptr;
     if (c.ex >= 0) {
-        const int2 ro = __ldg(reinterpret_cast<const int2 *>(P.exp_ro) + c.ex);
+        const int2 ro = c.ro_me;
         myraw = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         myraw[RAW_CARRY] = q;
     }
@@ -986,15 +1006,15 @@ template <int MODE>
 __global__ void __launch_bounds__(256, RR_MIN_CTAS) rr_wavefront_kernel(const __grid_constant__ rr_route_params P) {
     constexpr bool UNIT = (MODE == RR_MODE_UNIT);
     const int lane = threadIdx.x & 31;
-    int m, b, j;
+    int m, b, j, dep_lo, dep_hi;
     unsigned long long tk_next = 0, tk_end = 0;
     PROF_DECL
     for (;;) {
-        const bool more = next_item(P, lane, m, b, j, tk_next, tk_end);
+        const bool more = next_item(P, lane, m, b, j, dep_lo, dep_hi, tk_next, tk_end);
         PROF_MARK(0)
         if (!more) break;
         item_ctx c;
-        open_item<MODE>(P, c, lane, m, b, j);
+        open_item<MODE>(P, c, lane, m, b, j, dep_lo, dep_hi);
         PROF_MARK(1)
         // plan flag 0x40: no in-block edges and max in-degree <= RR_MAX_FAST_DEG
         if (!UNIT && P.K == 1 && (c.M.int_mask & 0x40)) register_fast_item<MODE>(P, c);
@@ -1040,11 +1060,11 @@ __global__ void __launch_bounds__(128, 1) rr_wavefront_tma_kernel(const __grid_c
     __syncthreads();
     uint32_t phase = 0;
     bool store_pending = false;
-    int m, b, j;
+    int m, b, j, dep_lo, dep_hi;
     unsigned long long tk_next = 0, tk_end = 0;
-    while (next_item(P, lane, m, b, j, tk_next, tk_end)) {
+    while (next_item(P, lane, m, b, j, dep_lo, dep_hi, tk_next, tk_end)) {
         item_ctx c;
-        open_item<MODE>(P, c, lane, m, b, j);
+        open_item<MODE>(P, c, lane, m, b, j, dep_lo, dep_hi);
         bool done_item = false;
         if (c.M.int_mask & 0x40) {
             done_item = tma_item<MODE>(P, c, region, phase, store_pending);

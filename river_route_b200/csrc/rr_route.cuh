@@ -22,7 +22,7 @@ struct rr_route_params {
     const int32_t *lvl_ptr, *lvl_blk;
     const double *c1, *c2, *c3, *c4;
     // ---- ticket schedule ----
-    const int2 *items;    // [n_items] (block, tile) of every ticket, in ticket order
+    const int4 *items;    // [n_items] {block, tile, dep_ptr[block], dep_ptr[block + 1]} of every ticket, in ticket order
     int64_t n_items;      // per member
     int32_t delta;
     int32_t n_tiles;

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(128) weights_kernel(int64_t n_rivers, int64_t 
 #pragma unroll
         for (int u = 0; u < TB; ++u) acc[u] = 0.0;
         const XT *blk = xt + (t0 / TB) * n_points * TB;
+        // (batching the row's gathers for more loads in flight was measured slower: the registers cost occupancy)
         for (int j = p0; j < p1; ++j) {
             const double wj = __ldg(w + j);
             vec8<XT> xv;

@@ -83,15 +83,12 @@ struct rr_device_state {
     // plan arrays
     int32_t *up_ptr = nullptr, *up_idx = nullptr, *slot_src = nullptr, *export_id = nullptr;
     int32_t *dep_ptr = nullptr, *dep_idx = nullptr, *down = nullptr, *exp_ro = nullptr, *edge_ro = nullptr;
-    int32_t *lvl_ptr = nullptr, *lvl_blk = nullptr;
     uint8_t *skew = nullptr;
     rr_blk_meta *meta = nullptr;
     double *coef = nullptr;  // c1|c2|c3|c4, each n
     uint64_t coeff_version = 0;
     // launch scratch
-    int64_t *key_start = nullptr;
-    size_t key_cap = 0;
-    int64_t sched_tiles = -1, sched_budget_rows = -1;
+    int64_t sched_budget_rows = -1;
     rr_schedule sched;
     struct key_table { int64_t n_tiles = -1, n_items = 0; int32_t *dev = nullptr; size_t cap = 0; uint64_t used = 0; };   // ticket -> (block, tile)
     key_table keys[4];
@@ -148,8 +145,6 @@ static int ensure_device(rr_plan *p) {
         rc |= upload(&d->dep_ptr, p->dep_ptr, d->bytes);
         rc |= upload(&d->dep_idx, p->dep_idx, d->bytes);
         rc |= upload(&d->down, p->down, d->bytes);
-        rc |= upload(&d->lvl_ptr, p->lvl_ptr, d->bytes);
-        rc |= upload(&d->lvl_blk, p->lvl_blk, d->bytes);
         rc |= upload(&d->skew, p->skew, d->bytes);
         rc |= upload(&d->meta, p->meta, d->bytes);
         if (!p->inv.empty()) rc |= upload(&d->inv, p->inv, d->bytes);
@@ -187,7 +182,7 @@ void rr_device_release(rr_plan *p) {
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {d->up_ptr, d->up_idx, d->slot_src, d->export_id, d->dep_ptr, d->dep_idx, d->down, d->exp_ro, d->edge_ro,
-                    d->lvl_ptr, d->lvl_blk, d->skew, d->meta, d->coef, d->key_start, d->raw, d->done, d->ticket, d->prof,
+                    d->skew, d->meta, d->coef, d->raw, d->done, d->ticket, d->prof,
                     d->s_inb[0], d->s_inb[1], d->s_outb[0], d->s_outb[1], d->s_lat, d->s_conv, d->s_route, d->d_q, d->d_qfull,
                     d->inv, d->p_lat, d->p_out, d->p_q};
     for (void *q : ptrs)
@@ -320,7 +315,6 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.export_id = d->export_id; P.meta = d->meta;
     P.dep_ptr = d->dep_ptr; P.dep_idx = d->dep_idx; P.down = d->down;
     P.exp_ro = d->exp_ro; P.edge_ro = d->edge_ro; P.raw_rows = d->sched.raw_rows;
-    P.lvl_ptr = d->lvl_ptr; P.lvl_blk = d->lvl_blk;
     P.c1 = d->coef; P.c2 = d->coef + p->n; P.c3 = d->coef + 2 * p->n; P.c4 = d->coef + 3 * p->n;
     P.items = reinterpret_cast<const int4 *>(kt->dev); P.n_items = kt->n_items;
     P.delta = d->sched.delta; P.n_tiles = (int32_t)n_tiles;
@@ -334,11 +328,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
         P.q_state[m] = q_state[m];
         P.q_full[m] = q_full ? q_full[m] : nullptr;
     }
-    {   // ticket batching: large launches are limited by the single-address atomic rate, small ones by latency
-        const char *env = getenv("RR_TICKET_BATCH");
-        const int64_t resident_warps = (int64_t)d->sm_count * 16;
-        P.ticket_batch = env ? std::max(1, atoi(env)) : 1;   // measured: batching hurts (neighbouring blocks should run concurrently)
-    }
+    P.ticket_batch = 1;   // larger batches were measured slower: neighbouring blocks should run concurrently
     CK(cudaMemsetAsync(d->done, 0, done_need * sizeof(int32_t), stream));
     CK(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), stream));
     int block = p->opts.threads_per_cta;

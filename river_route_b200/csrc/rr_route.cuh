@@ -19,7 +19,6 @@ struct rr_route_params {
     const rr_blk_meta *meta;
     const int32_t *dep_ptr, *dep_idx;
     const int32_t *down;      // [n] downstream reach (-1 outlet): the consumer of an exported series
-    const int32_t *lvl_ptr, *lvl_blk;
     const double *c1, *c2, *c3, *c4;
     // ---- ticket schedule ----
     const int4 *items;    // [n_items] {block, tile, dep_ptr[block], dep_ptr[block + 1]} of every ticket, in ticket order

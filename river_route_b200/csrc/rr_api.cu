@@ -732,7 +732,7 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
     const int64_t min_bytes = std::max<int64_t>(64ll << 20, (int64_t)p->max_level * (2ll << 20));
     int64_t min_rows = (min_bytes + row_bytes - 1) / row_bytes;
     // every chunk of a unit-hydrograph run also recomputes the n_ks - 1 rows of carry-over state
-    if (uh) min_rows = std::max<int64_t>(min_rows, 2 * src.tf->n_ks);
+    if (uh) min_rows = std::max<int64_t>(min_rows, src.tf->n_ks);
     const int64_t cap_rows = std::max<int64_t>(min_rows, (1ll << 30) / row_bytes);
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(T / 16, min_rows), cap_rows));
     if (const char *env = getenv("RR_STREAM_CHUNK_ROWS")) chunk = std::max(1, atoi(env));   // tests: force many chunks
@@ -782,8 +782,21 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
     if (!router_level)
         CK(cudaMemcpyAsync(d->d_qfull, q_full, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, d->s_comp));
 
-    const int64_t n_chunks = (T + chunk - 1) / chunk;
-    auto rows_of = [&](int64_t c) { return std::min<int64_t>(chunk, T - c * chunk); };
+    // Chunk boundaries.  The pipeline cannot overlap anything with the H2D + device work of the first chunk, so the
+    // first chunks are short (1/8, 1/4, 1/2 of the nominal length) when the call has enough of them.
+    std::vector<int64_t> start;   // start[c] = first row of chunk c, start[n_chunks] = T
+    {
+        int64_t at = 0;
+        const bool ramp = T >= 4 * chunk;
+        for (int shift = 3; at < T; shift = std::max(0, shift - 1)) {
+            int64_t len = ramp ? std::max<int64_t>(resample, ((chunk >> shift) / resample) * resample) : chunk;
+            start.push_back(at);
+            at += std::min<int64_t>(len, T - at);
+        }
+        start.push_back(T);
+    }
+    const int64_t n_chunks = (int64_t)start.size() - 1;
+    auto rows_of = [&](int64_t c) { return start[c + 1] - start[c]; };
     // a cumulative grid chunk starts with the last row of the previous chunk (its aggregate is the value to subtract)
     auto lead_of = [&](int64_t c) -> int64_t { return (grid && src.cumulative && c > 0) ? 1 : 0; };
     auto copy_in = [&](int64_t c) -> int {
@@ -792,7 +805,7 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
         const int64_t lead = lead_of(c), nrows = rows_of(c) + lead;
         const size_t width = grid ? (size_t)src.tf->n_points * es_in : (size_t)n * 8;
         const size_t h_pitch = grid ? (size_t)src.ldx * es_in : (size_t)src.ldl * 8, d_pitch = (size_t)ld_in * es_in;
-        const char *h = (const char *)h_src + (size_t)(c * chunk - lead) * h_pitch;
+        const char *h = (const char *)h_src + (size_t)(start[c] - lead) * h_pitch;
         size_t pitch = h_pitch;
         if (in_bounce) {
             if (c >= 2) CK(cudaEventSynchronize(d->ev_in[k]));           // H2D of chunk c-2 has left the bounce buffer
@@ -810,7 +823,7 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
         if (!out_bounce || c < 0) return 0;
         const int k = (int)(c & 1);
         CK(cudaEventSynchronize(d->ev_out[k]));
-        parallel_copy_2d((char *)out + (size_t)c * (chunk / resample) * ldo * es_out, (size_t)ldo * es_out,
+        parallel_copy_2d((char *)out + (size_t)(start[c] / resample) * ldo * es_out, (size_t)ldo * es_out,
                          (const char *)d->h_outb[k], (size_t)ldd * es_out, (size_t)n * es_out, rows_of(c) / resample);
         return 0;
     };
@@ -859,7 +872,7 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
         if (out_bounce)
             CK(cudaMemcpyAsync(d->h_outb[k], d->s_outb[k], (size_t)rows_out * ldd * es_out, cudaMemcpyDeviceToHost, d->s_out));
         else
-            CK(cudaMemcpy2DAsync((char *)out + (size_t)c * (chunk / resample) * ldo * es_out, ldo * es_out, d->s_outb[k],
+            CK(cudaMemcpy2DAsync((char *)out + (size_t)(start[c] / resample) * ldo * es_out, ldo * es_out, d->s_outb[k],
                                  ldd * es_out, n * es_out, rows_out, cudaMemcpyDeviceToHost, d->s_out));
         CK(cudaEventRecord(d->ev_out[k], d->s_out));
         // host work of the neighbouring chunks while the device is busy with this one

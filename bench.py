@@ -283,6 +283,10 @@ def main():
         raise SystemExit('bench.py needs a CUDA device: river_route_b200 has no CPU fallback')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa_bound = False
+    if world > 1:                                   # each rank streams over its own PCIe link from its own NUMA node
+        from river_route_b200.sharding import bind_to_gpu_numa
+        numa_bound = bind_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -447,7 +451,7 @@ def main():
                     'api': 'Plan.route_host with a float32 output array -> rr_route_host_ex: pinned fp64 lateral inflows '
                            'in, route, float32 cast on the device (TransformMuskingum.py:146), float32 discharge out; '
                            'chunked cudaMemcpyAsync on three streams',
-                    'host_equals_device_path': host_equals_dev, 'variants': variants},
+                    'host_equals_device_path': host_equals_dev, 'numa_bound': numa_bound, 'variants': variants},
             'gpu_launches': int(launches), 'kernel_phase_cycles': prof,
             'clocks': clocks,
             'checks': {'finite': finite, 'summary_per_rank[outlet_q_last_step, state_sum, reaches]': summary_all.tolist()},

@@ -653,10 +653,12 @@ int rr_weights_run(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t 
 // therefore bounces such arrays through its own pinned buffers with a few host threads doing the memcpy
 // (first-touch page faults of a fresh output array included) while the GPU and the DMA engines work on the
 // neighbouring chunks.  Pinned / registered arrays (rr_host_alloc, cudaHostRegister) are used in place.
-static bool host_is_pinned(const void *p) {
+enum { RR_PTR_PAGEABLE = 0, RR_PTR_PINNED = 1, RR_PTR_DEVICE = 2 };
+static int host_pointer_kind(const void *p) {
     cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return RR_PTR_PAGEABLE; }
+    if (a.type == cudaMemoryTypeDevice) return RR_PTR_DEVICE;
+    return (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged) ? RR_PTR_PINNED : RR_PTR_PAGEABLE;
 }
 static int copy_threads() {
     if (const char *env = getenv("RR_COPY_THREADS")) return std::max(1, atoi(env));
@@ -680,8 +682,13 @@ static void parallel_copy_2d(char *dst, size_t dst_pitch, const char *src, size_
     if (nt == 1) { work(0); return; }
     std::vector<std::thread> th;
     th.reserve(nt - 1);
-    for (int i = 1; i < nt; ++i) th.emplace_back(work, i);
+    int started = 1;   // slice 0 runs on the calling thread; slices that could not get a thread run there too
+    try {
+        for (; started < nt; ++started) th.emplace_back(work, started);
+    } catch (...) {
+    }
     work(0);
+    for (int i = started; i < nt; ++i) work(i);
     for (auto &t : th) t.join();
 }
 
@@ -700,8 +707,8 @@ struct rr_stream_source {
 //   s_in : H2D of chunk c+1        (cudaMemcpy2DAsync, pinned source gives full PCIe rate)
 //   s_comp: [weights -> unit hydrograph ->] route chunk c [-> resample / float32]   (state carried on the device)
 //   s_out: D2H of chunk c-1
-static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, const rr_stream_source &src, void *out,
-                        int64_t ldo, int64_t T, int64_t substeps, int out_f32, int64_t resample) {
+static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_full, const rr_stream_source &src, void *out,
+                             int64_t ldo, int64_t T, int64_t substeps, int out_f32, int64_t resample) {
     if (!p || !q_state || !out) { rr_set_error("null argument"); return 100; }
     if (T <= 0 || substeps <= 0) { rr_set_error("T and substeps must be positive"); return 100; }
     if (resample < 1 || T % resample != 0) { rr_set_error("T must be a multiple of the output resampling factor"); return 100; }
@@ -757,7 +764,12 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
         if ((rc = grow_bytes(&d->s_outb[k], &d->s_outb_cap[k], need_out))) return rc;
     }
     const void *h_src = grid ? src.runoff : (const void *)src.lateral;
-    const bool in_bounce = has_lat && !host_is_pinned(h_src), out_bounce = !host_is_pinned(out);
+    const int in_kind = has_lat ? host_pointer_kind(h_src) : RR_PTR_PINNED, out_kind = host_pointer_kind(out);
+    if (in_kind == RR_PTR_DEVICE || out_kind == RR_PTR_DEVICE || host_pointer_kind(q_state) == RR_PTR_DEVICE) {
+        rr_set_error("the host entry points take host pointers; use rr_route_dev for device-resident arrays");
+        return 100;
+    }
+    const bool in_bounce = in_kind == RR_PTR_PAGEABLE, out_bounce = out_kind == RR_PTR_PAGEABLE;
     auto grow_pinned = [&](void **buf, size_t *cap, size_t need) -> int {
         if (need <= *cap) return 0;
         CK(cudaDeviceSynchronize());
@@ -887,6 +899,20 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
     CK(cudaStreamSynchronize(d->s_out));
     CK(cudaStreamSynchronize(d->s_in));
     return 0;
+}
+
+static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, const rr_stream_source &src, void *out,
+                        int64_t ldo, int64_t T, int64_t substeps, int out_f32, int64_t resample) {
+    const int rc = stream_route_impl(p, mode, q_state, q_full, src, out, ldo, T, substeps, out_f32, resample);
+    if (rc && p && p->dev) {
+        // copies of earlier chunks may still be reading / writing the caller's arrays: let them finish before the
+        // caller gets control back (and possibly frees the arrays); keep the first error message
+        const std::string msg = rr_last_error();
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        rr_set_error(msg);
+    }
+    return rc;
 }
 
 extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,

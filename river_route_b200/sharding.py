@@ -28,3 +28,27 @@ def shard_by_basin(down: np.ndarray, n_parts: int, part_id: int):
     local = np.where(d >= 0, new_of_old[np.where(d >= 0, d, 0)], -1).astype(np.int32)
     assert not np.any((d >= 0) & (local < 0)), 'a basin was cut across ranks'
     return idx, local
+
+
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """
+    Pin the calling process to the CPUs NVML reports as local to the GPU, so that pinned host buffers are first
+    touched on the GPU's NUMA node (one process per GPU streams its own chunk of the arrays over its own PCIe
+    link).  Best effort: returns False when NVML or the cpuset does not allow it.
+    """
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        index = int(vis.split(',')[device_index]) if vis else device_index
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64 or 1)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False

@@ -89,3 +89,12 @@ def test_shards_partition_the_network_without_cutting_basins():
             assert int((local < 0).sum()) == len(set(basin[idx]))             # whole basins only
         assert np.all(seen == 1)
         assert max(sizes) - min(sizes) <= np.bincount(basin).max()
+
+
+def test_numa_binding_is_best_effort():
+    """Without NVML / a GPU the helper declines instead of raising, and never widens the affinity mask."""
+    from river_route_b200.sharding import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa(0) in (True, False)
+    assert os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)

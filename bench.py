@@ -290,7 +290,6 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')
         dist.init_process_group('nccl', device_id=dev)
 
     # ---- network, shard, plan ----

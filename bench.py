@@ -288,7 +288,13 @@ def main():
         from river_route_b200.sharding import bind_to_gpu_numa
         numa_bound = bind_to_gpu_numa(local_rank)
     dist = None
+    real_stdout = None
     if world > 1:
+        # stdout carries exactly one JSON line: anything libraries print there meanwhile (NCCL's version banner at
+        # communicator creation) goes to stderr instead
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
 
@@ -457,6 +463,9 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline(down, k, x, args.cpu_sample_reaches, rows)
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

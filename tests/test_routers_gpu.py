@@ -322,3 +322,39 @@ def test_qlateral_files_on_disk(route_golden, tmp_path):
     with ncio.open_nc(tmp_path / 'discharge_ql.nc') as ds:
         Q = ncio.read_array(ds.variables['Q'])
     np.testing.assert_allclose(Q, g['rapid_out'].astype(np.float32), rtol=1e-6, atol=1e-6 * g['rapid_out'].max())
+
+
+def test_initial_state_effect_decays(route_golden, tmp_path):
+    """tests/test_rapid_muskingum.py:46-92 of the reference: a different initial state changes the first step and
+    its influence decays along the run."""
+    g = route_golden
+    params, state = _files(g, tmp_path)
+    hot = str(tmp_path / 'hot.parquet')
+    pd.DataFrame({'Q': g['q0'] + 100.0}).to_parquet(hot)
+    T = g['ql'].shape[0]
+    long_ql = np.concatenate([g['ql']] * 6)                                   # long enough for the state to flush
+    runs = []
+    for st in (state, hot):
+        cap = Capture()
+        _inject(rr.RapidMuskingum, [long_ql], g['dt_runoff'])(
+            params_file=params, qlateral_files=[params], discharge_files=[str(tmp_path / 'q.nc')],
+            channel_state_init_file=st, dt_routing=int(g['dt_routing']), log=False).set_write_discharges(cap).route()
+        runs.append(cap.calls[0][1].astype(np.float64))
+    diff = np.abs(runs[1] - runs[0]).mean(axis=1)
+    assert diff[0] > 1.0                                                      # the first step sees the extra water
+    assert diff[-1] < 0.6 * diff[0] and diff[-1] < diff[T]                    # ... and it drains away
+
+
+def test_cumulative_runoff_equals_incremental():
+    """tests/test_runoff.py:67-99 of the reference: cumulative input differenced on the device gives the same lateral
+    inflows as the incremental input (up to the rounding of the running sum)."""
+    from tests.conftest import load_golden
+    g = load_golden('weights.npz')
+    table = {k: g[k] for k in ('river_id', 'x_index', 'y_index', 'proportion', 'area_sqm')}
+    inc = np.abs(g['grid']).astype(np.float64)
+    cum = np.cumsum(inc, axis=0)
+    a, _ = rr.weights_to_qlateral(table, inc, as_volumes=True)
+    b, _ = rr.weights_to_qlateral(table, cum, cumulative=True, as_volumes=True)
+    np.testing.assert_allclose(b, a, rtol=1e-9, atol=1e-9 * np.abs(a).max())
+    c, _ = rr.weights_to_qlateral(table, -inc, force_positive_runoff=True)
+    assert np.all(c == 0)                                                     # runoff.py:313-314

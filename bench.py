@@ -433,6 +433,17 @@ def main():
             'h2d_bytes_per_step': int(n_cells * er * 4 + n * 8), 'd2h_bytes_per_step': int(n * er * 4 + n * 8),
             'api': 'Plan.runoff_route_host -> rr_runoff_route_host (weights SpMM + route + float32 cast on the device)',
             'weight_table': f'{int(indptr[-1])} entries, 4-8 cells per river, {n_cells} grid cells'}
+        # (c) the same, copying back only the basin outlets (rr_plan_set_output_subset: the device-side form of the
+        #     reference's subset writer, docs/tutorial/advanced.md:147-170): neither PCIe direction is the bound any more
+        outlets_idx = np.flatnonzero(local_down < 0).astype(np.int32)
+        plan.set_output_subset(outlets_idx)
+        h_out_sub = rr.pinned_empty((er, outlets_idx.shape[0]), dtype=np.float32)
+        variants['grid_runoff_to_outlet_discharge_f32'] = {
+            'value': timed_host(lambda: plan.runoff_route_host(tf, rr.MODE_RAPID, h_q, h_grid, h_out_sub, 1, as_volumes=True)),
+            'h2d_bytes_per_step': int(n_cells * er * 4 + n * 8),
+            'd2h_bytes_per_step': int(outlets_idx.shape[0] * er * 4 + n * 8), 'outlets': int(outlets_idx.shape[0]),
+            'api': 'Plan.set_output_subset + Plan.runoff_route_host (all reaches routed, outlet columns copied back)'}
+        plan.set_output_subset(None)
         tf.close()
 
     if rank == 0:

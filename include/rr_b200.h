@@ -150,6 +150,13 @@ int rr_route_host_ex(rr_plan *p, int mode, double *q_state, double *q_full, cons
                      int64_t ldl, void *out, int64_t ldo, int64_t T, int64_t substeps, int out_f32,
                      int64_t resample);
 
+/* Restrict what the host streaming calls (rr_route_host, rr_route_host_ex, rr_runoff_route_host) copy back to a
+ * subset of river segments -- the device-side form of the reference's "save a subset of the routed flows" writer
+ * pattern (docs/tutorial/advanced.md:147-170), e.g. gauges or basin outlets only.  idx are params-file indices in
+ * any order; out then is [T / resample][ldo >= n_sub] with column s = segment idx[s].  All segments are still
+ * routed and q_state is still the full final state.  n_sub = 0 restores the full output. */
+int rr_plan_set_output_subset(rr_plan *p, int64_t n_sub, const int32_t *idx);
+
 /* Ensemble: n_members independent lateral arrays routed from the SAME initial state in one
  * launch (TransformMuskingum._execute_routing 'ensemble' mode, TransformMuskingum.py:121-126).
  * lateral[m], out[m], q_final[m] are device pointers per member; q_init [n] is shared. */

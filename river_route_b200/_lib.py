@@ -54,6 +54,7 @@ def _load() -> C.CDLL:
         'rr_plan_set_coefficients': (C.c_int, [vp, f64p, f64p, f64p, f64p]),
         'rr_route_dev': (C.c_int, [vp, C.c_int, vp, vp, vp, i64, vp, i64, i64, i64, vp]),
         'rr_route_host': (C.c_int, [vp, C.c_int, f64p, f64p, f64p, i64, f64p, i64, i64, i64]),
+        'rr_plan_set_output_subset': (C.c_int, [vp, i64, c_i32p]),
         'rr_route_host_ex': (C.c_int, [vp, C.c_int, f64p, f64p, f64p, i64, vp, i64, i64, i64, C.c_int, i64]),
         'rr_transform_create': (C.c_int, [i64, i64, c_i32p, c_i32p, f64p, f64p, i32, C.POINTER(vp)]),
         'rr_transform_set_uh': (C.c_int, [vp, i64, f64p, i64, f64p, i64]),
@@ -91,7 +92,7 @@ lib = _load()
 EXPORTED_SYMBOLS = (
     'rr_last_error', 'rr_version', 'rr_cuda_available', 'rr_downstream_index', 'rr_label_basins',
     'rr_plan_create', 'rr_plan_destroy', 'rr_plan_get_info', 'rr_plan_set_coefficients', 'rr_route_dev',
-    'rr_route_host', 'rr_route_host_ex', 'rr_transform_create', 'rr_transform_set_uh', 'rr_transform_get_uh_state',
+    'rr_route_host', 'rr_plan_set_output_subset', 'rr_route_host_ex', 'rr_transform_create', 'rr_transform_set_uh', 'rr_transform_get_uh_state',
     'rr_transform_destroy', 'rr_runoff_route_host', 'rr_route_ensemble_dev', 'rr_launch_count', 'rr_timing_enable', 'rr_timing_read', 'rr_uh_convolve_dev', 'rr_uh_convolve_host',
     'rr_weights_transform_dev', 'rr_weights_transform_host', 'rr_plan_read_profile', 'rr_host_alloc', 'rr_host_free', 'rr_synth_forest',
     'rr_plan_get_arrays', 'rr_plan_schedule',

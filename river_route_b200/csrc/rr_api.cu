@@ -104,6 +104,8 @@ struct rr_device_state {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     void *s_inb[2] = {nullptr, nullptr}, *s_outb[2] = {nullptr, nullptr};   // double-buffered chunk input / output
     size_t s_inb_cap[2] = {0, 0}, s_outb_cap[2] = {0, 0};                     // bytes
+    int32_t *out_subset = nullptr;                                            // device copy of rr_plan::out_subset
+    uint64_t out_subset_version = 0;
     void *h_inb[2] = {nullptr, nullptr}, *h_outb[2] = {nullptr, nullptr};   // pinned bounce buffers for pageable callers
     size_t h_inb_cap[2] = {0, 0}, h_outb_cap[2] = {0, 0};
     double *s_lat = nullptr, *s_conv = nullptr, *s_route = nullptr;           // compute-stream scratch of one chunk
@@ -184,7 +186,7 @@ void rr_device_release(rr_plan *p) {
     void *ptrs[] = {d->up_ptr, d->up_idx, d->slot_src, d->export_id, d->dep_ptr, d->dep_idx, d->down, d->exp_ro, d->edge_ro,
                     d->skew, d->meta, d->coef, d->raw, d->done, d->ticket, d->prof,
                     d->s_inb[0], d->s_inb[1], d->s_outb[0], d->s_outb[1], d->s_lat, d->s_conv, d->s_route, d->d_q, d->d_qfull,
-                    d->inv, d->p_lat, d->p_out, d->p_q};
+                    d->inv, d->p_lat, d->p_out, d->p_q, d->out_subset};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (auto &k : d->keys) if (k.dev) cudaFree(k.dev);
@@ -633,14 +635,15 @@ extern "C" int rr_transform_get_uh_state(rr_transform *t, double *state, int64_t
 // and the cast to float32 the writer receives (:146 / Muskingum.py:259, round to nearest even like numpy's astype).
 template <typename OT>
 __global__ void __launch_bounds__(256) finish_output(const double *__restrict__ src, int64_t lds, OT *__restrict__ dst,
-                                                     int64_t ldd, int64_t n, int k) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                                                     int64_t ldd, int64_t n_out, int k, const int32_t *__restrict__ subset) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_out) return;
+    const int64_t i = subset ? (int64_t)__ldg(subset + s) : s;      // output column s shows river segment i
     const double *p = src + (int64_t)blockIdx.y * k * lds + i;
     double acc = __ldg(p);
     for (int r = 1; r < k; ++r) acc += __ldg(p + (int64_t)r * lds);
     if (k > 1) acc = acc / (double)k;
-    dst[(int64_t)blockIdx.y * ldd + i] = (OT)acc;
+    dst[(int64_t)blockIdx.y * ldd + s] = (OT)acc;
 }
 
 int rr_weights_run(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr, const int32_t *indices,
@@ -722,25 +725,32 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
         if (mode == RR_MODE_UNIT && src.tf->n_ks <= 0) { rr_set_error("UnitMuskingum needs a unit hydrograph (rr_transform_set_uh)"); return 100; }
         if (src.as_volumes && !src.tf->area) { rr_set_error("as_volumes needs catchment areas in the weight table"); return 100; }
     }
-    if (ldo < p->n) { rr_set_error("output leading dimension smaller than n"); return 100; }
+    const int64_t n_out = p->out_subset.empty() ? p->n : (int64_t)p->out_subset.size();   // columns copied back
+    if (ldo < n_out) { rr_set_error("output leading dimension smaller than the number of output river segments"); return 100; }
     int rc = ensure_device(p);
     if (rc) return rc;
     rr_device_state *d = p->dev;
     if (grid && src.tf->device != d->device) { rr_set_error("weight table and plan live on different devices"); return 100; }
     const int64_t n = p->n;
     const int64_t ldd = ((n + 31) / 32) * 32;  // device rows start on 256-byte boundaries
-    const bool post = out_f32 || resample > 1;
+    const bool post = out_f32 || resample > 1 || !p->out_subset.empty();
     const bool uh = grid && mode == RR_MODE_UNIT;
     // Chunk length.  Short chunks keep the fill / drain of the three-stage pipeline small (aim: 1/16 of the call),
     // but every chunk is one wavefront launch whose dependency pipeline has to fill again (~20 us per level of the
-    // block DAG), so a chunk must carry enough bytes to hide that: at least 64 MiB and 2 MB per level.  At most
-    // ~1 GiB of fp64 rows per buffer unless the depth rule asks for more; whole 8-row groups and whole output rows.
+    // block DAG): a chunk should last at least 4x that, where a row lasts as long as its slowest stage -- H2D, D2H
+    // (~45 GB/s each, concurrently) or the device work (~14 ps per reach-substep).  Calls that copy little back
+    // (output subsets) or little in (grids) therefore get long, device-efficient chunks; qlateral-in / all-segments-out
+    // calls get short ones.  Bounded by ~1 GiB per transfer buffer and ~4 GiB of fp64 scratch rows; whole 8-row
+    // groups and whole output rows.
     const int64_t row_bytes = ldd * 8;
-    const int64_t min_bytes = std::max<int64_t>(64ll << 20, (int64_t)p->max_level * (2ll << 20));
-    int64_t min_rows = (min_bytes + row_bytes - 1) / row_bytes;
+    const double in_row = !has_lat ? 0.0 : (grid ? (double)src.tf->n_points * (src.x_is_f32 ? 4 : 8) : (double)n * 8);
+    const double out_row = (double)n_out * (out_f32 ? 4 : 8) / (double)resample;
+    const double t_row = std::max({in_row / 45e9, out_row / 45e9, (double)n * (double)substeps * 14e-12});
+    int64_t min_rows = (int64_t)std::ceil((double)(p->max_level + 1) * 80e-6 / t_row);
     // every chunk of a unit-hydrograph run also recomputes the n_ks - 1 rows of carry-over state
     if (uh) min_rows = std::max<int64_t>(min_rows, src.tf->n_ks);
-    const int64_t cap_rows = std::max<int64_t>(min_rows, (1ll << 30) / row_bytes);
+    const int64_t xfer_cap = std::max<int64_t>(min_rows, (int64_t)((double)(1ll << 30) / std::max({in_row, out_row, 1.0})));
+    const int64_t cap_rows = std::max<int64_t>(1, std::min<int64_t>(xfer_cap, (4ll << 30) / row_bytes));
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(T / 16, min_rows), cap_rows));
     if (const char *env = getenv("RR_STREAM_CHUNK_ROWS")) chunk = std::max(1, atoi(env));   // tests: force many chunks
     if (chunk >= 8) chunk = (chunk / 8) * 8;
@@ -749,7 +759,8 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
     const size_t es_in = grid ? (src.x_is_f32 ? 4 : 8) : 8, es_out = out_f32 ? 4 : 8;
     const int64_t ld_in = grid ? ((src.tf->n_points + 31) / 32) * 32 : ldd;
     const size_t need_in = has_lat ? (size_t)(chunk + (grid ? 1 : 0)) * ld_in * es_in : 0;
-    const size_t need_out = (size_t)(chunk / resample) * ldd * es_out;
+    const int64_t ldd_out = ((n_out + 31) / 32) * 32;
+    const size_t need_out = (size_t)(chunk / resample) * ldd_out * es_out;
     auto grow_bytes = [&](void **buf, size_t *cap, size_t need) -> int {
         if (need <= *cap) return 0;
         CK(cudaDeviceSynchronize());
@@ -759,6 +770,16 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
         *cap = need;
         return 0;
     };
+    if (d->out_subset_version != p->out_subset_version) {
+        CK(cudaDeviceSynchronize());
+        if (d->out_subset) CK(cudaFree(d->out_subset));
+        d->out_subset = nullptr;
+        if (!p->out_subset.empty()) {
+            CK(cudaMalloc((void **)&d->out_subset, p->out_subset.size() * sizeof(int32_t)));
+            CK(cudaMemcpy(d->out_subset, p->out_subset.data(), p->out_subset.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
+        d->out_subset_version = p->out_subset_version;
+    }
     for (int k = 0; k < 2; ++k) {
         if ((rc = grow_bytes(&d->s_inb[k], &d->s_inb_cap[k], need_in))) return rc;
         if ((rc = grow_bytes(&d->s_outb[k], &d->s_outb_cap[k], need_out))) return rc;
@@ -836,7 +857,7 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
         const int k = (int)(c & 1);
         CK(cudaEventSynchronize(d->ev_out[k]));
         parallel_copy_2d((char *)out + (size_t)(start[c] / resample) * ldo * es_out, (size_t)ldo * es_out,
-                         (const char *)d->h_outb[k], (size_t)ldd * es_out, (size_t)n * es_out, rows_of(c) / resample);
+                         (const char *)d->h_outb[k], (size_t)ldd_out * es_out, (size_t)n_out * es_out, rows_of(c) / resample);
         return 0;
     };
     if ((rc = copy_in(0))) return rc;
@@ -873,19 +894,20 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
         const int64_t rows_out = rows / resample;
         if (post) {
             rr_timer tm(3, d->s_comp);
-            dim3 g((unsigned)((n + 255) / 256), (unsigned)rows_out);
-            if (out_f32) finish_output<float><<<g, 256, 0, d->s_comp>>>(d->s_route, ldd, (float *)d->s_outb[k], ldd, n, (int)resample);
-            else finish_output<double><<<g, 256, 0, d->s_comp>>>(d->s_route, ldd, (double *)d->s_outb[k], ldd, n, (int)resample);
+            dim3 g((unsigned)((n_out + 255) / 256), (unsigned)rows_out);
+            const int32_t *sub = p->out_subset.empty() ? nullptr : d->out_subset;
+            if (out_f32) finish_output<float><<<g, 256, 0, d->s_comp>>>(d->s_route, ldd, (float *)d->s_outb[k], ldd_out, n_out, (int)resample, sub);
+            else finish_output<double><<<g, 256, 0, d->s_comp>>>(d->s_route, ldd, (double *)d->s_outb[k], ldd_out, n_out, (int)resample, sub);
             CK(cudaGetLastError());
             rr_count_launch(1);
         }
         CK(cudaEventRecord(d->ev_comp[k], d->s_comp));
         CK(cudaStreamWaitEvent(d->s_out, d->ev_comp[k], 0));
         if (out_bounce)
-            CK(cudaMemcpyAsync(d->h_outb[k], d->s_outb[k], (size_t)rows_out * ldd * es_out, cudaMemcpyDeviceToHost, d->s_out));
+            CK(cudaMemcpyAsync(d->h_outb[k], d->s_outb[k], (size_t)rows_out * ldd_out * es_out, cudaMemcpyDeviceToHost, d->s_out));
         else
             CK(cudaMemcpy2DAsync((char *)out + (size_t)(start[c] / resample) * ldo * es_out, ldo * es_out, d->s_outb[k],
-                                 ldd * es_out, n * es_out, rows_out, cudaMemcpyDeviceToHost, d->s_out));
+                                 ldd_out * es_out, n_out * es_out, rows_out, cudaMemcpyDeviceToHost, d->s_out));
         CK(cudaEventRecord(d->ev_out[k], d->s_out));
         // host work of the neighbouring chunks while the device is busy with this one
         if (c + 1 < n_chunks && (rc = copy_in(c + 1))) return rc;
@@ -913,6 +935,15 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
         rr_set_error(msg);
     }
     return rc;
+}
+
+extern "C" int rr_plan_set_output_subset(rr_plan *p, int64_t n_sub, const int32_t *idx) {
+    if (!p || n_sub < 0 || (n_sub > 0 && !idx)) { rr_set_error("bad argument"); return 100; }
+    for (int64_t s = 0; s < n_sub; ++s)
+        if (idx[s] < 0 || idx[s] >= p->n) { rr_set_error("output subset refers to a river segment outside the network"); return 100; }
+    p->out_subset.assign(idx, idx + n_sub);
+    p->out_subset_version++;
+    return 0;
 }
 
 extern "C" int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,

@@ -47,6 +47,8 @@ struct rr_plan {
     std::vector<double> c1, c2, c3, c4;
     bool have_c4 = false;
     uint64_t coeff_version = 0;
+    std::vector<int32_t> out_subset;   // river segments (user indices) the host streaming calls copy back; empty = all
+    uint64_t out_subset_version = 0;
     rr_device_state *dev = nullptr;
 };
 

@@ -88,6 +88,7 @@ class Plan:
         check(lib.rr_plan_create(self.n, _lib.as_i32p(down), C.byref(opts), C.byref(handle)))
         self._h = handle
         self._coeff_key = None
+        self.n_out = self.n                     # columns the host streaming calls copy back (see set_output_subset)
 
     def close(self):
         if getattr(self, '_h', None):
@@ -115,6 +116,18 @@ class Plan:
         check(lib.rr_plan_set_coefficients(self._h, *[_lib.as_f64p(a) for a in arrs],
                                            _lib.as_f64p(c4) if c4 is not None else None))
 
+    def set_output_subset(self, indices=None):
+        """
+        Copy back only these river segments (params-file indices, any order) from the host streaming calls -- the
+        device-side form of the reference's subset-writer pattern (docs/tutorial/advanced.md:147-170).  ``None``
+        or an empty list restores the full output.  The whole network is still routed.
+        """
+        idx = np.zeros(0, dtype=np.int32) if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
+        if idx.ndim != 1:
+            raise ValueError('indices must be a 1D list of river segment indices')
+        check(lib.rr_plan_set_output_subset(self._h, idx.shape[0], _lib.as_i32p(idx) if idx.shape[0] else None))
+        self.n_out = int(idx.shape[0]) or self.n
+
     # ---- host arrays (numpy) : H2D / route / D2H streamed inside the library ----
     def route_host(self, mode: int, q_state: np.ndarray, lateral, out: np.ndarray, substeps: int, q_full=None,
                    resample: int = 1):
@@ -128,8 +141,9 @@ class Plan:
         """
         if q_state.dtype != np.float64 or not q_state.flags.c_contiguous or q_state.shape != (self.n,):
             raise ValueError('q_state must be a contiguous float64 vector with one value per river segment')
-        if out.dtype not in (np.float64, np.float32) or out.ndim != 2 or out.shape[1] != self.n:
-            raise ValueError('discharge array must be float64 (or float32) with shape (T, n)')
+        if out.dtype not in (np.float64, np.float32) or out.ndim != 2 or out.shape[1] != self.n_out:
+            raise ValueError('discharge array must be float64 (or float32) with shape (T, n) '
+                             '(n = size of the output subset when one is set)')
         resample = int(resample)
         if resample < 1:
             raise ValueError('resample must be a positive integer')
@@ -149,7 +163,7 @@ class Plan:
             if q_full.dtype != np.float64 or not q_full.flags.c_contiguous or q_full.shape != (self.n,):
                 raise ValueError('q_full must be a contiguous float64 vector with one value per river segment')
             p_qf = _lib.as_f64p(q_full)
-        if out.dtype == np.float64 and resample == 1:
+        if out.dtype == np.float64 and resample == 1 and self.n_out == self.n:
             check(lib.rr_route_host(self._h, int(mode), _lib.as_f64p(q_state), p_qf, p_lat, ldl, _lib.as_f64p(out),
                                     ldo, T, int(substeps)))
         else:
@@ -167,8 +181,9 @@ class Plan:
         """
         if q_state.dtype != np.float64 or not q_state.flags.c_contiguous or q_state.shape != (self.n,):
             raise ValueError('q_state must be a contiguous float64 vector with one value per river segment')
-        if out.dtype not in (np.float64, np.float32) or out.ndim != 2 or out.shape[1] != self.n:
-            raise ValueError('discharge array must be float64 (or float32) with shape (T, n)')
+        if out.dtype not in (np.float64, np.float32) or out.ndim != 2 or out.shape[1] != self.n_out:
+            raise ValueError('discharge array must be float64 (or float32) with shape (T, n) '
+                             '(n = size of the output subset when one is set)')
         if transform.n_rivers != self.n:
             raise ValueError('weight table rows do not match the number of river segments')
         resample = int(resample)

@@ -232,6 +232,7 @@ class Muskingum:
         t1 = datetime.datetime.now()
         self._validate_configs()
         self._set_network_dependent_vectors()
+        self._apply_output_subset()
         self._read_initial_state()
         self._hook_before_route()
         self._execute_routing()
@@ -257,10 +258,10 @@ class Muskingum:
                               freq=pd.to_timedelta(self.dt_discharge, unit='s')).to_numpy()
         if _is_stock(self, '_router', Muskingum):
             # the writer receives float32 (Muskingum.py:259): cast on the device, copy back half the bytes
-            q32 = np.empty((num_output_steps, self.n), dtype=np.float32)
+            q32 = np.empty((num_output_steps, self._n_out), dtype=np.float32)
             self._route_channel(q32, num_routing_per_output)
         else:
-            q32 = self._router(num_output_steps, num_routing_per_output).astype(np.float32, copy=False)
+            q32 = self._host_subset(self._router(num_output_steps, num_routing_per_output)).astype(np.float32, copy=False)
         self._write(dates, q32, self.cfg.discharge_files[0])
 
     def _route_channel(self, discharge_array, num_routing_per_output):
@@ -275,7 +276,23 @@ class Muskingum:
 
     def _router(self, num_output_steps, num_routing_per_output):
         """The seam of Muskingum.py:262-290: returns the fp64 (num_output_steps, n) discharge array."""
-        return self._route_channel(np.zeros((num_output_steps, self.n), dtype=np.float64), num_routing_per_output)
+        return self._full_width(lambda: self._route_channel(
+            np.zeros((num_output_steps, self.n), dtype=np.float64), num_routing_per_output))
+
+    def _full_width(self, call):
+        """Run ``call`` with the device output subset switched off: the reference seams return all segments."""
+        idx = getattr(self, '_output_idx', None)
+        if idx is None:
+            return call()
+        self.plan.set_output_subset(None)
+        try:
+            return call()
+        finally:
+            self.plan.set_output_subset(idx)
+
+    def _host_subset(self, q_array):
+        idx = getattr(self, '_output_idx', None)
+        return q_array if idx is None else q_array[:, idx]
 
     def _hook_before_route(self):
         return
@@ -284,6 +301,35 @@ class Muskingum:
         return
 
     # ---------------- output ----------------
+    _output_river_ids = None
+
+    def set_output_rivers(self, river_ids=None):
+        """
+        Extension: hand the writer only these river segments (ids of the params file, any order) -- what the
+        reference's "save a subset of the routed flows" writer does on the host
+        (docs/tutorial/advanced.md:147-170), done on the device so that only those columns cross PCIe.  The writer
+        then receives a ``(time, len(river_ids))`` array and the default netCDF writer stores those ids.
+        """
+        self._output_river_ids = None if river_ids is None else np.asarray(river_ids, dtype=np.int64)
+        return self
+
+    def _apply_output_subset(self):
+        """Resolve the requested ids against the params file (after the network is known) -> plan subset."""
+        if self._output_river_ids is None:
+            self.plan.set_output_subset(None)
+            self._output_idx = None
+            return
+        pos = pd.Series(np.arange(self.n), index=self.river_ids)
+        missing = np.setdiff1d(self._output_river_ids, self.river_ids)
+        if missing.size:
+            raise ValueError(f'set_output_rivers: ids not in the params file: {missing[:10].tolist()}')
+        self._output_idx = pos.loc[self._output_river_ids].to_numpy(dtype=np.int32)
+        self.plan.set_output_subset(self._output_idx)
+
+    @property
+    def _n_out(self):
+        return self.n if getattr(self, '_output_idx', None) is None else int(self._output_idx.shape[0])
+
     def set_write_discharges(self, func):
         """Inject a writer ``func(dates, q_array, q_file, routed_file='')`` (Muskingum.py:308-317)."""
         self._writer = func
@@ -303,7 +349,8 @@ class Muskingum:
             tv.units = f'seconds since {pd.Timestamp(dates[0]).strftime("%Y-%m-%d %H:%M:%S")}'
             tv[:] = (dates - dates[0]).astype('timedelta64[s]').astype(np.int64)
             iv = ds.createVariable(self.cfg.var_river_id, 'i4', (self.cfg.var_river_id,))
-            iv[:] = self.river_ids.astype(np.int32)
+            ids = self.river_ids if getattr(self, '_output_idx', None) is None else self.river_ids[self._output_idx]
+            iv[:] = ids.astype(np.int32)
             qv = ds.createVariable(self.cfg.var_discharge, 'f4', ('time', self.cfg.var_river_id))
             qv[:] = q_array
             qv.long_name = 'Discharge at catchment outlet'
@@ -400,14 +447,14 @@ class TransformMuskingum(Muskingum):
             self._set_network_and_time_dependent_vectors(dates)
             k = self.num_runoff_steps_per_discharge if self.dt_discharge > self.dt_runoff else 1
             if device_tail:
-                q32 = np.empty((self.num_runoff_steps // k, self.n), dtype=np.float32)
+                q32 = np.empty((self.num_runoff_steps // k, self._n_out), dtype=np.float32)
                 q_t = self._route_runoff(data, q32, k) if kind == ['runoff'] else self._route_lateral(data, q32, k)
             else:
                 q_t, q_array = self._router(data)
                 if k > 1:                                                    # :128-139
                     q_array = q_array.reshape((int(self.dt_total / self.dt_discharge),
                                                int(self.dt_discharge / self.dt_runoff), self.n)).mean(axis=1)
-                q32 = q_array.astype(np.float32, copy=False)
+                q32 = self._host_subset(q_array).astype(np.float32, copy=False)
             if self.cfg.runoff_processing_mode == 'sequential':
                 self.channel_state = q_t
             else:                                                            # every member starts from the same state
@@ -441,15 +488,19 @@ class TransformMuskingum(Muskingum):
         return q_t
 
     _transform = None
-    _transform_factor = None
+    _transform_key = None
     _weight_table = None
 
-    def _ensure_transform(self, factor):
+    def _ensure_transform(self, factor, flat_shape=None):
         """Weight table netCDF -> device-resident CSR over the params-file river order (runoff.py:255-295), with the
-        unit conversion factor folded into the weights before duplicates are summed, as the reference does (:292-293)."""
+        unit conversion factor folded into the weights before duplicates are summed, as the reference does (:292-293).
+        ``flat_shape`` = (ny, nx): column indices become flat cell ids ``y * nx + x`` (entry order unchanged, so the
+        sums are too) and the SpMM reads the whole grid -- the pointwise gather of runoff.py:270-279 then happens on
+        the device instead of in numpy."""
         from .runoff import build_weight_csr, read_weight_table
         from .transforms import Transform
-        if self._transform is not None and factor == self._transform_factor:
+        key = (factor, flat_shape)
+        if self._transform is not None and key == self._transform_key:
             return
         if self._weight_table is None:
             self._weight_table = read_weight_table(self.cfg.grid_weights_file, self.cfg.var_river_id)
@@ -459,11 +510,28 @@ class TransformMuskingum(Muskingum):
         # the reference assumes this order (runoff.py:265) and would silently route the wrong catchments otherwise
         if rivers.shape[0] != self.n or not np.array_equal(np.asarray(rivers).astype(np.int64), self.river_ids):
             raise ValueError('grid_weights_file must list the river segments of params_file in the same order')
+        n_points = len(cx)
+        if flat_shape is not None:
+            ny, nx = flat_shape
+            if cx.max(initial=0) >= nx or cy.max(initial=0) >= ny:
+                raise ValueError('weight table refers to grid cells outside the runoff grid')
+            indices = (cy[indices] * nx + cx[indices]).astype(np.int32)
+            n_points = ny * nx
         self._detach_transform()
-        self._transform = Transform(indptr, indices, data, len(cx), area=area)
-        self._transform_factor = factor
+        self._transform = Transform(indptr, indices, data, n_points, area=area)
+        self._transform_key = key
         self._cells = (cx, cy)
         self._attach_unit_hydrograph()
+
+    def _count_weight_cells(self):
+        """Number of distinct grid cells the weight table touches."""
+        from .runoff import read_weight_table
+        if self._weight_table is None:
+            self._weight_table = read_weight_table(self.cfg.grid_weights_file, self.cfg.var_river_id)
+        if not hasattr(self, '_n_weight_cells'):
+            tb = self._weight_table
+            self._n_weight_cells = len(pd.MultiIndex.from_arrays([tb['x_index'], tb['y_index']]).unique())
+        return self._n_weight_cells
 
     def _attach_unit_hydrograph(self):
         return
@@ -476,12 +544,17 @@ class TransformMuskingum(Muskingum):
     def _gathered_runoff_generator(self) -> Iterator[tuple]:
         """Yields (dates, gathered runoff (T, n_points) in the file's dtype, input file, output file) per grid file:
         the pointwise ``isel`` of runoff.py:267-280; everything after it happens on the device."""
-        from .runoff import _conversion_factor, gather_grid_runoff, grid_runoff_unit
+        from .runoff import _conversion_factor, gather_grid_runoff, grid_layout, grid_runoff_unit
+        names = dict(var_runoff=self.cfg.var_grid_runoff, var_x=self.cfg.var_x, var_y=self.cfg.var_y, var_t=self.cfg.var_t)
         for runoff_file, discharge_file in zip(self.cfg.grid_runoff_files, self.cfg.discharge_files):
-            self._ensure_transform(_conversion_factor(grid_runoff_unit(runoff_file, self.cfg.var_grid_runoff)))
+            factor = _conversion_factor(grid_runoff_unit(runoff_file, self.cfg.var_grid_runoff))
+            # catchments covering a good part of a (time, y, x) grid: ship the grid as it is and let the SpMM index
+            # it (numpy's pointwise gather of a million cells per time step costs more than routing them)
+            dims, ny, nx = grid_layout(runoff_file, **names)
+            flat = dims == (self.cfg.var_t, self.cfg.var_y, self.cfg.var_x) and 4 * self._count_weight_cells() >= ny * nx
+            self._ensure_transform(factor, (ny, nx) if flat else None)
             cx, cy = self._cells
-            dates, raw = gather_grid_runoff(runoff_file, cx, cy, var_runoff=self.cfg.var_grid_runoff,
-                                            var_x=self.cfg.var_x, var_y=self.cfg.var_y, var_t=self.cfg.var_t)
+            dates, raw = gather_grid_runoff(runoff_file, cx, cy, flat=flat, **names)
             if len(dates) > 2 and not np.all(np.diff(dates) == dates[1] - dates[0]):
                 # irregular time axis: the reference resamples the lateral inflows on the host (runoff.py:316-329)
                 ds = runoff_to_qlateral(runoff_file, grid_weights_file=self.cfg.grid_weights_file,
@@ -497,7 +570,7 @@ class TransformMuskingum(Muskingum):
     def _router(self, qlateral):
         """The seam of TransformMuskingum.py:150-152: (final state, fp64 (T, n) discharge array)."""
         discharge_array = np.zeros((self.num_runoff_steps, self.n), dtype=np.float64)
-        q_t = self._route_lateral(qlateral, discharge_array)
+        q_t = self._full_width(lambda: self._route_lateral(qlateral, discharge_array))
         return q_t, discharge_array
 
 

@@ -16,7 +16,7 @@ from .transforms import weights_transform
 logger = logging.getLogger(__name__)
 
 __all__ = ['runoff_to_qlateral', 'weights_to_qlateral', 'build_weight_csr', 'read_weight_table', 'gather_grid_runoff',
-           'grid_runoff_unit', 'QlateralDataset']
+           'grid_runoff_unit', 'grid_layout', 'QlateralDataset']
 
 
 def _conversion_factor(unit):
@@ -102,12 +102,26 @@ def grid_runoff_unit(runoff_data, var_runoff='ro'):
         return ncio.attrs_of(ds.variables[var_runoff]).get('units', 'm')
 
 
+def grid_layout(runoff_data, *, var_runoff='ro', var_x='lon', var_y='lat', var_t='time'):
+    """(dimension names of the runoff variable in file order, ny, nx) of the first runoff file."""
+    from . import ncio
+    with ncio.open_nc(_as_list(runoff_data)[0]) as ds:
+        var = ds.variables[var_runoff]
+        dims = tuple(var.dimensions)
+        if sorted(dims) != sorted((var_t, var_y, var_x)):
+            raise ValueError(f'{var_runoff} must have dimensions ({var_t}, {var_y}, {var_x}), found {dims}')
+        return dims, int(var.shape[dims.index(var_y)]), int(var.shape[dims.index(var_x)])
+
+
 def gather_grid_runoff(runoff_data, cells_x, cells_y, *, var_runoff='ro', var_x='lon', var_y='lat', var_t='time',
-                       slab_rows=64):
+                       slab_rows=64, flat=False):
     """
     The pointwise gather of runoff.py:267-280: (time axis as datetime64[s], (T, n_points) runoff in the file's dtype)
     for the unique cells (x_index, y_index) of the weight table.  Files are concatenated along time like
     ``xr.open_mfdataset`` does for consecutive files; the grid is read in slabs of time steps.
+    ``flat=True`` skips the gather and returns the whole grid as (T, ny * nx) -- for weight tables whose column
+    indices are flat cell ids ``y * nx + x``, i.e. the gather happens inside the device SpMM (files stored as
+    (time, y, x) only).
     """
     from . import ncio
     dates, parts = [], []
@@ -127,7 +141,12 @@ def gather_grid_runoff(runoff_data, cells_x, cells_y, *, var_runoff='ro', var_x=
                 slab = np.moveaxis(np.asarray(var[tuple(sel)]), (at, ay, ax), (0, 1, 2))
                 if isinstance(slab, np.ma.MaskedArray):
                     slab = slab.filled(np.nan)
-                g = slab[:, cells_y, cells_x]
+                if flat:
+                    if (at, ay, ax) != (0, 1, 2):
+                        raise ValueError('flat grids need the runoff stored as (time, y, x)')
+                    g = slab.reshape(slab.shape[0], -1)
+                else:
+                    g = slab[:, cells_y, cells_x]
                 parts.append(np.ascontiguousarray(g, dtype=g.dtype.newbyteorder('=')))
     return np.concatenate(dates), np.concatenate(parts, axis=0)
 

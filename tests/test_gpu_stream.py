@@ -222,3 +222,41 @@ def test_pinned_and_pageable_callers_agree(rows, chunk_rows):
     plan.route_host(rr.MODE_RAPID, q_c, wide_in[:, :n], wide_out[:, :n], 1)
     assert np.array_equal(wide_out[:, :n], out_a) and np.all(wide_out[:, n:] == -1.0) and np.array_equal(q_c, q_a)
     plan.close()
+
+
+@pytest.mark.parametrize('rows,k', [(0, 1), (3, 2)])
+def test_output_subset_columns(rows, k, chunk_rows):
+    """rr_plan_set_output_subset: only the chosen river segments are copied back, bit-identical to the columns of the
+    full output, for every host streaming call; q_state stays the full final state."""
+    n, n_points, T = 4000 + 9, 900, 24
+    down, a = _network(n, 3, 17, 3600, 3600)
+    plan = rr.Plan(down)
+    plan.set_coefficients(a['c1'], a['c2'], a['c3'], a['c4_dt'])
+    indptr, indices, data, area = _weight_case(n, n_points, 5, True)
+    tf = Transform(indptr, indices, data, n_points, area=area)
+    x = _runoff(T, n_points, 6, True, False)
+    ql = synth.lateral_volumes(T, n, 12)
+    q0 = np.random.default_rng(5).uniform(0, 10, n)
+    idx = np.array([n - 1, 0, 77, 77, 2048, 31, 32], dtype=np.int32)
+    chunk_rows(rows)
+    q_full, out_full = q0.copy(), np.empty((T // k, n), dtype=np.float32)
+    plan.route_host(rr.MODE_RAPID, q_full, ql, out_full, 1, resample=k)
+    g_full, gout_full = q0.copy(), np.empty((T // k, n))
+    plan.runoff_route_host(tf, rr.MODE_RAPID, g_full, x, gout_full, 1, as_volumes=True, resample=k)
+    plan.set_output_subset(idx)
+    q_sub, out_sub = q0.copy(), np.full((T // k, idx.shape[0]), np.nan, dtype=np.float32)
+    plan.route_host(rr.MODE_RAPID, q_sub, ql, out_sub, 1, resample=k)
+    assert np.array_equal(out_sub, out_full[:, idx]) and np.array_equal(q_sub, q_full)
+    g_sub, gout_sub = q0.copy(), np.full((T // k, idx.shape[0]), np.nan)
+    plan.runoff_route_host(tf, rr.MODE_RAPID, g_sub, x, gout_sub, 1, as_volumes=True, resample=k)
+    assert np.array_equal(gout_sub, gout_full[:, idx]) and np.array_equal(g_sub, g_full)
+    with pytest.raises(ValueError, match='shape'):
+        plan.route_host(rr.MODE_RAPID, q0.copy(), ql, np.empty((T // k, n), dtype=np.float32), 1, resample=k)
+    with pytest.raises(RuntimeError, match='outside the network'):
+        plan.set_output_subset([n])
+    plan.set_output_subset(None)
+    again = np.empty((T // k, n), dtype=np.float32)
+    plan.route_host(rr.MODE_RAPID, q0.copy(), ql, again, 1, resample=k)
+    assert np.array_equal(again, out_full)
+    tf.close()
+    plan.close()

@@ -125,6 +125,15 @@ def test_grid_gather_matches_pointwise_isel(tmp_path, dims):
     assert raw2.shape[0] == 75 and np.array_equal(raw2[70:], ro[:5][:, cy, cx]) and d2.shape[0] == 75
     write_grid(str(tmp_path / 'g3.nc'), ro[:2], units=None)
     assert grid_runoff_unit(str(tmp_path / 'g3.nc')) == 'm'                       # runoff.py:268 default
+    # flat layout for the device-side gather: the whole (time, y, x) grid with columns = flat cell ids y * nx + x
+    from river_route_b200.runoff import grid_layout
+    assert grid_layout(str(tmp_path / 'g.nc'), var_x='lon', var_y='lat') == (dims, 9, 13)
+    if dims == ('time', 'lat', 'lon'):
+        _, flat = gather_grid_runoff(str(tmp_path / 'g.nc'), cx, cy, var_x='lon', var_y='lat', flat=True, slab_rows=32)
+        assert flat.shape == (70, 9 * 13) and np.array_equal(flat[:, cy * 13 + cx], raw)
+    else:
+        with pytest.raises(ValueError, match='stored as .time, y, x.'):
+            gather_grid_runoff(str(tmp_path / 'g.nc'), cx, cy, var_x='lon', var_y='lat', flat=True)
 
 
 def test_weight_csr_equals_scipy_construction():

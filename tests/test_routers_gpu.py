@@ -185,7 +185,7 @@ def test_weights_to_qlateral_and_unit_hydrograph_classes():
 # ------------------------------------------------------------------------------------------------------
 # file level: YAML config -> params parquet + grid runoff netCDF + weight table netCDF -> discharge netCDF
 # ------------------------------------------------------------------------------------------------------
-def _grid_case(tmp_path, n=3000, T=30, ny=15, nx=22, cumulative=False, units='m'):
+def _grid_case(tmp_path, n=3000, T=30, ny=15, nx=22, cumulative=False, units='m', dims=('time', 'lat', 'lon')):
     from river_route_b200 import synth
     from tests.test_io_cpu import synthetic_table, write_grid, write_weight_table
     down = synth.forest(n, 3, seed=21, depth_bias=0.6)
@@ -208,7 +208,7 @@ def _grid_case(tmp_path, n=3000, T=30, ny=15, nx=22, cumulative=False, units='m'
         if cumulative:
             ro = np.cumsum(ro, axis=0, dtype=np.float32)
         path = str(tmp_path / f'runoff_{f}.nc')
-        write_grid(path, ro, t0=f'2020-01-0{1 + f} 00:00:00', dt_hours=1, units=units)
+        write_grid(path, ro, t0=f'2020-01-0{1 + f} 00:00:00', dt_hours=1, units=units, dims=dims)
         grids.append((path, ro))
     return dict(down=down, k=k, x=x, ids=ids, q0=q0, table=table, grids=grids, params=params, state=state, n=n, T=T)
 
@@ -247,12 +247,15 @@ def _oracle_grid_chain(c, dt, cumulative, units, unit_hydrograph=None):
     return outs, q
 
 
-@pytest.mark.parametrize('cumulative,units', [(False, 'm'), (True, 'mm')])
-def test_rapid_muskingum_from_grid_files_yaml_config(tmp_path, cumulative, units):
-    """The fused device path behind the unchanged config surface (examples/config.yaml keys): nothing is injected."""
+@pytest.mark.parametrize('cumulative,units,dims', [(False, 'm', ('time', 'lat', 'lon')), (True, 'mm', ('time', 'lat', 'lon')),
+                                                   (False, 'mm', ('lat', 'time', 'lon'))])
+def test_rapid_muskingum_from_grid_files_yaml_config(tmp_path, cumulative, units, dims):
+    """The fused device path behind the unchanged config surface (examples/config.yaml keys): nothing is injected.
+    (time, y, x) files are shipped whole and gathered by the SpMM on the device (flat cell ids); other dimension
+    orders are gathered on the host first."""
     import yaml
     from river_route_b200 import ncio
-    c = _grid_case(tmp_path, cumulative=cumulative, units=units)
+    c = _grid_case(tmp_path, cumulative=cumulative, units=units, dims=dims)
     out_dir = tmp_path / 'out'
     out_dir.mkdir()
     cfg = dict(params_file=c['params'], grid_runoff_files=[g[0] for g in c['grids']], grid_weights_file=str(tmp_path / 'weights.nc'),
@@ -264,6 +267,7 @@ def test_rapid_muskingum_from_grid_files_yaml_config(tmp_path, cumulative, units
     before = rr.launch_count()
     r.route()
     assert rr.launch_count() > before and r._transform is not None      # the device-resident path ran
+    assert (r._transform_key[1] is not None) == (dims == ('time', 'lat', 'lon'))   # device-side gather only for (t, y, x)
     outs, q_final = _oracle_grid_chain(c, 3600, cumulative, units)
     for f, ref in enumerate(outs):
         with ncio.open_nc(out_dir / f'discharge_runoff_{f}.nc') as ds:
@@ -358,3 +362,37 @@ def test_cumulative_runoff_equals_incremental():
     np.testing.assert_allclose(b, a, rtol=1e-9, atol=1e-9 * np.abs(a).max())
     c, _ = rr.weights_to_qlateral(table, -inc, force_positive_runoff=True)
     assert np.all(c == 0)                                                     # runoff.py:313-314
+
+
+def test_output_subset_of_rivers(route_golden, tmp_path):
+    """``set_output_rivers``: the device-side form of the reference's subset writer (docs/tutorial/advanced.md:147-170):
+    the writer sees exactly the columns of the full run, the state is the full state, unknown ids are rejected."""
+    from river_route_b200 import ncio
+    g = route_golden
+    params, state = _files(g, tmp_path)
+    common = dict(params_file=params, qlateral_files=[params], channel_state_init_file=state,
+                  dt_routing=int(g['dt_routing']), log=False)
+    full = Capture()
+    r0 = _inject(rr.RapidMuskingum, [g['ql']], g['dt_runoff'])(**common, discharge_files=[str(tmp_path / 'full.nc')])
+    r0.set_write_discharges(full).route()
+    ids = g['river_ids']
+    pick = ids[[len(ids) - 1, 0, len(ids) // 2, 0]]                     # any order, repeats allowed
+    r1 = _inject(rr.RapidMuskingum, [g['ql']], g['dt_runoff'])(**common, discharge_files=[str(tmp_path / 'sub.nc')])
+    r1.set_output_rivers(pick).route()                                  # default netCDF writer
+    with ncio.open_nc(tmp_path / 'sub.nc') as ds:
+        Q = ncio.read_array(ds.variables['Q'])
+        assert np.array_equal(ncio.read_array(ds.variables['river_id']), pick.astype(np.int32))
+    cols = [int(np.flatnonzero(ids == p)[0]) for p in pick]
+    assert Q.shape == (g['ql'].shape[0], 4) and np.array_equal(Q, full.calls[0][1][:, cols])
+    assert np.array_equal(r1.channel_state, r0.channel_state)
+
+    class Seam(rr.RapidMuskingum):                                      # overridden seam -> subset taken on the host
+        def _router(self, qlateral):
+            return super()._router(qlateral)
+    cap = Capture()
+    _inject(Seam, [g['ql']], g['dt_runoff'])(**common, discharge_files=[str(tmp_path / 's2.nc')]) \
+        .set_output_rivers(pick).set_write_discharges(cap).route()
+    assert np.array_equal(cap.calls[0][1], Q)
+    with pytest.raises(ValueError, match='ids not in the params file'):
+        _inject(rr.RapidMuskingum, [g['ql']], g['dt_runoff'])(**common, discharge_files=[str(tmp_path / 'x.nc')]) \
+            .set_output_rivers([int(ids.max()) + 12345]).route()

@@ -326,6 +326,41 @@ def c4():
     emit(config='C4', stage='one_year_streamed', api='Plan.route_host -> rr_route_host_ex (float32 out)', reaches=n,
          steps=year, wall_s=s, reach_steps_per_s=n * year / s, h2d_GB=n * year * 8 / 1e9, d2h_GB=n * year * 4 / 1e9,
          state_finite=bool(np.isfinite(qy).all()), state_sum=float(qy.sum()))
+    # ---- the same year from gridded runoff (ERA5 0.25 degree, float32) to the hydrographs of the 5000 outlets:
+    #      weight table -> route on the device, outlet columns copied back (rr_plan_set_output_subset) ----
+    from river_route_b200.transforms import Transform
+    n_cells = 721 * 1440
+    rng = np.random.default_rng(77)
+    per = rng.integers(4, 9, n)
+    indptr = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(per, out=indptr[1:])
+    first = rng.integers(0, n_cells - 8, n)
+    indices = (np.repeat(first, per) + (np.arange(indptr[-1]) - np.repeat(indptr[:-1], per))).astype(np.int32)
+    w = rng.random(indptr[-1])
+    w /= np.repeat(np.add.reduceat(w, indptr[:-1]), per)
+    tf = Transform(indptr, indices, w, n_cells, area=rng.uniform(1e5, 5e8, n))
+    gr = 192
+    grid = rr.pinned_empty((gr, n_cells), dtype=np.float32)
+    grid[:] = (rng.gamma(0.3, 2e-3, (gr, n_cells)) * (rng.random((gr, n_cells)) < 0.4)).astype(np.float32)
+    outlets = np.flatnonzero(down < 0).astype(np.int32)
+    plan.set_output_subset(outlets)
+    hyd = rr.pinned_empty((gr, outlets.shape[0]), dtype=np.float32)
+    qy[:] = 0.0
+    plan.runoff_route_host(tf, rr.MODE_RAPID, qy, grid, hyd, 1, as_volumes=True)       # warm-up
+    qy[:] = 0.0
+    t = time.perf_counter()
+    done = 0
+    while done < year:
+        r = min(gr, year - done)
+        plan.runoff_route_host(tf, rr.MODE_RAPID, qy, grid[:r], hyd[:r], 1, as_volumes=True)
+        done += r
+    s = time.perf_counter() - t
+    emit(config='C4', stage='one_year_grid_to_outlet_hydrographs',
+         api='Plan.set_output_subset + Plan.runoff_route_host (float32 grid in, float32 outlet discharge out)', reaches=n,
+         outlets=int(outlets.shape[0]), steps=year, wall_s=s, reach_steps_per_s=n * year / s,
+         h2d_GB=n_cells * year * 4 / 1e9, d2h_GB=outlets.shape[0] * year * 4 / 1e9, state_finite=bool(np.isfinite(qy).all()))
+    plan.set_output_subset(None)
+    tf.close()
     plan.close()
 
 

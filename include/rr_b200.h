@@ -48,7 +48,8 @@ typedef struct rr_plan_opts {
     int32_t staging;        /* renumbered plans: 0 auto (= 2), 1 register path on row-major working arrays,
                                2 register path on tile-major working arrays, 3 bulk-async-copy (TMA)
                                staged kernel on tile-major working arrays, 4 as 2 with reach-major
-                               discharge tiles (experiments; 0 is the measured best)               */
+                               discharge tiles, 5 as 2 with [row group][lane][4] lateral tiles: warp-coalesced
+                               256-bit lateral loads (experiments; 0 is the measured best)          */
 } rr_plan_opts;
 
 /* Host-visible description of a built plan (for tests, DESIGN.md numbers and bench.py). */
@@ -229,6 +230,13 @@ int rr_runoff_route_host(rr_plan *p, rr_transform *t, int mode, double *q_state,
 /* Diagnostic cycle counters of the routing kernel (builds with -DRR_PROFILE; zeros otherwise), summed over warps:
  * [0] ticket + decode, [1] per-item constants + dependency waits, [2] item body, [3] publish.  Resets on read. */
 int rr_plan_read_profile(rr_plan *p, uint64_t *out8);
+
+/* Memory-system probe for the routing kernel's access shapes (diagnostic; tools/sector_probe.py): copies
+ * rows x row_doubles doubles from src to dst (device pointers) with 256-bit loads / stores, mode 0 coalesced,
+ * mode 1 one 512-byte-style series per lane with rows in order, mode 2 the same with source rows scattered by
+ * perm[] (the exchange-row pattern).  Returns the best kernel time of `reps` launches in *ms_best. */
+int rr_probe_sector_bandwidth(int mode, int64_t rows, int32_t row_doubles, const double *src, double *dst,
+                              const int32_t *perm, int32_t reps, double *ms_best);
 
 /* ---- pinned host memory for the streaming path ---------------------------------------------- */
 int rr_host_alloc(void **ptr, int64_t bytes);

@@ -380,6 +380,7 @@ __device__ __forceinline__ int64_t working_index(int64_t t, int64_t k, int64_t l
     const int64_t j = t / tile_rows, r = t - j * tile_rows;
     if (layout == 1) return ((j * n_blocks + (k >> 5)) * tile_rows + r) * RR_BLOCK + (k & 31);
     const int64_t pitch = (tile_rows + 3) & ~(int64_t)3;
+    if (layout == 3) return (((j * n_blocks + (k >> 5)) * (pitch >> 2) + (r >> 2)) * RR_BLOCK + (k & 31)) * 4 + (r & 3);
     return ((j * n_blocks + (k >> 5)) * RR_BLOCK + (k & 31)) * pitch + r;
 }
 __device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) {
@@ -404,6 +405,13 @@ __global__ void __launch_bounds__(256) permute_to_working(const double *__restri
         double *q = dst + working_index(t0, k, ldd, tile_rows, n_blocks, 2);
 #pragma unroll
         for (int r = 0; r < ROWS; r += 4) st256(q + r, v[r], v[r + 1], v[r + 2], v[r + 3]);
+        return;
+    }
+    if (layout == 3 && (tile_rows % ROWS) == 0) {
+        // groups of 4 rows are one sector each, 1 KB apart (the 32 lanes of the block sit in between)
+        double *q = dst + working_index(t0, k, ldd, tile_rows, n_blocks, 3);
+#pragma unroll
+        for (int r = 0; r < ROWS; r += 4) st256(q + (size_t)(r >> 2) * (RR_BLOCK * 4), v[r], v[r + 1], v[r + 2], v[r + 3]);
         return;
     }
 #pragma unroll
@@ -436,7 +444,7 @@ static int permute(bool to_working, const double *src, int64_t lds, double *dst,
                    int64_t n, int64_t T, cudaStream_t stream, int64_t tile_rows = 0, int64_t n_blocks = 0, int layout = 0) {
     rr_timer tm(to_working ? 1 : 2, stream);
     const unsigned gx = (unsigned)((n + 255) / 256);
-    if (to_working && layout == 2 && (tile_rows % 16) == 0) {
+    if (to_working && (layout == 2 || layout == 3) && (tile_rows % 16) == 0) {
         dim3 grid(gx, (unsigned)((T + 15) / 16));
         permute_to_working<16><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
     } else if (to_working) {
@@ -484,7 +492,7 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     const bool tiled = (K == 1 && p->opts.staging != 1 && !(unit && p->opts.staging == 3));
     // lateral: reach-major tiles (whole-sector scatter in the permute, 256-bit loads in the kernel); discharge:
     // row-major tiles (coalesced row stores in the kernel, sector-sharing gathers in the permute) -- measured best
-    const int layout = !tiled ? 0 : (p->opts.staging == 3 ? 1 : 2);
+    const int layout = !tiled ? 0 : (p->opts.staging == 3 ? 1 : (p->opts.staging == 5 ? 3 : 2));
     const int out_layout = !tiled ? 0 : (p->opts.staging == 4 ? 2 : 1);
     const int64_t trows = tiled ? tile_rows_for(p, T, K) : 0;
     const int64_t tpitch = ((trows + 3) & ~(int64_t)3);

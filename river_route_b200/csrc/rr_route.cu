@@ -117,11 +117,18 @@ __device__ __forceinline__ void st_sector(double *p, double a, double b, double 
 
 // Lateral inflow of working reach u at row `row` of tile j (UnitMuskingum reads its upstreams' laterals).
 __device__ __forceinline__ const double *lat_ptr(const rr_route_params &P, int m, int j, int t0, int64_t u, int row) {
+    if (P.tile_major == 3)   // [tile][block][group of 4 rows][lane][4]: a warp's 256-bit loads of its own rows are one contiguous KB
+        return P.lateral[m] + ((((size_t)j * P.n_blocks + (size_t)(u >> 5)) * (size_t)(P.tile_pitch >> 2) + (size_t)(row >> 2)) * RR_BLOCK +
+                               (size_t)(u & 31)) * 4 + (row & 3);
     if (P.tile_major == 2)
         return P.lateral[m] + (((size_t)j * P.n_blocks + (size_t)(u >> 5)) * RR_BLOCK + (size_t)(u & 31)) * (size_t)P.tile_pitch + row;
     if (P.tile_major == 1)
         return P.lateral[m] + (((size_t)j * P.n_blocks + (size_t)(u >> 5)) * (size_t)P.tile_rows + row) * RR_BLOCK + (u & 31);
     return P.lateral[m] + (size_t)(t0 + row) * P.ldl + u;
+}
+// offset of row r of one reach's lateral series from its row 0 (layout 3: groups of 4 rows are 32 lanes x 4 doubles apart)
+__device__ __forceinline__ size_t lat_row_off(int layout, int64_t stride, int r) {
+    return layout == 3 ? (((size_t)(r >> 2)) << 7) + (size_t)(r & 3) : (size_t)r * (size_t)stride;
 }
 
 struct item_ctx {
@@ -187,7 +194,7 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
     auto lat_group = [&](int s0) -> d4 {
         d4 v{0, 0, 0, 0};
         if (!(HAS_LAT && c.valid) || s0 >= TT) return v;
-        if (VEC) return ld_sector_ro(lat + s0);    // this reach's rows are contiguous (padded to a multiple of 4)
+        if (VEC) return ld_sector_ro(lat + lat_row_off(P.tile_major, 1, s0));   // 4 rows of this reach: one aligned sector
         const double *lp = lat + (size_t)s0 * ldl;
         v.a = ld_stream(lp);
         if (s0 + 1 < TT) v.b = ld_stream(lp + ldl);
@@ -414,7 +421,7 @@ __device__ __forceinline__ void unit_fast_item(const rr_route_params &P, const i
     auto group = [&](const double *p, int64_t stride, int s0, bool on, bool vec) -> d4 {
         d4 v{0, 0, 0, 0};
         if (!on || s0 >= TT) return v;
-        if (vec) return ld_sector_ro(p + s0);
+        if (vec) return ld_sector_ro(p + lat_row_off(P.tile_major, 1, s0));
         const double *lp = p + (size_t)s0 * stride;
         v.a = ld_stream(lp);
         if (s0 + 1 < TT) v.b = ld_stream(lp + stride);
@@ -422,7 +429,7 @@ __device__ __forceinline__ void unit_fast_item(const rr_route_params &P, const i
         if (s0 + 3 < TT) v.d = ld_stream(lp + 3 * stride);
         return v;
     };
-    const bool uvec = P.tile_major == 2;
+    const bool uvec = P.tile_major >= 2;
     // state carried between groups: per inner upstream its q_full before the group's first substep
     double qfo[NA];
     d4 exn[NA], lun[NA];
@@ -723,7 +730,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
                 for (int k = 0; k < GEN_SLOTS; ++k) {
                     if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) { eo[k] = en[k]; en[k] = rp[k][RAW_S0 + s + 1]; }
                 }
-                if (HAS_LAT && sub == 0) ql_nx = ld_stream(lat + (size_t)row * c.lstride);
+                if (HAS_LAT && sub == 0) ql_nx = ld_stream(lat + lat_row_off(P.tile_major, c.lstride, row));
             }
         }
     }
@@ -786,8 +793,10 @@ __device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c,
     c.raw_m = P.raw + (size_t)m * (size_t)P.raw_rows * P.raw_pitch;
     // Working-array layouts (renumbered plans; the caller's arrays are permuted into them on the device):
     //   0 row-major (T, ld)   1 [tile][block][row][lane]   2 [tile][block][lane][row] (tile_pitch doubles per reach)
+    //   3 [tile][block][row / 4][lane][row % 4] (lateral only)
     auto place = [&](int layout, const double *base, int64_t ld, const double *&p0, int64_t &stride) {
-        if (layout == 2) { p0 = base + (((size_t)j * P.n_blocks + b) * RR_BLOCK + lane) * (size_t)P.tile_pitch; stride = 1; }
+        if (layout == 3) { p0 = base + (((size_t)j * P.n_blocks + b) * (size_t)(P.tile_pitch >> 2) * RR_BLOCK + lane) * 4; stride = 1; }
+        else if (layout == 2) { p0 = base + (((size_t)j * P.n_blocks + b) * RR_BLOCK + lane) * (size_t)P.tile_pitch; stride = 1; }
         else if (layout == 1) { p0 = base + ((size_t)j * P.n_blocks + b) * (size_t)P.tile_rows * RR_BLOCK + lane; stride = RR_BLOCK; }
         else { p0 = base + (size_t)c.t0 * ld + i; stride = ld; }
     };
@@ -803,9 +812,9 @@ __device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c,
         // not survive in L2 until it is used: the chip streams ~L2-size bytes during one item)
         const bool fast = (c.M.int_mask & 0x40) && P.K == 1 && MODE != RR_MODE_UNIT;
         const int pf_rows = fast ? min(c.rows, 16) : c.rows;
-        if (P.tile_major == 2) {
+        if (P.tile_major >= 2) {
             prefetch_l2(c.lat0);                                   // this lane's first line (16 rows)
-            if (!fast) for (int r = 16; r < c.rows; r += 16) prefetch_l2(c.lat0 + r);
+            if (!fast) for (int r = 16; r < c.rows; r += 16) prefetch_l2(c.lat0 + lat_row_off(P.tile_major, 1, r));
         } else if (P.tile_major) {
             const char *t = (const char *)(c.lat0 - lane);
             for (int l = lane; l < pf_rows * 2; l += 32) prefetch_l2(t + (size_t)l * 128);
@@ -981,7 +990,7 @@ __device__ __forceinline__ bool tma_item(const rr_route_params &P, const item_ct
 
 template <int MODE>
 __device__ __forceinline__ void register_fast_item(const rr_route_params &P, const item_ctx &c) {
-    if (P.tile_major == 2) {
+    if (P.tile_major >= 2) {
         switch (c.M.max_deg) {
             case 0: fast_item<MODE, 0, true>(P, c); break;
             case 1: fast_item<MODE, 1, true>(P, c); break;
@@ -1025,7 +1034,7 @@ __global__ void __launch_bounds__(256, RR_MIN_CTAS) rr_wavefront_kernel(const __
                 default: fast_item_k<MODE, 2>(P, c); break;
             }
         } else if (UNIT && P.K == 1 && (c.M.int_mask & 0x40) && c.M.max_deg <= 2) {
-            const bool vec = P.tile_major == 2;
+            const bool vec = P.tile_major >= 2;
             switch (c.M.max_deg) {
                 case 0: if (vec) unit_fast_item<0, true>(P, c); else unit_fast_item<0, false>(P, c); break;
                 case 1: if (vec) unit_fast_item<1, true>(P, c); else unit_fast_item<1, false>(P, c); break;

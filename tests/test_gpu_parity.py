@@ -103,12 +103,12 @@ SYNTH = [
 ]
 
 
-@pytest.mark.parametrize('renumber', ['never', 'always', 'always-registers', 'always-tma'])
+@pytest.mark.parametrize('renumber', ['never', 'always', 'always-registers', 'always-tma', 'always-lateral-grouped'])
 @pytest.mark.parametrize('n,nbas,bias,stem,T,dt_runoff,dt_routing,opts', SYNTH)
 def test_rapid_and_muskingum_vs_oracle(n, nbas, bias, stem, T, dt_runoff, dt_routing, opts, renumber):
     # 'always': level-sorted working order (register-blocked path on tile-major working arrays); '-registers':
     # row-major working arrays; '-tma': bulk-async-copy staged kernel; 'never': params-file order
-    opts = dict(opts, renumber=renumber.split('-')[0], staging=renumber.split('-')[1] if '-' in renumber else 'auto')
+    opts = dict(opts, renumber=renumber.split('-')[0], staging=renumber.split('-', 1)[1] if '-' in renumber else 'auto')
     base = synth.forest(n, nbas, seed=n % 97, depth_bias=bias, main_stem=stem)
     k, x = synth.muskingum_params(n, 1)
     K = dt_runoff // dt_routing
@@ -135,10 +135,10 @@ def test_rapid_and_muskingum_vs_oracle(n, nbas, bias, stem, T, dt_runoff, dt_rou
         plan.close()
 
 
-@pytest.mark.parametrize('renumber', ['never', 'always'])
+@pytest.mark.parametrize('renumber', ['never', 'always', 'always-lateral-grouped'])
 @pytest.mark.parametrize('n,nbas,bias,stem,T,dt_runoff,dt_routing,opts', SYNTH[:5])
 def test_unit_vs_oracle(n, nbas, bias, stem, T, dt_runoff, dt_routing, opts, renumber):
-    opts = dict(opts, renumber=renumber)
+    opts = dict(opts, renumber=renumber.split('-')[0], staging=renumber.split('-', 1)[1] if '-' in renumber else 'auto')
     base = synth.forest(n, nbas, seed=n % 89, depth_bias=bias, main_stem=stem)
     k, x = synth.muskingum_params(n, 2)
     K = dt_runoff // dt_routing

@@ -1,11 +1,7 @@
 """GPU parity of the unit-hydrograph convolution and the grid-weight transform (through the C ABI)."""
-import ctypes as C
-
 import numpy as np
 import pytest
 
-import river_route_b200 as rr
-from river_route_b200 import _lib
 from river_route_b200.transforms import uh_convolve, weights_transform
 from oracle import oracle
 from tests.conftest import load_golden, require_cuda

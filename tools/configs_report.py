@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import river_route_b200 as rr  # noqa: E402
-from river_route_b200 import synth, _lib  # noqa: E402
+from river_route_b200 import synth  # noqa: E402
 from river_route_b200.plan import timing_enable, timing_read  # noqa: E402
 from river_route_b200._lib import lib, check  # noqa: E402
 from oracle import oracle  # noqa: E402

@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """How much the kind of host memory matters for the router-level call (rr_route_host_ex): pinned vs pageable
 numpy arrays, fresh vs touched output pages, and cudaHostRegister on the caller's arrays.  One JSON line."""
-import ctypes as C
 import json
 import os
 import sys

@@ -530,7 +530,8 @@ class TransformMuskingum(Muskingum):
             self._weight_table = read_weight_table(self.cfg.grid_weights_file, self.cfg.var_river_id)
         if not hasattr(self, '_n_weight_cells'):
             tb = self._weight_table
-            self._n_weight_cells = len(pd.MultiIndex.from_arrays([tb['x_index'], tb['y_index']]).unique())
+            x, y = np.asarray(tb['x_index']).astype(np.int64), np.asarray(tb['y_index']).astype(np.int64)
+            self._n_weight_cells = len(pd.unique(x * (int(y.max(initial=0)) + 1) + y))
         return self._n_weight_cells
 
     def _attach_unit_hydrograph(self):

@@ -39,23 +39,26 @@ def build_weight_csr(river_id, x_index, y_index, proportion, area_sqm, conversio
     river_id = np.asarray(river_id)
     x_index = np.asarray(x_index).astype(np.int64)
     y_index = np.asarray(y_index).astype(np.int64)
-    cell_key = pd.MultiIndex.from_arrays([x_index, y_index])
-    point_idx, uniq_cells = pd.factorize(cell_key)          # first-appearance numbering == drop_duplicates order
+    # first-appearance numbering == drop_duplicates order; (x, y) packed into one integer key (a hash factorize of
+    # int64 keys and a stable integer sort are ~10x faster than the tuple / lexsort route at 10^7-10^8 table rows)
+    if x_index.size and (x_index.min() < 0 or y_index.min() < 0):
+        raise ValueError('x_index / y_index must be non-negative grid indices')
+    y_span = int(y_index.max()) + 1 if y_index.size else 1
+    point_idx, uniq_keys = pd.factorize(x_index * y_span + y_index)
     river_idx, river_ids_ordered = pd.factorize(river_id)
-    n_riv, n_pts = len(river_ids_ordered), len(uniq_cells)
+    n_riv, n_pts = len(river_ids_ordered), len(uniq_keys)
     vals = np.asarray(proportion, dtype=np.float64) * conversion_factor
-    order = np.lexsort((np.arange(river_idx.shape[0]), point_idx, river_idx))
+    order = np.argsort(river_idx.astype(np.int64) * max(n_pts, 1) + point_idx, kind='stable')   # by (river, cell), ties in file order
     r, p, v = river_idx[order], point_idx[order], vals[order]
     first = np.ones(r.shape[0], dtype=bool)
     first[1:] = (r[1:] != r[:-1]) | (p[1:] != p[:-1])
     starts = np.flatnonzero(first)
     data = np.add.reduceat(v, starts) if starts.size else np.zeros(0)
     indptr = np.zeros(n_riv + 1, dtype=np.int32)
-    np.add.at(indptr, r[first] + 1, 1)
-    np.cumsum(indptr, out=indptr)
+    np.cumsum(np.bincount(r[first], minlength=n_riv), out=indptr[1:])
     area = pd.Series(np.asarray(area_sqm, dtype=np.float64)).groupby(river_idx).sum().reindex(np.arange(n_riv)).to_numpy()
-    cells_x = np.asarray(uniq_cells.get_level_values(0), dtype=np.int64)
-    cells_y = np.asarray(uniq_cells.get_level_values(1), dtype=np.int64)
+    uniq_keys = np.asarray(uniq_keys, dtype=np.int64)
+    cells_x, cells_y = uniq_keys // y_span, uniq_keys % y_span
     return indptr, p[first].astype(np.int32), data, cells_x, cells_y, np.asarray(river_ids_ordered), area
 
 

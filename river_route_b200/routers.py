@@ -319,11 +319,13 @@ class Muskingum:
             self.plan.set_output_subset(None)
             self._output_idx = None
             return
-        pos = pd.Series(np.arange(self.n), index=self.river_ids)
-        missing = np.setdiff1d(self._output_river_ids, self.river_ids)
+        sorter = np.argsort(self.river_ids, kind='stable')
+        where = np.searchsorted(self.river_ids, self._output_river_ids, sorter=sorter)
+        found = sorter[np.minimum(where, self.n - 1)]
+        missing = self._output_river_ids[self.river_ids[found] != self._output_river_ids]
         if missing.size:
-            raise ValueError(f'set_output_rivers: ids not in the params file: {missing[:10].tolist()}')
-        self._output_idx = pos.loc[self._output_river_ids].to_numpy(dtype=np.int32)
+            raise ValueError(f'set_output_rivers: ids not in the params file: {np.unique(missing)[:10].tolist()}')
+        self._output_idx = found.astype(np.int32)
         self.plan.set_output_subset(self._output_idx)
 
     @property

@@ -1,0 +1,236 @@
+"""
+Host logic of the router classes without a GPU: the device calls (`Plan.route_host`, `Plan.runoff_route_host`,
+`Transform`) are replaced by oracle-backed stand-ins with the same contracts, so that everything around them runs on
+the CPU box -- YAML config -> params parquet / weight-table + grid / qlateral netCDF -> time bookkeeping -> fused or
+unfused path selection -> device-side gather mapping (flat cell ids) -> output subset -> dt_discharge resample ->
+state chaining across files -> UH carry-over sync -> discharge netCDF.  Expected values come from the plain oracle
+chain on the gathered arrays (tests/test_routers_gpu.py::_oracle_grid_chain), i.e. from a different route through the
+data than the one under test.  The GPU suite runs the same scenarios against the real library.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse
+
+import river_route_b200 as rr
+from river_route_b200 import ncio, plan as plan_mod, routers, transforms
+from oracle import oracle
+from tests.helpers import network_arrays, parity_error
+from tests.test_routers_gpu import Capture, _grid_case, _oracle_grid_chain
+
+
+class FakeTransform:
+    """Same constructor / methods as transforms.Transform; keeps everything on the host."""
+
+    def __init__(self, indptr, indices, data, n_points, area=None, device=-1):
+        self.indptr, self.indices, self.data = np.asarray(indptr), np.asarray(indices), np.asarray(data)
+        self.n_rivers, self.n_points, self.area = len(indptr) - 1, int(n_points), area
+        self.n_ks, self.kernel, self.state = 0, None, None
+        assert self.indices.max(initial=-1) < self.n_points
+
+    def set_unit_hydrograph(self, kernel, state=None):
+        self.kernel = np.array(kernel, dtype=np.float64)
+        self.state = np.zeros_like(self.kernel) if state is None else np.array(state, dtype=np.float64)
+        self.n_ks = self.kernel.shape[0]
+        return self
+
+    def uh_state(self):
+        return self.state.copy()
+
+    def close(self):
+        pass
+
+
+def _finish(plan, full, out, resample):
+    """The output tail the library applies on the device: subset columns, mean over `resample` rows, cast."""
+    sub = getattr(plan, '_fake_subset', None)
+    if sub is not None:
+        full = full[:, sub]
+    if resample > 1:
+        full = full.reshape(full.shape[0] // resample, resample, full.shape[1]).mean(axis=1)
+    out[...] = full.astype(out.dtype)
+
+
+def _route(plan, mode, q_state, lateral, T, substeps):
+    a = plan._fake_arrays
+    full = np.zeros((T, plan.n))
+    if mode == rr.MODE_RAPID:
+        oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q_state, lateral, full, substeps)
+    elif mode == rr.MODE_MUSKINGUM:
+        oracle.muskingum_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], q_state, full, T, substeps)
+    else:
+        sp = oracle.unit_split(plan.down.astype(np.int64))
+        inner, hw, ai, ah = sp['inner_idx'], sp['hw_idx'], sp['a_inner'], sp['a_hw']
+        c1i, c2i, c3i = a['c1'][inner], a['c2'][inner], a['c3'][inner]
+        q_ch = q_state[inner].copy()
+        q_full = q_ch.copy()
+        oracle.unit_route(ai[0], ai[1], -c1i[ai[1]], ai[0], ai[1], ai[2], ah[0], ah[1], ah[2], c1i, c2i, c3i, hw, inner,
+                          q_ch, q_full, lateral, full, substeps)
+        q_state[hw] = lateral[-1][hw]
+        q_state[inner] = q_full
+    return full
+
+
+@pytest.fixture
+def host_only(monkeypatch):
+    """Oracle-backed stand-ins for the three device entry points the routers use."""
+    def set_coefficients(self, c1, c2, c3, c4_dt=None):
+        indptr, indices = oracle.csc_from_down(self.down)
+        self._fake_arrays = dict(indptr=indptr, indices=indices, c1=np.array(c1), c2=np.array(c2), c3=np.array(c3),
+                                 c4_dt=None if c4_dt is None else np.array(c4_dt), lhs_off=oracle.lhs_off_data(np.array(c1), indices))
+
+    def set_output_subset(self, indices=None):
+        idx = None if indices is None or len(indices) == 0 else np.asarray(indices, dtype=np.int64)
+        assert idx is None or (idx.min() >= 0 and idx.max() < self.n)
+        self._fake_subset = idx
+        self.n_out = self.n if idx is None else int(idx.shape[0])
+
+    def route_host(self, mode, q_state, lateral, out, substeps, q_full=None, resample=1):
+        assert out.shape[1] == self.n_out and out.dtype in (np.float32, np.float64) and q_state.shape == (self.n,)
+        T = out.shape[0] * resample
+        assert mode == rr.MODE_MUSKINGUM or lateral.shape == (T, self.n)
+        _finish(self, _route(self, mode, q_state, None if lateral is None else np.ascontiguousarray(lateral, dtype=np.float64),
+                             T, substeps), out, resample)
+
+    def runoff_route_host(self, transform, mode, q_state, runoff, out, substeps, cumulative=False, force_positive=False,
+                          as_volumes=False, resample=1):
+        T = out.shape[0] * resample
+        assert runoff.shape == (T, transform.n_points) and out.shape[1] == self.n_out
+        unit = mode == rr.MODE_UNIT
+        ql = oracle.weights_transform(transform.indptr, transform.indices, transform.data, runoff, cumulative=cumulative,
+                                      force_positive=force_positive, area=transform.area if (as_volumes and not unit) else None)
+        if unit:
+            ql = oracle.uh_convolve(ql, transform.kernel, transform.state)
+        _finish(self, _route(self, mode, q_state, ql, T, substeps), out, resample)
+
+    monkeypatch.setattr(plan_mod.Plan, 'set_coefficients', set_coefficients)
+    monkeypatch.setattr(plan_mod.Plan, 'set_output_subset', set_output_subset)
+    monkeypatch.setattr(plan_mod.Plan, 'route_host', route_host)
+    monkeypatch.setattr(plan_mod.Plan, 'runoff_route_host', runoff_route_host)
+    monkeypatch.setattr(transforms, 'Transform', FakeTransform)
+    monkeypatch.setattr(transforms, 'uh_convolve', lambda lat, ker, st: oracle.uh_convolve(np.ascontiguousarray(lat), ker, st))
+    monkeypatch.setattr('river_route_b200.uhkernels.uh_convolve', lambda lat, ker, st: oracle.uh_convolve(np.ascontiguousarray(lat), ker, st))
+    monkeypatch.setattr(transforms, 'weights_transform',
+                        lambda indptr, indices, data, raw, cumulative=False, force_positive=False, area=None:
+                        oracle.weights_transform(indptr, indices, data, raw, cumulative=cumulative, force_positive=force_positive, area=area))
+    monkeypatch.setattr('river_route_b200.runoff.weights_transform', transforms.weights_transform)
+
+
+@pytest.mark.parametrize('cumulative,units,dims', [(False, 'm', ('time', 'lat', 'lon')), (True, 'mm', ('time', 'lat', 'lon')),
+                                                   (False, 'mm', ('lon', 'time', 'lat'))])
+def test_rapid_from_grid_files_yaml(tmp_path, host_only, cumulative, units, dims):
+    import yaml
+    c = _grid_case(tmp_path, n=600, T=12, ny=9, nx=14, cumulative=cumulative, units=units, dims=dims)
+    out_dir = tmp_path / 'out'
+    out_dir.mkdir()
+    cfg = dict(params_file=c['params'], grid_runoff_files=[g[0] for g in c['grids']], grid_weights_file=str(tmp_path / 'weights.nc'),
+               discharge_dir=str(out_dir), channel_state_init_file=c['state'], channel_state_final_file=str(tmp_path / 'final.parquet'),
+               grid_accumulation_type='cumulative' if cumulative else 'incremental', var_x='lon', var_y='lat', log=False)
+    with open(tmp_path / 'config.yaml', 'w') as f:
+        yaml.safe_dump(cfg, f)
+    r = rr.RapidMuskingum(str(tmp_path / 'config.yaml')).route()
+    flat = dims == ('time', 'lat', 'lon')
+    assert (r._transform_key[1] == (9, 14)) if flat else (r._transform_key[1] is None)
+    assert r._transform.n_points == (9 * 14 if flat else len(r._cells[0]))
+    outs, q_final = _oracle_grid_chain(c, 3600, cumulative, units)
+    for f, ref in enumerate(outs):
+        with ncio.open_nc(out_dir / f'discharge_runoff_{f}.nc') as ds:
+            Q = ncio.read_array(ds.variables['Q'])
+            tv = ds.variables['time']
+            dates = ncio.decode_time(ncio.read_array(tv), ncio.attrs_of(tv)['units'])
+        assert Q.dtype == np.float32 and np.array_equal(Q, ref.astype(np.float32))       # same arithmetic, other data path
+        assert dates[0] == np.datetime64(f'2020-01-0{1 + f}T00:00:00') and dates.shape[0] == c['T']
+    assert np.array_equal(pd.read_parquet(tmp_path / 'final.parquet')['Q'].values, q_final)
+    # a weight table whose rivers are not the params file's rivers is refused instead of silently misrouted
+    from tests.test_io_cpu import write_weight_table
+    bad = dict(c['table'])
+    bad['river_id'] = c['table']['river_id'][::-1].copy()
+    write_weight_table(str(tmp_path / 'bad.nc'), bad)
+    with pytest.raises(ValueError, match='same order'):
+        rr.RapidMuskingum(**dict(cfg, grid_weights_file=str(tmp_path / 'bad.nc'))).route()
+
+
+def test_unit_from_grid_files_resampled_with_state_files(tmp_path, host_only):
+    c = _grid_case(tmp_path, n=500, T=10, ny=8, nx=11)
+    rng = np.random.default_rng(9)
+    ker = rng.uniform(0, 1, (5, c['n'])) * (rng.random((5, c['n'])) < 0.7)
+    kfile = str(tmp_path / 'uh.npz')
+    scipy.sparse.save_npz(kfile, scipy.sparse.csr_matrix(ker))
+    s0 = rng.uniform(0, 1e-3, ker.shape)
+    s0[-1] = 0
+    pd.DataFrame(s0.T).to_parquet(tmp_path / 'uh0.parquet')
+    cap = Capture()
+    r = rr.UnitMuskingum(params_file=c['params'], grid_runoff_files=[g[0] for g in c['grids']],
+                         grid_weights_file=str(tmp_path / 'weights.nc'), discharge_dir=str(tmp_path),
+                         channel_state_init_file=c['state'], uh_kernel_file=kfile, uh_state_init_file=str(tmp_path / 'uh0.parquet'),
+                         uh_state_final_file=str(tmp_path / 'uh1.parquet'), var_x='lon', var_y='lat', dt_discharge=7200, log=False)
+    r.set_write_discharges(cap).route()
+    st = s0.copy()
+    outs, q_final = _oracle_grid_chain(c, 3600, False, 'm', unit_hydrograph=(ker, st))
+    for (dates, q, _, _), ref in zip(cap.calls, outs):
+        ref2 = ref.reshape(c['T'] // 2, 2, -1).mean(axis=1).astype(np.float32)
+        assert np.array_equal(q, ref2) and dates.shape[0] == c['T'] // 2 and dates[1] - dates[0] == np.timedelta64(7200, 's')
+    assert np.array_equal(r.channel_state, q_final)
+    assert np.array_equal(pd.read_parquet(tmp_path / 'uh1.parquet').T.to_numpy(), st)   # carry-over came back from the "device"
+
+
+def test_output_subset_and_overridden_seam(tmp_path, host_only):
+    c = _grid_case(tmp_path, n=400, T=8, ny=7, nx=9)
+    ids = c['ids']
+    pick = ids[[399, 0, 200, 0]]
+    cfg = dict(params_file=c['params'], grid_runoff_files=[c['grids'][0][0]], grid_weights_file=str(tmp_path / 'weights.nc'),
+               discharge_files=[str(tmp_path / 'q.nc')], channel_state_init_file=c['state'], var_x='lon', var_y='lat', log=False)
+    full, sub = Capture(), Capture()
+    r0 = rr.RapidMuskingum(**cfg).set_write_discharges(full).route()
+    r1 = rr.RapidMuskingum(**cfg).set_output_rivers(pick).set_write_discharges(sub).route()
+    cols = [int(np.flatnonzero(ids == p)[0]) for p in pick]
+    assert sub.calls[0][1].shape == (8, 4) and np.array_equal(sub.calls[0][1], full.calls[0][1][:, cols])
+    assert np.array_equal(r1.channel_state, r0.channel_state)
+
+    class Seam(rr.RapidMuskingum):                      # the reference's sequence on fp64 host arrays
+        seen = None
+
+        def _router(self, qlateral):
+            Seam.seen = qlateral.shape
+            q_t, arr = super()._router(qlateral)
+            assert arr.shape == (8, 400) and arr.dtype == np.float64       # the seam always sees all segments in fp64
+            return q_t, arr
+    s2 = Capture()
+    Seam(**cfg).set_output_rivers(pick).set_write_discharges(s2).route()
+    assert Seam.seen == (8, 400) and np.array_equal(s2.calls[0][1], sub.calls[0][1])
+    rr.RapidMuskingum(**cfg).set_output_rivers(pick).route()               # default writer stores the subset ids
+    with ncio.open_nc(tmp_path / 'q.nc') as ds:
+        assert np.array_equal(ncio.read_array(ds.variables['river_id']), pick.astype(np.int32))
+        assert ncio.read_array(ds.variables['Q']).shape == (8, 4)
+    with pytest.raises(ValueError, match='ids not in the params file'):
+        rr.RapidMuskingum(**cfg).set_output_rivers([int(ids.max()) + 5]).route()
+
+
+def test_qlateral_files_two_files_chain_state(tmp_path, host_only):
+    from river_route_b200.runoff import QlateralDataset
+    from river_route_b200 import synth
+    n, T = 300, 6
+    down = synth.forest(n, 2, seed=3, depth_bias=0.6)
+    k, x = synth.muskingum_params(n, 3)
+    ids = np.arange(n, dtype=np.int64) + 1
+    params = str(tmp_path / 'p.parquet')
+    pd.DataFrame({'river_id': ids, 'downstream_river_id': np.where(down >= 0, ids[np.where(down >= 0, down, 0)], -1),
+                  'k': k, 'x': x}).to_parquet(params)
+    files, laterals = [], []
+    for f in range(2):
+        ql = synth.lateral_volumes(T, n, 30 + f)
+        t = (np.datetime64('2021-05-01') + (np.arange(T) + f * T) * np.timedelta64(3, 'h')).astype('datetime64[s]')
+        QlateralDataset(ql, ids, t, 'm3').to_netcdf(str(tmp_path / f'ql_{f}.nc'))
+        files.append(str(tmp_path / f'ql_{f}.nc'))
+        laterals.append(ql)
+    r = rr.RapidMuskingum(params_file=params, qlateral_files=files, discharge_dir=str(tmp_path), dt_routing=3600,
+                          log=False).route()                                # no state file: zero initial state + warning
+    a = network_arrays(down, k, x, 3600, 10800)
+    q = np.zeros(n)
+    for f, ql in enumerate(laterals):
+        ref = np.zeros((T, n))
+        oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q, ql, ref, 3)
+        with ncio.open_nc(tmp_path / f'discharge_ql_{f}.nc') as ds:
+            assert np.array_equal(ncio.read_array(ds.variables['Q']), ref.astype(np.float32))
+    assert np.array_equal(r.channel_state, q) and r.num_routing_steps_per_runoff == 3
+    assert parity_error(r.channel_state, q) == 0.0

@@ -49,7 +49,9 @@ typedef struct rr_plan_opts {
                                2 register path on tile-major working arrays, 3 bulk-async-copy (TMA)
                                staged kernel on tile-major working arrays, 4 as 2 with reach-major
                                discharge tiles, 5 as 2 with [row group][lane][4] lateral tiles: warp-coalesced
-                               256-bit lateral loads (experiments; 0 is the measured best)          */
+                               256-bit lateral loads, 6 "direct exchange": reach-major discharge tiles hold
+                               the raw series and double as the exchange buffer (no rings, no export
+                               stores; experiments; 0 is the measured best)                        */
 } rr_plan_opts;
 
 /* Host-visible description of a built plan (for tests, DESIGN.md numbers and bench.py). */

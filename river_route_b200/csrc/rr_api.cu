@@ -233,7 +233,7 @@ static int64_t tile_rows_for(const rr_plan *p, int64_t T, int64_t K) {
 static int launch_route(rr_plan *p, int mode, int n_members, const double *q_init, const double *const *lateral,
                         int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
                         int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream, int tile_major = 0,
-                        int out_layout = 0) {
+                        int out_layout = 0, int direct = 0) {
     if (mode < 0 || mode > 2) { rr_set_error("unknown router mode"); return 100; }
     if (T <= 0 || K <= 0 || T > 0x7fffffff || K > 0x7fffffff) { rr_set_error("T and substeps must be positive"); return 100; }
     if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
@@ -293,7 +293,9 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     }
     kt->used = ++d->key_clock;
     // one spare row: the kernel prefetches a few lines past the row it is reading
-    const size_t raw_need = ((size_t)n_members * (size_t)d->sched.raw_rows + 1) * pitch * sizeof(double);
+    // direct exchange needs no rings: the working discharge array is the exchange buffer
+    const size_t raw_need = direct ? (size_t)pitch * sizeof(double)
+                                   : ((size_t)n_members * (size_t)d->sched.raw_rows + 1) * pitch * sizeof(double);
     if (raw_need > d->raw_bytes) {
         CK(cudaDeviceSynchronize());
         if (d->raw) CK(cudaFree(d->raw));
@@ -336,6 +338,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     int block = p->opts.threads_per_cta;
     P.tile_major = tile_major;
     P.out_layout = out_layout;
+    P.direct = direct;
     P.tile_pitch = (int32_t)((rows + 3) & ~(int64_t)3);
     if (tile_major == 1 && K == 1 && mode != RR_MODE_UNIT) {
         // TMA-staged kernel: 4 warps per CTA, each with [tile | upstream row slots | mbarrier] in shared memory
@@ -421,7 +424,7 @@ __global__ void __launch_bounds__(256) permute_to_working(const double *__restri
 template <int ROWS>
 __global__ void __launch_bounds__(256) permute_to_user(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
                                                        int64_t ldd, const int32_t *__restrict__ inv, int64_t n, int64_t T,
-                                                       int64_t tile_rows, int64_t n_blocks, int layout) {
+                                                       int64_t tile_rows, int64_t n_blocks, int layout, int clamp) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t k = __ldg(inv + i);
@@ -436,12 +439,17 @@ __global__ void __launch_bounds__(256) permute_to_user(const double *__restrict_
         for (int r = 0; r < ROWS; ++r)
             v[r] = (t0 + r < T) ? src[working_index(t0 + r, k, lds, tile_rows, n_blocks, layout)] : 0.0;
     }
+    if (clamp) {   // direct exchange: the working array holds the raw series; the reference's clamp (_numba_kernels.py:44-46, :82-84)
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) v[r] = v[r] > 0.0 ? v[r] : 0.0;
+    }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
         if (t0 + r < T) dst[(t0 + r) * ldd + i] = v[r];
 }
 static int permute(bool to_working, const double *src, int64_t lds, double *dst, int64_t ldd, const int32_t *inv,
-                   int64_t n, int64_t T, cudaStream_t stream, int64_t tile_rows = 0, int64_t n_blocks = 0, int layout = 0) {
+                   int64_t n, int64_t T, cudaStream_t stream, int64_t tile_rows = 0, int64_t n_blocks = 0, int layout = 0,
+                   int clamp = 0) {
     rr_timer tm(to_working ? 1 : 2, stream);
     const unsigned gx = (unsigned)((n + 255) / 256);
     if (to_working && (layout == 2 || layout == 3) && (tile_rows % 16) == 0) {
@@ -452,10 +460,10 @@ static int permute(bool to_working, const double *src, int64_t lds, double *dst,
         permute_to_working<PERM_ROWS><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
     } else if (layout == 2 && (tile_rows % 16) == 0) {
         dim3 grid(gx, (unsigned)((T + 15) / 16));
-        permute_to_user<16><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
+        permute_to_user<16><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout, clamp);
     } else {
         dim3 grid(gx, (unsigned)((T + PERM_ROWS - 1) / PERM_ROWS));
-        permute_to_user<PERM_ROWS><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout);
+        permute_to_user<PERM_ROWS><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, inv, n, T, tile_rows, n_blocks, layout, clamp);
     }
     CK(cudaGetLastError());
     rr_count_launch(1);
@@ -493,7 +501,10 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     // lateral: reach-major tiles (whole-sector scatter in the permute, 256-bit loads in the kernel); discharge:
     // row-major tiles (coalesced row stores in the kernel, sector-sharing gathers in the permute) -- measured best
     const int layout = !tiled ? 0 : (p->opts.staging == 3 ? 1 : (p->opts.staging == 5 ? 3 : 2));
-    const int out_layout = !tiled ? 0 : (p->opts.staging == 4 ? 2 : 1);
+    // staging 6, "direct exchange": the working discharge array (reach-major tiles, raw values) is the exchange buffer
+    // (default for level-sorted plans with one substep per row; staging 2 / 4 / 5 keep the exchange rings)
+    const bool direct = tiled && !unit && (p->opts.staging == 6 || p->opts.staging == 0);
+    const int out_layout = !tiled ? 0 : ((p->opts.staging == 4 || direct) ? 2 : 1);
     const int64_t trows = tiled ? tile_rows_for(p, T, K) : 0;
     const int64_t tpitch = ((trows + 3) & ~(int64_t)3);
     const int64_t n_tiles = tiled ? (T + trows - 1) / trows : 0;
@@ -513,15 +524,18 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
         qf_w[m] = d->p_q + (size_t)(1 + n_members + m) * ldp;
         if (has_lat && (rc = permute(true, lateral[m], ldl, d->p_lat + (size_t)m * member_elems, ldp, d->inv, n, T, stream, trows, p->n_blocks, layout))) return rc;
         if (!first_call) {
-            if ((rc = permute(true, q_state[m], n, qs_w[m], ldp, d->inv, n, 1, stream))) return rc;
+            // direct exchange reads upstream start-of-call values during the launch, so the running state (which the
+            // launch overwrites in place) is first copied to the shared, read-only initial-state vector
+            if ((rc = permute(true, q_state[m], n, direct ? w_init : qs_w[m], ldp, d->inv, n, 1, stream))) return rc;
             if (unit && (rc = permute(true, q_full[m], n, qf_w[m], ldp, d->inv, n, 1, stream))) return rc;
         }
     }
+    if (direct && !first_call && n_members != 1) { rr_set_error("direct exchange: continued calls support one member"); return 100; }
     rc = launch_route(p, mode, n_members, w_init, has_lat ? lat_w : nullptr, ldp, out_w, ldp, qs_w, qf_w, T, K,
-                      first_call, last_call, stream, layout, out_layout);
+                      direct ? 1 : first_call, last_call, stream, layout, out_layout, direct ? 1 : 0);
     if (rc) return rc;
     for (int m = 0; m < n_members; ++m) {
-        if ((rc = permute(false, out_w[m], ldp, out[m], ldo, d->inv, n, T, stream, trows, p->n_blocks, out_layout))) return rc;
+        if ((rc = permute(false, out_w[m], ldp, out[m], ldo, d->inv, n, T, stream, trows, p->n_blocks, out_layout, direct ? 1 : 0))) return rc;
         if ((rc = permute(false, qs_w[m], ldp, q_state[m], n, d->inv, n, 1, stream))) return rc;
         if (unit && !(last_call) && (rc = permute(false, qf_w[m], ldp, q_full[m], n, d->inv, n, 1, stream))) return rc;
     }

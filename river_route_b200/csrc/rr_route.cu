@@ -126,6 +126,19 @@ __device__ __forceinline__ const double *lat_ptr(const rr_route_params &P, int m
         return P.lateral[m] + (((size_t)j * P.n_blocks + (size_t)(u >> 5)) * (size_t)P.tile_rows + row) * RR_BLOCK + (u & 31);
     return P.lateral[m] + (size_t)(t0 + row) * P.ldl + u;
 }
+// Direct exchange (P.direct; level-sorted plans, one substep per row, reach-major discharge tiles): the working
+// discharge array holds the RAW series and doubles as the exchange buffer -- a consumer reads its upstream reach's
+// rows straight from that reach's discharge tile, the clamp moves into permute_to_user, and the separate exchange
+// write (8 of ~40 B per reach-timestep), the ring buffer and the ring-reuse waits disappear.
+// Row 0 of reach u's series in tile jj:
+__device__ __forceinline__ const double *direct_tile(const rr_route_params &P, int m, int jj, int64_t u) {
+    return P.out[m] + (((size_t)jj * P.n_blocks + (size_t)(u >> 5)) * RR_BLOCK + (size_t)(u & 31)) * (size_t)P.tile_pitch;
+}
+// value of reach u before the first substep of tile j: the shared initial state, or the last row of its previous tile
+__device__ __forceinline__ double direct_carry(const rr_route_params &P, int m, int j, int64_t u) {
+    if (j == 0) return P.q_init[u];
+    return direct_tile(P, m, j - 1, u)[P.tile_rows - 1];
+}
 // offset of row r of one reach's lateral series from its row 0 (layout 3: groups of 4 rows are 32 lanes x 4 doubles apart)
 __device__ __forceinline__ size_t lat_row_off(int layout, int64_t stride, int r) {
     return layout == 3 ? (((size_t)(r >> 2)) << 7) + (size_t)(r & 3) : (size_t)r * (size_t)stride;
@@ -147,6 +160,7 @@ struct item_ctx {
     int2 ro_me;                  // {first row, ring depth} of this lane's exported series (valid when ex >= 0)
     int2 ro_up[RR_MAX_FAST_DEG]; // the same pair for the first upstream slots (fast-path blocks)
     int dep_lo, dep_hi;          // this block's range in dep_idx (from the ticket table)
+    int32_t up_u[RR_MAX_FAST_DEG]; // direct exchange: working index of the first upstream reaches
     const double *lat0;          // this lane's lateral value of the tile's first row
     int64_t lstride;             // distance between consecutive rows of the lateral tile
     double *out0;                // this lane's discharge value of the tile's first row
@@ -175,15 +189,17 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
         up[k] = c.raw_m;
         if (has[k]) {
             const int2 ro = c.ro_up[k];
-            up[k] = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
+            up[k] = P.direct ? direct_tile(P, c.m, j, c.up_u[k]) - RAW_S0
+                             : c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         }
     }
     double *myraw = nullptr;
-    if (ex >= 0) {
+    if (ex >= 0 && !P.direct) {
         const int2 ro = c.ro_me;
         myraw = c.raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         myraw[RAW_CARRY] = q;
     }
+    const bool raw_out = P.direct != 0;   // the discharge tile keeps the raw series; permute_to_user clamps
     const double *lat = c.lat0;
     double *outp = c.out0;
     const int64_t ldl = c.lstride, ldo = c.ostride;
@@ -209,7 +225,7 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
         old[k] = 0.0;
         nxt[k] = fut[k] = d4{0, 0, 0, 0};
         if (has[k]) {
-            old[k] = up[k][RAW_CARRY];
+            old[k] = P.direct ? direct_carry(P, c.m, j, c.up_u[k]) : up[k][RAW_CARRY];
             nxt[k] = ld_sector(up[k] + RAW_S0);
             if (4 < TT) fut[k] = ld_sector(up[k] + RAW_S0 + 4);
         }
@@ -261,7 +277,9 @@ __device__ __forceinline__ void fast_item(const rr_route_params &P, const item_c
             for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].d, r);
             r3 = r;
         }
-        if (c.valid && ldo == 1) {   // this reach's rows are contiguous in the working discharge array
+        if (c.valid && ldo == 1 && raw_out) {
+            st_sector(outp + s, r0, r1, r2, r3);
+        } else if (c.valid && ldo == 1) {   // this reach's rows are contiguous in the working discharge array
             st_sector(outp + s, r0 > 0.0 ? r0 : 0.0, r1 > 0.0 ? r1 : 0.0, r2 > 0.0 ? r2 : 0.0, r3 > 0.0 ? r3 : 0.0);
         } else if (c.valid) {
             // K == 1: the interval mean is the value itself; clamp as :44-46 / :82-84
@@ -547,7 +565,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
         ug[k] = 0;
         if (src[k] != SLOT_NONE) {
             if (src[k] >= 0) {
-                rp[k] = raw_row(e0 + k);
+                rp[k] = P.direct ? direct_tile(P, m, j, __ldg(P.up_idx + e0 + k)) - RAW_S0 : raw_row(e0 + k);
                 // items on this path sit on the critical path of deep networks (chains inside a block): get the
                 // whole upstream series moving towards L2 now, the loop then only pays L1 / L2 hits
                 for (int e = 0; e < TT; e += 16) prefetch_l2_now(rp[k] + RAW_S0 + e);
@@ -565,7 +583,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
         qf_prev = qf_cur;
     }
     double *myraw = nullptr;
-    if (ex >= 0) {
+    if (ex >= 0 && !P.direct) {
         const int2 ro = c.ro_me;
         myraw = raw_m + ((size_t)ro.x + (size_t)(j % ro.y)) * P.raw_pitch;
         myraw[RAW_CARRY] = qcur;                 // carry-in for consumers
@@ -579,7 +597,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
     for (int k = 0; k < GEN_SLOTS; ++k) {
         eo[k] = en[k] = lu[k] = lu_old[k] = 0.0;
         if (rp[k] && !(UNIT && (src[k] & RR_SLOT_HW_BIT))) {
-            eo[k] = UNIT ? rp[k][RAW_QF] : rp[k][RAW_CARRY];
+            eo[k] = UNIT ? rp[k][RAW_QF] : (P.direct ? direct_carry(P, m, j, __ldg(P.up_idx + e0 + k)) : rp[k][RAW_CARRY]);
             en[k] = rp[k][RAW_S0];
         }
     }
@@ -662,7 +680,10 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
                 const int il = (sk < 0 && sk != SLOT_NONE) ? ((-sk - 1) & 31) : lane;
                 double v = __shfl_sync(FULL_MASK, UNIT ? qf_prev : qprev, il);
                 bool use = act && k < deg;
-                if (use && sk >= 0) {
+                if (use && sk >= 0 && P.direct) {
+                    const int64_t uu = __ldg(P.up_idx + e0 + k);
+                    v = s == 0 ? direct_carry(P, m, j, uu) : direct_tile(P, m, j, uu)[s - 1];
+                } else if (use && sk >= 0) {
                     const double *q = raw_row(e0 + k);
                     if (UNIT) {
                         if (sk & RR_SLOT_HW_BIT) use = false;
@@ -696,6 +717,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
                 bool use = act && k < deg;
                 if (use && sk >= 0) {
                     if (UNIT && (sk & RR_SLOT_HW_BIT)) use = false;
+                    else if (P.direct) v = direct_tile(P, m, j, __ldg(P.up_idx + e0 + k))[s];
                     else v = raw_row(e0 + k)[RAW_S0 + s];
                 } else if (use && UNIT && (((-sk - 1) >> 6) & 1)) use = false;
                 if (use) r = fma(c1, v, r);
@@ -718,7 +740,7 @@ __device__ __noinline__ void general_item(const rr_route_params &P, const item_c
             if (++sub == K) {
                 double v;
                 if (UNIT && !inner) v = ql;     // headwater: lateral inflow, unclamped (:122-123)
-                else { v = acc * inv_k; v = v > 0.0 ? v : 0.0; }   // :44-46 / :82-84 / :169-171
+                else { v = acc * inv_k; if (!P.direct) v = v > 0.0 ? v : 0.0; }   // :44-46 / :82-84 / :169-171 (direct: clamped by permute_to_user)
                 outp[(size_t)row * c.ostride] = v;
                 acc = 0.0;
                 sub = 0;
@@ -849,13 +871,17 @@ __device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c,
 #pragma unroll
     for (int k = 0; k < RR_MAX_FAST_DEG; ++k) {
         c.ro_up[k] = make_int2(0, 1);
-        if ((c.M.int_mask & 0x40) && k < c.deg) c.ro_up[k] = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + c.e0 + k);
+        c.up_u[k] = 0;
+        if ((c.M.int_mask & 0x40) && k < c.deg) {
+            if (P.direct) c.up_u[k] = __ldg(P.up_idx + c.e0 + k);
+            else c.ro_up[k] = __ldg(reinterpret_cast<const int2 *>(P.edge_ro) + c.e0 + k);
+        }
     }
     int32_t *done = P.done + (size_t)m * P.n_blocks;
     if (lane == 0 && j > 0) wait_ge(done + b, j);                       // own previous tile (acquire)
     if (dep_blk >= 0) wait_ge(done + dep_blk, j + 1);                   // upstream blocks, this tile
     for (int e = dep_lo + 32 + lane; e < dep_hi; e += 32) wait_ge(done + __ldg(P.dep_idx + e), j + 1);
-    if (c.ex >= 0 && j >= c.ro_me.y) wait_ge(done + down_blk, j - c.ro_me.y + 1);   // exchange-ring reuse
+    if (c.ex >= 0 && !P.direct && j >= c.ro_me.y) wait_ge(done + down_blk, j - c.ro_me.y + 1);   // exchange-ring reuse
     __syncwarp();
 #ifdef RR_PROFILE
     c.prof_wait = (unsigned long long)(clock64() - w0_);

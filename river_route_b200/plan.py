@@ -83,7 +83,7 @@ class Plan:
         self.n = int(down.shape[0])
         self.down = down
         opts = _lib.PlanOpts(int(time_tile), int(tile_stride), int(device), int(threads_per_cta), int(raw_budget_bytes),
-                             self.RENUMBER[renumber], {'auto': 0, 'registers': 1, 'registers-tiled': 2, 'tma': 3, 'out-reach-major': 4, 'lateral-grouped': 5}[staging])
+                             self.RENUMBER[renumber], {'auto': 0, 'registers': 1, 'registers-tiled': 2, 'tma': 3, 'out-reach-major': 4, 'lateral-grouped': 5, 'direct': 6}[staging])
         handle = C.c_void_p()
         check(lib.rr_plan_create(self.n, _lib.as_i32p(down), C.byref(opts), C.byref(handle)))
         self._h = handle

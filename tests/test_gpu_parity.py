@@ -103,7 +103,8 @@ SYNTH = [
 ]
 
 
-@pytest.mark.parametrize('renumber', ['never', 'always', 'always-registers', 'always-tma', 'always-lateral-grouped'])
+@pytest.mark.parametrize('renumber', ['never', 'always', 'always-registers', 'always-tma', 'always-lateral-grouped',
+                                      'always-direct'])
 @pytest.mark.parametrize('n,nbas,bias,stem,T,dt_runoff,dt_routing,opts', SYNTH)
 def test_rapid_and_muskingum_vs_oracle(n, nbas, bias, stem, T, dt_runoff, dt_routing, opts, renumber):
     # 'always': level-sorted working order (register-blocked path on tile-major working arrays); '-registers':

@@ -260,3 +260,27 @@ def test_output_subset_columns(rows, k, chunk_rows):
     assert np.array_equal(again, out_full)
     tf.close()
     plan.close()
+
+
+@pytest.mark.parametrize('rows', [0, 5])
+def test_direct_exchange_staging_matches_default(rows, chunk_rows):
+    """staging='direct' (the working discharge array doubles as the exchange buffer) gives the same bits as the default
+    exchange rings, also when a call is continued chunk by chunk from the running state."""
+    n, T = 9000 + 3, 37
+    down, a = _network(n, 4, 23, 3600, 3600)
+    ql = synth.lateral_volumes(T, n, 8)
+    q0 = np.random.default_rng(9).uniform(0, 20, n)
+    res = {}
+    chunk_rows(rows)
+    for staging in ('registers-tiled', 'direct'):
+        plan = rr.Plan(down, renumber='always', staging=staging)
+        plan.set_coefficients(a['c1'], a['c2'], a['c3'], a['c4_dt'])
+        q, out = q0.copy(), np.empty((T, n))
+        plan.route_host(rr.MODE_RAPID, q, ql, out, 1)
+        qm, outm = q0.copy(), np.empty((T, n))
+        plan.route_host(rr.MODE_MUSKINGUM, qm, None, outm, 1)
+        res[staging] = (q, out, qm, outm)
+        plan.close()
+    for x, y in zip(res['registers-tiled'], res['direct']):
+        assert np.array_equal(x, y)
+    assert (res['direct'][1] >= 0).all() and (res['direct'][1] == 0).any()      # clamp applied by the permutation

@@ -451,6 +451,9 @@ def main():
         kernel_ms = ktimes['route']['ms'] / max(ktimes['route']['launches'], 1)   # the routing kernel alone (CUDA events)
         achieved = B_ALG * n * rows / (kernel_ms * 1e-3) / 1e9
         traffic = ncu_traffic()
+        if traffic and args.staging != 'registers-tiled':
+            # the committed capture is of the ring-exchange kernel; the default (direct exchange) moves fewer bytes
+            traffic = {'source': 'none for this kernel variant: ' + str(traffic.get('applies_to', traffic.get('source')))}
         line = {
             'metric': 'reach-timesteps/sec (RapidMuskingum, fp64)', 'value': value, 'unit': 'reach-timesteps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms_max / args.steps,

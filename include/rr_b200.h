@@ -167,6 +167,10 @@ int rr_route_ensemble_dev(rr_plan *p, int mode, const double *q_init, int32_t n_
                           const double *const *lateral, int64_t ldl, double *const *out, int64_t ldo,
                           double *const *q_final, int64_t T, int64_t substeps, void *stream);
 
+/* Output rows one work item of the wavefront kernel covers in a call of T rows x substeps (the time tile the
+ * per-call cost model picks; bench.py's roofline arithmetic: coefficients and topology are read once per tile). */
+int64_t rr_plan_tile_rows(const rr_plan *p, int64_t T, int64_t substeps);
+
 /* Kernel launches issued by this library on this thread since the last reset (bench.py's
  * gpu_launches claim). */
 int64_t rr_launch_count(int reset);
@@ -193,7 +197,9 @@ int rr_uh_convolve_host(int64_t n, int64_t n_ks, int64_t T,
  * y[t,r] = sum_j w[j] * x[t, col[j]] over CSR row r in stored order, then
  * cumulative->incremental, optional clip at 0, NaN->0, optional multiply by area[r].
  * x is the gathered grid runoff [T][ldx], float32 (x_is_f32 != 0) or float64; the product
- * is formed in fp64 as the reference's scipy call does.  Device pointers. */
+ * is formed in fp64 as the reference's scipy call does.  Device pointers.
+ * force_positive: bit 0 = clip at zero (force_positive_runoff, :313-314); bit 1 = leave NaN in place -- for the
+ * rare irregular-time-axis path, where the reference resamples the series (:316-329) BEFORE it zeroes NaN. */
 int rr_weights_transform_dev(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr,
                              const int32_t *indices, const double *w, const void *x, int x_is_f32,
                              int64_t ldx, double *y, int64_t ldy, int cumulative, int force_positive,
@@ -232,13 +238,6 @@ int rr_runoff_route_host(rr_plan *p, rr_transform *t, int mode, double *q_state,
 /* Diagnostic cycle counters of the routing kernel (builds with -DRR_PROFILE; zeros otherwise), summed over warps:
  * [0] ticket + decode, [1] per-item constants + dependency waits, [2] item body, [3] publish.  Resets on read. */
 int rr_plan_read_profile(rr_plan *p, uint64_t *out8);
-
-/* Memory-system probe for the routing kernel's access shapes (diagnostic; tools/sector_probe.py): copies
- * rows x row_doubles doubles from src to dst (device pointers) with 256-bit loads / stores, mode 0 coalesced,
- * mode 1 one 512-byte-style series per lane with rows in order, mode 2 the same with source rows scattered by
- * perm[] (the exchange-row pattern).  Returns the best kernel time of `reps` launches in *ms_best. */
-int rr_probe_sector_bandwidth(int mode, int64_t rows, int32_t row_doubles, const double *src, double *dst,
-                              const int32_t *perm, int32_t reps, double *ms_best);
 
 /* ---- pinned host memory for the streaming path ---------------------------------------------- */
 int rr_host_alloc(void **ptr, int64_t bytes);

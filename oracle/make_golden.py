@@ -292,6 +292,48 @@ def main():
     np.savez_compressed(os.path.join(OUT, 'weights.npz'), **golden_w)
     print('wrote weights')
 
+    # ---------------- irregular time axis: runoff.py:316-337 with NaN cells carried through the resample ----------
+    # (round 2; a separate file and a separate generator so that the fixtures above stay byte-identical)
+    from river_route.runoff import _cumulative_to_incremental, _incremental_to_cumulative
+    rng_i = np.random.default_rng(20260218)
+    Ti = 9
+    hours = np.array([0, 3, 6, 9, 15, 21, 24, 30, 36])                    # 3-hourly, then 6-hourly
+    time_index = (np.datetime64('2020-01-01T00:00:00') + hours.astype('timedelta64[h]')).astype('datetime64[ns]')
+    grid_i = rng_i.gamma(0.3, 2e-3, (Ti, ncell_y, ncell_x)).astype(np.float32)
+    grid_i[rng_i.random(grid_i.shape) < 0.5] = 0.0
+    grid_i[4, 2, 5] = np.nan
+    grid_i[0, 7, 1] = np.nan
+    raw_i = grid_i[:, unique_indexes['y_index'].values, unique_indexes['x_index'].values]
+    weights = scipy.sparse.csr_matrix((weight_df['proportion'].values * 1, (river_idx, point_idx)),
+                                      shape=(len(river_ids_ordered), len(unique_indexes)))
+    golden_i = dict(runoff_raw=raw_i, time_index=time_index.astype('datetime64[s]').astype(np.int64))
+    for cumulative in (False, True):
+        for as_volumes in (False, True):
+            src = np.cumsum(raw_i.astype(np.float64), axis=0).astype(np.float32) if cumulative else raw_i
+            qlateral = np.asarray(weights @ src.T).T
+            if cumulative:
+                for i in range(qlateral.shape[0] - 1, 0, -1):
+                    qlateral[i] -= qlateral[i - 1]
+            timestep = int((time_index[1] - time_index[0]) / np.timedelta64(1, 's'))
+            df = pd.DataFrame(qlateral, index=time_index, columns=river_ids_ordered)
+            df = (_incremental_to_cumulative(df).resample(rule=f'{timestep}s').interpolate(method='linear'))
+            df = _cumulative_to_incremental(df)
+            t_out = df.index.values
+            # pandas 3 (copy-on-write) hands back a read-only view here, on which the reference's own in-place NaN
+            # fill (runoff.py:331-333) raises; a writable copy gives what it computes with the pandas it was written for
+            qlateral = df.to_numpy(dtype=np.float64).copy()
+            mask = np.isnan(qlateral)
+            if mask.any():
+                qlateral[mask] = 0.0
+            if as_volumes:
+                qlateral *= catchment_area[np.newaxis, :]
+            golden_i[f'ql_cum{int(cumulative)}_vol{int(as_volumes)}'] = np.ascontiguousarray(qlateral)
+            golden_i['time_out'] = t_out.astype('datetime64[s]').astype(np.int64)
+            if cumulative:
+                golden_i['runoff_raw_cumulative'] = src
+    np.savez_compressed(os.path.join(OUT, 'weights_irregular.npz'), **golden_i)
+    print('wrote weights_irregular')
+
     # ---------------- tools.adjacency_matrix known answers (tools.py:75-109) -------------------------
     # 9-reach network of docs/references/math.md:70-80 and the rejection cases of tests/test_tools.py:48-60
     ids9 = np.arange(1, 10)

@@ -263,7 +263,7 @@ def weights_csr(river_idx, point_idx, values, n_rivers, n_points):
 
 
 def weights_transform(indptr, indices, data, runoff_raw, cumulative=False, force_positive=False, area=None,
-                      fma=False):
+                      fma=False, keep_nan=False):
     """
     (T, n_points) gathered grid runoff -> (T, n_rivers) qlateral: the SpMM of
     runoff.py:298 plus the tail of :309-337 (cumulative diff, clip, NaN->0, x area).
@@ -282,7 +282,7 @@ def weights_transform(indptr, indices, data, runoff_raw, cumulative=False, force
     rc = _lib(fma).rr_oracle_weights_transform(
         _i64(n_rivers), _i64(T), p_i, p_j, p_w,
         x.ctypes.data_as(_pf64), _i64(x.shape[1]), y.ctypes.data_as(_pf64), _i64(n_rivers),
-        C.c_int(int(cumulative)), C.c_int(int(force_positive)), p_a)
+        C.c_int(int(cumulative)), C.c_int(int(bool(force_positive)) | (2 if keep_nan else 0)), p_a)
     assert rc == 0
     return y
 

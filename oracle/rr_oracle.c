@@ -249,8 +249,8 @@ RR_EXPORT int rr_oracle_weights_transform(
     for (int64_t t = 0; t < T; ++t)
         for (int64_t r = 0; r < n_rivers; ++r) {
             double v = y[t * ldy + r];
-            if (force_positive && v < 0.0) v = 0.0;            /* :313-314 */
-            if (v != v) v = 0.0;                               /* :331-333 */
+            if ((force_positive & 1) && v < 0.0) v = 0.0;      /* :313-314 */
+            if (!(force_positive & 2) && v != v) v = 0.0;      /* :331-333; bit 1: the caller resamples first (:316-329) */
             if (area) v *= area[r];                            /* :335-336 */
             y[t * ldy + r] = v;
         }

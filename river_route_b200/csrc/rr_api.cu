@@ -230,6 +230,11 @@ static int64_t tile_rows_for(const rr_plan *p, int64_t T, int64_t K) {
     return std::max<int64_t>(1, std::min<int64_t>(T, tile / K));
 }
 
+extern "C" int64_t rr_plan_tile_rows(const rr_plan *p, int64_t T, int64_t substeps) {
+    if (!p || T <= 0 || substeps <= 0) return 0;
+    return tile_rows_for(p, T, substeps);
+}
+
 static int launch_route(rr_plan *p, int mode, int n_members, const double *q_init, const double *const *lateral,
                         int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
                         int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream, int tile_major = 0,

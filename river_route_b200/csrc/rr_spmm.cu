@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(128) weights_kernel(int64_t n_rivers, int64_t 
             if (t0 + u < te && t0 + u >= t_skip) {   // rows before t_skip only seed `prev` (streamed chunks)
                 double q = acc[u];
                 if (cumulative) { if (t0 + u > 0) q = acc[u] - prev; prev = acc[u]; }
-                if (force_positive && q < 0.0) q = 0.0;   // :313-314
-                if (q != q) q = 0.0;                      // :331-333
+                if ((force_positive & 1) && q < 0.0) q = 0.0;        // :313-314
+                if (!(force_positive & 2) && q != q) q = 0.0;        // :331-333 (bit 1: the caller resamples first, :316-329)
                 if (area) q *= a;                         // :335-336
                 y[(t0 + u - t_skip) * ldy + r] = q;
             } else if (cumulative && t0 + u < te) prev = acc[u];

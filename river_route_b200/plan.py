@@ -218,6 +218,10 @@ class Plan:
                                         int(ldo), arr(*q_final_ptrs), int(T), int(substeps),
                                         C.c_void_p(stream or None)))
 
+    def tile_rows(self, T: int, substeps: int = 1) -> int:
+        """Output rows per work item the library picks for a call of T rows (its per-call cost model)."""
+        return int(lib.rr_plan_tile_rows(self._h, int(T), int(substeps)))
+
     def read_profile(self):
         """Cycle counters of -DRR_PROFILE builds: ticket/decode, constants+waits, item body, publish (summed over warps)."""
         out = (C.c_uint64 * 8)()

@@ -147,9 +147,11 @@ class Muskingum:
         raw = _read_config_file(configs) if configs not in (None, '') and not isinstance(configs, Configs) else {}
         if isinstance(configs, Configs):
             raw = dataclasses.asdict(configs)
+            if raw.get('discharge_dir'):
+                raw['discharge_files'] = []      # derived from discharge_dir by Configs itself; passing both is an error
         raw.update(kwargs)
         raw.pop('_router', None)
-        self.cfg = Configs(**raw)
+        self.cfg = configs if isinstance(configs, Configs) and not kwargs else Configs(**raw)
         self.logger = logging.getLogger(f'river_route_b200.{id(self):x}')
         self.logger.disabled = not self.cfg.log
         self.logger.setLevel(PROGRESS if self.cfg.log_level == 'PROGRESS' else self.cfg.log_level)
@@ -197,9 +199,15 @@ class Muskingum:
         self.k = df['k'].to_numpy(dtype=np.float64, copy=False)
         self.x = df['x'].to_numpy(dtype=np.float64, copy=False)
         # duplicate ids, unknown downstream ids and topological order raise the reference's ValueErrors
-        self.down = downstream_index(self.river_ids, df['downstream_river_id'].to_numpy(dtype=np.int64, copy=False))
+        down = downstream_index(self.river_ids, df['downstream_river_id'].to_numpy(dtype=np.int64, copy=False))
         self.n = int(self.river_ids.shape[0])
-        self.plan = Plan(self.down)
+        if self.plan is None or not np.array_equal(down, getattr(self, 'down', None)):
+            # a new plan has no coefficients yet: forget the cached time signature so that the next file sets them
+            # (the reference keeps c1..c3 and its CSC arrays on self, so a second route() just works there)
+            self.plan = Plan(down)
+            self._network_time_signature = None
+            self._detach_transform()
+        self.down = down
         self.logger.log(PROGRESS, f'Network: {self.n} river segments')
 
     @property
@@ -298,6 +306,9 @@ class Muskingum:
         return
 
     def _hook_after_route(self):
+        return
+
+    def _detach_transform(self):
         return
 
     # ---------------- output ----------------

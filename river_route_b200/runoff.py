@@ -186,6 +186,23 @@ class QlateralDataset(dict):
             qv[:] = self['qlateral'].values
 
 
+def resample_irregular(ql, time_index, rivers, area=None):
+    """
+    The rare irregular-time-axis branch of ``runoff_to_qlateral`` (runoff.py:316-337), kept on the host with pandas as
+    the reference has it: incremental depths -> cumulative -> resample to the first time step -> linear interpolation
+    -> incremental; only then NaN -> 0 and the optional multiplication by catchment area.  ``ql`` must still carry
+    its NaNs (``weights_transform(..., keep_nan=True)``): the reference lets them run through cumsum / interpolate.
+    """
+    timestep = int((time_index[1] - time_index[0]) / np.timedelta64(1, 's'))
+    logger.warning(f'Time steps are not uniform, resampling to the first timestep: {timestep} seconds')
+    df = pd.DataFrame(ql, index=time_index, columns=rivers).cumsum().resample(rule=f'{timestep}s').interpolate(method='linear')
+    out = np.vstack([df.values[0, :], np.diff(df.values, axis=0)])
+    out[np.isnan(out)] = 0.0
+    if area is not None:
+        out *= np.asarray(area)[np.newaxis, :]
+    return out, df.index.values
+
+
 def runoff_to_qlateral(runoff_data, grid_weights_file, *, var_runoff='ro', var_x='lon', var_y='lat', var_t='time',
                        var_river_id='river_id', runoff_depth_unit=None, cumulative=False, force_positive_runoff=False,
                        force_uniform_timesteps=True, as_volumes=False):
@@ -201,16 +218,9 @@ def runoff_to_qlateral(runoff_data, grid_weights_file, *, var_runoff='ro', var_x
     resample = (not uniform) and force_uniform_timesteps
     # the non-uniform-time resample (runoff.py:316-329, rare) works on incremental depths before NaN / area handling
     ql = weights_transform(indptr, indices, data, raw, cumulative=cumulative, force_positive=force_positive_runoff,
-                           area=None if resample else (area if as_volumes else None))
+                           area=None if resample else (area if as_volumes else None), keep_nan=resample)
     if resample:
-        timestep = int((time_index[1] - time_index[0]) / np.timedelta64(1, 's'))
-        logger.warning(f'Time steps are not uniform, resampling to the first timestep: {timestep} seconds')
-        df = pd.DataFrame(ql, index=time_index, columns=rivers).cumsum().resample(rule=f'{timestep}s').interpolate(method='linear')
-        ql = np.vstack([df.values[0, :], np.diff(df.values, axis=0)])
-        time_index = df.index.values
-        ql[np.isnan(ql)] = 0.0
-        if as_volumes:
-            ql *= area[np.newaxis, :]
+        ql, time_index = resample_irregular(ql, time_index, rivers, area if as_volumes else None)
     units = 'm3' if as_volumes else 'm'
     try:
         import xarray as xr

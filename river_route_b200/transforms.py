@@ -40,10 +40,11 @@ def uh_convolve(lateral: np.ndarray, kernel: np.ndarray, state: np.ndarray) -> n
 
 
 def weights_transform(indptr, indices, data, runoff_raw: np.ndarray, cumulative: bool = False,
-                      force_positive: bool = False, area=None) -> np.ndarray:
+                      force_positive: bool = False, area=None, keep_nan: bool = False) -> np.ndarray:
     """
     CSR weights (n_rivers x n_points, scipy layout: int32 indptr/indices, float64 data) applied to the gathered
     grid runoff (T, n_points), float32 or float64, followed by the reference's tail.  Returns (T, n_rivers) fp64.
+    ``keep_nan`` skips the NaN -> 0 step (runoff.py:331-333) for callers that resample the series first (:316-329).
     """
     indptr = np.ascontiguousarray(indptr, dtype=np.int32)
     indices = np.ascontiguousarray(indices, dtype=np.int32)
@@ -59,7 +60,7 @@ def weights_transform(indptr, indices, data, runoff_raw: np.ndarray, cumulative:
     y = np.empty((T, n_rivers), dtype=np.float64)
     check(lib.rr_weights_transform_host(n_rivers, n_points, T, _lib.as_i32p(indptr), _lib.as_i32p(indices),
                                         _lib.as_f64p(data), x.ctypes.data_as(C.c_void_p), int(x.dtype == np.float32),
-                                        n_points, _lib.as_f64p(y), n_rivers, int(cumulative), int(force_positive),
+                                        n_points, _lib.as_f64p(y), n_rivers, int(cumulative), int(bool(force_positive)) | (2 if keep_nan else 0),
                                         _lib.as_f64p(a) if a is not None else None))
     return y
 

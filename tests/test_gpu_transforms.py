@@ -80,6 +80,23 @@ def test_weights_golden(unit):
             assert parity_error(ql, ref) < TOL
 
 
+def test_weights_irregular_time_axis_golden():
+    """keep_nan + the host resample tail == the reference's runoff.py:316-337 on a grid with NaN cells."""
+    from river_route_b200.runoff import resample_irregular
+    g, gi = load_golden('weights.npz'), load_golden('weights_irregular.npz')
+    indptr, indices, data = g['csr_indptr_m'], g['csr_indices_m'], g['csr_data_m']
+    t_in = gi['time_index'].astype('datetime64[s]')
+    for cumulative in (False, True):
+        src = gi['runoff_raw_cumulative'] if cumulative else gi['runoff_raw']
+        for vol in (False, True):
+            ql = weights_transform(indptr, indices, data, src, cumulative=cumulative, keep_nan=True)
+            assert np.isnan(ql).any()
+            out, _ = resample_irregular(ql, t_in, g['river_ids_ordered'], g['catchment_area'] if vol else None)
+            ref = gi[f'ql_cum{int(cumulative)}_vol{int(vol)}']
+            assert parity_error(out, ref) < TOL
+            assert np.array_equal(out == 0.0, ref == 0.0)
+
+
 @pytest.mark.parametrize('f32', [True, False])
 def test_weights_vs_oracle(f32):
     rng = np.random.default_rng(31)

@@ -141,6 +141,25 @@ def test_weight_csr_and_transform_match_scipy(unit):
             assert parity_error(ql, ref) < TOL
 
 
+def test_irregular_time_axis_resample_matches_reference():
+    """runoff.py:316-337 with NaN cells: the NaNs run through cumsum / resample / interpolate and are zeroed after."""
+    from river_route_b200.runoff import resample_irregular   # host-side pandas tail of the product (no GPU work)
+    g, gi = load_golden('weights.npz'), load_golden('weights_irregular.npz')
+    indptr, indices, data = g['csr_indptr_m'], g['csr_indices_m'], g['csr_data_m']
+    t_in = gi['time_index'].astype('datetime64[s]')
+    for cumulative in (False, True):
+        src = gi['runoff_raw_cumulative'] if cumulative else gi['runoff_raw']
+        assert np.isnan(src).any()
+        for vol in (False, True):
+            ql = oracle.weights_transform(indptr, indices, data, src, cumulative=cumulative, keep_nan=True)
+            assert np.isnan(ql).any()
+            out, t_out = resample_irregular(ql, t_in, g['river_ids_ordered'], g['catchment_area'] if vol else None)
+            ref = gi[f'ql_cum{int(cumulative)}_vol{int(vol)}']
+            assert out.shape == ref.shape and np.array_equal(t_out.astype('datetime64[s]').astype(np.int64), gi['time_out'])
+            assert parity_error(out, ref) < TOL
+            assert np.array_equal(out == 0.0, ref == 0.0)
+
+
 def test_tools_known_answers():
     g = load_golden('tools.npz')
     down = oracle.downstream_index(g['ids9'], g['ds9'])  # 9-reach network of docs/references/math.md:70-80

@@ -111,8 +111,9 @@ def host_only(monkeypatch):
     monkeypatch.setattr(transforms, 'uh_convolve', lambda lat, ker, st: oracle.uh_convolve(np.ascontiguousarray(lat), ker, st))
     monkeypatch.setattr('river_route_b200.uhkernels.uh_convolve', lambda lat, ker, st: oracle.uh_convolve(np.ascontiguousarray(lat), ker, st))
     monkeypatch.setattr(transforms, 'weights_transform',
-                        lambda indptr, indices, data, raw, cumulative=False, force_positive=False, area=None:
-                        oracle.weights_transform(indptr, indices, data, raw, cumulative=cumulative, force_positive=force_positive, area=area))
+                        lambda indptr, indices, data, raw, cumulative=False, force_positive=False, area=None, keep_nan=False:
+                        oracle.weights_transform(indptr, indices, data, raw, cumulative=cumulative, force_positive=force_positive,
+                                                 area=area, keep_nan=keep_nan))
     monkeypatch.setattr('river_route_b200.runoff.weights_transform', transforms.weights_transform)
 
 
@@ -234,3 +235,51 @@ def test_qlateral_files_two_files_chain_state(tmp_path, host_only):
             assert np.array_equal(ncio.read_array(ds.variables['Q']), ref.astype(np.float32))
     assert np.array_equal(r.channel_state, q) and r.num_routing_steps_per_runoff == 3
     assert parity_error(r.channel_state, q) == 0.0
+
+
+def test_route_twice_and_configs_instance(tmp_path, host_only):
+    """A second route() on the same instance works (the reference keeps c1..c3 on self; here a rebuilt plan must get
+    its coefficients again), and a Configs instance made with discharge_dir can be handed to a router."""
+    from river_route_b200.runoff import QlateralDataset
+    from river_route_b200 import synth
+    n, T = 200, 5
+    down = synth.forest(n, 2, seed=5, depth_bias=0.6)
+    k, x = synth.muskingum_params(n, 5)
+    ids = np.arange(n, dtype=np.int64) + 1
+    params = str(tmp_path / 'p.parquet')
+    pd.DataFrame({'river_id': ids, 'downstream_river_id': np.where(down >= 0, ids[np.where(down >= 0, down, 0)], -1),
+                  'k': k, 'x': x}).to_parquet(params)
+    ql = synth.lateral_volumes(T, n, 41)
+    t = (np.datetime64('2021-05-01') + np.arange(T) * np.timedelta64(1, 'h')).astype('datetime64[s]')
+    QlateralDataset(ql, ids, t, 'm3').to_netcdf(str(tmp_path / 'ql.nc'))
+    cfg = rr.Configs(params_file=params, qlateral_files=[str(tmp_path / 'ql.nc')], discharge_dir=str(tmp_path), log=False)
+    assert cfg.discharge_files == [str(tmp_path / 'discharge_ql.nc')]
+    r = rr.RapidMuskingum(cfg)                                              # used to raise 'not both'
+    assert r.cfg is cfg
+    r2 = rr.RapidMuskingum(cfg, dt_routing=1800)                            # kwargs still override a Configs instance
+    assert r2.cfg.dt_routing == 1800 and r2.cfg.discharge_files == cfg.discharge_files
+    a = network_arrays(down, k, x, 3600, 3600)
+    q = np.zeros(n)
+    cap = Capture()
+    r.set_write_discharges(cap)
+    for call in range(2):                                                   # state chains from the first call into the second
+        r.route()
+        plan_first = r.plan if call == 0 else plan_first
+        ref = np.zeros((T, n))
+        oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q, ql, ref, 1)
+        assert np.array_equal(cap.calls[call][1], ref.astype(np.float32))
+        assert hasattr(r.plan, '_fake_arrays')                              # set_coefficients reached the plan in use
+    assert r.plan is plan_first                                             # unchanged network: the plan is reused
+    # a changed params file (the first basin only) gives a new plan, and the new plan gets coefficients
+    m = int(np.flatnonzero(down < 0)[0]) + 1
+    assert 0 < m < n and not np.any(down[:m] >= m)
+    pd.DataFrame({'river_id': ids[:m], 'downstream_river_id': np.where(down[:m] >= 0, ids[np.where(down[:m] >= 0, down[:m], 0)], -1),
+                  'k': k[:m], 'x': x[:m]}).to_parquet(params)
+    QlateralDataset(ql[:, :m], ids[:m], t, 'm3').to_netcdf(str(tmp_path / 'ql.nc'))
+    del r.channel_state
+    r.route()
+    assert r.plan is not plan_first and hasattr(r.plan, '_fake_arrays') and r.n == m
+    am = network_arrays(down[:m], k[:m], x[:m], 3600, 3600)
+    qm, refm = np.zeros(m), np.zeros((T, m))
+    oracle.rapid_route(am['indptr'], am['indices'], am['lhs_off'], am['c2'], am['c3'], am['c4_dt'], qm, ql[:, :m].copy(), refm, 1)
+    assert np.array_equal(cap.calls[2][1], refm.astype(np.float32))

@@ -103,5 +103,38 @@ def traffic(report, pattern, reaches, rows_):
                       'source': f'ncu --set full, {report}: {r[col["Kernel Name"]][:40]}, {reaches} reaches x {rows_} steps'}, indent=1))
 
 
+def traffic_step(report, reaches, rows_, variant, out_path):
+    """DRAM bytes per reach-timestep of every kernel class of one bench step (largest launch of each class) ->
+    profiles/traffic.json entry `variants[variant]` (what bench.py's roofline.traffic / frac_dram read)."""
+    hdr, units, rows = raw(report)
+    col = {h: i for i, h in enumerate(hdr)}
+    per = float(reaches) * float(rows_)
+    classes = {'route': 'rr_wavefront', 'permute_to_working': 'permute_to_working|stage_in', 'permute_to_user': 'permute_to_user|stage_out'}
+    entry = {'reaches': int(reaches), 'rows': int(rows_), 'source': f'ncu --set full --clock-control none, {report}'}
+    for cls, pat in classes.items():
+        best = None
+        for r in rows:
+            if re.search(pat, r[col['Kernel Name']]):
+                ms = float(r[col['gpu__time_duration.sum']])
+                if best is None or ms > best[0]:
+                    best = (ms, r)
+        if best is None:
+            continue
+        r = best[1]
+        rd = to_bytes(r[col['dram__bytes_read.sum']], units[col['dram__bytes_read.sum']])
+        wr = to_bytes(r[col['dram__bytes_write.sum']], units[col['dram__bytes_write.sum']])
+        entry[cls] = {'kernel': r[col['Kernel Name']][:48], 'dram_read_per_reach_step': rd / per, 'dram_write_per_reach_step': wr / per,
+                      'dram_bytes_per_reach_step': (rd + wr) / per, 'ncu_ms': best[0],
+                      'l2_sector_bytes_per_reach_step': float(r[col['lts__t_sectors.sum']]) * 32 / per,
+                      'l2_hit_pct': float(r[col['lts__t_sector_hit_rate.pct']])}
+    try:
+        doc = json.load(open(out_path))
+    except Exception:
+        doc = {}
+    doc.setdefault('variants', {})[variant] = entry
+    json.dump(doc, open(out_path, 'w'), indent=1)
+    print(json.dumps(entry, indent=1))
+
+
 if __name__ == '__main__':
-    {'full': full, 'list': launch_list, 'traffic': traffic}[sys.argv[1]](*sys.argv[2:])
+    {'full': full, 'list': launch_list, 'traffic': traffic, 'traffic_step': traffic_step}[sys.argv[1]](*sys.argv[2:])

@@ -16,7 +16,13 @@
 
 #include <string>
 
-#include "rr_internal.h"
+#include <cstdint>
+
+// diagnostic library of its own (tools/librr_probe.so, built by `make -C river_route_b200/csrc probe`): not part of
+// the product library or its C ABI
+static thread_local std::string g_probe_err;
+static void rr_set_error(const std::string &msg) { g_probe_err = msg; }
+extern "C" const char *rr_probe_last_error(void) { return g_probe_err.c_str(); }
 
 namespace {
 

@@ -10,7 +10,18 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
-from river_route_b200._lib import lib, check  # noqa: E402
+
+LIB = os.path.join(ROOT, 'tools', 'librr_probe.so')   # make -C river_route_b200/csrc probe
+lib = C.CDLL(LIB)
+lib.rr_probe_sector_bandwidth.restype = C.c_int
+lib.rr_probe_sector_bandwidth.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                          C.POINTER(C.c_double)]
+lib.rr_probe_last_error.restype = C.c_char_p
+
+
+def check(rc):
+    if rc:
+        raise RuntimeError(lib.rr_probe_last_error().decode())
 
 dev = torch.device('cuda:0')
 res = {'probe': 'sector bandwidth, read + write bytes / kernel time, best of 5'}

@@ -71,7 +71,7 @@ def parse():
     ap.add_argument('--time-tile', type=int, default=0)
     ap.add_argument('--tile-stride', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--staging', default='auto', choices=['auto', 'registers', 'registers-tiled', 'tma', 'out-reach-major', 'lateral-grouped', 'direct'])
+    ap.add_argument('--staging', default='auto', choices=['auto', 'registers', 'registers-tiled', 'tma', 'out-reach-major', 'lateral-grouped', 'direct', 'direct-nohw'])
     ap.add_argument('--order', default='growth', choices=['growth', 'level'],
                     help='reach order of the synthetic params file: generator order or sorted by topological level')
     return ap.parse_args()

@@ -45,13 +45,14 @@ typedef struct rr_plan_opts {
     int32_t renumber;       /* 0 auto, 1 keep the params_file order, 2 always work on reaches sorted
                                by topological level (inputs/outputs stay in params_file order; the
                                library permutes them on the device)                             */
-    int32_t staging;        /* renumbered plans: 0 auto (= 2), 1 register path on row-major working arrays,
-                               2 register path on tile-major working arrays, 3 bulk-async-copy (TMA)
-                               staged kernel on tile-major working arrays, 4 as 2 with reach-major
-                               discharge tiles, 5 as 2 with [row group][lane][4] lateral tiles: warp-coalesced
-                               256-bit lateral loads, 6 "direct exchange": reach-major discharge tiles hold
-                               the raw series and double as the exchange buffer (no rings, no export
-                               stores; experiments; 0 is the measured best)                        */
+    int32_t staging;        /* renumbered plans: 0 auto: the direct pipeline (rr_direct.cu: staging kernels + direct-exchange
+                               wavefront; headwater blocks routed while staging when the network has >= 2^18 reaches)
+                               whenever it applies (one substep per row, RapidMuskingum / Muskingum, time_tile a multiple
+                               of 16), else as 2.  6: direct pipeline, headwaters always routed while staging; 7: never.
+                               Experiments kept for comparison: 1 register path on row-major working arrays, 2 register
+                               path on tile-major working arrays with exchange rings, 3 bulk-async-copy (TMA) staged
+                               kernel, 4 as 2 with reach-major discharge tiles, 5 as 2 with [row group][lane][4]
+                               lateral tiles                                                                   */
 } rr_plan_opts;
 
 /* Host-visible description of a built plan (for tests, DESIGN.md numbers and bench.py). */
@@ -69,6 +70,10 @@ typedef struct rr_plan_info {
     int64_t device_bytes;    /* bytes of plan-owned device memory (after first upload)       */
     int32_t renumbered;      /* 1 when the plan works on level-sorted reaches                */
     int32_t reach_depth;     /* longest upstream-to-outlet path, in reaches                  */
+    int32_t all_fast;        /* 1 when every block is fast-path eligible (no in-block edge, in-degree <= 4) */
+    int32_t narrow_blocks;   /* blocks in levels narrower than 4096 blocks (progress published per 16 rows) */
+    int64_t n_headwaters;    /* reaches without upstream (level 0)                                          */
+    int64_t n_work;          /* working slots: n, or more when every level is padded to whole 32-reach blocks */
 } rr_plan_info;
 
 const char *rr_last_error(void);
@@ -152,6 +157,13 @@ int rr_route_host(rr_plan *p, int mode, double *q_state, double *q_full, const d
 int rr_route_host_ex(rr_plan *p, int mode, double *q_state, double *q_full, const double *lateral,
                      int64_t ldl, void *out, int64_t ldo, int64_t T, int64_t substeps, int out_f32,
                      int64_t resample);
+
+/* As rr_route_host_ex with lateral inflows stored as float32 (lateral_f32 != 0; ldl in float32 elements): the rows
+ * cross PCIe as they are stored and are upcast on the device.  The reference upcasts a float32 qlateral variable on the
+ * host with astype(float64) (routers/TransformMuskingum.py:36); the conversion is exact, so results are bit-identical
+ * while the host-to-device traffic halves. */
+int rr_route_host_typed(rr_plan *p, int mode, double *q_state, double *q_full, const void *lateral, int lateral_f32,
+                        int64_t ldl, void *out, int64_t ldo, int64_t T, int64_t substeps, int out_f32, int64_t resample);
 
 /* Restrict what the host streaming calls (rr_route_host, rr_route_host_ex, rr_runoff_route_host) copy back to a
  * subset of river segments -- the device-side form of the reference's "save a subset of the routed flows" writer
@@ -262,7 +274,7 @@ int rr_plan_get_arrays(const rr_plan *p,
                        const int32_t **dep_ptr,  /* [n_blocks+1]                                 */
                        const int32_t **dep_idx,  /* distinct upstream blocks                     */
                        const int32_t **exp_span, /* [n_export] block-level distance producer -> consumer */
-                       const int32_t **perm      /* [n] user index of each working reach, NULL if not renumbered */);
+                       const int32_t **perm      /* [n_work] user index of each working slot (-1: padding), NULL if not renumbered */);
 /* Ticket -> (block, tile) decode used by the kernel, for schedule-validity tests. */
 int rr_plan_schedule(const rr_plan *p, int64_t n_tiles, int32_t tile_stride, int64_t *n_items,
                      int32_t *item_block /* [n_blocks*n_tiles] or NULL */,

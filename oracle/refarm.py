@@ -45,6 +45,8 @@ def import_reference():
     os.environ.setdefault('NUMBA_CACHE_DIR', os.path.join(tempfile.gettempdir(), 'rr_refarm_numba_cache'))
     sys.dont_write_bytecode = True
 
+    stubs = []
+
     def stub(name, **attrs):
         if name in sys.modules:
             return
@@ -57,6 +59,7 @@ def import_reference():
         for k, v in attrs.items():
             setattr(m, k, v)
         sys.modules[name] = m
+        stubs.append(name)
 
     stub('xarray', Dataset=type('Dataset', (), {}), DataArray=type('DataArray', (), {}))
     stub('netCDF4')
@@ -67,6 +70,8 @@ def import_reference():
     if REF_DIR not in sys.path:
         sys.path.insert(0, REF_DIR)
     import river_route
+    for name in stubs:            # needed at import time only; other code in this process must not find them
+        sys.modules.pop(name, None)
     return river_route
 
 

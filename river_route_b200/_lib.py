@@ -31,7 +31,8 @@ class PlanInfo(C.Structure):
     _fields_ = [('n', C.c_int64), ('n_edges', C.c_int64), ('n_blocks', C.c_int64), ('n_export', C.c_int64),
                 ('n_internal_edges', C.c_int64), ('max_skew', C.c_int32), ('max_indegree', C.c_int32),
                 ('max_block_level', C.c_int32), ('n_outlets_lo', C.c_int32), ('n_dep_edges', C.c_int64),
-                ('device_bytes', C.c_int64), ('renumbered', C.c_int32), ('reach_depth', C.c_int32)]
+                ('device_bytes', C.c_int64), ('renumbered', C.c_int32), ('reach_depth', C.c_int32),
+                ('all_fast', C.c_int32), ('narrow_blocks', C.c_int32), ('n_headwaters', C.c_int64), ('n_work', C.c_int64)]
 
 
 def _load() -> C.CDLL:
@@ -56,6 +57,7 @@ def _load() -> C.CDLL:
         'rr_route_host': (C.c_int, [vp, C.c_int, f64p, f64p, f64p, i64, f64p, i64, i64, i64]),
         'rr_plan_set_output_subset': (C.c_int, [vp, i64, c_i32p]),
         'rr_route_host_ex': (C.c_int, [vp, C.c_int, f64p, f64p, f64p, i64, vp, i64, i64, i64, C.c_int, i64]),
+        'rr_route_host_typed': (C.c_int, [vp, C.c_int, f64p, f64p, vp, C.c_int, i64, vp, i64, i64, i64, C.c_int, i64]),
         'rr_transform_create': (C.c_int, [i64, i64, c_i32p, c_i32p, f64p, f64p, i32, C.POINTER(vp)]),
         'rr_transform_set_uh': (C.c_int, [vp, i64, f64p, i64, f64p, i64]),
         'rr_transform_get_uh_state': (C.c_int, [vp, f64p, i64]),
@@ -93,7 +95,7 @@ lib = _load()
 EXPORTED_SYMBOLS = (
     'rr_last_error', 'rr_version', 'rr_cuda_available', 'rr_downstream_index', 'rr_label_basins',
     'rr_plan_create', 'rr_plan_destroy', 'rr_plan_get_info', 'rr_plan_set_coefficients', 'rr_route_dev',
-    'rr_route_host', 'rr_plan_set_output_subset', 'rr_route_host_ex', 'rr_transform_create', 'rr_transform_set_uh', 'rr_transform_get_uh_state',
+    'rr_route_host', 'rr_plan_set_output_subset', 'rr_route_host_ex', 'rr_route_host_typed', 'rr_transform_create', 'rr_transform_set_uh', 'rr_transform_get_uh_state',
     'rr_transform_destroy', 'rr_runoff_route_host', 'rr_route_ensemble_dev', 'rr_plan_tile_rows', 'rr_launch_count', 'rr_timing_enable', 'rr_timing_read', 'rr_uh_convolve_dev', 'rr_uh_convolve_host',
     'rr_weights_transform_dev', 'rr_weights_transform_host', 'rr_plan_read_profile', 'rr_host_alloc', 'rr_host_free', 'rr_synth_forest',
     'rr_plan_get_arrays', 'rr_plan_schedule',

@@ -16,6 +16,14 @@
 
 cudaError_t rr_launch_wavefront(int mode, const rr_route_params &P, int grid, int block, cudaStream_t stream);
 int rr_wavefront_occupancy(int mode, int block);
+// rr_direct.cu: the pipeline of level-sorted plans with one substep per row
+cudaError_t rr_launch_direct(int mode, const rr_route_params &P, int grid, cudaStream_t stream);
+int rr_direct_occupancy(int mode);
+int rr_stage_in(const void *src, int src_f32, int64_t lds, double *lat_w, double *out_w, const int32_t *inv, int64_t n, int64_t T,
+                int64_t tile_rows, int64_t n_blocks, int64_t hw_cut, const double *c3, const double *c4,
+                const double *q_init, double *q_final, int sm_count, cudaStream_t stream);
+int rr_stage_out(const double *out_w, void *dst, int dst_f32, int64_t ldd, const int32_t *inv, const int32_t *subset,
+                 int64_t n_out, int64_t T, int64_t tile_rows, int64_t n_blocks, cudaStream_t stream);
 
 static thread_local int64_t g_launches = 0;
 extern "C" int64_t rr_launch_count(int reset) {
@@ -90,7 +98,7 @@ struct rr_device_state {
     // launch scratch
     int64_t sched_budget_rows = -1;
     rr_schedule sched;
-    struct key_table { int64_t n_tiles = -1, n_items = 0; int32_t *dev = nullptr; size_t cap = 0; uint64_t used = 0; };   // ticket -> (block, tile)
+    struct key_table { int64_t n_tiles = -1, first_block = 0, n_items = 0; int32_t *dev = nullptr; size_t cap = 0; uint64_t used = 0; };   // ticket -> (block, tile)
     key_table keys[4];
     uint64_t key_clock = 0;
     double *raw = nullptr;
@@ -98,7 +106,7 @@ struct rr_device_state {
     int32_t *done = nullptr;
     size_t done_cap = 0;
     unsigned long long *ticket = nullptr, *prof = nullptr;
-    int occ[3] = {0, 0, 0};
+    int occ[3] = {0, 0, 0}, occ_direct[3] = {0, 0, 0};
     // host streaming path
     cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -151,8 +159,8 @@ static int ensure_device(rr_plan *p) {
         rc |= upload(&d->meta, p->meta, d->bytes);
         if (!p->inv.empty()) rc |= upload(&d->inv, p->inv, d->bytes);
         if (rc) return rc;
-        CK(cudaMalloc((void **)&d->coef, sizeof(double) * 4 * (size_t)p->n));
-        d->bytes += sizeof(double) * 4 * (size_t)p->n;
+        CK(cudaMalloc((void **)&d->coef, sizeof(double) * 4 * (size_t)p->n_work));
+        d->bytes += sizeof(double) * 4 * (size_t)p->n_work;
         CK(cudaMalloc((void **)&d->ticket, sizeof(unsigned long long)));
         CK(cudaMalloc((void **)&d->prof, 8 * sizeof(unsigned long long)));
         CK(cudaMemset(d->prof, 0, 8 * sizeof(unsigned long long)));
@@ -168,11 +176,11 @@ static int ensure_device(rr_plan *p) {
     rr_device_state *d = p->dev;
     if (d->coeff_version != p->coeff_version) {
         if (p->c1.empty()) { rr_set_error("coefficients not set: call rr_plan_set_coefficients first"); return 100; }
-        const size_t nb = sizeof(double) * (size_t)p->n;
+        const size_t nb = sizeof(double) * (size_t)p->n_work;
         CK(cudaMemcpy(d->coef, p->c1.data(), nb, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(d->coef + p->n, p->c2.data(), nb, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(d->coef + 2 * p->n, p->c3.data(), nb, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(d->coef + 3 * p->n, p->c4.data(), nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d->coef + p->n_work, p->c2.data(), nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d->coef + 2 * p->n_work, p->c3.data(), nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d->coef + 3 * p->n_work, p->c4.data(), nb, cudaMemcpyHostToDevice));
         d->coeff_version = p->coeff_version;
     }
     return 0;
@@ -238,7 +246,7 @@ extern "C" int64_t rr_plan_tile_rows(const rr_plan *p, int64_t T, int64_t subste
 static int launch_route(rr_plan *p, int mode, int n_members, const double *q_init, const double *const *lateral,
                         int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
                         int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream, int tile_major = 0,
-                        int out_layout = 0, int direct = 0) {
+                        int out_layout = 0, int direct = 0, int64_t rows_in = 0, int64_t first_block = 0, int pipeline = 0) {
     if (mode < 0 || mode > 2) { rr_set_error("unknown router mode"); return 100; }
     if (T <= 0 || K <= 0 || T > 0x7fffffff || K > 0x7fffffff) { rr_set_error("T and substeps must be positive"); return 100; }
     if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
@@ -250,7 +258,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     rr_device_state *d = p->dev;
 
     // tile geometry: aim for `time_tile` routing substeps per work item
-    const int64_t rows = tile_rows_for(p, T, K);
+    const int64_t rows = rows_in > 0 ? rows_in : tile_rows_for(p, T, K);
     const int64_t n_tiles = (T + rows - 1) / rows;
     // row pitch of the exchange buffer: [14] q_full carry, [15] carry, [16+s] substeps (rr_route.cu); sized for the
     // plan's nominal tile so that short calls (the last chunk of a stream) reuse the same rings
@@ -279,13 +287,13 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     // ticket keys per call length: a few tables are cached (the streaming path alternates between the
     // full chunk and the last, shorter one)
     rr_device_state::key_table *kt = nullptr;
-    for (auto &k : d->keys) if (k.n_tiles == n_tiles) kt = &k;
+    for (auto &k : d->keys) if (k.n_tiles == n_tiles && k.first_block == first_block) kt = &k;
     if (!kt) {
         kt = &d->keys[0];
         for (auto &k : d->keys) if (k.used < kt->used) kt = &k;
-        rr_build_keys(*p, n_tiles, d->sched);
+        rr_build_keys(*p, n_tiles, d->sched, first_block);
         std::vector<int32_t> items;
-        rr_build_items(*p, n_tiles, d->sched, items);
+        rr_build_items(*p, n_tiles, d->sched, items, first_block);
         CK(cudaDeviceSynchronize());
         if (items.size() > kt->cap) {
             if (kt->dev) CK(cudaFree(kt->dev));
@@ -294,7 +302,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
             kt->cap = items.size();
         }
         CK(cudaMemcpy(kt->dev, items.data(), items.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        kt->n_tiles = n_tiles; kt->n_items = d->sched.n_items;
+        kt->n_tiles = n_tiles; kt->first_block = first_block; kt->n_items = d->sched.n_items;
     }
     kt->used = ++d->key_clock;
     // one spare row: the kernel prefetches a few lines past the row it is reading
@@ -319,12 +327,12 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
 
     rr_route_params P;
     std::memset(&P, 0, sizeof(P));
-    P.n = p->n; P.n_blocks = (int32_t)p->n_blocks; P.max_level = p->max_level;
+    P.n = p->n_work; P.n_blocks = (int32_t)p->n_blocks; P.max_level = p->max_level;
     P.up_ptr = d->up_ptr; P.up_idx = d->up_idx; P.slot_src = d->slot_src; P.skew = d->skew;
     P.export_id = d->export_id; P.meta = d->meta;
     P.dep_ptr = d->dep_ptr; P.dep_idx = d->dep_idx; P.down = d->down;
     P.exp_ro = d->exp_ro; P.edge_ro = d->edge_ro; P.raw_rows = d->sched.raw_rows;
-    P.c1 = d->coef; P.c2 = d->coef + p->n; P.c3 = d->coef + 2 * p->n; P.c4 = d->coef + 3 * p->n;
+    P.c1 = d->coef; P.c2 = d->coef + p->n_work; P.c3 = d->coef + 2 * p->n_work; P.c4 = d->coef + 3 * p->n_work;
     P.items = reinterpret_cast<const int4 *>(kt->dev); P.n_items = kt->n_items;
     P.delta = d->sched.delta; P.n_tiles = (int32_t)n_tiles;
     P.T = (int32_t)T; P.K = (int32_t)K; P.tile_rows = (int32_t)rows;
@@ -339,12 +347,32 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     }
     P.ticket_batch = 1;   // larger batches were measured slower: neighbouring blocks should run concurrently
     CK(cudaMemsetAsync(d->done, 0, done_need * sizeof(int32_t), stream));
+    // blocks the staging kernel has routed already (whole-headwater blocks) count as finished for every tile
+    for (int m = 0; m < n_members && first_block > 0; ++m)
+        CK(cudaMemsetAsync(d->done + (size_t)m * p->n_blocks, 0x3f, (size_t)first_block * sizeof(int32_t), stream));
     CK(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), stream));
     int block = p->opts.threads_per_cta;
     P.tile_major = tile_major;
     P.out_layout = out_layout;
     P.direct = direct;
     P.tile_pitch = (int32_t)((rows + 3) & ~(int64_t)3);
+    P.gpt = (int32_t)((rows + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS);
+    if (pipeline) {
+        // rr_direct.cu: done[] counts 16-row groups; 8 warps per CTA share 32 KB of output staging
+        if (!d->occ_direct[mode]) {
+            d->occ_direct[mode] = rr_direct_occupancy(mode);
+            if (d->occ_direct[mode] <= 0) { rr_set_error("occupancy query failed for the direct wavefront kernel"); return 200; }
+        }
+        const int64_t total = kt->n_items * n_members;
+        int64_t g = (int64_t)d->sm_count * d->occ_direct[mode];
+        g = std::max<int64_t>(1, std::min<int64_t>(g, (total + 7) / 8));
+        {
+            rr_timer tm(0, stream);
+            CK(rr_launch_direct(mode, P, (int)g, stream));
+        }
+        rr_count_launch(1);
+        return 0;
+    }
     if (tile_major == 1 && K == 1 && mode != RR_MODE_UNIT) {
         // TMA-staged kernel: 4 warps per CTA, each with [tile | upstream row slots | mbarrier] in shared memory
         int max_smem = 0;
@@ -480,37 +508,64 @@ static int grow(double **buf, size_t *cap, size_t need) {
     if (*buf) CK(cudaFree(*buf));
     *buf = nullptr; *cap = 0;
     CK(cudaMalloc((void **)buf, need * sizeof(double)));
+    CK(cudaMemset(*buf, 0, need * sizeof(double)));   // padding slots of level-sorted plans are routed along: keep them finite
     *cap = need;
     return 0;
+}
+
+// Where a call's discharge goes when the caller wants the router loop's tail fused into the last device pass:
+// float32 cast (TransformMuskingum.py:146) and / or an output subset, written straight from the working tiles.
+struct rr_out_spec {
+    void *dst = nullptr;
+    int f32 = 0;
+    int64_t ld = 0;
+    const int32_t *subset = nullptr;   // device pointer; nullptr = all segments
+    int64_t n_out = 0;
+};
+
+// The rr_direct.cu pipeline serves level-sorted plans whose blocks are all fast-path eligible, one substep per row,
+// RapidMuskingum / Muskingum, tile lengths that are whole 16-row groups.
+static bool pipeline_ok(const rr_plan *p, int mode, int64_t K) {
+    const int st = p->opts.staging;
+    return !p->perm.empty() && p->all_fast && K == 1 && mode != RR_MODE_UNIT && (st == 0 || st == 6 || st == 7) &&
+           (p->opts.time_tile % RR_FLAG_ROWS) == 0;
 }
 
 // Route with all arrays in the caller's (params_file) order, whatever order the plan works in.
 static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, const double *const *lateral,
                      int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
-                     int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream) {
-    if (p->perm.empty())
+                     int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream,
+                     const rr_out_spec *spec = nullptr, int lat_f32 = 0) {
+    if (lat_f32 && !(pipeline_ok(p, mode, K) && !p->perm.empty())) { rr_set_error("internal: float32 lateral inflows need the direct pipeline"); return 101; }
+    if (p->perm.empty()) {
+        if (spec) { rr_set_error("internal: fused output needs a level-sorted plan"); return 101; }
         return launch_route(p, mode, n_members, q_init, lateral, ldl, out, ldo, q_state, q_full, T, K, first_call,
                             last_call, stream);
+    }
     int rc = ensure_device(p);
     if (rc) return rc;
     rr_device_state *d = p->dev;
-    const int64_t n = p->n, ldp = ((n + 31) / 32) * 32;
+    const int64_t n = p->n, ldp = ((p->n_work + 31) / 32) * 32;   // user segments; slots per working row
     const bool has_lat = mode != RR_MODE_MUSKINGUM;
     const bool unit = mode == RR_MODE_UNIT;
     if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
     if (T <= 0 || K <= 0) { rr_set_error("T and substeps must be positive"); return 100; }
-    // working arrays: tile-major for the TMA-staged kernel (one substep per row, not UnitMuskingum), else row-major
+    const bool pipeline = pipeline_ok(p, mode, K);
+    if (spec && !pipeline) { rr_set_error("internal: fused output is a feature of the direct pipeline"); return 101; }
     // working arrays: row-major (staging 1, substeps), [tile][block][row][lane] for the TMA-staged
     // kernel (3), [tile][block][lane][row] otherwise (register path: whole-sector accesses everywhere)
     const bool tiled = (K == 1 && p->opts.staging != 1 && !(unit && p->opts.staging == 3));
     // lateral: reach-major tiles (whole-sector scatter in the permute, 256-bit loads in the kernel); discharge:
     // row-major tiles (coalesced row stores in the kernel, sector-sharing gathers in the permute) -- measured best
     const int layout = !tiled ? 0 : (p->opts.staging == 3 ? 1 : (p->opts.staging == 5 ? 3 : 2));
-    // staging 6, "direct exchange": the working discharge array (reach-major tiles, raw values) is the exchange buffer
+    // "direct exchange": the working discharge array (reach-major tiles, raw values) is the exchange buffer
     // (default for level-sorted plans with one substep per row; staging 2 / 4 / 5 keep the exchange rings)
-    const bool direct = tiled && !unit && (p->opts.staging == 6 || p->opts.staging == 0);
+    const bool direct = tiled && !unit && (p->opts.staging == 6 || p->opts.staging == 0 || p->opts.staging == 7);
     const int out_layout = !tiled ? 0 : ((p->opts.staging == 4 || direct) ? 2 : 1);
-    const int64_t trows = tiled ? tile_rows_for(p, T, K) : 0;
+    int64_t trows = tiled ? tile_rows_for(p, T, K) : 0;
+    // the pipeline's tiles are whole 16-row groups (short calls get one padded tile)
+    if (pipeline) trows = std::min<int64_t>(tile_rows_for(p, std::max<int64_t>(T, RR_FLAG_ROWS), K) / RR_FLAG_ROWS * RR_FLAG_ROWS,
+                                            (T + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS * RR_FLAG_ROWS);
     const int64_t tpitch = ((trows + 3) & ~(int64_t)3);
     const int64_t n_tiles = tiled ? (T + trows - 1) / trows : 0;
     const size_t member_elems = tiled ? (size_t)n_tiles * p->n_blocks * tpitch * RR_BLOCK : (size_t)T * ldp;
@@ -521,26 +576,42 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     double *w_init = d->p_q;
     const double *lat_w[RR_MAX_MEMBERS];
     double *out_w[RR_MAX_MEMBERS], *qs_w[RR_MAX_MEMBERS], *qf_w[RR_MAX_MEMBERS];
+    // whole blocks of headwaters are routed by the staging kernel of the pipeline (RapidMuskingum: their lateral rows
+    // pass through its registers anyway); small networks keep them in the wavefront (staging 7 forces that, 6 the former)
+    int64_t hw_cut = 0;
+    if (pipeline && mode == RR_MODE_RAPID && p->opts.staging != 7 && (p->opts.staging == 6 || n >= (1 << 18)))
+        hw_cut = p->lvl0_slots;   // level 0 fills whole blocks (headwaters + padding)
     if (first_call && (rc = permute(true, q_init, n, w_init, ldp, d->inv, n, 1, stream))) return rc;
     for (int m = 0; m < n_members; ++m) {
         lat_w[m] = has_lat ? d->p_lat + (size_t)m * member_elems : nullptr;
         out_w[m] = d->p_out + (size_t)m * member_elems;
         qs_w[m] = d->p_q + (size_t)(1 + m) * ldp;
         qf_w[m] = d->p_q + (size_t)(1 + n_members + m) * ldp;
-        if (has_lat && (rc = permute(true, lateral[m], ldl, d->p_lat + (size_t)m * member_elems, ldp, d->inv, n, T, stream, trows, p->n_blocks, layout))) return rc;
         if (!first_call) {
             // direct exchange reads upstream start-of-call values during the launch, so the running state (which the
             // launch overwrites in place) is first copied to the shared, read-only initial-state vector
             if ((rc = permute(true, q_state[m], n, direct ? w_init : qs_w[m], ldp, d->inv, n, 1, stream))) return rc;
             if (unit && (rc = permute(true, q_full[m], n, qf_w[m], ldp, d->inv, n, 1, stream))) return rc;
         }
+        if (has_lat && pipeline) {
+            rr_timer tm(1, stream);
+            rc = rr_stage_in(lateral[m], lat_f32, ldl, d->p_lat + (size_t)m * member_elems, out_w[m], d->inv, n, T, trows, p->n_blocks,
+                             hw_cut, d->coef + 2 * p->n_work, d->coef + 3 * p->n_work, w_init, qs_w[m], d->sm_count, stream);
+            if (rc) return rc;
+        } else if (has_lat && (rc = permute(true, lateral[m], ldl, d->p_lat + (size_t)m * member_elems, ldp, d->inv, n, T, stream, trows, p->n_blocks, layout))) return rc;
     }
     if (direct && !first_call && n_members != 1) { rr_set_error("direct exchange: continued calls support one member"); return 100; }
     rc = launch_route(p, mode, n_members, w_init, has_lat ? lat_w : nullptr, ldp, out_w, ldp, qs_w, qf_w, T, K,
-                      direct ? 1 : first_call, last_call, stream, layout, out_layout, direct ? 1 : 0);
+                      direct ? 1 : first_call, last_call, stream, layout, out_layout, direct ? 1 : 0, pipeline ? trows : 0,
+                      hw_cut / RR_BLOCK, pipeline ? 1 : 0);
     if (rc) return rc;
     for (int m = 0; m < n_members; ++m) {
-        if ((rc = permute(false, out_w[m], ldp, out[m], ldo, d->inv, n, T, stream, trows, p->n_blocks, out_layout, direct ? 1 : 0))) return rc;
+        if (pipeline) {
+            rr_timer tm(2, stream);
+            if (spec) rc = rr_stage_out(out_w[m], spec->dst, spec->f32, spec->ld, d->inv, spec->subset, spec->n_out, T, trows, p->n_blocks, stream);
+            else rc = rr_stage_out(out_w[m], out[m], 0, ldo, d->inv, nullptr, n, T, trows, p->n_blocks, stream);
+            if (rc) return rc;
+        } else if ((rc = permute(false, out_w[m], ldp, out[m], ldo, d->inv, n, T, stream, trows, p->n_blocks, out_layout, direct ? 1 : 0))) return rc;
         if ((rc = permute(false, qs_w[m], ldp, q_state[m], n, d->inv, n, 1, stream))) return rc;
         if (unit && !(last_call) && (rc = permute(false, qf_w[m], ldp, q_full[m], n, d->inv, n, 1, stream))) return rc;
     }
@@ -673,6 +744,12 @@ __global__ void __launch_bounds__(256) finish_output(const double *__restrict__ 
     dst[(int64_t)blockIdx.y * ldd + s] = (OT)acc;
 }
 
+__global__ void __launch_bounds__(256) upcast_rows(const float *__restrict__ src, int64_t lds, double *__restrict__ dst, int64_t ldd,
+                                                    int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[(int64_t)blockIdx.y * ldd + i] = (double)__ldg(src + (int64_t)blockIdx.y * lds + i);
+}
+
 int rr_weights_run(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *indptr, const int32_t *indices,
                    const double *w, const void *x, int x_is_f32, int64_t ldx, double *y, int64_t ldy, int cumulative,
                    int force_positive, const double *area, int64_t t_skip, cudaStream_t stream);
@@ -725,7 +802,8 @@ static void parallel_copy_2d(char *dst, size_t dst_pitch, const char *src, size_
 // What feeds the router, chunk by chunk: host lateral inflows (qlateral files) or gathered grid runoff that the
 // weight table (and, for UnitMuskingum, the unit hydrograph) turns into lateral inflows on the device.
 struct rr_stream_source {
-    const double *lateral = nullptr;
+    const void *lateral = nullptr;     // host lateral inflows, float64 or (lat_f32) float32
+    int lat_f32 = 0;
     int64_t ldl = 0;
     rr_transform *tf = nullptr;
     const void *runoff = nullptr;
@@ -770,7 +848,7 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
     // calls get short ones.  Bounded by ~1 GiB per transfer buffer and ~4 GiB of fp64 scratch rows; whole 8-row
     // groups and whole output rows.
     const int64_t row_bytes = ldd * 8;
-    const double in_row = !has_lat ? 0.0 : (grid ? (double)src.tf->n_points * (src.x_is_f32 ? 4 : 8) : (double)n * 8);
+    const double in_row = !has_lat ? 0.0 : (grid ? (double)src.tf->n_points * (src.x_is_f32 ? 4 : 8) : (double)n * (src.lat_f32 ? 4 : 8));
     const double out_row = (double)n_out * (out_f32 ? 4 : 8) / (double)resample;
     const double t_row = std::max({in_row / 45e9, out_row / 45e9, (double)n * (double)substeps * 14e-12});
     int64_t min_rows = (int64_t)std::ceil((double)(p->max_level + 1) * 80e-6 / t_row);
@@ -780,10 +858,13 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
     const int64_t cap_rows = std::max<int64_t>(1, std::min<int64_t>(xfer_cap, (4ll << 30) / row_bytes));
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(T / 16, min_rows), cap_rows));
     if (const char *env = getenv("RR_STREAM_CHUNK_ROWS")) chunk = std::max(1, atoi(env));   // tests: force many chunks
-    if (chunk >= 8) chunk = (chunk / 8) * 8;
+    // fused output tail (cast / subset written straight from the working tiles) when the direct pipeline runs the call
+    const bool fused = post && resample == 1 && pipeline_ok(p, mode, substeps);
+    if (pipeline_ok(p, mode, substeps) && chunk >= RR_FLAG_ROWS) chunk = (chunk / RR_FLAG_ROWS) * RR_FLAG_ROWS;   // whole 16-row groups
+    else if (chunk >= 8) chunk = (chunk / 8) * 8;
     chunk = std::max<int64_t>(resample, (chunk / resample) * resample);
     chunk = std::min<int64_t>(chunk, T);
-    const size_t es_in = grid ? (src.x_is_f32 ? 4 : 8) : 8, es_out = out_f32 ? 4 : 8;
+    const size_t es_in = grid ? (src.x_is_f32 ? 4 : 8) : (src.lat_f32 ? 4 : 8), es_out = out_f32 ? 4 : 8;
     const int64_t ld_in = grid ? ((src.tf->n_points + 31) / 32) * 32 : ldd;
     const size_t need_in = has_lat ? (size_t)(chunk + (grid ? 1 : 0)) * ld_in * es_in : 0;
     const int64_t ldd_out = ((n_out + 31) / 32) * 32;
@@ -832,9 +913,12 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
         if (out_bounce && (rc = grow_pinned(&d->h_outb[k], &d->h_outb_cap[k], need_out))) return rc;
     }
     const size_t need_f64 = (size_t)chunk * ldd * 8;
-    if (grid && (rc = grow_bytes((void **)&d->s_lat, &d->s_lat_cap, need_f64))) return rc;
+    // float32 lateral inflows: the direct pipeline's staging kernel upcasts them on the fly; other paths get an exact
+    // upcast into the fp64 scratch first
+    const bool lat_cast = !grid && has_lat && src.lat_f32 && !pipeline_ok(p, mode, substeps);
+    if ((grid || lat_cast) && (rc = grow_bytes((void **)&d->s_lat, &d->s_lat_cap, need_f64))) return rc;
     if (uh && (rc = grow_bytes((void **)&d->s_conv, &d->s_conv_cap, need_f64))) return rc;
-    if (post && (rc = grow_bytes((void **)&d->s_route, &d->s_route_cap, need_f64))) return rc;
+    if (post && !fused && (rc = grow_bytes((void **)&d->s_route, &d->s_route_cap, need_f64))) return rc;
     if (!d->d_q) CK(cudaMalloc((void **)&d->d_q, sizeof(double) * (size_t)n));
     if (mode == RR_MODE_UNIT && !d->d_qfull) CK(cudaMalloc((void **)&d->d_qfull, sizeof(double) * (size_t)n));
     CK(cudaMemcpyAsync(d->d_q, q_state, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, d->s_comp));
@@ -863,8 +947,8 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
         if (!has_lat) return 0;
         const int k = (int)(c & 1);
         const int64_t lead = lead_of(c), nrows = rows_of(c) + lead;
-        const size_t width = grid ? (size_t)src.tf->n_points * es_in : (size_t)n * 8;
-        const size_t h_pitch = grid ? (size_t)src.ldx * es_in : (size_t)src.ldl * 8, d_pitch = (size_t)ld_in * es_in;
+        const size_t width = grid ? (size_t)src.tf->n_points * es_in : (size_t)n * es_in;
+        const size_t h_pitch = grid ? (size_t)src.ldx * es_in : (size_t)src.ldl * es_in, d_pitch = (size_t)ld_in * es_in;
         const char *h = (const char *)h_src + (size_t)(start[c] - lead) * h_pitch;
         size_t pitch = h_pitch;
         if (in_bounce) {
@@ -894,6 +978,14 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
         if (has_lat) CK(cudaStreamWaitEvent(d->s_comp, d->ev_in[k], 0));
         if (c >= 2) CK(cudaStreamWaitEvent(d->s_comp, d->ev_out[k], 0));  // out buffer drained
         const double *lat = (const double *)d->s_inb[k];
+        if (lat_cast) {
+            rr_timer tm(3, d->s_comp);
+            dim3 g((unsigned)((n + 255) / 256), (unsigned)rows);
+            upcast_rows<<<g, 256, 0, d->s_comp>>>((const float *)d->s_inb[k], ld_in, d->s_lat, ldd, n);
+            CK(cudaGetLastError());
+            rr_count_launch(1);
+            lat = d->s_lat;
+        }
         if (grid) {
             const rr_transform *t = src.tf;
             {
@@ -915,11 +1007,15 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
         double *route_out = post ? d->s_route : (double *)d->s_outb[k];
         const double *lat1[1] = {lat};
         double *out1[1] = {route_out}, *qs1[1] = {d->d_q}, *qf1[1] = {d->d_qfull};
+        rr_out_spec spec;
+        spec.dst = d->s_outb[k]; spec.f32 = out_f32; spec.ld = ldd_out; spec.n_out = n_out;
+        spec.subset = p->out_subset.empty() ? nullptr : d->out_subset;
         rc = route_any(p, mode, 1, d->d_q, lat1, ldd, out1, ldd, qs1, qf1, rows, substeps,
-                       router_level && c == 0, router_level && c == n_chunks - 1, d->s_comp);
+                       router_level && c == 0, router_level && c == n_chunks - 1, d->s_comp, fused ? &spec : nullptr,
+                       (!grid && has_lat && src.lat_f32 && !lat_cast) ? 1 : 0);
         if (rc) return rc;
         const int64_t rows_out = rows / resample;
-        if (post) {
+        if (post && !fused) {
             rr_timer tm(3, d->s_comp);
             dim3 g((unsigned)((n_out + 255) / 256), (unsigned)rows_out);
             const int32_t *sub = p->out_subset.empty() ? nullptr : d->out_subset;
@@ -985,6 +1081,14 @@ extern "C" int rr_route_host_ex(rr_plan *p, int mode, double *q_state, double *q
                                 int64_t resample) {
     rr_stream_source src;
     src.lateral = lateral; src.ldl = ldl;
+    return stream_route(p, mode, q_state, q_full, src, out, ldo, T, substeps, out_f32, resample);
+}
+
+extern "C" int rr_route_host_typed(rr_plan *p, int mode, double *q_state, double *q_full, const void *lateral,
+                                   int lateral_f32, int64_t ldl, void *out, int64_t ldo, int64_t T, int64_t substeps,
+                                   int out_f32, int64_t resample) {
+    rr_stream_source src;
+    src.lateral = lateral; src.lat_f32 = lateral_f32; src.ldl = ldl;
     return stream_route(p, mode, q_state, q_full, src, out, ldo, T, substeps, out_f32, resample);
 }
 

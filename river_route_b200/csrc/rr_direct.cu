@@ -1,0 +1,374 @@
+// rr_direct.cu -- the routing pipeline of level-sorted plans with one routing substep per row
+// (RapidMuskingum / Muskingum; river_route/routers/_numba_kernels.py rapid_route :49-84, muskingum_route :9-46):
+//
+//   stage_in   caller's (T, n) lateral inflows (params-file order) -> working tiles [tile][block][reach][row];
+//              whole blocks of headwater reaches (level 0: no upstream, q' = c3*q + c4_dt*ql) are routed right here,
+//              while their lateral rows pass through registers, and only their discharge series is written
+//   wavefront  rr_direct_kernel: persistent warps, one (block of 32 same-level reaches, time tile) per ticket.  The
+//              working discharge array keeps the RAW series and is the exchange buffer: a reach reads its upstream
+//              reaches' series straight from their discharge tiles ("direct exchange").  done[block] counts finished
+//              16-row groups (one 128-byte line per reach): blocks of narrow levels publish every group and consume
+//              their upstream blocks group by group, so that deep, narrow parts of the network pipeline at a few
+//              microseconds per level instead of one whole work item per level.
+//   stage_out  working discharge tiles -> caller's layout with the reference's clamp (:44-46 / :82-84), optionally cast
+//              to float32 (TransformMuskingum.py:146) and restricted to an output subset.
+//
+// Per reach i with upstream set U(i) in ascending params-file index (the reference's summation order):
+//     q'[i] = c3*q[i] + c4_dt*ql[t,i] + sum_u c2[i]*q[u] + sum_u c1[i]*q'[u]
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+
+#include "rr_device.cuh"
+
+using namespace rrdev;
+
+void rr_count_launch(int64_t k);
+
+namespace {
+
+// row 0 of working reach u's series in tile jj (reach-major tiles, tile_pitch doubles per reach)
+__device__ __forceinline__ const double *tile_of(const double *base, const rr_route_params &P, int jj, int64_t u) {
+    return base + (((size_t)jj * P.n_blocks + (size_t)(u >> 5)) * RR_BLOCK + (size_t)(u & 31)) * (size_t)P.tile_pitch;
+}
+
+struct dctx {
+    int m, b, j, lane, TT, deg;
+    int64_t i;
+    bool valid, narrow, prog;    // prog: upstream blocks were not complete at the start -> consume them group by group
+    double c1, c2, c3, c4, q;
+    int32_t up_u[RR_MAX_FAST_DEG];
+    int32_t dep_blk;             // this lane's entry of the block's upstream-block list (-1: none)
+    int32_t *done;               // this member's progress counters
+    const double *lat0;
+    double *out0;
+};
+
+// all lanes: wait until every upstream block has published `want`; sets full when they are all past `full_want`
+__device__ __forceinline__ void wait_groups(const dctx &c, int32_t want, int32_t full_want, bool &full) {
+    unsigned ns = 32;
+    for (;;) {
+        const int32_t p = c.dep_blk >= 0 ? ld_relaxed(c.done + c.dep_blk) : 0x7fffffff;
+        if (__all_sync(RR_FULL_MASK, p >= want)) {
+            full = __all_sync(RR_FULL_MASK, p >= full_want);
+            break;
+        }
+        __nanosleep(ns);
+        if (ns < 256) ns <<= 1;
+    }
+    if (c.dep_blk >= 0) (void)ld_acquire(c.done + c.dep_blk);
+    __syncwarp();
+}
+
+// One work item.  Software pipeline over groups of four rows: while rows s..s+3 are computed the sectors of rows
+// s+4.. and s+8.. are in flight.  Results are parked in shared memory and leave as whole 128-byte lines every 16
+// rows (four back-to-back 256-bit stores per reach): a line written one sector per ~600 cycles left L2 partially
+// dirty and cost DRAM read-modify-write traffic (ncu: 11.5 B written + 1.6 B read more than the 8 + 17.4 B the
+// kernel asks for, per reach-timestep).
+template <int MODE, int NS>
+__device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx &c, double *stage) {
+    constexpr bool HAS_LAT = (MODE == RR_MODE_RAPID);
+    constexpr int NA = NS > 0 ? NS : 1;
+    const double c1 = c.c1, c2 = c.c2, c3 = c.c3, c4 = c.c4;
+    const int TT = c.TT, j = c.j, lane = c.lane;
+    const int32_t gbase = j * P.gpt;
+    double q = c.q;
+    const double *up[NA];
+    bool has[NA];
+    double old[NA];
+    d4 nxt[NA], fut[NA];
+    bool full = !c.prog;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        has[k] = k < c.deg;
+        up[k] = P.out[c.m];
+        old[k] = 0.0;
+        nxt[k] = fut[k] = d4{0, 0, 0, 0};
+        if (has[k]) {
+            up[k] = tile_of(P.out[c.m], P, j, c.up_u[k]);
+            // value before the tile's first row: the start-of-call state, or the last row of the previous tile
+            old[k] = j == 0 ? P.q_init[c.up_u[k]] : tile_of(P.out[c.m], P, j - 1, c.up_u[k])[P.tile_rows - 1];
+            nxt[k] = ld_sector(up[k]);                       // rows 0..7 are in group 0, which is published
+            if (4 < TT) fut[k] = ld_sector(up[k] + 4);
+        }
+    }
+    const double *lat = c.lat0;
+    auto lat_group = [&](int s0) -> d4 {
+        if (!(HAS_LAT && c.valid) || s0 >= TT) return d4{0, 0, 0, 0};
+        return ld_sector_ro(lat + s0);
+    };
+    d4 lcur = lat_group(0), lnxt = lat_group(4);
+    double *st = stage + lane;                     // [row & 15][lane]
+    for (int s = 0; s < TT; s += 4) {
+        // rows s+8..s+11: first rows of upstream group (s+8)/16 when that is a multiple of 16
+        if (NS > 0 && !full && ((s + 8) & 15) == 0 && s + 8 < TT) wait_groups(c, gbase + ((s + 8) >> 4) + 1, gbase + P.gpt, full);
+        d4 far[NA];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            far[k] = d4{0, 0, 0, 0};
+            if (has[k] && s + 8 < TT) far[k] = ld_sector(up[k] + s + 8);
+        }
+        const d4 lfar = lat_group(s + 8);
+        double r0, r1, r2, r3;
+        {
+            double r = c3 * q;                                       // _numba_kernels.py:27-28 / :68-69
+            if (HAS_LAT) r = fma(c4, lcur.a, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c2, old[k], r);     // :29-33 / :70-74, ascending upstream
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].a, r);   // :36-39 / :75-78 (lhs_off = -c1)
+            r0 = r;
+            r = c3 * r0;
+            if (HAS_LAT) r = fma(c4, lcur.b, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c2, nxt[k].a, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].b, r);
+            r1 = r;
+            r = c3 * r1;
+            if (HAS_LAT) r = fma(c4, lcur.c, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c2, nxt[k].b, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].c, r);
+            r2 = r;
+            r = c3 * r2;
+            if (HAS_LAT) r = fma(c4, lcur.d, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c2, nxt[k].c, r);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r = fma(c1, nxt[k].d, r);
+            r3 = r;
+        }
+        const int rr = s & 15;
+        st[(rr + 0) * RR_BLOCK] = r0;
+        st[(rr + 1) * RR_BLOCK] = r1;
+        st[(rr + 2) * RR_BLOCK] = r2;
+        st[(rr + 3) * RR_BLOCK] = r3;
+        q = (s + 3 < TT) ? r3 : ((s + 2 < TT) ? r2 : ((s + 1 < TT) ? r1 : r0));
+        if (rr == 12 || s + 4 >= TT) {
+            // one whole line (or the tail of the tile) of this reach's series; rows past TT inside the last sector are
+            // never read (consumers and stage_out stop at TT)
+            if (c.valid) {
+                double *o = c.out0 + (s - rr);
+#pragma unroll
+                for (int v = 0; v < 16; v += 4)
+                    if (v <= rr) st_sector(o + v, st[(v + 0) * RR_BLOCK], st[(v + 1) * RR_BLOCK], st[(v + 2) * RR_BLOCK], st[(v + 3) * RR_BLOCK]);
+            }
+            if (c.narrow && s + 4 < TT) {
+                __syncwarp();
+                if (lane == 0) st_release(c.done + c.b, gbase + (s >> 4) + 1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { old[k] = nxt[k].d; nxt[k] = fut[k]; fut[k] = far[k]; }
+        lcur = lnxt;
+        lnxt = lfar;
+    }
+    if (c.valid) P.q_state[c.m][c.i] = q;
+}
+
+// reaches with three or four upstreams are rare: their (register-hungry) instantiations live in a function of their own
+// so that they do not set the register allocation -- and the spills -- of the common paths
+template <int MODE>
+__device__ __noinline__ void direct_item_wide(const rr_route_params &P, const dctx &c, double *stage, int max_deg) {
+    if (max_deg == 3) direct_item<MODE, 3>(P, c, stage);
+    else direct_item<MODE, 4>(P, c, stage);
+}
+
+}  // namespace
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant__ rr_route_params P) {
+    __shared__ double stage_all[8][16 * RR_BLOCK];
+    constexpr bool HAS_LAT = (MODE == RR_MODE_RAPID);
+    const int lane = threadIdx.x & 31;
+    double *stage = stage_all[threadIdx.x >> 5];
+    int m, b, j, dep_lo, dep_hi;
+    while (next_ticket(P, lane, m, b, j, dep_lo, dep_hi)) {
+        dctx c;
+        const int64_t i = (int64_t)b * RR_BLOCK + lane;
+        const bool valid = i < P.n;
+        const int64_t ic = valid ? i : P.n - 1;
+        c.m = m; c.b = b; c.j = j; c.lane = lane; c.i = i; c.valid = valid;
+        c.c1 = __ldg(P.c1 + ic); c.c2 = __ldg(P.c2 + ic); c.c3 = __ldg(P.c3 + ic);
+        c.c4 = HAS_LAT ? __ldg(P.c4 + ic) : 0.0;
+        const int e0 = __ldg(P.up_ptr + ic);
+        c.deg = valid ? __ldg(P.up_ptr + ic + 1) - e0 : 0;
+        const rr_blk_meta M = P.meta[b];
+        c.narrow = (M.int_mask & RR_META_NARROW) != 0;
+        const int t0 = j * P.tile_rows;
+        c.TT = min(P.tile_rows, P.T - t0);
+        c.dep_blk = dep_lo + lane < dep_hi ? __ldg(P.dep_idx + dep_lo + lane) : -1;
+#pragma unroll
+        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) c.up_u[k] = k < c.deg ? __ldg(P.up_idx + e0 + k) : 0;
+        c.done = P.done + (size_t)m * P.n_blocks;
+        c.lat0 = HAS_LAT ? tile_of(P.lateral[m], P, j, i) : nullptr;
+        c.out0 = const_cast<double *>(tile_of(P.out[m], P, j, i));
+        // ---- dependencies: own previous tile complete; upstream blocks complete, or (narrow levels with at most 32
+        //      upstream blocks) their first group published ----
+        const int32_t full_want = (j + 1) * P.gpt;
+        if (lane == 0 && j > 0) wait_ge(c.done + b, j * P.gpt);
+        c.prog = false;
+        if (c.narrow && dep_hi - dep_lo <= 32 && dep_hi > dep_lo) {
+            bool full = false;
+            wait_groups(c, j * P.gpt + 1, full_want, full);
+            c.prog = !full;
+        } else {
+            if (c.dep_blk >= 0) wait_ge(c.done + c.dep_blk, full_want);
+            for (int e = dep_lo + 32 + lane; e < dep_hi; e += 32) wait_ge(c.done + __ldg(P.dep_idx + e), full_want);
+        }
+        __syncwarp();
+        c.q = 0.0;
+        if (valid) c.q = (j == 0) ? P.q_init[i] : P.q_state[m][i];
+        switch (M.max_deg) {
+            case 0: direct_item<MODE, 0>(P, c, stage); break;
+            case 1: direct_item<MODE, 1>(P, c, stage); break;
+            case 2: direct_item<MODE, 2>(P, c, stage); break;
+            default: direct_item_wide<MODE>(P, c, stage, M.max_deg); break;
+        }
+        __syncwarp();
+        if (lane == 0) st_release(c.done + b, full_want);
+        __syncwarp();
+    }
+}
+
+cudaError_t rr_launch_direct(int mode, const rr_route_params &P, int grid, cudaStream_t stream) {
+    switch (mode) {
+        case RR_MODE_MUSKINGUM: rr_direct_kernel<RR_MODE_MUSKINGUM><<<grid, 256, 0, stream>>>(P); break;
+        case RR_MODE_RAPID: rr_direct_kernel<RR_MODE_RAPID><<<grid, 256, 0, stream>>>(P); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+int rr_direct_occupancy(int mode) {
+    int nb = 0;
+    cudaError_t e = mode == RR_MODE_MUSKINGUM
+                        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM>, 256, 0)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID>, 256, 0);
+    return e == cudaSuccess ? nb : -1;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// stage_in / stage_out
+// -----------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ int64_t tile_index(int64_t t, int64_t k, int64_t tile_rows, int64_t pitch, int64_t n_blocks) {
+    const int64_t j = t / tile_rows, r = t - j * tile_rows;
+    return ((j * n_blocks + (k >> 5)) * RR_BLOCK + (k & 31)) * pitch + r;
+}
+
+// One thread per river segment of the caller's array (coalesced reads of the caller's rows), 16 rows per iteration:
+// every store is one whole 128-byte line of the segment's series.  Segments whose working index is below hw_cut are
+// headwaters in whole-headwater blocks: their recursion q' = c3*q + c4_dt*ql (_numba_kernels.py:68-69 with no
+// upstream terms) runs here and their RAW discharge series goes to the discharge tiles instead.
+// ST = float: lateral inflows stored as float32 (qlateral files may be; the reference upcasts them with
+// astype(float64), TransformMuskingum.py:36 -- the conversion is exact, so doing it here changes no bit).
+template <bool ROUTE_HW, typename ST>
+__global__ void __launch_bounds__(256) stage_in_kernel(const ST *__restrict__ src, int64_t lds, double *__restrict__ lat_w,
+                                                       double *__restrict__ out_w, const int32_t *__restrict__ inv, int64_t n,
+                                                       int64_t T, int64_t tile_rows, int64_t pitch, int64_t n_blocks,
+                                                       int64_t hw_cut, const double *__restrict__ c3, const double *__restrict__ c4,
+                                                       const double *__restrict__ q_init, double *__restrict__ q_final,
+                                                       int64_t rows_per_slice) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t k = __ldg(inv + i);
+    const bool hw = ROUTE_HW && k < hw_cut;
+    // plain copies split time over grid.y; with headwater routing every thread walks the whole call (a headwater's rows
+    // are a recursion, and letting its neighbours take other slices would read each sector of the caller's rows twice)
+    const int64_t ta = (int64_t)blockIdx.y * rows_per_slice, tb = min(T, ta + rows_per_slice);
+    double q = 0.0, a3 = 0.0, a4 = 0.0;
+    if (hw) { q = q_init[k]; a3 = __ldg(c3 + k); a4 = __ldg(c4 + k); }
+    double *dst = hw ? out_w : lat_w;
+    for (int64_t t0 = ta; t0 < tb; t0 += 16) {
+        double v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = (t0 + r < T) ? (double)__ldg(src + (t0 + r) * lds + i) : 0.0;
+        if (hw) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (t0 + r < T) { q = fma(a4, v[r], a3 * q); v[r] = q; }
+        }
+        double *p = dst + tile_index(t0, k, tile_rows, pitch, n_blocks);
+#pragma unroll
+        for (int r = 0; r < 16; r += 4) st_sector(p + r, v[r], v[r + 1], v[r + 2], v[r + 3]);
+    }
+    if (hw) q_final[k] = q;
+}
+
+// working discharge tiles -> caller's rows: column s of the output shows segment subset[s] (or s); clamp as the
+// reference does on the interval mean (K == 1: the value itself); OT = float rounds like numpy's astype(float32)
+template <typename OT>
+__global__ void __launch_bounds__(256) stage_out_kernel(const double *__restrict__ out_w, OT *__restrict__ dst, int64_t ldd,
+                                                        const int32_t *__restrict__ inv, const int32_t *__restrict__ subset,
+                                                        int64_t n_out, int64_t T, int64_t tile_rows, int64_t pitch,
+                                                        int64_t n_blocks) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_out) return;
+    const int64_t i = subset ? (int64_t)__ldg(subset + s) : s;
+    const int64_t k = __ldg(inv + i);
+    const int64_t t0 = (int64_t)blockIdx.y * 16;
+    const double *p = out_w + tile_index(t0, k, tile_rows, pitch, n_blocks);
+    double v[16];
+#pragma unroll
+    for (int r = 0; r < 16; r += 4) {
+        const d4 x = ld_sector_ro(p + r);
+        v[r] = x.a; v[r + 1] = x.b; v[r + 2] = x.c; v[r + 3] = x.d;
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+        if (t0 + r < T) {
+            const double val = v[r] > 0.0 ? v[r] : 0.0;              // _numba_kernels.py:44-46 / :82-84
+            dst[(t0 + r) * ldd + s] = (OT)val;
+        }
+}
+
+}  // namespace
+
+#define CKD(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            rr_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+            return 200;                                                                            \
+        }                                                                                          \
+    } while (0)
+
+// tile_rows must be a multiple of 16 (the caller checks).  hw_cut = 0 copies every segment's lateral inflows.
+int rr_stage_in(const void *src, int src_f32, int64_t lds, double *lat_w, double *out_w, const int32_t *inv, int64_t n, int64_t T,
+                int64_t tile_rows, int64_t n_blocks, int64_t hw_cut, const double *c3, const double *c4,
+                const double *q_init, double *q_final, int sm_count, cudaStream_t stream) {
+    const int64_t pitch = (tile_rows + 3) & ~(int64_t)3;
+    const unsigned gx = (unsigned)((n + 255) / 256);
+    // enough slices to fill the machine a few times over, each a whole number of 16-row groups
+    int64_t slices = std::max<int64_t>(1, std::min<int64_t>((T + 15) / 16, ((int64_t)sm_count * 8 * 4 + gx - 1) / gx));
+    if (hw_cut > 0) slices = 1;
+    int64_t rows_per_slice = (((T + slices - 1) / slices + 15) / 16) * 16;
+    slices = (T + rows_per_slice - 1) / rows_per_slice;
+    dim3 grid(gx, (unsigned)slices);
+#define STAGE_IN(HW, ST) stage_in_kernel<HW, ST><<<grid, 256, 0, stream>>>((const ST *)src, lds, lat_w, out_w, inv, n, T, tile_rows, \
+                                                                          pitch, n_blocks, hw_cut, c3, c4, q_init, q_final, rows_per_slice)
+    if (hw_cut > 0) { if (src_f32) STAGE_IN(true, float); else STAGE_IN(true, double); }
+    else { if (src_f32) STAGE_IN(false, float); else STAGE_IN(false, double); }
+#undef STAGE_IN
+    CKD(cudaGetLastError());
+    rr_count_launch(1);
+    return 0;
+}
+
+int rr_stage_out(const double *out_w, void *dst, int dst_f32, int64_t ldd, const int32_t *inv, const int32_t *subset,
+                 int64_t n_out, int64_t T, int64_t tile_rows, int64_t n_blocks, cudaStream_t stream) {
+    const int64_t pitch = (tile_rows + 3) & ~(int64_t)3;
+    dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)((T + 15) / 16));
+    if (dst_f32)
+        stage_out_kernel<float><<<grid, 256, 0, stream>>>(out_w, (float *)dst, ldd, inv, subset, n_out, T, tile_rows, pitch, n_blocks);
+    else
+        stage_out_kernel<double><<<grid, 256, 0, stream>>>(out_w, (double *)dst, ldd, inv, subset, n_out, T, tile_rows, pitch, n_blocks);
+    CKD(cudaGetLastError());
+    rr_count_launch(1);
+    return 0;
+}

@@ -9,6 +9,11 @@
 #define RR_BLOCK 32          // reaches per block == lanes per warp
 #define RR_MAX_FAST_DEG 4    // upstream slots held in registers by the kernel
 #define RR_SLOT_HW_BIT 0x40000000  // external slot: upstream reach is a headwater (in-degree 0)
+#define RR_META_FAST 0x40    // rr_blk_meta::int_mask: no in-block edges, in-degree <= RR_MAX_FAST_DEG
+#define RR_META_NARROW 0x20  // rr_blk_meta::int_mask: fewer than RR_NARROW_BLOCKS blocks in the block's level -- launches are
+                             // dependency-latency bound there: such blocks publish and consume progress per 16-row group
+#define RR_NARROW_BLOCKS 4096
+#define RR_FLAG_ROWS 16      // direct kernel: rows per progress unit of done[] (one 128-byte line of a reach's series)
 
 void rr_set_error(const std::string &msg);
 
@@ -17,7 +22,8 @@ struct rr_blk_meta {
     uint16_t max_deg;     // largest in-degree of a lane
     uint8_t max_skew;     // largest systolic delay in the block
     uint8_t int_mask;     // bit k (k < RR_MAX_FAST_DEG): some lane's k-th upstream is in-block;
-                          // bit 7: some lane has an in-block upstream at slot >= RR_MAX_FAST_DEG
+                          // bit 7: some lane has an in-block upstream at slot >= RR_MAX_FAST_DEG;
+                          // bit 6 (0x40): fast-path eligible; bit 5 (0x20): the block's level is narrow
     int32_t level;        // level in the block dependency DAG
 };
 
@@ -25,9 +31,13 @@ struct rr_device_state;  // defined in rr_api.cu
 
 struct rr_plan {
     int64_t n = 0, n_edges = 0, n_blocks = 0, n_export = 0, n_internal = 0, n_outlets = 0;
+    int64_t n_work = 0;              // working slots: n, or more when a renumbered plan pads every level to whole blocks
+    int64_t lvl0_slots = 0;          // renumbered plans: slots of level 0 (whole blocks of headwaters and padding); else 0
+    int64_t n_hw = 0;                // reaches without upstream (level 0)
+    bool all_fast = false;           // every block is fast-path eligible (RR_META_FAST)
     rr_plan_opts opts{};
-    std::vector<int32_t> down;       // [n] downstream reach in the WORKING order (user order unless renumbered)
-    std::vector<int32_t> perm, inv;  // renumbered plans: perm[working] = user index, inv[user] = working index
+    std::vector<int32_t> down;       // [n_work] downstream slot in the WORKING order (user order unless renumbered)
+    std::vector<int32_t> perm, inv;  // renumbered plans: perm[working slot] = user index (-1: padding), inv[user] = slot
     int32_t reach_depth = 0;         // longest upstream-to-outlet path, in reaches
     bool auto_tile = true;           // choose the tile length per call (opts.time_tile is then the largest one)
     std::vector<int32_t> up_ptr;     // [n+1]
@@ -67,8 +77,11 @@ struct rr_schedule {
 // rings fit `budget_rows` rows).
 void rr_build_schedule(const rr_plan &p, int64_t n_tiles, int32_t delta, int64_t budget_rows, rr_schedule &s);
 void rr_build_rings(const rr_plan &p, int32_t delta, int64_t budget_rows, rr_schedule &s);
-void rr_build_keys(const rr_plan &p, int64_t n_tiles, rr_schedule &s);
-void rr_build_items(const rr_plan &p, int64_t n_tiles, const rr_schedule &s, std::vector<int32_t> &items);  // [n_items][4] block, tile, dep range
+// first_block > 0 leaves blocks [0, first_block) out of the schedule (whole-headwater blocks of a level-sorted plan that
+// the staging kernel routes; they are level-0 blocks)
+void rr_build_keys(const rr_plan &p, int64_t n_tiles, rr_schedule &s, int64_t first_block = 0);
+void rr_build_items(const rr_plan &p, int64_t n_tiles, const rr_schedule &s, std::vector<int32_t> &items,
+                    int64_t first_block = 0);  // [n_items][4] block, tile, dep range
 // Host mirror of the kernel's ticket decode.
 void rr_decode_ticket(const rr_plan &p, const rr_schedule &s, int64_t n_tiles, int64_t ticket,
                       int32_t *block, int32_t *tile);

@@ -92,7 +92,7 @@ extern "C" int rr_downstream_index(int64_t n, const int64_t *river_ids, const in
 // Builds every derived structure of the plan from p->down (the working order; p->inv maps user ->
 // working index when the plan is renumbered).
 static int build_structures(rr_plan *p) {
-    const int64_t n = p->n;
+    const int64_t n = p->n_work;   // working slots (padding slots are isolated reaches: no upstream, no downstream)
     const int32_t *down = p->down.data();
     const int64_t nb = p->n_blocks;
     p->n_edges = p->n_export = p->n_internal = p->n_outlets = 0;
@@ -101,20 +101,24 @@ static int build_structures(rr_plan *p) {
     // upstream-CSR: counting sort by downstream index keeps upstream indices ascending per row
     p->up_ptr.assign(n + 1, 0);
     for (int64_t i = 0; i < n; ++i)
-        if (down[i] >= 0) { p->up_ptr[down[i] + 1]++; p->n_edges++; } else p->n_outlets++;
+        if (down[i] >= 0) { p->up_ptr[down[i] + 1]++; p->n_edges++; } else if (p->perm.empty() || p->perm[i] >= 0) p->n_outlets++;
     for (int64_t i = 0; i < n; ++i) p->up_ptr[i + 1] += p->up_ptr[i];
     p->up_idx.resize(p->n_edges);
     {
         // rows are filled in ascending USER index so that every confluence sums its inflows in the
         // reference's order even when the plan works on renumbered reaches
         std::vector<int32_t> fill(p->up_ptr.begin(), p->up_ptr.end() - 1);
-        for (int64_t u = 0; u < n; ++u) {
+        for (int64_t u = 0; u < p->n; ++u) {
             const int64_t i = p->inv.empty() ? u : p->inv[u];
             if (down[i] >= 0) p->up_idx[fill[down[i]]++] = (int32_t)i;
         }
     }
     p->is_hw.resize(n);
-    for (int64_t i = 0; i < n; ++i) p->is_hw[i] = p->up_ptr[i + 1] == p->up_ptr[i];
+    p->n_hw = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        p->is_hw[i] = p->up_ptr[i + 1] == p->up_ptr[i];
+        if (p->is_hw[i] && (p->perm.empty() || p->perm[i] >= 0)) p->n_hw++;
+    }
 
     // in-block systolic delays: every in-block edge gets lag exactly 1
     //   height[i] = longest in-block chain ending at i; roots (reaches whose downstream is in
@@ -172,7 +176,7 @@ static int build_structures(rr_plan *p) {
         int32_t lvl = 0;
         for (int32_t ub : tmp) lvl = std::max(lvl, p->meta[ub].level + 1);
         m.level = lvl;
-        if (m.int_mask == 0 && m.max_skew == 0 && m.max_deg <= RR_MAX_FAST_DEG) m.int_mask |= 0x40;  // fast-path eligible
+        if (m.int_mask == 0 && m.max_skew == 0 && m.max_deg <= RR_MAX_FAST_DEG) m.int_mask |= RR_META_FAST;  // fast-path eligible
         p->dep_idx.insert(p->dep_idx.end(), tmp.begin(), tmp.end());
         p->dep_ptr[b + 1] = (int32_t)p->dep_idx.size();
         p->max_level = std::max(p->max_level, lvl);
@@ -197,6 +201,12 @@ static int build_structures(rr_plan *p) {
         std::vector<int32_t> fill(p->lvl_ptr.begin(), p->lvl_ptr.end() - 1);
         for (int64_t b = 0; b < nb; ++b) p->lvl_blk[fill[p->blk_level[b]]++] = (int32_t)b;
     }
+    p->all_fast = true;
+    for (int64_t b = 0; b < nb; ++b) {
+        rr_blk_meta &m = p->meta[b];
+        if (!(m.int_mask & RR_META_FAST)) p->all_fast = false;
+        if (p->lvl_ptr[m.level + 1] - p->lvl_ptr[m.level] < RR_NARROW_BLOCKS) m.int_mask |= RR_META_NARROW;
+    }
     return 0;
 }
 
@@ -219,6 +229,7 @@ extern "C" int rr_plan_create(int64_t n, const int32_t *down, const rr_plan_opts
     if (p->opts.raw_budget_bytes <= 0) p->opts.raw_budget_bytes = 16ll << 30;
     if (!opts || opts->device < 0) p->opts.device = -1;
     p->n = n;
+    p->n_work = n;
     p->n_blocks = (n + RR_BLOCK - 1) / RR_BLOCK;
     p->down.assign(down, down + n);
     // topological level of every reach (0 = headwater) in the user's order
@@ -246,18 +257,29 @@ extern "C" int rr_plan_create(int64_t n, const int32_t *down, const rr_plan_opts
             (p->max_level > 2 * (int64_t)depth + 16 || fast_blocks * 10 < p->n_blocks * 9)) renumber = true;
     }
     if (renumber) {
-        // working order = stable sort by level: perm[k] = user index of working reach k
-        std::vector<int64_t> start(depth + 1, 0);
-        for (int64_t i = 0; i < n; ++i) start[lvl[i] + 1]++;
-        for (int32_t l = 0; l < depth; ++l) start[l + 1] += start[l];
-        p->perm.resize(n);
+        // working order = stable sort by level, every level padded to whole 32-slot blocks: a block then holds reaches
+        // of ONE level, which never connect, so no block has in-block edges and all of them run the register-blocked
+        // fast path (deep levels with a handful of reaches each used to share blocks, chained inside them, and fell
+        // back to the systolic path).  Padding slots are isolated dummy reaches (perm = -1, coefficients 0); at most
+        // 31 per level.  perm[k] = user index of working slot k
+        std::vector<int64_t> count(depth + 1, 0), start(depth + 1, 0);
+        for (int64_t i = 0; i < n; ++i) count[lvl[i]]++;
+        int64_t off = 0;
+        for (int32_t l = 0; l < depth; ++l) { start[l] = off; off += (count[l] + RR_BLOCK - 1) / RR_BLOCK * RR_BLOCK; }
+        if (off > 0x7ffffff0ll) { rr_set_error("reach count must be in [1, 2^31)"); delete p; return 100; }
+        p->n_work = off;
+        p->lvl0_slots = depth > 1 ? start[1] : off;
+        p->n_blocks = off / RR_BLOCK;
+        p->perm.assign(off, -1);
         p->inv.resize(n);
         for (int64_t i = 0; i < n; ++i) {
             const int64_t k = start[lvl[i]]++;
             p->perm[k] = (int32_t)i;
             p->inv[i] = (int32_t)k;
         }
-        for (int64_t k = 0; k < n; ++k) {
+        p->down.assign(off, -1);
+        for (int64_t k = 0; k < off; ++k) {
+            if (p->perm[k] < 0) continue;
             const int32_t d = down[p->perm[k]];
             p->down[k] = d >= 0 ? p->inv[d] : -1;
         }
@@ -290,6 +312,11 @@ extern "C" int rr_plan_get_info(const rr_plan *p, rr_plan_info *info) {
     info->device_bytes = 0;
     info->renumbered = p->perm.empty() ? 0 : 1;
     info->reach_depth = p->reach_depth;
+    info->all_fast = p->all_fast ? 1 : 0;
+    info->narrow_blocks = 0;
+    for (const rr_blk_meta &m : p->meta) info->narrow_blocks += (m.int_mask & RR_META_NARROW) ? 1 : 0;
+    info->n_headwaters = p->n_hw;
+    info->n_work = p->n_work;
     return 0;
 }
 
@@ -297,13 +324,13 @@ extern "C" int rr_plan_set_coefficients(rr_plan *p, const double *c1, const doub
                                         const double *c4_dt) {
     if (!p || !c1 || !c2 || !c3) { rr_set_error("null argument"); return 100; }
     auto put = [&](std::vector<double> &dst, const double *src) {
-        dst.resize(p->n);
+        dst.resize(p->n_work);
         if (p->perm.empty()) std::copy(src, src + p->n, dst.begin());
-        else for (int64_t k = 0; k < p->n; ++k) dst[k] = src[p->perm[k]];
+        else for (int64_t k = 0; k < p->n_work; ++k) dst[k] = p->perm[k] >= 0 ? src[p->perm[k]] : 0.0;
     };
     put(p->c1, c1); put(p->c2, c2); put(p->c3, c3);
     p->have_c4 = c4_dt != nullptr;
-    if (c4_dt) put(p->c4, c4_dt); else p->c4.assign(p->n, 0.0);
+    if (c4_dt) put(p->c4, c4_dt); else p->c4.assign(p->n_work, 0.0);
     p->coeff_version++;
     return 0;
 }
@@ -371,29 +398,40 @@ void rr_build_rings(const rr_plan &p, int32_t delta, int64_t budget_rows, rr_sch
 }
 
 // Ticket keys for a call of n_tiles tiles (small: max_level + n_tiles * delta entries).
-void rr_build_keys(const rr_plan &p, int64_t n_tiles, rr_schedule &s) {
+// blocks of level l that take part in the schedule (all of them, or without the leading first_block level-0 blocks)
+static inline int64_t level_count(const rr_plan &p, int32_t l, int64_t first_block) {
+    const int64_t c = p.lvl_ptr[l + 1] - p.lvl_ptr[l];
+    return l == 0 ? c - first_block : c;
+}
+
+void rr_build_keys(const rr_plan &p, int64_t n_tiles, rr_schedule &s, int64_t first_block) {
     s.n_keys = (int64_t)p.max_level + (n_tiles - 1) * (int64_t)s.delta + 1;
     s.key_start.assign(s.n_keys + 1, 0);
     for (int64_t j = 0; j < n_tiles; ++j)
         for (int32_t l = 0; l <= p.max_level; ++l)
-            s.key_start[l + j * s.delta + 1] += p.lvl_ptr[l + 1] - p.lvl_ptr[l];
+            s.key_start[l + j * s.delta + 1] += level_count(p, l, first_block);
     for (int64_t k = 0; k < s.n_keys; ++k) s.key_start[k + 1] += s.key_start[k];
     s.n_items = s.key_start[s.n_keys];
 }
 
-// Ticket table: {block, tile, dep_ptr[block], dep_ptr[block + 1]} of every ticket in ticket order -- keys ascending, within a key tiles ascending,
+// Ticket table: {block, tile, dep_ptr[block], dep_ptr[block + 1]} of every ticket in ticket order -- keys ascending, within a key tiles descending,
 // within a (key, tile) the blocks of that level in (level, id) order.  One 16-byte load decodes a ticket on the
 // device (the search over key_start that rr_decode_ticket does costs a dozen dependent loads per work item).
-void rr_build_items(const rr_plan &p, int64_t n_tiles, const rr_schedule &s, std::vector<int32_t> &items) {
+void rr_build_items(const rr_plan &p, int64_t n_tiles, const rr_schedule &s, std::vector<int32_t> &items, int64_t first_block) {
     items.resize(4 * (size_t)s.n_items);
     size_t t = 0;
     for (int64_t key = 0; key < s.n_keys; ++key) {
-        int64_t j = key > p.max_level ? (key - p.max_level + s.delta - 1) / s.delta : 0;
+        const int64_t jlo = key > p.max_level ? (key - p.max_level + s.delta - 1) / s.delta : 0;
         const int64_t jhi = std::min<int64_t>(n_tiles - 1, key / s.delta);
-        for (; j <= jhi; ++j) {
+        // newest tile (lowest level) first: an item's producers -- the upstream blocks of the same tile and its own
+        // previous tile, all in the previous key -- then sit about one whole key of tickets behind it.  (Oldest tile
+        // first put the level-1 items of a key right behind their level-0 producers at the end of the previous key: on
+        // networks with few blocks per level the consumers were drawn while the producers still ran.)
+        for (int64_t j = jhi; j >= jlo; --j) {
             const int64_t l = key - j * s.delta;
             for (int32_t r = p.lvl_ptr[l]; r < p.lvl_ptr[l + 1]; ++r) {
                 const int32_t blk = p.lvl_blk[r];
+                if (blk < first_block) continue;   // lvl_blk is sorted by (level, id): these are level-0 blocks
                 items[4 * t] = blk;
                 items[4 * t + 1] = (int32_t)j;
                 items[4 * t + 2] = p.dep_ptr[blk];        // the block's upstream-block list, so that the kernel can
@@ -417,9 +455,9 @@ void rr_decode_ticket(const rr_plan &p, const rr_schedule &s, int64_t n_tiles, i
         if (s.key_start[mid] <= ticket) lo = mid; else hi = mid;
     }
     int64_t r = ticket - s.key_start[lo];
-    int64_t j = lo > p.max_level ? (lo - p.max_level + s.delta - 1) / s.delta : 0;
+    const int64_t jlo = lo > p.max_level ? (lo - p.max_level + s.delta - 1) / s.delta : 0;
     const int64_t jhi = std::min<int64_t>(n_tiles - 1, lo / s.delta);
-    for (; j <= jhi; ++j) {
+    for (int64_t j = jhi; j >= jlo; --j) {
         const int64_t l = lo - j * s.delta;
         const int64_t w = p.lvl_ptr[l + 1] - p.lvl_ptr[l];
         if (r < w) { *block = p.lvl_blk[p.lvl_ptr[l] + r]; *tile = (int32_t)j; return; }

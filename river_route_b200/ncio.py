@@ -29,7 +29,7 @@ def backend() -> str:
         return 'scipy'
 
 
-def open_nc(path, mode: str = 'r'):
+def open_nc(path, mode: str = 'r', mmap: bool = False):
     """Open (or create, ``mode='w'``) a netCDF file.  New files are NETCDF4 with netCDF4 installed (as the reference
     writes them, Muskingum.py:337), else 64-bit-offset classic files."""
     path = str(path)
@@ -40,7 +40,7 @@ def open_nc(path, mode: str = 'r'):
     if mode == 'w':
         return netcdf_file(path, mode='w', version=2)
     try:
-        return netcdf_file(path, mode='r', mmap=False, maskandscale=True)
+        return netcdf_file(path, mode='r', mmap=bool(mmap), maskandscale=True)
     except TypeError as e:
         raise ImportError(f'{path} is not a classic netCDF-3 file; reading NETCDF4/HDF5 files needs the netCDF4 '
                           f'package') from e

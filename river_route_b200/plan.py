@@ -83,7 +83,7 @@ class Plan:
         self.n = int(down.shape[0])
         self.down = down
         opts = _lib.PlanOpts(int(time_tile), int(tile_stride), int(device), int(threads_per_cta), int(raw_budget_bytes),
-                             self.RENUMBER[renumber], {'auto': 0, 'registers': 1, 'registers-tiled': 2, 'tma': 3, 'out-reach-major': 4, 'lateral-grouped': 5, 'direct': 6}[staging])
+                             self.RENUMBER[renumber], {'auto': 0, 'registers': 1, 'registers-tiled': 2, 'tma': 3, 'out-reach-major': 4, 'lateral-grouped': 5, 'direct': 6, 'direct-nohw': 7}[staging])
         handle = C.c_void_p()
         check(lib.rr_plan_create(self.n, _lib.as_i32p(down), C.byref(opts), C.byref(handle)))
         self._h = handle
@@ -149,21 +149,27 @@ class Plan:
             raise ValueError('resample must be a positive integer')
         T = out.shape[0] * resample
         ldo = _lib.rows_ld(out)
-        p_lat, ldl = None, self.n
+        p_lat, ldl, lat_f32 = None, self.n, False
         if mode != MODE_MUSKINGUM:
             if lateral.ndim != 2 or lateral.shape[1] != self.n or lateral.shape[0] != T:
                 raise ValueError(f'lateral inflow shape {lateral.shape} does not match (T, n) = {(T, self.n)}')
-            if lateral.dtype != np.float64 or (self.n > 1 and lateral.strides[1] != 8):
+            if lateral.dtype == np.float32 and (self.n == 1 or lateral.strides[1] == 4):
+                lat_f32 = True       # crosses PCIe as stored, upcast (exactly) on the device: rr_route_host_typed
+            elif lateral.dtype != np.float64 or (self.n > 1 and lateral.strides[1] != 8):
                 # the reference's grid path hands over an F-ordered transposed view (runoff.py:298)
                 lateral = np.ascontiguousarray(lateral, dtype=np.float64)
             ldl = _lib.rows_ld(lateral)
-            p_lat = _lib.as_f64p(lateral)
+            p_lat = lateral.ctypes.data_as(_lib.c_f64p)
         p_qf = None
         if q_full is not None:
             if q_full.dtype != np.float64 or not q_full.flags.c_contiguous or q_full.shape != (self.n,):
                 raise ValueError('q_full must be a contiguous float64 vector with one value per river segment')
             p_qf = _lib.as_f64p(q_full)
-        if out.dtype == np.float64 and resample == 1 and self.n_out == self.n:
+        if lat_f32:
+            check(lib.rr_route_host_typed(self._h, int(mode), _lib.as_f64p(q_state), p_qf, C.cast(p_lat, C.c_void_p), 1, ldl,
+                                          out.ctypes.data_as(C.c_void_p), ldo, T, int(substeps),
+                                          int(out.dtype == np.float32), resample))
+        elif out.dtype == np.float64 and resample == 1 and self.n_out == self.n:
             check(lib.rr_route_host(self._h, int(mode), _lib.as_f64p(q_state), p_qf, p_lat, ldl, _lib.as_f64p(out),
                                     ldo, T, int(substeps)))
         else:
@@ -233,20 +239,25 @@ class Plan:
         inf = self.info
         ptrs = [_lib.c_i32p(), _lib.c_i32p(), _lib.c_u8p()] + [_lib.c_i32p() for _ in range(7)]
         check(lib.rr_plan_get_arrays(self._h, *[C.byref(p) for p in ptrs]))
-        n, e, nb, nd = inf['n'], inf['n_edges'], inf['n_blocks'], inf['n_dep_edges']
+        n, e, nb, nd = inf['n_work'], inf['n_edges'], inf['n_blocks'], inf['n_dep_edges']   # working slots (see 'perm')
         sizes = [n + 1, e, n, e, n, nb, nb + 1, nd, inf['n_export'], n if inf['renumbered'] else 0]
         names = ['up_ptr', 'up_idx', 'skew', 'slot_src', 'export_id', 'blk_level', 'dep_ptr', 'dep_idx', 'exp_span',
                  'perm']
         out = {}
         for name, p, sz in zip(names, ptrs, sizes):
             out[name] = np.ctypeslib.as_array(p, shape=(sz,)).copy() if sz > 0 else np.zeros(0, dtype=np.int32)
-        # downstream index in the WORKING order (== self.down unless the plan is renumbered)
+        # downstream slot in the WORKING order (== self.down unless the plan is renumbered).  A renumbered plan pads
+        # every level to whole blocks: perm[slot] is the user index of the slot, -1 for padding
         if inf['renumbered']:
             perm = out['perm']
-            inv = np.empty(n, dtype=np.int64)
-            inv[perm] = np.arange(n)
-            d = self.down[perm]
-            out['down'] = np.where(d >= 0, inv[np.where(d >= 0, d, 0)], -1).astype(np.int32)
+            real = perm >= 0
+            inv = np.empty(self.n, dtype=np.int64)
+            inv[perm[real]] = np.flatnonzero(real)
+            d = self.down[perm[real]]
+            down_w = np.full(n, -1, dtype=np.int32)
+            down_w[real] = np.where(d >= 0, inv[np.where(d >= 0, d, 0)], -1)
+            out['down'] = down_w
+            out['inv'] = inv
         else:
             out['perm'] = None
             out['down'] = self.down

@@ -149,6 +149,9 @@ class Muskingum:
             raw = dataclasses.asdict(configs)
             if raw.get('discharge_dir'):
                 raw['discharge_files'] = []      # derived from discharge_dir by Configs itself; passing both is an error
+        # _shard: a river_route_b200.distributed.Shard -- this process routes only the drainage basins packed to its rank
+        # (one process per GPU under torchrun; see distributed.py).  Not a config key.
+        self._shard = kwargs.pop('_shard', None)
         raw.update(kwargs)
         raw.pop('_router', None)
         self.cfg = configs if isinstance(configs, Configs) and not kwargs else Configs(**raw)
@@ -184,12 +187,25 @@ class Muskingum:
             self.logger.warning('channel_state_init_file not provided. Defaulting to zero initial conditions')
             self.channel_state = np.zeros(self.n, dtype=np.float64)
             return
-        self.channel_state = pd.read_parquet(self.cfg.channel_state_init_file).values.flatten() \
-            .astype(np.float64, copy=False)
+        self.channel_state = self._mine(pd.read_parquet(self.cfg.channel_state_init_file).values.flatten()
+                                        .astype(np.float64, copy=False))
 
     def _write_final_state(self):
         if self.cfg.channel_state_final_file:
-            pd.DataFrame({'Q': self.channel_state}).to_parquet(self.cfg.channel_state_final_file)
+            state = self._gathered(self.channel_state)
+            if state is not None:
+                pd.DataFrame({'Q': state}).to_parquet(self.cfg.channel_state_final_file)
+
+    # ---------------- basin sharding (river_route_b200.distributed) ----------------
+    def _mine(self, full, axis=-1):
+        """This rank's river segments of an array over all segments of the params file."""
+        return full if self._shard is None else self._shard.take(full, axis=axis)
+
+    def _gathered(self, local):
+        """Per-segment vector or (T, segments) array of this rank -> params-file order on rank 0, None elsewhere."""
+        if self._shard is None:
+            return local
+        return self._shard.gather_vector(local) if local.ndim == 1 else self._shard.gather_columns(local)
 
     # ---------------- network ----------------
     def _set_network_dependent_vectors(self):
@@ -200,11 +216,20 @@ class Muskingum:
         self.x = df['x'].to_numpy(dtype=np.float64, copy=False)
         # duplicate ids, unknown downstream ids and topological order raise the reference's ValueErrors
         down = downstream_index(self.river_ids, df['downstream_river_id'].to_numpy(dtype=np.int64, copy=False))
+        self.river_ids_all = self.river_ids            # what the output files list: every segment of the params file
+        device = -1
+        if self._shard is not None:
+            # whole drainage basins only, original relative order kept: confluences sum in the reference's order
+            idx, down = self._shard.split(down)
+            self.river_ids, self.k, self.x = self.river_ids[idx], np.ascontiguousarray(self.k[idx]), np.ascontiguousarray(self.x[idx])
+            device = self._shard.device_index
+            if self._output_river_ids is not None:
+                raise ValueError('set_output_rivers is not available in basin-sharded runs')
         self.n = int(self.river_ids.shape[0])
         if self.plan is None or not np.array_equal(down, getattr(self, 'down', None)):
             # a new plan has no coefficients yet: forget the cached time signature so that the next file sets them
             # (the reference keeps c1..c3 and its CSC arrays on self, so a second route() just works there)
-            self.plan = Plan(down)
+            self.plan = Plan(down, device=device)
             self._network_time_signature = None
             self._detach_transform()
         self.down = down
@@ -349,27 +374,20 @@ class Muskingum:
         return self
 
     def _write(self, dates, q_array, q_file, routed_file=''):
-        (self._writer or self._write_discharges)(dates, q_array, q_file, routed_file)
+        q_array = self._gathered(q_array)              # sharded runs: all segments, params-file order, on rank 0
+        if q_array is not None:
+            (self._writer or self._write_discharges)(dates, q_array, q_file, routed_file)
 
     def _write_discharges(self, dates, q_array, q_file, routed_file=''):
         """The reference's netCDF layout (Muskingum.py:337-351): time f8, river id i4, Q f4 (time, river_id)."""
-        from . import ncio
-        with ncio.open_nc(q_file, 'w') as ds:
-            ds.createDimension('time', q_array.shape[0])
-            ds.createDimension(self.cfg.var_river_id, q_array.shape[1])
-            ds.runoff_file = str(routed_file)
-            tv = ds.createVariable('time', 'f8', ('time',))
-            tv.units = f'seconds since {pd.Timestamp(dates[0]).strftime("%Y-%m-%d %H:%M:%S")}'
-            tv[:] = (dates - dates[0]).astype('timedelta64[s]').astype(np.int64)
-            iv = ds.createVariable(self.cfg.var_river_id, 'i4', (self.cfg.var_river_id,))
-            ids = self.river_ids if getattr(self, '_output_idx', None) is None else self.river_ids[self._output_idx]
-            iv[:] = ids.astype(np.int32)
-            qv = ds.createVariable(self.cfg.var_discharge, 'f4', ('time', self.cfg.var_river_id))
-            qv[:] = q_array
-            qv.long_name = 'Discharge at catchment outlet'
-            qv.standard_name = 'discharge'
-            qv.aggregation_method = 'mean'
-            qv.units = 'm3 s-1'
+        with self._open_discharge_file(dates, q_array.shape[1], q_file, routed_file) as out:
+            out.write_rows(0, q_array)
+
+    def _open_discharge_file(self, dates, n_cols, q_file, routed_file=''):
+        """The same file, opened for writing row slabs as they come back from the GPU (streamed runs)."""
+        ids = getattr(self, 'river_ids_all', self.river_ids) if getattr(self, '_output_idx', None) is None \
+            else self.river_ids[self._output_idx]
+        return _DischargeFile(q_file, dates, ids, n_cols, self.cfg.var_river_id, self.cfg.var_discharge, routed_file)
 
 
 class TransformMuskingum(Muskingum):
@@ -449,6 +467,9 @@ class TransformMuskingum(Muskingum):
         """
         self._ensemble_member_states = []
         device_tail = _is_stock(self, '_router', TransformMuskingum)
+        if (device_tail and self.cfg.qlateral_files and _is_stock(self, '_qlateral_generator', TransformMuskingum)
+                and _is_stock(self, '_route_lateral', TransformMuskingum, UnitMuskingum)):
+            return self._execute_routing_streamed()
         fused_grid = (device_tail and not self.cfg.qlateral_files and self.cfg.grid_runoff_files
                       and self.cfg.grid_weights_file and _is_stock(self, '_qlateral_generator', TransformMuskingum))
         files = self._gathered_runoff_generator() if fused_grid else self._qlateral_generator()
@@ -459,6 +480,8 @@ class TransformMuskingum(Muskingum):
             self.logger.info(f'Routing qlateral: {runoff_file}')
             self._set_network_and_time_dependent_vectors(dates)
             k = self.num_runoff_steps_per_discharge if self.dt_discharge > self.dt_runoff else 1
+            if kind != ['runoff']:
+                data = self._mine(data, axis=1)         # lateral inflows of this rank's segments
             if device_tail:
                 q32 = np.empty((self.num_runoff_steps // k, self._n_out), dtype=np.float32)
                 q_t = self._route_runoff(data, q32, k) if kind == ['runoff'] else self._route_lateral(data, q32, k)
@@ -477,6 +500,127 @@ class TransformMuskingum(Muskingum):
             self._write(dates, q32, discharge_file, runoff_file)
         if self.cfg.runoff_processing_mode == 'ensemble':
             self.channel_state = np.array(self._ensemble_member_states).mean(axis=0)   # :145-146
+
+    # ---------------- qlateral files, streamed: file slab -> pinned buffer -> GPU -> pinned buffer -> file slab --------
+    def _execute_routing_streamed(self):
+        """
+        The per-file loop of TransformMuskingum.py:108-148 for ``qlateral_files`` without ever holding a (T, n) array of
+        a file on the host: row slabs are read into page-locked buffers in the dtype they are stored in (a float32
+        variable crosses PCIe as float32 and is upcast on the device -- the same bits as ``astype(float64)``, :36),
+        routed with the channel state chained on the way, and the float32 rows the writer gets (:146) land in page-locked
+        buffers and are written slab by slab.  A reader and a writer thread keep the next and the previous slab moving
+        while the GPU works on the current one.  An injected writer (``set_write_discharges``) still receives one whole
+        array per file, as its protocol says.
+        """
+        from concurrent.futures import ThreadPoolExecutor
+        pairs = list(zip(self.cfg.qlateral_files, self.cfg.discharge_files))
+        if self.cfg.progress_bar:
+            from tqdm import tqdm
+            pairs = tqdm(pairs, total=len(pairs), desc='Files Routed')
+        with ThreadPoolExecutor(max_workers=2) as pool:
+            for lateral_file, discharge_file in pairs:
+                self.logger.info(f'Routing qlateral: {lateral_file}')
+                with _LateralFile(lateral_file) as src:
+                    dates = src.dates
+                    self._set_network_and_time_dependent_vectors(dates)
+                    n_all = int(getattr(self, 'river_ids_all', self.river_ids).shape[0])
+                    self._check_lateral_shape(src.shape, n_all)
+                    q_t = self._route_file_in_slabs(src, dates, lateral_file, discharge_file, pool)
+                if self.cfg.runoff_processing_mode == 'sequential':
+                    self.channel_state = q_t
+                else:                                                        # every member starts from the same state
+                    self._ensemble_member_states.append(q_t.copy())
+        if self.cfg.runoff_processing_mode == 'ensemble':
+            self.channel_state = np.array(self._ensemble_member_states).mean(axis=0)   # :145-146
+
+    def _slab_rows(self, T, k, row_bytes):
+        """Rows per slab: about RR_ROUTER_SLAB_BYTES (2 GiB) of lateral inflows, whole 16-row groups of the device
+        pipeline and whole dt_discharge intervals."""
+        if os.environ.get('RR_ROUTER_SLAB_ROWS'):
+            rows = int(os.environ['RR_ROUTER_SLAB_ROWS'])
+        else:
+            rows = int(float(os.environ.get('RR_ROUTER_SLAB_BYTES', 2 << 30)) // max(row_bytes, 1))
+        unit = int(np.lcm(16, k))
+        rows = max(unit, rows // unit * unit)
+        return T if rows >= T else rows
+
+    def _pinned(self, key, shape, dtype):
+        """Page-locked scratch array, kept (and grown) across slabs and files: pinning costs ~0.3 s per GB."""
+        from ._lib import pinned_empty
+        pool = self.__dict__.setdefault('_pinned_pool', {})
+        need = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        buf = pool.get(key)
+        if buf is None or buf.nbytes < need:
+            buf = pool[key] = pinned_empty((max(need, 1),), np.uint8)
+        return buf[:need].view(dtype).reshape(shape)
+
+    def _route_file_in_slabs(self, src, dates, lateral_file, discharge_file, pool):
+        T, n = self.num_runoff_steps, self.n
+        k = self.num_runoff_steps_per_discharge if self.dt_discharge > self.dt_runoff else 1
+        dates_out = dates[::k] if k > 1 else dates
+        slab = self._slab_rows(T, k, src.shape[1] * src.dtype.itemsize)
+        starts = list(range(0, T, slab))
+        sharded = self._shard is not None and self._shard.world > 1
+        lat_bufs = [self._pinned(('lat', b), (slab, n), src.dtype) for b in range(2)]
+        out_bufs = [self._pinned(('out', b), (slab // k, self._n_out), np.float32) for b in range(2)]
+        wide = np.empty((slab, src.shape[1]), dtype=src.dtype) if sharded else None   # full rows before this rank's columns are taken
+
+        def read(s):
+            t0, t1 = starts[s], min(T, starts[s] + slab)
+            if sharded:
+                src.read(t0, t1, wide)
+                np.take(wide[:t1 - t0], self._shard.idx, axis=1, out=lat_bufs[s % 2][:t1 - t0])
+                return lat_bufs[s % 2][:t1 - t0]
+            return src.read(t0, t1, lat_bufs[s % 2])
+
+        whole = None                                   # an injected writer gets the file's whole array
+        out_file = None
+        if self._writer is not None:
+            whole = np.empty((T // k, self._n_out), dtype=np.float32)
+        elif not sharded or self._shard.is_root:
+            n_cols = self._n_out if not sharded else int(self.river_ids_all.shape[0])
+            out_file = self._open_discharge_file(dates_out, n_cols, discharge_file, lateral_file)
+
+        def write(s, rows):
+            r0 = starts[s] // k
+            if whole is not None:
+                whole[r0:r0 + rows.shape[0]] = rows
+                return
+            rows = self._gathered(rows)                # sharded: all segments in params-file order on rank 0
+            if out_file is not None:
+                out_file.write_rows(r0, rows)
+
+        q_t = self.channel_state.astype(np.float64, copy=True)
+        try:
+            nxt = pool.submit(read, 0)
+            pending = [None, None]
+            for s in range(len(starts)):
+                lat = nxt.result()
+                if s + 1 < len(starts):
+                    nxt = pool.submit(read, s + 1)
+                if pending[s % 2] is not None:
+                    pending[s % 2].result()            # this output buffer has been written
+                out = out_bufs[s % 2][:lat.shape[0] // k]
+                self._route_rows(lat, out, k, q_t, s == 0, s == len(starts) - 1)
+                # collectives of a sharded run stay on the calling thread (one communicator, ordered calls)
+                if sharded:
+                    write(s, out)
+                else:
+                    pending[s % 2] = pool.submit(write, s, out)
+            for f in pending:
+                if f is not None:
+                    f.result()
+        finally:
+            if out_file is not None:
+                out_file.close()
+        if whole is not None:
+            self._write(dates_out, whole, discharge_file, lateral_file)
+        return q_t
+
+    def _route_rows(self, qlateral, out, resample, q_t, first=True, last=True):
+        """One slab of a file's lateral inflows -> ``out``; the channel state ``q_t`` is read and updated in place
+        (``first`` / ``last``: the slab opens / closes the file)."""
+        self.plan.route_host(self._mode, q_t, qlateral, out, self.num_routing_steps_per_runoff, resample=resample)
 
     def _check_lateral_shape(self, shape, width):
         if tuple(shape) != (self.num_runoff_steps, width):
@@ -521,8 +665,12 @@ class TransformMuskingum(Muskingum):
         indptr, indices, data, cx, cy, rivers, area = build_weight_csr(
             tb['river_id'], tb['x_index'], tb['y_index'], tb['proportion'], tb['area_sqm'], factor)
         # the reference assumes this order (runoff.py:265) and would silently route the wrong catchments otherwise
-        if rivers.shape[0] != self.n or not np.array_equal(np.asarray(rivers).astype(np.int64), self.river_ids):
+        if rivers.shape[0] != self.river_ids_all.shape[0] or \
+                not np.array_equal(np.asarray(rivers).astype(np.int64), self.river_ids_all):
             raise ValueError('grid_weights_file must list the river segments of params_file in the same order')
+        if self._shard is not None:                     # this rank's rows of the weight matrix; every cell column stays
+            indptr, indices, data = _csr_rows(indptr, indices, data, self._shard.idx)
+            area = self._mine(np.asarray(area))
         n_points = len(cx)
         if flat_shape is not None:
             ny, nx = flat_shape
@@ -588,6 +736,16 @@ class TransformMuskingum(Muskingum):
         return q_t, discharge_array
 
 
+def _csr_rows(indptr, indices, data, rows):
+    """Rows ``rows`` (ascending) of a CSR matrix, entry order within a row unchanged."""
+    counts = np.diff(indptr)[rows]
+    new_ptr = np.zeros(rows.shape[0] + 1, dtype=np.int32)
+    np.cumsum(counts, out=new_ptr[1:])
+    pos = np.arange(int(new_ptr[-1]), dtype=np.int64) - np.repeat(new_ptr[:-1].astype(np.int64), counts) \
+        + np.repeat(indptr[rows].astype(np.int64), counts)
+    return new_ptr, np.ascontiguousarray(indices[pos]), np.ascontiguousarray(data[pos])
+
+
 def _is_stock(obj, name, *owners) -> bool:
     """True when ``obj.<name>`` is still the implementation of one of ``owners`` (not overridden by a subclass or
     patched on the instance): only then may the host-visible fp64 intermediate be skipped."""
@@ -617,6 +775,9 @@ class UnitMuskingum(TransformMuskingum):
             self._uh = UnitHydrograph(self.cfg.uh_kernel_file)
             if self.cfg.uh_state_init_file:
                 self._uh.set_state(self.cfg.uh_state_init_file)
+            if self._shard is not None:                 # this rank's basins of the (n_kernel_steps, n_basins) arrays
+                self._uh.kernel = self._mine(self._uh.kernel, axis=1)
+                self._uh.state = self._mine(self._uh.state, axis=1)
         if not hasattr(self, 'hw_idx'):
             incoming = np.bincount(self.down[self.down >= 0], minlength=self.n)
             self.hw_idx = np.where(incoming == 0)[0]
@@ -637,6 +798,22 @@ class UnitMuskingum(TransformMuskingum):
             self._attach_unit_hydrograph()
         return super()._route_lateral(convolved, out, resample)
 
+    def _route_rows(self, qlateral, out, resample, q_t, first=True, last=True):
+        self._sync_uh_state()
+        convolved = self._uh.convolve(qlateral)     # UnitMuskingum.py:75; the carry-over state chains the slabs
+        if self._transform is not None and self._transform.n_ks:
+            self._attach_unit_hydrograph()
+        # Inside a file q_ch and q_full are two vectors (q_full = q_ch + lateral, _numba_kernels.py:165); they become
+        # one only where the reference recombines them, at the end of a file (UnitMuskingum.py:94-98).  Slabs of one file
+        # therefore chain the kernel-level pair (q_t is q_ch), and only the last slab recombines.
+        if first:
+            self._q_full = q_t.copy()               # :78-79  q_ch = q_full = channel_state
+        self.plan.route_host(self._mode, q_t, convolved, out, self.num_routing_steps_per_runoff, q_full=self._q_full,
+                             resample=resample)
+        if last:
+            q_t[self.inner_idx] = self._q_full[self.inner_idx]
+            q_t[self.hw_idx] = convolved[-1][self.hw_idx]
+
     def _attach_unit_hydrograph(self):
         # the carry-over state moves to the device and stays there between files (UnitHydrograph.py:100-105)
         self._transform.set_unit_hydrograph(self._uh.kernel, self._uh.state)
@@ -653,7 +830,92 @@ class UnitMuskingum(TransformMuskingum):
         self._sync_uh_state()
         super()._write_final_state()
         if self.cfg.uh_state_final_file and self._uh is not None:
-            self._uh.write_state(self.cfg.uh_state_final_file)
+            state = self._gathered(self._uh.state)
+            if state is not None:
+                pd.DataFrame(state.T).to_parquet(self.cfg.uh_state_final_file)   # UnitHydrograph.write_state layout
+
+
+class _DischargeFile:
+    """Discharge netCDF with the reference's layout (Muskingum.py:337-351), written in row slabs."""
+
+    def __init__(self, path, dates, river_ids, n_cols, var_river_id, var_discharge, routed_file=''):
+        from . import ncio
+        self.ds = ncio.open_nc(path, 'w')
+        ds = self.ds
+        ds.createDimension('time', len(dates))
+        ds.createDimension(var_river_id, n_cols)
+        ds.runoff_file = str(routed_file)
+        tv = ds.createVariable('time', 'f8', ('time',))
+        tv.units = f'seconds since {pd.Timestamp(dates[0]).strftime("%Y-%m-%d %H:%M:%S")}'
+        tv[:] = (dates - dates[0]).astype('timedelta64[s]').astype(np.int64)
+        iv = ds.createVariable(var_river_id, 'i4', (var_river_id,))
+        iv[:] = np.asarray(river_ids).astype(np.int32)
+        qv = ds.createVariable(var_discharge, 'f4', ('time', var_river_id))
+        qv.long_name = 'Discharge at catchment outlet'
+        qv.standard_name = 'discharge'
+        qv.aggregation_method = 'mean'
+        qv.units = 'm3 s-1'
+        self.qv = qv
+
+    def write_rows(self, t0, rows):
+        self.qv[t0:t0 + rows.shape[0], :] = rows
+
+    def close(self):
+        if self.ds is not None:
+            self.ds.close()
+            self.ds = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class _LateralFile:
+    """qlateral netCDF -- variable ``qlateral(time, river_id)``, docs/references/io-file-schema.md:52-55 -- opened for
+    reading row slabs straight into (pinned) buffers, in the dtype it is stored in when that is float32 / float64."""
+
+    def __init__(self, path):
+        from . import ncio
+        self.ds = ncio.open_nc(path, mmap=True)
+        tv = self.ds.variables['time']
+        self.dates = ncio.decode_time(ncio.read_array(tv), ncio.attrs_of(tv).get('units', ''))
+        self.var = self.ds.variables['qlateral']
+        self.time_major = tuple(self.var.dimensions)[0] == 'time'
+        shape = tuple(int(x) for x in self.var.shape)
+        self.shape = shape if self.time_major else shape[::-1]
+        kind = np.dtype(self.var.dtype if hasattr(self.var, 'dtype') else self.var.data.dtype)
+        self.dtype = np.dtype(np.float32) if (kind.kind == 'f' and kind.itemsize == 4) else np.dtype(np.float64)
+        self._whole = None
+
+    def read(self, t0, t1, out):
+        """rows [t0, t1) -> out[:t1 - t0] (masked entries become NaN like the reference's xarray read)."""
+        if self.time_major:
+            a = self.var[t0:t1]
+        else:
+            if self._whole is None:
+                self._whole = np.asarray(self.var[:]).T
+            a = self._whole[t0:t1]
+        if isinstance(a, np.ma.MaskedArray):
+            a = a.filled(np.nan)
+        out[:t1 - t0] = a
+        return out[:t1 - t0]
+
+    def close(self):
+        self._whole = self.var = None
+        if self.ds is not None:
+            try:
+                self.ds.close()
+            except Exception:
+                pass
+            self.ds = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 def _read_qlateral(path):

@@ -27,14 +27,22 @@ def emulate(plan, mode, c1, c2, c3, c4, q0, lat, T, K, tile_substeps=32, delta=1
     n = plan.n
     perm = a['perm']
     if perm is not None:
-        # renumbered plan: run in the working order, hand results back in the caller's order
-        inv = np.empty(n, dtype=np.int64)
-        inv[perm] = np.arange(n)
-        c1, c2, c3 = c1[perm], c2[perm], c3[perm]
-        c4 = None if c4 is None else c4[perm]
-        q0 = np.asarray(q0)[perm]
-        lat = None if lat is None else np.ascontiguousarray(lat[:, perm])
-        qfull0 = None if qfull0 is None else np.asarray(qfull0)[perm]
+        # renumbered plan: run in the working order (every level padded to whole blocks; padding slots are isolated
+        # dummy reaches with zero coefficients), hand results back in the caller's order
+        inv = a['inv']
+        n = perm.shape[0]
+
+        def spread(v, rows=False):
+            if v is None:
+                return None
+            v = np.asarray(v, dtype=np.float64)
+            w = np.zeros(((v.shape[0], n) if rows else (n,)))
+            w[..., inv] = v
+            return w
+        c1, c2, c3, c4 = spread(c1), spread(c2), spread(c3), spread(c4)
+        q0 = spread(q0)
+        lat = spread(lat, rows=True)
+        qfull0 = spread(qfull0)
     nb = (n + B - 1) // B
     rows_tile = max(1, min(T, tile_substeps // K))
     n_tiles = (T + rows_tile - 1) // rows_tile

@@ -98,13 +98,15 @@ SYNTH = [
     (15000, 1, 0.5, 2000, 50, 3600, 3600, dict(time_tile=8)),    # deep main stem, short tiles
     (9000, 9, 0.2, 0, 33, 3600, 1800, dict(time_tile=16, tile_stride=1)),
     (9000, 9, 0.2, 0, 33, 3600, 1800, dict(time_tile=4, raw_budget_bytes=1 << 20)),   # tiny exchange budget -> deep rings off
+    (15000, 1, 0.5, 2000, 150, 3600, 3600, dict(time_tile=32)),  # deep main stem: narrow levels consume upstream tiles group by group
+    (300000, 20, 0.5, 0, 100, 3600, 3600, {}),                   # wide and narrow levels; headwater blocks routed by the staging kernel
     (31, 1, 0.5, 0, 5, 3600, 3600, {}),                          # a single partial block
     (1, 1, 0.5, 0, 3, 3600, 3600, {}),                           # one reach
 ]
 
 
-@pytest.mark.parametrize('renumber', ['never', 'always', 'always-registers', 'always-tma', 'always-lateral-grouped',
-                                      'always-direct'])
+@pytest.mark.parametrize('renumber', ['never', 'always', 'always-registers', 'always-registers-tiled', 'always-tma',
+                                      'always-lateral-grouped', 'always-direct', 'always-direct-nohw'])
 @pytest.mark.parametrize('n,nbas,bias,stem,T,dt_runoff,dt_routing,opts', SYNTH)
 def test_rapid_and_muskingum_vs_oracle(n, nbas, bias, stem, T, dt_runoff, dt_routing, opts, renumber):
     # 'always': level-sorted working order (register-blocked path on tile-major working arrays); '-registers':

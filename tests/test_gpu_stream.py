@@ -284,3 +284,38 @@ def test_direct_exchange_staging_matches_default(rows, chunk_rows):
     for x, y in zip(res['registers-tiled'], res['direct']):
         assert np.array_equal(x, y)
     assert (res['direct'][1] >= 0).all() and (res['direct'][1] == 0).any()      # clamp applied by the permutation
+
+
+@pytest.mark.parametrize('staging', ['auto', 'direct', 'registers-tiled'])
+@pytest.mark.parametrize('rows', [0, 16, 5])
+def test_float32_lateral_inflows_cross_pcie_as_stored(staging, rows, chunk_rows):
+    """rr_route_host_typed: a float32 qlateral array gives the very bits of routing its astype(float64) copy
+    (TransformMuskingum.py:36), whether the direct pipeline upcasts while staging or another path upcasts first; the
+    float32 output / output subset written straight from the working tiles equals the two-pass result."""
+    n, T = 40000 + 7, 56
+    down, a = _network(n, 6, 13, 3600, 3600)
+    plan = rr.Plan(down, renumber='always', staging=staging)
+    plan.set_coefficients(a['c1'], a['c2'], a['c3'], a['c4_dt'])
+    ql32 = synth.lateral_volumes(T, n, 8).astype(np.float32)
+    q0 = np.random.default_rng(4).uniform(0, 40, n)
+    chunk_rows(0)
+    q_ref, ref = q0.copy(), np.empty((T, n))
+    plan.route_host(rr.MODE_RAPID, q_ref, ql32.astype(np.float64), ref, 1)
+    chunk_rows(rows)
+    q, out = q0.copy(), np.full((T, n), np.nan)
+    plan.route_host(rr.MODE_RAPID, q, ql32, out, 1)
+    assert np.array_equal(out, ref) and np.array_equal(q, q_ref)
+    q, out32 = q0.copy(), np.full((T, n), np.nan, dtype=np.float32)
+    plan.route_host(rr.MODE_RAPID, q, ql32, out32, 1)
+    assert np.array_equal(out32, ref.astype(np.float32)) and np.array_equal(q, q_ref)
+    pick = np.array([n - 1, 0, 777, 0, 31999], dtype=np.int32)
+    plan.set_output_subset(pick)
+    q, sub = q0.copy(), np.full((T, pick.shape[0]), np.nan, dtype=np.float32)
+    plan.route_host(rr.MODE_RAPID, q, ql32, sub, 1)
+    assert np.array_equal(sub, ref.astype(np.float32)[:, pick]) and np.array_equal(q, q_ref)
+    plan.set_output_subset(None)
+    # and against the CPU oracle
+    q_o, ref_o = q0.copy(), np.zeros((T, n))
+    oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q_o, ql32.astype(np.float64), ref_o, 1)
+    assert parity_error(ref, ref_o) < TOL and parity_error(q_ref, q_o) < TOL
+    plan.close()

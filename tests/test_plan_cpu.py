@@ -114,12 +114,25 @@ def test_plan_structures(name, renumber):
         down = a['down']
         assert inf['renumbered'] == (renumber == 'always') and inf['reach_depth'] == synth.depth(user_down)
         perm = a['perm'] if a['perm'] is not None else np.arange(n)
-        assert np.array_equal(np.sort(perm), np.arange(n))
+        real = perm >= 0                                                      # renumbered plans pad levels to whole blocks
+        assert np.array_equal(np.sort(perm[real]), np.arange(n)) and perm.shape[0] == inf['n_work']
         assert np.all(down[down >= 0] > np.flatnonzero(down >= 0))          # working order is topological too
+        assert np.all(down[~real] < 0)                                        # padding slots are isolated
         # upstream-CSR lists each reach's upstreams in ascending USER index (the reference's summation order)
-        for i in range(n):
+        for i in range(perm.shape[0]):
             ups = a['up_idx'][a['up_ptr'][i]:a['up_ptr'][i + 1]]
-            assert np.array_equal(perm[ups], np.flatnonzero(user_down == perm[i])), label
+            want = np.flatnonzero(user_down == perm[i]) if real[i] else np.zeros(0, dtype=np.int64)
+            assert np.array_equal(perm[ups], want), label
+        if renumber == 'always':
+            # one level per block: no in-block edges, every block on the register-blocked path, DAG depth = network depth
+            lv = synth.levels(user_down)
+            for b in range(inf['n_blocks']):
+                members = perm[b * 32:(b + 1) * 32]
+                assert len(set(lv[members[members >= 0]].tolist())) <= 1, label
+            assert inf['n_internal_edges'] == 0 and inf['all_fast'] == 1 and inf['max_skew'] == 0
+            assert inf['max_block_level'] == inf['reach_depth'] - 1
+            assert inf['n_work'] - n < 32 * inf['reach_depth'] and inf['n_headwaters'] == int((lv == 0).sum())
+        n = perm.shape[0]
         blk = np.arange(n) // 32
         has = down >= 0
         internal = has & (blk == np.where(has, down, 0) // 32)

@@ -16,105 +16,14 @@ import river_route_b200 as rr
 from river_route_b200 import ncio, plan as plan_mod, routers, transforms
 from oracle import oracle
 from tests.helpers import network_arrays, parity_error
+from tests import fakes
 from tests.test_routers_gpu import Capture, _grid_case, _oracle_grid_chain
-
-
-class FakeTransform:
-    """Same constructor / methods as transforms.Transform; keeps everything on the host."""
-
-    def __init__(self, indptr, indices, data, n_points, area=None, device=-1):
-        self.indptr, self.indices, self.data = np.asarray(indptr), np.asarray(indices), np.asarray(data)
-        self.n_rivers, self.n_points, self.area = len(indptr) - 1, int(n_points), area
-        self.n_ks, self.kernel, self.state = 0, None, None
-        assert self.indices.max(initial=-1) < self.n_points
-
-    def set_unit_hydrograph(self, kernel, state=None):
-        self.kernel = np.array(kernel, dtype=np.float64)
-        self.state = np.zeros_like(self.kernel) if state is None else np.array(state, dtype=np.float64)
-        self.n_ks = self.kernel.shape[0]
-        return self
-
-    def uh_state(self):
-        return self.state.copy()
-
-    def close(self):
-        pass
-
-
-def _finish(plan, full, out, resample):
-    """The output tail the library applies on the device: subset columns, mean over `resample` rows, cast."""
-    sub = getattr(plan, '_fake_subset', None)
-    if sub is not None:
-        full = full[:, sub]
-    if resample > 1:
-        full = full.reshape(full.shape[0] // resample, resample, full.shape[1]).mean(axis=1)
-    out[...] = full.astype(out.dtype)
-
-
-def _route(plan, mode, q_state, lateral, T, substeps):
-    a = plan._fake_arrays
-    full = np.zeros((T, plan.n))
-    if mode == rr.MODE_RAPID:
-        oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q_state, lateral, full, substeps)
-    elif mode == rr.MODE_MUSKINGUM:
-        oracle.muskingum_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], q_state, full, T, substeps)
-    else:
-        sp = oracle.unit_split(plan.down.astype(np.int64))
-        inner, hw, ai, ah = sp['inner_idx'], sp['hw_idx'], sp['a_inner'], sp['a_hw']
-        c1i, c2i, c3i = a['c1'][inner], a['c2'][inner], a['c3'][inner]
-        q_ch = q_state[inner].copy()
-        q_full = q_ch.copy()
-        oracle.unit_route(ai[0], ai[1], -c1i[ai[1]], ai[0], ai[1], ai[2], ah[0], ah[1], ah[2], c1i, c2i, c3i, hw, inner,
-                          q_ch, q_full, lateral, full, substeps)
-        q_state[hw] = lateral[-1][hw]
-        q_state[inner] = q_full
-    return full
 
 
 @pytest.fixture
 def host_only(monkeypatch):
-    """Oracle-backed stand-ins for the three device entry points the routers use."""
-    def set_coefficients(self, c1, c2, c3, c4_dt=None):
-        indptr, indices = oracle.csc_from_down(self.down)
-        self._fake_arrays = dict(indptr=indptr, indices=indices, c1=np.array(c1), c2=np.array(c2), c3=np.array(c3),
-                                 c4_dt=None if c4_dt is None else np.array(c4_dt), lhs_off=oracle.lhs_off_data(np.array(c1), indices))
-
-    def set_output_subset(self, indices=None):
-        idx = None if indices is None or len(indices) == 0 else np.asarray(indices, dtype=np.int64)
-        assert idx is None or (idx.min() >= 0 and idx.max() < self.n)
-        self._fake_subset = idx
-        self.n_out = self.n if idx is None else int(idx.shape[0])
-
-    def route_host(self, mode, q_state, lateral, out, substeps, q_full=None, resample=1):
-        assert out.shape[1] == self.n_out and out.dtype in (np.float32, np.float64) and q_state.shape == (self.n,)
-        T = out.shape[0] * resample
-        assert mode == rr.MODE_MUSKINGUM or lateral.shape == (T, self.n)
-        _finish(self, _route(self, mode, q_state, None if lateral is None else np.ascontiguousarray(lateral, dtype=np.float64),
-                             T, substeps), out, resample)
-
-    def runoff_route_host(self, transform, mode, q_state, runoff, out, substeps, cumulative=False, force_positive=False,
-                          as_volumes=False, resample=1):
-        T = out.shape[0] * resample
-        assert runoff.shape == (T, transform.n_points) and out.shape[1] == self.n_out
-        unit = mode == rr.MODE_UNIT
-        ql = oracle.weights_transform(transform.indptr, transform.indices, transform.data, runoff, cumulative=cumulative,
-                                      force_positive=force_positive, area=transform.area if (as_volumes and not unit) else None)
-        if unit:
-            ql = oracle.uh_convolve(ql, transform.kernel, transform.state)
-        _finish(self, _route(self, mode, q_state, ql, T, substeps), out, resample)
-
-    monkeypatch.setattr(plan_mod.Plan, 'set_coefficients', set_coefficients)
-    monkeypatch.setattr(plan_mod.Plan, 'set_output_subset', set_output_subset)
-    monkeypatch.setattr(plan_mod.Plan, 'route_host', route_host)
-    monkeypatch.setattr(plan_mod.Plan, 'runoff_route_host', runoff_route_host)
-    monkeypatch.setattr(transforms, 'Transform', FakeTransform)
-    monkeypatch.setattr(transforms, 'uh_convolve', lambda lat, ker, st: oracle.uh_convolve(np.ascontiguousarray(lat), ker, st))
-    monkeypatch.setattr('river_route_b200.uhkernels.uh_convolve', lambda lat, ker, st: oracle.uh_convolve(np.ascontiguousarray(lat), ker, st))
-    monkeypatch.setattr(transforms, 'weights_transform',
-                        lambda indptr, indices, data, raw, cumulative=False, force_positive=False, area=None, keep_nan=False:
-                        oracle.weights_transform(indptr, indices, data, raw, cumulative=cumulative, force_positive=force_positive,
-                                                 area=area, keep_nan=keep_nan))
-    monkeypatch.setattr('river_route_b200.runoff.weights_transform', transforms.weights_transform)
+    """Oracle-backed stand-ins for the device entry points the routers use (tests/fakes.py)."""
+    fakes.install(monkeypatch.setattr)
 
 
 @pytest.mark.parametrize('cumulative,units,dims', [(False, 'm', ('time', 'lat', 'lon')), (True, 'mm', ('time', 'lat', 'lon')),
@@ -283,3 +192,85 @@ def test_route_twice_and_configs_instance(tmp_path, host_only):
     qm, refm = np.zeros(m), np.zeros((T, m))
     oracle.rapid_route(am['indptr'], am['indices'], am['lhs_off'], am['c2'], am['c3'], am['c4_dt'], qm, ql[:, :m].copy(), refm, 1)
     assert np.array_equal(cap.calls[2][1], refm.astype(np.float32))
+
+
+@pytest.mark.parametrize('router,f32,k,injected', [('rapid', False, 1, False), ('rapid', True, 2, False), ('rapid', True, 1, True),
+                                                   ('unit', False, 2, False)])
+def test_qlateral_files_streamed_in_slabs(tmp_path, host_only, monkeypatch, router, f32, k, injected):
+    """Slab streaming (16-row slabs over 40-row files: 16 + 16 + 8) writes exactly what one whole-file call computes:
+    float32 qlateral variables are routed as stored, dt_discharge resampling falls on slab boundaries, the channel
+    state and the UH carry-over chain through slabs and files, and an injected writer still gets one array per file."""
+    from river_route_b200.runoff import QlateralDataset
+    from river_route_b200 import synth
+    monkeypatch.setenv('RR_ROUTER_SLAB_ROWS', '16')
+    n, T = 260, 40
+    down = synth.forest(n, 3, seed=8, depth_bias=0.6)
+    kk, x = synth.muskingum_params(n, 8)
+    ids = np.arange(n, dtype=np.int64) + 100
+    params = str(tmp_path / 'p.parquet')
+    pd.DataFrame({'river_id': ids, 'downstream_river_id': np.where(down >= 0, ids[np.where(down >= 0, down, 0)], -1),
+                  'k': kk, 'x': x}).to_parquet(params)
+    files, laterals = [], []
+    for f in range(2):
+        ql = synth.lateral_volumes(T, n, 50 + f) * (1.0 if router == 'rapid' else 1e-7)
+        if f32:
+            ql = ql.astype(np.float32)
+        t = (np.datetime64('2022-01-01') + (np.arange(T) + f * T) * np.timedelta64(1, 'h')).astype('datetime64[s]')
+        ds = QlateralDataset(ql, ids, t, 'm3')
+        ds.to_netcdf(str(tmp_path / f'ql_{f}.nc'))
+        if f32:                                          # store the variable as float32
+            with ncio.open_nc(str(tmp_path / f'ql_{f}.nc'), 'w') as nc:
+                nc.createDimension('time', T)
+                nc.createDimension('river_id', n)
+                tv = nc.createVariable('time', 'f8', ('time',))
+                tv.units = 'seconds since 2022-01-01 00:00:00'
+                tv[:] = (np.arange(T) + f * T) * 3600.0
+                nc.createVariable('river_id', 'i4', ('river_id',))[:] = ids.astype(np.int32)
+                nc.createVariable('qlateral', 'f4', ('time', 'river_id'))[:] = ql
+        files.append(str(tmp_path / f'ql_{f}.nc'))
+        laterals.append(ql.astype(np.float64))
+    cfg = dict(params_file=params, qlateral_files=files, discharge_dir=str(tmp_path), dt_discharge=3600 * k, log=False)
+    cap = Capture()
+    if router == 'unit':
+        rng = np.random.default_rng(2)
+        ker = rng.uniform(0, 1, (5, n)) * (rng.random((5, n)) < 0.7)
+        scipy.sparse.save_npz(str(tmp_path / 'uh.npz'), scipy.sparse.csr_matrix(ker))
+        r = rr.UnitMuskingum(uh_kernel_file=str(tmp_path / 'uh.npz'), **cfg)
+    else:
+        r = rr.RapidMuskingum(**cfg)
+    if injected:
+        r.set_write_discharges(cap)
+    r.route()
+    a = network_arrays(down, kk, x, 3600, 3600)
+    q = np.zeros(n)
+    st = np.zeros((5, n))
+    for f, ql in enumerate(laterals):
+        ref = np.zeros((T, n))
+        if router == 'unit':
+            conv = oracle.uh_convolve(ql, ker, st)
+            sp = oracle.unit_split(down.astype(np.int64))
+            inner, hw, ai, ah = sp['inner_idx'], sp['hw_idx'], sp['a_inner'], sp['a_hw']
+            c1i, c2i, c3i = a['c1'][inner], a['c2'][inner], a['c3'][inner]
+            q_ch = q[inner].copy()
+            q_fu = q_ch.copy()
+            oracle.unit_route(ai[0], ai[1], -c1i[ai[1]], ai[0], ai[1], ai[2], ah[0], ah[1], ah[2], c1i, c2i, c3i, hw, inner,
+                              q_ch, q_fu, conv, ref, 1)
+            q[hw] = conv[-1][hw]
+            q[inner] = q_fu
+        else:
+            oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q, ql, ref, 1)
+        want = (ref.reshape(T // k, k, n).mean(axis=1) if k > 1 else ref).astype(np.float32)
+        if injected:
+            dates, got, q_file, routed = cap.calls[f]
+            assert got.shape == want.shape and dates.shape[0] == T // k and routed == files[f]
+        else:
+            with ncio.open_nc(tmp_path / f'discharge_ql_{f}.nc') as ds:
+                got = ncio.read_array(ds.variables['Q'])
+                assert ncio.read_array(ds.variables['time']).shape[0] == T // k
+        if router == 'unit':
+            # slab-wise UH convolution re-associates nothing (chunk-invariant by construction); the oracle's FFT-free
+            # direct sum is the same arithmetic
+            assert parity_error(got, want) < 1e-6
+        else:
+            assert np.array_equal(got, want), (f, router, f32, k)
+    assert parity_error(r.channel_state, q) < 1e-12

@@ -183,6 +183,16 @@ int rr_route_ensemble_dev(rr_plan *p, int mode, const double *q_init, int32_t n_
  * per-call cost model picks; bench.py's roofline arithmetic: coefficients and topology are read once per tile). */
 int64_t rr_plan_tile_rows(const rr_plan *p, int64_t T, int64_t substeps);
 
+/* Ensemble from host arrays (pinned for full PCIe rate): lateral[m] / out[m] are host pointers per member, float64 or
+ * float32 as flagged; time is cut into chunks, and the members of a chunk are routed by one launch.  q_init is the
+ * shared initial state [n] (ld_init = 0) or, for a later time slab of the same members, one state per member
+ * [n_members][ld_init]; q_final (optional, [n_members][ldq]) receives every member's final state and q_mean (optional,
+ * [n]) their mean, accumulated in member order and divided by the count exactly as np.array(states).mean(axis=0) does
+ * (TransformMuskingum.py:145-146).  out_f32 / resample as rr_route_host_ex.  RR_MODE_RAPID / RR_MODE_MUSKINGUM. */
+int rr_route_ensemble_host(rr_plan *p, int mode, const double *q_init, int64_t ld_init, int32_t n_members, const void *const *lateral,
+                           int lateral_f32, int64_t ldl, void *const *out, int64_t ldo, int out_f32, double *q_final,
+                           int64_t ldq, double *q_mean, int64_t T, int64_t substeps, int64_t resample);
+
 /* Kernel launches issued by this library on this thread since the last reset (bench.py's
  * gpu_launches claim). */
 int64_t rr_launch_count(int reset);

@@ -98,7 +98,7 @@ struct rr_device_state {
     // launch scratch
     int64_t sched_budget_rows = -1;
     rr_schedule sched;
-    struct key_table { int64_t n_tiles = -1, first_block = 0, n_items = 0; int32_t *dev = nullptr; size_t cap = 0; uint64_t used = 0; };   // ticket -> (block, tile)
+    struct key_table { int64_t n_tiles = -1, first_block = 0, n_items = 0; int32_t delta = 0; int32_t *dev = nullptr; size_t cap = 0; uint64_t used = 0; };   // ticket -> (block, tile)
     key_table keys[4];
     uint64_t key_clock = 0;
     double *raw = nullptr;
@@ -119,6 +119,8 @@ struct rr_device_state {
     double *s_lat = nullptr, *s_conv = nullptr, *s_route = nullptr;           // compute-stream scratch of one chunk
     size_t s_lat_cap = 0, s_conv_cap = 0, s_route_cap = 0;
     double *d_q = nullptr, *d_qfull = nullptr;
+    double *ens_q = nullptr;                                                   // ensemble calls: [q_init][mean][member states]
+    size_t ens_q_cap = 0;
     // renumbered plans: user -> working index and scratch in the working order
     int32_t *inv = nullptr;
     double *p_lat = nullptr, *p_out = nullptr, *p_q = nullptr;
@@ -194,7 +196,7 @@ void rr_device_release(rr_plan *p) {
     void *ptrs[] = {d->up_ptr, d->up_idx, d->slot_src, d->export_id, d->dep_ptr, d->dep_idx, d->down, d->exp_ro, d->edge_ro,
                     d->skew, d->meta, d->coef, d->raw, d->done, d->ticket, d->prof,
                     d->s_inb[0], d->s_inb[1], d->s_outb[0], d->s_outb[1], d->s_lat, d->s_conv, d->s_route, d->d_q, d->d_qfull,
-                    d->inv, d->p_lat, d->p_out, d->p_q, d->out_subset};
+                    d->inv, d->p_lat, d->p_out, d->p_q, d->out_subset, d->ens_q};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (auto &k : d->keys) if (k.dev) cudaFree(k.dev);
@@ -238,15 +240,19 @@ static int64_t tile_rows_for(const rr_plan *p, int64_t T, int64_t K) {
     return std::max<int64_t>(1, std::min<int64_t>(T, tile / K));
 }
 
+static bool pipeline_ok(const rr_plan *p, int mode, int64_t K);
 extern "C" int64_t rr_plan_tile_rows(const rr_plan *p, int64_t T, int64_t substeps) {
     if (!p || T <= 0 || substeps <= 0) return 0;
+    if (pipeline_ok(p, RR_MODE_RAPID, substeps))
+        return std::min<int64_t>(p->opts.time_tile / RR_FLAG_ROWS * RR_FLAG_ROWS, (T + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS * RR_FLAG_ROWS);
     return tile_rows_for(p, T, substeps);
 }
 
 static int launch_route(rr_plan *p, int mode, int n_members, const double *q_init, const double *const *lateral,
                         int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
                         int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream, int tile_major = 0,
-                        int out_layout = 0, int direct = 0, int64_t rows_in = 0, int64_t first_block = 0, int pipeline = 0) {
+                        int out_layout = 0, int direct = 0, int64_t rows_in = 0, int64_t first_block = 0, int pipeline = 0,
+                        int64_t q_init_stride = 0) {
     if (mode < 0 || mode > 2) { rr_set_error("unknown router mode"); return 100; }
     if (T <= 0 || K <= 0 || T > 0x7fffffff || K > 0x7fffffff) { rr_set_error("T and substeps must be positive"); return 100; }
     if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
@@ -286,14 +292,24 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     }
     // ticket keys per call length: a few tables are cached (the streaming path alternates between the
     // full chunk and the last, shorter one)
+    // Ticket-key distance between consecutive tiles of a block.  Ring-exchange launches take it from the ring sizing.
+    // The pipeline has no rings; its natural value is the number of levels a dependency chain advances while one block
+    // works through a tile: narrow levels pass results on every 16-row group, so one level costs about one group and a
+    // tile about gpt of them.  With that stride the fronts of all tiles in flight share a ticket key and fit the
+    // resident warps; with stride 1 they spread over 3 x n_tiles keys and most of them wait for a warp (C2: the 3000-level
+    // stem ran 23 tiles in batches of ~7).
+    const int32_t delta_use = pipeline ? (p->opts.tile_stride > 0 ? p->opts.tile_stride : (int32_t)((rows + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS))
+                                       : d->sched.delta;
     rr_device_state::key_table *kt = nullptr;
-    for (auto &k : d->keys) if (k.n_tiles == n_tiles && k.first_block == first_block) kt = &k;
+    for (auto &k : d->keys) if (k.n_tiles == n_tiles && k.first_block == first_block && k.delta == delta_use) kt = &k;
     if (!kt) {
         kt = &d->keys[0];
         for (auto &k : d->keys) if (k.used < kt->used) kt = &k;
-        rr_build_keys(*p, n_tiles, d->sched, first_block);
+        rr_schedule tmp;
+        tmp.delta = delta_use;
+        rr_build_keys(*p, n_tiles, tmp, first_block);
         std::vector<int32_t> items;
-        rr_build_items(*p, n_tiles, d->sched, items, first_block);
+        rr_build_items(*p, n_tiles, tmp, items, first_block);
         CK(cudaDeviceSynchronize());
         if (items.size() > kt->cap) {
             if (kt->dev) CK(cudaFree(kt->dev));
@@ -302,7 +318,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
             kt->cap = items.size();
         }
         CK(cudaMemcpy(kt->dev, items.data(), items.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        kt->n_tiles = n_tiles; kt->first_block = first_block; kt->n_items = d->sched.n_items;
+        kt->n_tiles = n_tiles; kt->first_block = first_block; kt->delta = delta_use; kt->n_items = tmp.n_items;
     }
     kt->used = ++d->key_clock;
     // one spare row: the kernel prefetches a few lines past the row it is reading
@@ -334,11 +350,11 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.exp_ro = d->exp_ro; P.edge_ro = d->edge_ro; P.raw_rows = d->sched.raw_rows;
     P.c1 = d->coef; P.c2 = d->coef + p->n_work; P.c3 = d->coef + 2 * p->n_work; P.c4 = d->coef + 3 * p->n_work;
     P.items = reinterpret_cast<const int4 *>(kt->dev); P.n_items = kt->n_items;
-    P.delta = d->sched.delta; P.n_tiles = (int32_t)n_tiles;
+    P.delta = delta_use; P.n_tiles = (int32_t)n_tiles;
     P.T = (int32_t)T; P.K = (int32_t)K; P.tile_rows = (int32_t)rows;
     P.raw_pitch = (int32_t)pitch; P.n_members = n_members; P.first_call = first_call; P.last_call = last_call;
     P.ldl = ldl; P.ldo = ldo;
-    P.raw = d->raw; P.done = d->done; P.ticket = d->ticket; P.prof = d->prof; P.q_init = q_init;
+    P.raw = d->raw; P.done = d->done; P.ticket = d->ticket; P.prof = d->prof; P.q_init = q_init; P.q_init_stride = q_init_stride;
     for (int m = 0; m < n_members; ++m) {
         P.lateral[m] = lateral ? lateral[m] : nullptr;
         P.out[m] = out[m];
@@ -357,6 +373,11 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.direct = direct;
     P.tile_pitch = (int32_t)((rows + 3) & ~(int64_t)3);
     P.gpt = (int32_t)((rows + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS);
+    // stress-test hooks (tests/test_gpu_stress.py): fewer persistent CTAs than the device holds, and pseudo-random delays
+    // around the flag operations -- any grid size and any timing must give the same bits
+    int64_t grid_cap = 0;
+    if (const char *env = getenv("RR_GRID_CTAS")) grid_cap = std::max(1, atoi(env));
+    if (const char *env = getenv("RR_JITTER")) P.jitter = std::max(0, atoi(env));
     if (pipeline) {
         // rr_direct.cu: done[] counts 16-row groups; 8 warps per CTA share 32 KB of output staging
         if (!d->occ_direct[mode]) {
@@ -366,6 +387,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
         const int64_t total = kt->n_items * n_members;
         int64_t g = (int64_t)d->sm_count * d->occ_direct[mode];
         g = std::max<int64_t>(1, std::min<int64_t>(g, (total + 7) / 8));
+        if (grid_cap) g = std::min<int64_t>(g, grid_cap);
         {
             rr_timer tm(0, stream);
             CK(rr_launch_direct(mode, P, (int)g, stream));
@@ -393,6 +415,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     const int64_t total_items = kt->n_items * n_members;
     int64_t grid = (int64_t)d->sm_count * (P.smem_region > 0 ? 1 : d->occ[mode]);
     grid = std::max<int64_t>(1, std::min<int64_t>(grid, (total_items + warps_per_cta - 1) / warps_per_cta));
+    if (grid_cap) grid = std::min<int64_t>(grid, grid_cap);
     {
         rr_timer tm(0, stream);
         CK(rr_launch_wavefront(mode, P, (int)grid, block, stream));
@@ -535,7 +558,7 @@ static bool pipeline_ok(const rr_plan *p, int mode, int64_t K) {
 static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, const double *const *lateral,
                      int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
                      int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream,
-                     const rr_out_spec *spec = nullptr, int lat_f32 = 0) {
+                     const rr_out_spec *spec = nullptr /* one per member */, int lat_f32 = 0) {
     if (lat_f32 && !(pipeline_ok(p, mode, K) && !p->perm.empty())) { rr_set_error("internal: float32 lateral inflows need the direct pipeline"); return 101; }
     if (p->perm.empty()) {
         if (spec) { rr_set_error("internal: fused output needs a level-sorted plan"); return 101; }
@@ -564,16 +587,18 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     const int out_layout = !tiled ? 0 : ((p->opts.staging == 4 || direct) ? 2 : 1);
     int64_t trows = tiled ? tile_rows_for(p, T, K) : 0;
     // the pipeline's tiles are whole 16-row groups (short calls get one padded tile)
-    if (pipeline) trows = std::min<int64_t>(tile_rows_for(p, std::max<int64_t>(T, RR_FLAG_ROWS), K) / RR_FLAG_ROWS * RR_FLAG_ROWS,
-                                            (T + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS * RR_FLAG_ROWS);
+    // (the per-call tile model of tile_rows_for does not apply: narrow levels hand results on every 16 rows whatever
+    // the tile length, so long tiles cost no latency and save per-item setup)
+    if (pipeline) trows = std::min<int64_t>(p->opts.time_tile / RR_FLAG_ROWS * RR_FLAG_ROWS, (T + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS * RR_FLAG_ROWS);
     const int64_t tpitch = ((trows + 3) & ~(int64_t)3);
     const int64_t n_tiles = tiled ? (T + trows - 1) / trows : 0;
     const size_t member_elems = tiled ? (size_t)n_tiles * p->n_blocks * tpitch * RR_BLOCK : (size_t)T * ldp;
     if (has_lat && (rc = grow(&d->p_lat, &d->p_lat_cap, (size_t)n_members * member_elems + 64))) return rc;
     if ((rc = grow(&d->p_out, &d->p_out_cap, (size_t)n_members * member_elems + 64))) return rc;
-    // state scratch: [init][member states][member q_full]
-    if ((rc = grow(&d->p_q, &d->p_q_cap, (size_t)(1 + 2 * n_members) * ldp))) return rc;
+    // state scratch: [start-of-call state: one shared, or one per member on continued calls][member states][member q_full]
+    if ((rc = grow(&d->p_q, &d->p_q_cap, (size_t)(3 * n_members) * ldp))) return rc;
     double *w_init = d->p_q;
+    const int64_t init_stride = (direct && !first_call) ? ldp : 0;
     const double *lat_w[RR_MAX_MEMBERS];
     double *out_w[RR_MAX_MEMBERS], *qs_w[RR_MAX_MEMBERS], *qf_w[RR_MAX_MEMBERS];
     // whole blocks of headwaters are routed by the staging kernel of the pipeline (RapidMuskingum: their lateral rows
@@ -585,30 +610,30 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     for (int m = 0; m < n_members; ++m) {
         lat_w[m] = has_lat ? d->p_lat + (size_t)m * member_elems : nullptr;
         out_w[m] = d->p_out + (size_t)m * member_elems;
-        qs_w[m] = d->p_q + (size_t)(1 + m) * ldp;
-        qf_w[m] = d->p_q + (size_t)(1 + n_members + m) * ldp;
+        qs_w[m] = d->p_q + (size_t)(n_members + m) * ldp;
+        qf_w[m] = d->p_q + (size_t)(2 * n_members + m) * ldp;
         if (!first_call) {
             // direct exchange reads upstream start-of-call values during the launch, so the running state (which the
             // launch overwrites in place) is first copied to the shared, read-only initial-state vector
-            if ((rc = permute(true, q_state[m], n, direct ? w_init : qs_w[m], ldp, d->inv, n, 1, stream))) return rc;
+            if ((rc = permute(true, q_state[m], n, direct ? w_init + (size_t)m * ldp : qs_w[m], ldp, d->inv, n, 1, stream))) return rc;
             if (unit && (rc = permute(true, q_full[m], n, qf_w[m], ldp, d->inv, n, 1, stream))) return rc;
         }
         if (has_lat && pipeline) {
             rr_timer tm(1, stream);
             rc = rr_stage_in(lateral[m], lat_f32, ldl, d->p_lat + (size_t)m * member_elems, out_w[m], d->inv, n, T, trows, p->n_blocks,
-                             hw_cut, d->coef + 2 * p->n_work, d->coef + 3 * p->n_work, w_init, qs_w[m], d->sm_count, stream);
+                             hw_cut, d->coef + 2 * p->n_work, d->coef + 3 * p->n_work, w_init + (size_t)m * init_stride, qs_w[m],
+                             d->sm_count, stream);
             if (rc) return rc;
         } else if (has_lat && (rc = permute(true, lateral[m], ldl, d->p_lat + (size_t)m * member_elems, ldp, d->inv, n, T, stream, trows, p->n_blocks, layout))) return rc;
     }
-    if (direct && !first_call && n_members != 1) { rr_set_error("direct exchange: continued calls support one member"); return 100; }
     rc = launch_route(p, mode, n_members, w_init, has_lat ? lat_w : nullptr, ldp, out_w, ldp, qs_w, qf_w, T, K,
                       direct ? 1 : first_call, last_call, stream, layout, out_layout, direct ? 1 : 0, pipeline ? trows : 0,
-                      hw_cut / RR_BLOCK, pipeline ? 1 : 0);
+                      hw_cut / RR_BLOCK, pipeline ? 1 : 0, init_stride);
     if (rc) return rc;
     for (int m = 0; m < n_members; ++m) {
         if (pipeline) {
             rr_timer tm(2, stream);
-            if (spec) rc = rr_stage_out(out_w[m], spec->dst, spec->f32, spec->ld, d->inv, spec->subset, spec->n_out, T, trows, p->n_blocks, stream);
+            if (spec) rc = rr_stage_out(out_w[m], spec[m].dst, spec[m].f32, spec[m].ld, d->inv, spec[m].subset, spec[m].n_out, T, trows, p->n_blocks, stream);
             else rc = rr_stage_out(out_w[m], out[m], 0, ldo, d->inv, nullptr, n, T, trows, p->n_blocks, stream);
             if (rc) return rc;
         } else if ((rc = permute(false, out_w[m], ldp, out[m], ldo, d->inv, n, T, stream, trows, p->n_blocks, out_layout, direct ? 1 : 0))) return rc;
@@ -1052,6 +1077,156 @@ static int stream_route(rr_plan *p, int mode, double *q_state, double *q_full, c
     if (rc && p && p->dev) {
         // copies of earlier chunks may still be reading / writing the caller's arrays: let them finish before the
         // caller gets control back (and possibly frees the arrays); keep the first error message
+        const std::string msg = rr_last_error();
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        rr_set_error(msg);
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Ensembles from host arrays: the members of one time chunk are routed by ONE wavefront launch (tickets x members),
+// every member from the same initial state (TransformMuskingum.py:121-126); chunks are double-buffered like the
+// single-member stream (H2D of chunk c+1 | device work of chunk c | D2H of chunk c-1).  The member states stay on the
+// device between chunks; at the end they are copied back and averaged in member order (:145-146).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) member_mean_kernel(const double *__restrict__ states, int64_t ld, int n_members, int64_t n,
+                                                           double *__restrict__ mean) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc = states[i];                                  // np.array(states).mean(axis=0): rows added in member order,
+    for (int m = 1; m < n_members; ++m) acc += states[(int64_t)m * ld + i];
+    mean[i] = acc / (double)n_members;                       // then divided by the count
+}
+
+static int ensemble_host_impl(rr_plan *p, int mode, const double *q_init, int64_t ld_init, int M, const void *const *lateral, int lat_f32,
+                              int64_t ldl, void *const *out, int64_t ldo, int out_f32, double *q_final, int64_t ldq,
+                              double *q_mean, int64_t T, int64_t K, int64_t resample) {
+    if (!p || !q_init || !out || M < 1 || M > RR_MAX_MEMBERS) { rr_set_error("bad ensemble arguments (1..64 members)"); return 100; }
+    if (mode == RR_MODE_UNIT) { rr_set_error("ensemble calls support Muskingum / RapidMuskingum"); return 100; }
+    const bool has_lat = mode != RR_MODE_MUSKINGUM;
+    if (has_lat && !lateral) { rr_set_error("null argument"); return 100; }
+    if (T <= 0 || K <= 0 || resample < 1 || T % resample) { rr_set_error("T must be positive and a multiple of the resampling factor"); return 100; }
+    if (!p->out_subset.empty()) { rr_set_error("ensemble calls copy back all river segments (clear the output subset)"); return 100; }
+    int rc = ensure_device(p);
+    if (rc) return rc;
+    rr_device_state *d = p->dev;
+    const int64_t n = p->n, ldd = ((n + 31) / 32) * 32;
+    if (ldo < n || (has_lat && ldl < n) || (q_final && ldq < n) || (ld_init != 0 && ld_init < n)) { rr_set_error("leading dimension smaller than n"); return 100; }
+    const bool pipe = pipeline_ok(p, mode, K);
+    const bool fused = pipe && resample == 1;
+    const bool cast_first = has_lat && lat_f32 && !pipe;
+    const size_t es_in = lat_f32 ? 4 : 8, es_out = out_f32 ? 4 : 8;
+    // chunk rows: all members of a chunk are resident at once -- transfer buffers (x2), working tiles and scratch
+    const double per_row = (double)M * (double)ldd * (2.0 * es_in + 2.0 * es_out + 16.0 + ((!fused) ? 8.0 : 0.0) + (cast_first ? 8.0 : 0.0));
+    int64_t chunk = std::max<int64_t>(1, (int64_t)((double)(24ll << 30) / per_row));
+    if (const char *env = getenv("RR_STREAM_CHUNK_ROWS")) chunk = std::max(1, atoi(env));
+    const int64_t unit = pipe ? RR_FLAG_ROWS : 8;
+    if (chunk >= unit) chunk = chunk / unit * unit;
+    chunk = std::max<int64_t>(resample, chunk / resample * resample);
+    chunk = std::min<int64_t>(chunk, T);
+    const int64_t rows_out_max = chunk / resample;
+    auto grow_bytes = [&](void **buf, size_t *cap, size_t need) -> int {
+        if (need <= *cap) return 0;
+        CK(cudaDeviceSynchronize());
+        if (*buf) CK(cudaFree(*buf));
+        *buf = nullptr; *cap = 0;
+        CK(cudaMalloc(buf, need));
+        *cap = need;
+        return 0;
+    };
+    const size_t in_member = (size_t)chunk * ldd * es_in, out_member = (size_t)rows_out_max * ldd * es_out;
+    for (int k = 0; k < 2; ++k) {
+        if (has_lat && (rc = grow_bytes(&d->s_inb[k], &d->s_inb_cap[k], in_member * M))) return rc;
+        if ((rc = grow_bytes(&d->s_outb[k], &d->s_outb_cap[k], out_member * M))) return rc;
+    }
+    const size_t f64_member = (size_t)chunk * ldd * 8;
+    if (cast_first && (rc = grow_bytes((void **)&d->s_lat, &d->s_lat_cap, f64_member * M))) return rc;
+    if (!fused && (rc = grow_bytes((void **)&d->s_route, &d->s_route_cap, f64_member * M))) return rc;
+    if ((rc = grow_bytes((void **)&d->ens_q, &d->ens_q_cap, (size_t)(M + 2) * ldd * 8))) return rc;
+    double *d_q0 = d->ens_q, *d_mean = d->ens_q + ldd, *d_qm = d->ens_q + 2 * ldd;
+    // shared initial state (a reference call), or one state per member (a later time slab of the same members)
+    const bool shared_init = ld_init == 0;
+    if (shared_init) CK(cudaMemcpyAsync(d_q0, q_init, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, d->s_comp));
+    else CK(cudaMemcpy2DAsync(d_qm, (size_t)ldd * 8, q_init, (size_t)ld_init * 8, (size_t)n * 8, M, cudaMemcpyHostToDevice, d->s_comp));
+    const int64_t n_chunks = (T + chunk - 1) / chunk;
+    auto copy_in = [&](int64_t c) -> int {
+        if (!has_lat) return 0;
+        const int k = (int)(c & 1);
+        const int64_t rows = std::min<int64_t>(chunk, T - c * chunk);
+        if (c >= 2) CK(cudaStreamWaitEvent(d->s_in, d->ev_comp[k], 0));
+        for (int m = 0; m < M; ++m)
+            CK(cudaMemcpy2DAsync((char *)d->s_inb[k] + in_member * m, (size_t)ldd * es_in,
+                                 (const char *)lateral[m] + (size_t)(c * chunk) * ldl * es_in, (size_t)ldl * es_in, (size_t)n * es_in,
+                                 rows, cudaMemcpyHostToDevice, d->s_in));
+        CK(cudaEventRecord(d->ev_in[k], d->s_in));
+        return 0;
+    };
+    if ((rc = copy_in(0))) return rc;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int k = (int)(c & 1);
+        const int64_t rows = std::min<int64_t>(chunk, T - c * chunk), rows_out = rows / resample;
+        if (has_lat) CK(cudaStreamWaitEvent(d->s_comp, d->ev_in[k], 0));
+        if (c >= 2) CK(cudaStreamWaitEvent(d->s_comp, d->ev_out[k], 0));
+        const double *lat_m[RR_MAX_MEMBERS];
+        double *out_m[RR_MAX_MEMBERS], *qs_m[RR_MAX_MEMBERS];
+        rr_out_spec spec[RR_MAX_MEMBERS];
+        for (int m = 0; m < M; ++m) {
+            const char *in = (const char *)d->s_inb[k] + in_member * m;
+            if (cast_first) {
+                double *dst = d->s_lat + (f64_member / 8) * m;
+                dim3 g((unsigned)((n + 255) / 256), (unsigned)rows);
+                upcast_rows<<<g, 256, 0, d->s_comp>>>((const float *)in, ldd, dst, ldd, n);
+                rr_count_launch(1);
+                in = (const char *)dst;
+            }
+            lat_m[m] = (const double *)in;
+            out_m[m] = fused ? nullptr : d->s_route + (f64_member / 8) * m;
+            qs_m[m] = d_qm + (size_t)m * ldd;
+            spec[m].dst = (char *)d->s_outb[k] + out_member * m; spec[m].f32 = out_f32; spec[m].ld = ldd;
+            spec[m].subset = nullptr; spec[m].n_out = n;
+        }
+        rc = route_any(p, mode, M, d_q0, has_lat ? lat_m : nullptr, ldd, out_m, ldd, qs_m, nullptr, rows, K, c == 0 && shared_init, c == n_chunks - 1,
+                       d->s_comp, fused ? spec : nullptr, (has_lat && lat_f32 && !cast_first) ? 1 : 0);
+        if (rc) return rc;
+        if (!fused) {
+            for (int m = 0; m < M; ++m) {
+                dim3 g((unsigned)((n + 255) / 256), (unsigned)rows_out);
+                if (out_f32) finish_output<float><<<g, 256, 0, d->s_comp>>>(out_m[m], ldd, (float *)spec[m].dst, ldd, n, (int)resample, nullptr);
+                else finish_output<double><<<g, 256, 0, d->s_comp>>>(out_m[m], ldd, (double *)spec[m].dst, ldd, n, (int)resample, nullptr);
+                rr_count_launch(1);
+            }
+            CK(cudaGetLastError());
+        }
+        CK(cudaEventRecord(d->ev_comp[k], d->s_comp));
+        CK(cudaStreamWaitEvent(d->s_out, d->ev_comp[k], 0));
+        for (int m = 0; m < M; ++m)
+            CK(cudaMemcpy2DAsync((char *)out[m] + (size_t)(c * chunk / resample) * ldo * es_out, (size_t)ldo * es_out, spec[m].dst,
+                                 (size_t)ldd * es_out, (size_t)n * es_out, rows_out, cudaMemcpyDeviceToHost, d->s_out));
+        CK(cudaEventRecord(d->ev_out[k], d->s_out));
+        if (c + 1 < n_chunks && (rc = copy_in(c + 1))) return rc;
+    }
+    if (q_mean) {
+        member_mean_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d->s_comp>>>(d_qm, ldd, M, n, d_mean);
+        CK(cudaGetLastError());
+        rr_count_launch(1);
+        CK(cudaMemcpyAsync(q_mean, d_mean, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, d->s_comp));
+    }
+    if (q_final) CK(cudaMemcpy2DAsync(q_final, (size_t)ldq * 8, d_qm, (size_t)ldd * 8, (size_t)n * 8, M, cudaMemcpyDeviceToHost, d->s_comp));
+    CK(cudaStreamSynchronize(d->s_comp));
+    CK(cudaStreamSynchronize(d->s_out));
+    CK(cudaStreamSynchronize(d->s_in));
+    return 0;
+}
+
+extern "C" int rr_route_ensemble_host(rr_plan *p, int mode, const double *q_init, int64_t ld_init, int32_t n_members,
+                                      const void *const *lateral, int lateral_f32, int64_t ldl, void *const *out, int64_t ldo,
+                                      int out_f32, double *q_final, int64_t ldq, double *q_mean, int64_t T, int64_t substeps,
+                                      int64_t resample) {
+    const int rc = ensemble_host_impl(p, mode, q_init, ld_init, n_members, lateral, lateral_f32, ldl, out, ldo, out_f32, q_final, ldq, q_mean,
+                                      T, substeps, resample);
+    if (rc && p && p->dev) {
         const std::string msg = rr_last_error();
         cudaDeviceSynchronize();
         cudaGetLastError();

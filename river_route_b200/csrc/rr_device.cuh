@@ -39,6 +39,15 @@ __device__ __forceinline__ void wait_ge(const int32_t *flag, int32_t want) {
     (void)ld_acquire(flag);
 }
 
+// stress tests: a delay of 0 .. 2^bits ns that differs per (block, tile, site, SM clock)
+__device__ __forceinline__ void jitter_delay(int jitter, int b, int j, int site) {
+    if (jitter > 0) {
+        unsigned h = (unsigned)b * 2654435761u ^ (unsigned)j * 40503u ^ (unsigned)site * 69069u ^ (unsigned)clock();
+        h ^= h >> 13;
+        __nanosleep(h & ((1u << min(jitter, 14)) - 1u));
+    }
+}
+
 struct d4 { double a, b, c, d; };
 // one aligned 32-byte sector written by another SM earlier in this launch: coherent load, ordered after the acquire;
 // L2 fetches the whole 128-byte line (this and the next three sectors of the series) in one DRAM burst

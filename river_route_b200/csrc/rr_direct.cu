@@ -45,11 +45,14 @@ struct dctx {
     double *out0;
 };
 
-// all lanes: wait until every upstream block has published `want`; sets full when they are all past `full_want`
+// all lanes: wait until every upstream block has published `want`; sets full when they are all past `full_want`.
+// Polls with acquire loads: this wait sits on the critical path of deep, narrow networks, where a separate acquire after
+// a relaxed poll would add one more L2 round trip per level (the L1 invalidation an acquire costs does not matter to a
+// warp that is waiting anyway).
 __device__ __forceinline__ void wait_groups(const dctx &c, int32_t want, int32_t full_want, bool &full) {
     unsigned ns = 32;
     for (;;) {
-        const int32_t p = c.dep_blk >= 0 ? ld_relaxed(c.done + c.dep_blk) : 0x7fffffff;
+        const int32_t p = c.dep_blk >= 0 ? ld_acquire(c.done + c.dep_blk) : 0x7fffffff;
         if (__all_sync(RR_FULL_MASK, p >= want)) {
             full = __all_sync(RR_FULL_MASK, p >= full_want);
             break;
@@ -57,7 +60,6 @@ __device__ __forceinline__ void wait_groups(const dctx &c, int32_t want, int32_t
         __nanosleep(ns);
         if (ns < 256) ns <<= 1;
     }
-    if (c.dep_blk >= 0) (void)ld_acquire(c.done + c.dep_blk);
     __syncwarp();
 }
 
@@ -88,7 +90,7 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
         if (has[k]) {
             up[k] = tile_of(P.out[c.m], P, j, c.up_u[k]);
             // value before the tile's first row: the start-of-call state, or the last row of the previous tile
-            old[k] = j == 0 ? P.q_init[c.up_u[k]] : tile_of(P.out[c.m], P, j - 1, c.up_u[k])[P.tile_rows - 1];
+            old[k] = j == 0 ? P.q_init[(size_t)c.m * P.q_init_stride + c.up_u[k]] : tile_of(P.out[c.m], P, j - 1, c.up_u[k])[P.tile_rows - 1];
             nxt[k] = ld_sector(up[k]);                       // rows 0..7 are in group 0, which is published
             if (4 < TT) fut[k] = ld_sector(up[k] + 4);
         }
@@ -101,13 +103,24 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
     d4 lcur = lat_group(0), lnxt = lat_group(4);
     double *st = stage + lane;                     // [row & 15][lane]
     for (int s = 0; s < TT; s += 4) {
-        // rows s+8..s+11: first rows of upstream group (s+8)/16 when that is a multiple of 16
-        if (NS > 0 && !full && ((s + 8) & 15) == 0 && s + 8 < TT) wait_groups(c, gbase + ((s + 8) >> 4) + 1, gbase + P.gpt, full);
+        // Upstream blocks still running (narrow levels): their series is consumed one published 16-row group at a time
+        // and WITHOUT look-ahead into the next group -- waiting at row s for group (s+8)/16 made every level lag its
+        // upstream by a whole extra group (measured on the 3000-reach stem of C2: ~6.5 us per level instead of ~2.5).
+        if (NS > 0 && !full && (s & 15) == 0 && s > 0) {
+            wait_groups(c, gbase + (s >> 4) + 1, gbase + P.gpt, full);
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (has[k]) {
+                    nxt[k] = ld_sector(up[k] + s);
+                    if (s + 4 < TT) fut[k] = ld_sector(up[k] + s + 4);
+                }
+        }
+        const bool ahead = full || ((s + 8) >> 4) == (s >> 4);   // rows s+8.. lie in a published group
         d4 far[NA];
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             far[k] = d4{0, 0, 0, 0};
-            if (has[k] && s + 8 < TT) far[k] = ld_sector(up[k] + s + 8);
+            if (has[k] && s + 8 < TT && ahead) far[k] = ld_sector(up[k] + s + 8);
         }
         const d4 lfar = lat_group(s + 8);
         double r0, r1, r2, r3;
@@ -157,6 +170,7 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
                     if (v <= rr) st_sector(o + v, st[(v + 0) * RR_BLOCK], st[(v + 1) * RR_BLOCK], st[(v + 2) * RR_BLOCK], st[(v + 3) * RR_BLOCK]);
             }
             if (c.narrow && s + 4 < TT) {
+                jitter_delay(P.jitter, c.b, j, 1 + (s >> 4));
                 __syncwarp();
                 if (lane == 0) st_release(c.done + c.b, gbase + (s >> 4) + 1);
             }
@@ -209,6 +223,7 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
         // ---- dependencies: own previous tile complete; upstream blocks complete, or (narrow levels with at most 32
         //      upstream blocks) their first group published ----
         const int32_t full_want = (j + 1) * P.gpt;
+        jitter_delay(P.jitter, b, j, 100);
         if (lane == 0 && j > 0) wait_ge(c.done + b, j * P.gpt);
         c.prog = false;
         if (c.narrow && dep_hi - dep_lo <= 32 && dep_hi > dep_lo) {
@@ -221,13 +236,14 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
         }
         __syncwarp();
         c.q = 0.0;
-        if (valid) c.q = (j == 0) ? P.q_init[i] : P.q_state[m][i];
+        if (valid) c.q = (j == 0) ? P.q_init[(size_t)m * P.q_init_stride + i] : P.q_state[m][i];
         switch (M.max_deg) {
             case 0: direct_item<MODE, 0>(P, c, stage); break;
             case 1: direct_item<MODE, 1>(P, c, stage); break;
             case 2: direct_item<MODE, 2>(P, c, stage); break;
             default: direct_item_wide<MODE>(P, c, stage, M.max_deg); break;
         }
+        jitter_delay(P.jitter, b, j, 200);
         __syncwarp();
         if (lane == 0) st_release(c.done + b, full_want);
         __syncwarp();

@@ -136,7 +136,7 @@ __device__ __forceinline__ const double *direct_tile(const rr_route_params &P, i
 }
 // value of reach u before the first substep of tile j: the shared initial state, or the last row of its previous tile
 __device__ __forceinline__ double direct_carry(const rr_route_params &P, int m, int j, int64_t u) {
-    if (j == 0) return P.q_init[u];
+    if (j == 0) return P.q_init[(size_t)m * P.q_init_stride + u];
     return direct_tile(P, m, j - 1, u)[P.tile_rows - 1];
 }
 // offset of row r of one reach's lateral series from its row 0 (layout 3: groups of 4 rows are 32 lanes x 4 doubles apart)
@@ -892,7 +892,7 @@ __device__ __forceinline__ void open_item(const rr_route_params &P, item_ctx &c,
     // from the member's own running state.
     c.use_init = (j == 0) && P.first_call;
     c.q = 0.0;
-    if (valid) c.q = c.use_init ? P.q_init[i] : P.q_state[m][i];
+    if (valid) c.q = c.use_init ? P.q_init[(size_t)m * P.q_init_stride + i] : P.q_state[m][i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1075,6 +1075,11 @@ __global__ void __launch_bounds__(256, RR_MIN_CTAS) rr_wavefront_kernel(const __
 #ifdef RR_PROFILE
         prof_acc[4] += c.prof_wait; prof_acc[6] += 1;
 #endif
+        if (P.jitter > 0) {   // stress tests: pseudo-random delay before publishing
+            unsigned h = (unsigned)b * 2654435761u ^ (unsigned)j * 40503u ^ (unsigned)clock();
+            __nanosleep((h ^ (h >> 13)) & ((1u << min(P.jitter, 14)) - 1u));
+            __syncwarp();
+        }
         if (lane == 0) st_release(P.done + (size_t)m * P.n_blocks + b, j + 1);
         __syncwarp();
         PROF_MARK(3)

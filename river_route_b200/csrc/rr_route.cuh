@@ -38,6 +38,7 @@ struct rr_route_params {
     int32_t direct;       // 1: out holds the raw series and is the exchange buffer (see rr_route.cu, direct_tile)
     int32_t tile_pitch;   // layout 2: tile_rows rounded up to a multiple of 4
     int32_t gpt;          // direct pipeline: progress units (16-row groups) of done[] per tile
+    int32_t jitter;       // stress tests (RR_JITTER): pseudo-random delays around the flag operations, 0 = none
     int32_t smem_region;  // > 0: TMA-staged kernel; bytes of shared memory per warp (tile + row slots + mbarrier)
     int32_t row_slots;    // upstream exchange rows a warp's region can hold
     int32_t first_call;   // UNIT: 1 when q_state holds the start-of-file state (q_ch = q_full = state)
@@ -50,7 +51,8 @@ struct rr_route_params {
     int32_t *done;        // [member][n_blocks] tiles completed
     unsigned long long *ticket;
     unsigned long long *prof;   // optional [8] cycle counters (RR_PROFILE builds), else nullptr
-    const double *q_init;                       // shared initial state
+    const double *q_init;                       // start-of-call state: member m reads q_init + m * q_init_stride
+    int64_t q_init_stride;                      // 0: one state shared by all members (TransformMuskingum.py:121-126)
     const double *lateral[RR_MAX_MEMBERS];
     double *out[RR_MAX_MEMBERS];
     double *q_state[RR_MAX_MEMBERS];            // per-member running / final state (UNIT: q_ch)

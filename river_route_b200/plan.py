@@ -224,6 +224,49 @@ class Plan:
                                         int(ldo), arr(*q_final_ptrs), int(T), int(substeps),
                                         C.c_void_p(stream or None)))
 
+    def route_ensemble_host(self, mode: int, q_init: np.ndarray, laterals, outs, substeps: int, resample: int = 1,
+                            q_final: np.ndarray | None = None):
+        """
+        ``len(outs)`` ensemble members from host arrays (pinned for full PCIe rate) in one call: every member starts
+        from ``q_init`` (n,) (TransformMuskingum.py:121-126) -- or, for a later time slab of the same members, from its
+        own row of ``q_init`` (members, n) --, the members of each time chunk share one launch, and the
+        returned vector is the mean of the members' final states in member order (:145-146).  ``laterals[m]`` is
+        (T, n) float64 or float32 (all members the same dtype; None for MODE_MUSKINGUM), ``outs[m]`` (T / resample, n)
+        float64 or float32 (all the same dtype); ``q_final`` (members, n), if given, receives the members' states.
+        """
+        M = len(outs)
+        if M < 1 or (mode != MODE_MUSKINGUM and len(laterals) != M):
+            raise ValueError('one lateral array and one discharge array per member')
+        if q_init.dtype != np.float64 or not q_init.flags.c_contiguous or q_init.shape not in ((self.n,), (M, self.n)):
+            raise ValueError('q_init must be a contiguous float64 (n,) vector or (members, n) array')
+        ld_init = self.n if q_init.ndim == 2 else 0
+        resample = int(resample)
+        T = outs[0].shape[0] * resample
+        odt = outs[0].dtype
+        for o in outs:
+            if o.dtype != odt or odt not in (np.float64, np.float32) or o.shape != (T // resample, self.n) or \
+                    _lib.rows_ld(o) != _lib.rows_ld(outs[0]):
+                raise ValueError('discharge arrays must share dtype (float64 / float32), shape (T, n) and row stride')
+        arr = C.c_void_p * M
+        p_lat, ldl, lat_f32 = None, self.n, 0
+        if mode != MODE_MUSKINGUM:
+            ldt = laterals[0].dtype
+            lat_f32 = int(ldt == np.float32)
+            for a in laterals:
+                if a.dtype != ldt or ldt not in (np.float64, np.float32) or a.shape != (T, self.n) or \
+                        _lib.rows_ld(a) != _lib.rows_ld(laterals[0]):
+                    raise ValueError('lateral arrays must share dtype (float64 / float32), shape (T, n) and row stride')
+            ldl = _lib.rows_ld(laterals[0])
+            p_lat = arr(*[a.ctypes.data for a in laterals])
+        q_mean = np.empty(self.n, dtype=np.float64)
+        if q_final is not None and (q_final.dtype != np.float64 or q_final.shape != (M, self.n) or not q_final.flags.c_contiguous):
+            raise ValueError('q_final must be a contiguous float64 (members, n) array')
+        check(lib.rr_route_ensemble_host(self._h, int(mode), _lib.as_f64p(q_init), ld_init, M, p_lat, lat_f32, ldl,
+                                         arr(*[o.ctypes.data for o in outs]), _lib.rows_ld(outs[0]), int(odt == np.float32),
+                                         _lib.as_f64p(q_final) if q_final is not None else None, self.n,
+                                         _lib.as_f64p(q_mean), T, int(substeps), resample))
+        return q_mean
+
     def tile_rows(self, T: int, substeps: int = 1) -> int:
         """Output rows per work item the library picks for a call of T rows (its per-call cost model)."""
         return int(lib.rr_plan_tile_rows(self._h, int(T), int(substeps)))

@@ -514,6 +514,10 @@ class TransformMuskingum(Muskingum):
         """
         from concurrent.futures import ThreadPoolExecutor
         pairs = list(zip(self.cfg.qlateral_files, self.cfg.discharge_files))
+        if (self.cfg.runoff_processing_mode == 'ensemble' and len(pairs) > 1 and self._mode != MODE_UNIT
+                and self._writer is None and (self._shard is None or self._shard.world == 1)
+                and _is_stock(self, '_route_rows', TransformMuskingum)):
+            return self._execute_ensemble_batched(pairs)
         if self.cfg.progress_bar:
             from tqdm import tqdm
             pairs = tqdm(pairs, total=len(pairs), desc='Files Routed')
@@ -532,6 +536,81 @@ class TransformMuskingum(Muskingum):
                     self._ensemble_member_states.append(q_t.copy())
         if self.cfg.runoff_processing_mode == 'ensemble':
             self.channel_state = np.array(self._ensemble_member_states).mean(axis=0)   # :145-146
+
+    def _execute_ensemble_batched(self, pairs):
+        """
+        ``runoff_processing_mode='ensemble'`` (TransformMuskingum.py:121-126, :145-146) with the members batched: every
+        file is one member, all members start from the same channel state, and the members of a time slab are routed by
+        ONE device call (``rr_route_ensemble_host``: one wavefront launch per chunk covers all of them).  Members are
+        taken in groups that fit the page-locked slab budget; each member's float32 rows go to its own discharge file;
+        the final channel state is the mean of the members' final states in member (= file) order.  The reference
+        routes the members one after the other (or in separate processes, docs/references/parallelism.md:77-112).
+        """
+        from concurrent.futures import ThreadPoolExecutor
+        n, M = self.n, len(pairs)
+        states = np.empty((M, n), dtype=np.float64)
+        budget = float(os.environ.get('RR_ROUTER_SLAB_BYTES', 2 << 30))
+        q0 = self.channel_state.astype(np.float64, copy=True)
+        done = 0
+        with ThreadPoolExecutor(max_workers=4) as pool:
+            while done < M:
+                srcs = [_LateralFile(pairs[done][0])]
+                try:
+                    dates = srcs[0].dates
+                    self._set_network_and_time_dependent_vectors(dates)
+                    T = self.num_runoff_steps
+                    k = self.num_runoff_steps_per_discharge if self.dt_discharge > self.dt_runoff else 1
+                    dates_out = dates[::k] if k > 1 else dates
+                    unit = int(np.lcm(16, k))
+                    G = int(max(1, min(M - done, 64, budget // max(1, unit * n * srcs[0].dtype.itemsize))))
+                    for f in range(done + 1, done + G):
+                        srcs.append(_LateralFile(pairs[f][0]))
+                    for src, (lat_file, _) in zip(srcs, pairs[done:done + G]):
+                        self.logger.info(f'Routing qlateral: {lat_file}')
+                        self._check_lateral_shape(src.shape, n)
+                        if not np.array_equal(src.dates, dates):
+                            raise ValueError('ensemble members must share one time axis')
+                    dtype = srcs[0].dtype if all(s_.dtype == srcs[0].dtype for s_ in srcs) else np.dtype(np.float64)
+                    slab = self._slab_rows(T, k, G * n * dtype.itemsize)
+                    starts = list(range(0, T, slab))
+                    lat = [[self._pinned(('elat', b, m), (slab, n), dtype) for m in range(G)] for b in range(2)]
+                    out = [[self._pinned(('eout', b, m), (slab // k, n), np.float32) for m in range(G)] for b in range(2)]
+                    files = [self._open_discharge_file(dates_out, n, pairs[done + m][1], pairs[done + m][0]) for m in range(G)]
+                    try:
+                        def read(s_):
+                            t0, t1 = starts[s_], min(T, starts[s_] + slab)
+                            list(pool.map(lambda m: srcs[m].read(t0, t1, lat[s_ % 2][m]), range(G)))
+                            return t1 - t0
+                        nxt = pool.submit(read, 0)
+                        pending = [None, None]
+                        q_members = None
+                        for s_ in range(len(starts)):
+                            rows = nxt.result()
+                            if s_ + 1 < len(starts):
+                                nxt = pool.submit(read, s_ + 1)
+                            if pending[s_ % 2] is not None:
+                                pending[s_ % 2].result()
+                            lat_s = [a[:rows] for a in lat[s_ % 2]]
+                            out_s = [a[:rows // k] for a in out[s_ % 2]]
+                            group_states = states[done:done + G]
+                            mean = self.plan.route_ensemble_host(self._mode, q0 if q_members is None else q_members, lat_s, out_s,
+                                                                 self.num_routing_steps_per_runoff, resample=k, q_final=group_states)
+                            q_members = np.ascontiguousarray(group_states)
+                            r0 = starts[s_] // k
+                            pending[s_ % 2] = pool.submit(lambda r0=r0, out_s=out_s: [f.write_rows(r0, o) for f, o in zip(files, out_s)])
+                        for f in pending:
+                            if f is not None:
+                                f.result()
+                    finally:
+                        for f in files:
+                            f.close()
+                finally:
+                    for src in srcs:
+                        src.close()
+                done += G
+        self._ensemble_member_states = list(states)
+        # one group: the device mean (member order, then / M) is the answer; several groups: numpy over all members
+        self.channel_state = mean if G == M else np.array(self._ensemble_member_states).mean(axis=0)   # :145-146
 
     def _slab_rows(self, T, k, row_bytes):
         """Rows per slab: about RR_ROUTER_SLAB_BYTES (2 GiB) of lateral inflows, whole 16-row groups of the device

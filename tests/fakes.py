@@ -102,7 +102,21 @@ def install(setattr_fn):
     setattr_fn(_lib, 'pinned_empty', lambda shape, dtype=np.float64: np.empty(shape, dtype=dtype))   # no CUDA on this tier
     setattr_fn(plan_mod.Plan, 'set_coefficients', set_coefficients)
     setattr_fn(plan_mod.Plan, 'set_output_subset', set_output_subset)
+    def route_ensemble_host(self, mode, q_init, laterals, outs, substeps, resample=1, q_final=None):
+        M = len(outs)
+        T = outs[0].shape[0] * resample
+        finals = np.empty((M, self.n))
+        for m in range(M):
+            q = (q_init if q_init.ndim == 1 else q_init[m]).copy()
+            lat = None if mode == rr.MODE_MUSKINGUM else np.ascontiguousarray(laterals[m], dtype=np.float64)
+            _finish(self, _route(self, mode, q, lat, T, substeps), outs[m], resample)
+            finals[m] = q
+        if q_final is not None:
+            q_final[...] = finals
+        return np.array(list(finals)).mean(axis=0)
+
     setattr_fn(plan_mod.Plan, 'route_host', route_host)
+    setattr_fn(plan_mod.Plan, 'route_ensemble_host', route_ensemble_host)
     setattr_fn(plan_mod.Plan, 'runoff_route_host', runoff_route_host)
     setattr_fn(transforms, 'Transform', FakeTransform)
     setattr_fn(transforms, 'uh_convolve', lambda lat, ker, st: oracle.uh_convolve(np.ascontiguousarray(lat), ker, st))

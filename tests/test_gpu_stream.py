@@ -319,3 +319,54 @@ def test_float32_lateral_inflows_cross_pcie_as_stored(staging, rows, chunk_rows)
     oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q_o, ql32.astype(np.float64), ref_o, 1)
     assert parity_error(ref, ref_o) < TOL and parity_error(q_ref, q_o) < TOL
     plan.close()
+
+
+@pytest.mark.parametrize('staging,K', [('auto', 1), ('direct', 1), ('registers-tiled', 1), ('auto', 2)])
+@pytest.mark.parametrize('f32,rows', [(False, 0), (True, 16)])
+def test_ensemble_host_members_match_oracle(staging, K, f32, rows, chunk_rows):
+    """rr_route_ensemble_host: every member equals its own single-member oracle run (1e-10), the float32 rows equal the
+    cast of the fp64 result, time slabs chain per-member states bit-identically to one call, and the mean state is
+    numpy's member-order mean bit for bit (TransformMuskingum.py:121-126, :145-146)."""
+    n, T, M = 25000 + 3, 48, 5
+    down, a = _network(n, 5, 17, 3600 // K, 3600)
+    plan = rr.Plan(down, renumber='always', staging=staging)
+    plan.set_coefficients(a['c1'], a['c2'], a['c3'], a['c4_dt'])
+    base = synth.lateral_volumes(T, n, 9)
+    lats = [base * s for s in np.random.default_rng(1).lognormal(0, 0.3, M)]
+    if f32:
+        lats = [x.astype(np.float32) for x in lats]
+    q0 = np.random.default_rng(2).uniform(0, 40, n)
+    chunk_rows(rows)
+    outs = [np.full((T, n), np.nan, dtype=np.float32) for _ in range(M)]
+    finals = np.empty((M, n))
+    mean = plan.route_ensemble_host(rr.MODE_RAPID, q0, lats, outs, K, q_final=finals)
+    refs, qrefs = [], []
+    for m in range(M):
+        q, ref = q0.copy(), np.zeros((T, n))
+        oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q, lats[m].astype(np.float64), ref, K)
+        refs.append(ref)
+        qrefs.append(q)
+        assert parity_error(finals[m], q) < TOL, m
+        assert np.allclose(outs[m], ref.astype(np.float32), rtol=3e-7, atol=1e-30), m
+        # bit-level: the member alone through the single-member call
+        q1, o1 = q0.copy(), np.empty((T, n), dtype=np.float32)
+        plan.route_host(rr.MODE_RAPID, q1, lats[m], o1, K)
+        assert np.array_equal(o1, outs[m]) and np.array_equal(q1, finals[m]), m
+    assert np.array_equal(mean, np.array(list(finals)).mean(axis=0))
+    # two time slabs through per-member initial states == one call
+    outs_a = [np.empty((32, n), dtype=np.float32) for _ in range(M)]
+    outs_b = [np.empty((T - 32, n), dtype=np.float32) for _ in range(M)]
+    st = np.empty((M, n))
+    plan.route_ensemble_host(rr.MODE_RAPID, q0, [x[:32] for x in lats], outs_a, K, q_final=st)
+    st2 = np.empty((M, n))
+    mean2 = plan.route_ensemble_host(rr.MODE_RAPID, np.ascontiguousarray(st), [x[32:] for x in lats], outs_b, K, q_final=st2)
+    for m in range(M):
+        assert np.array_equal(np.vstack([outs_a[m], outs_b[m]]), outs[m]), m
+    assert np.array_equal(st2, finals) and np.array_equal(mean2, mean)
+    # Muskingum members (no lateral): all members identical to one run
+    outs_m = [np.empty((T, n)) for _ in range(2)]
+    plan.route_ensemble_host(rr.MODE_MUSKINGUM, q0, None, outs_m, K)
+    q1, o1 = q0.copy(), np.empty((T, n))
+    plan.route_host(rr.MODE_MUSKINGUM, q1, None, o1, K)
+    assert np.array_equal(outs_m[0], o1) and np.array_equal(outs_m[1], o1)
+    plan.close()

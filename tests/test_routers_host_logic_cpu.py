@@ -274,3 +274,69 @@ def test_qlateral_files_streamed_in_slabs(tmp_path, host_only, monkeypatch, rout
         else:
             assert np.array_equal(got, want), (f, router, f32, k)
     assert parity_error(r.channel_state, q) < 1e-12
+
+
+@pytest.mark.parametrize('f32,k,slab_rows,group_bytes', [(False, 1, 0, 0), (True, 2, 16, 0), (False, 1, 16, 16 * 180 * 8 * 2)])
+def test_ensemble_mode_batches_members(tmp_path, host_only, monkeypatch, f32, k, slab_rows, group_bytes):
+    """runoff_processing_mode='ensemble' with qlateral files: members are routed by batched device calls (one per time
+    slab and member group), every member from the same state; each member's file equals a single-member run and the
+    final state is the member mean in file order (TransformMuskingum.py:121-126, :145-146)."""
+    from river_route_b200.runoff import QlateralDataset
+    from river_route_b200 import synth
+    if slab_rows:
+        monkeypatch.setenv('RR_ROUTER_SLAB_ROWS', str(slab_rows))
+    if group_bytes:
+        monkeypatch.setenv('RR_ROUTER_SLAB_BYTES', str(group_bytes))      # two members per group
+    n, T, M = 180, 40, 5
+    down = synth.forest(n, 3, seed=12, depth_bias=0.6)
+    kk, x = synth.muskingum_params(n, 12)
+    ids = np.arange(n, dtype=np.int64) + 7
+    params = str(tmp_path / 'p.parquet')
+    pd.DataFrame({'river_id': ids, 'downstream_river_id': np.where(down >= 0, ids[np.where(down >= 0, down, 0)], -1),
+                  'k': kk, 'x': x}).to_parquet(params)
+    q0 = np.random.default_rng(5).uniform(0, 25, n)
+    pd.DataFrame({'Q': q0}).to_parquet(tmp_path / 'q0.parquet')
+    t = (np.datetime64('2023-03-01') + np.arange(T) * np.timedelta64(1, 'h')).astype('datetime64[s]')
+    files, laterals = [], []
+    base = synth.lateral_volumes(T, n, 60)
+    for m in range(M):
+        ql = base * np.random.default_rng(70 + m).lognormal(0, 0.3)
+        if f32:
+            ql = ql.astype(np.float32)
+        path = str(tmp_path / f'member_{m}.nc')
+        with ncio.open_nc(path, 'w') as nc:
+            nc.createDimension('time', T)
+            nc.createDimension('river_id', n)
+            tv = nc.createVariable('time', 'f8', ('time',))
+            tv.units = 'seconds since 2023-03-01 00:00:00'
+            tv[:] = np.arange(T) * 3600.0
+            nc.createVariable('river_id', 'i4', ('river_id',))[:] = ids.astype(np.int32)
+            nc.createVariable('qlateral', 'f4' if f32 else 'f8', ('time', 'river_id'))[:] = ql
+        files.append(path)
+        laterals.append(ql.astype(np.float64))
+    calls = []
+    real = plan_mod.Plan.route_ensemble_host
+
+    def spy(self, mode, q_init, lats, outs, substeps, resample=1, q_final=None):
+        calls.append((len(outs), outs[0].shape[0] * resample, q_init.ndim))
+        return real(self, mode, q_init, lats, outs, substeps, resample=resample, q_final=q_final)
+    monkeypatch.setattr(plan_mod.Plan, 'route_ensemble_host', spy)
+    r = rr.RapidMuskingum(params_file=params, qlateral_files=files, discharge_dir=str(tmp_path), dt_discharge=3600 * k,
+                          channel_state_init_file=str(tmp_path / 'q0.parquet'), runoff_processing_mode='ensemble',
+                          channel_state_final_file=str(tmp_path / 'final.parquet'), log=False).route()
+    assert calls and all(c[0] > 1 for c in calls if group_bytes == 0) and sum(c[0] for c in calls if c[2] == 1) == M
+    if slab_rows:
+        assert [c[1] for c in calls][:3] == [16, 16, 8]                   # slabs chain the members' own states
+    if group_bytes:
+        assert {c[0] for c in calls} == {2, 1}                            # groups of two, then the odd member
+    a = network_arrays(down, kk, x, 3600, 3600)
+    finals = []
+    for m, ql in enumerate(laterals):
+        q, ref = q0.copy(), np.zeros((T, n))
+        oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q, ql, ref, 1)
+        finals.append(q)
+        want = (ref.reshape(T // k, k, n).mean(axis=1) if k > 1 else ref).astype(np.float32)
+        with ncio.open_nc(tmp_path / f'discharge_member_{m}.nc') as ds:
+            assert np.array_equal(ncio.read_array(ds.variables['Q']), want), m
+    assert np.array_equal(r.channel_state, np.array(finals).mean(axis=0))
+    assert np.array_equal(pd.read_parquet(tmp_path / 'final.parquet')['Q'].values, r.channel_state)

@@ -396,3 +396,106 @@ def test_output_subset_of_rivers(route_golden, tmp_path):
     with pytest.raises(ValueError, match='ids not in the params file'):
         _inject(rr.RapidMuskingum, [g['ql']], g['dt_runoff'])(**common, discharge_files=[str(tmp_path / 'x.nc')]) \
             .set_output_rivers([int(ids.max()) + 12345]).route()
+
+
+def _write_ql(path, ql, ids, t0_hours=0):
+    from river_route_b200 import ncio
+    T, n = ql.shape
+    with ncio.open_nc(path, 'w') as nc:
+        nc.createDimension('time', T)
+        nc.createDimension('river_id', n)
+        tv = nc.createVariable('time', 'f8', ('time',))
+        tv.units = 'seconds since 2022-01-01 00:00:00'
+        tv[:] = (np.arange(T) + t0_hours) * 3600.0
+        nc.createVariable('river_id', 'i4', ('river_id',))[:] = ids.astype(np.int32)
+        nc.createVariable('qlateral', 'f4' if ql.dtype == np.float32 else 'f8', ('time', 'river_id'))[:] = ql
+
+
+def _stream_case(tmp_path, n=5000, T=40, files=2, f32=False, seed=3):
+    from river_route_b200 import synth
+    down = synth.forest(n, 6, seed=seed, depth_bias=0.6)
+    k, x = synth.muskingum_params(n, seed)
+    ids = np.arange(n, dtype=np.int64) + 1000
+    params = str(tmp_path / 'p.parquet')
+    pd.DataFrame({'river_id': ids, 'downstream_river_id': np.where(down >= 0, ids[np.where(down >= 0, down, 0)], -1),
+                  'k': k, 'x': x}).to_parquet(params)
+    q0 = np.random.default_rng(seed).uniform(0, 30, n)
+    pd.DataFrame({'Q': q0}).to_parquet(tmp_path / 'q0.parquet')
+    paths, laterals = [], []
+    for f in range(files):
+        ql = synth.lateral_volumes(T, n, 80 + f)
+        if f32:
+            ql = ql.astype(np.float32)
+        _write_ql(str(tmp_path / f'ql_{f}.nc'), ql, ids, f * T)
+        paths.append(str(tmp_path / f'ql_{f}.nc'))
+        laterals.append(ql)
+    return dict(params=params, state=str(tmp_path / 'q0.parquet'), files=paths, laterals=laterals, down=down, k=k, x=x, q0=q0,
+                ids=ids, n=n, T=T)
+
+
+def _read_q(path):
+    from river_route_b200 import ncio
+    with ncio.open_nc(path) as ds:
+        return ncio.read_array(ds.variables['Q'])
+
+
+@pytest.mark.parametrize('router,f32,k', [('rapid', False, 1), ('rapid', True, 2), ('unit', False, 1)])
+def test_qlateral_files_streamed_through_pinned_slabs(tmp_path, monkeypatch, router, f32, k):
+    """Slab streaming on the real library: 16-row slabs give the bytes of one whole-file slab (float32 variables routed as
+    stored, resample on slab boundaries, channel state / UH carry-over chained through slabs and files), and the
+    float32 discharge agrees with the CPU oracle."""
+    from oracle import oracle
+    from tests.helpers import network_arrays
+    c = _stream_case(tmp_path, f32=f32)
+    scale = 1.0 if router == 'rapid' else 1e-7
+    if router == 'unit':
+        for f, ql in enumerate(c['laterals']):
+            c['laterals'][f] = ql * scale
+            _write_ql(c['files'][f], c['laterals'][f], c['ids'], f * c['T'])
+        ker = np.random.default_rng(2).uniform(0, 1, (6, c['n'])) * (np.random.default_rng(3).random((6, c['n'])) < 0.7)
+        scipy.sparse.save_npz(str(tmp_path / 'uh.npz'), scipy.sparse.csr_matrix(ker))
+    outs = {}
+    for label, rows in (('whole', None), ('slabs', '16')):
+        out_dir = tmp_path / label
+        out_dir.mkdir()
+        if rows:
+            monkeypatch.setenv('RR_ROUTER_SLAB_ROWS', rows)
+        else:
+            monkeypatch.delenv('RR_ROUTER_SLAB_ROWS', raising=False)
+        cfg = dict(params_file=c['params'], qlateral_files=c['files'], discharge_dir=str(out_dir), dt_discharge=3600 * k,
+                   channel_state_init_file=c['state'], log=False)
+        r = (rr.UnitMuskingum(uh_kernel_file=str(tmp_path / 'uh.npz'), **cfg) if router == 'unit' else rr.RapidMuskingum(**cfg)).route()
+        outs[label] = ([_read_q(out_dir / f'discharge_ql_{f}.nc') for f in range(2)], r.channel_state.copy())
+    for f in range(2):
+        assert np.array_equal(outs['whole'][0][f], outs['slabs'][0][f]), f
+    assert np.array_equal(outs['whole'][1], outs['slabs'][1])
+    if router == 'rapid':
+        a = network_arrays(c['down'], c['k'], c['x'], 3600, 3600)
+        q = c['q0'].copy()
+        for f, ql in enumerate(c['laterals']):
+            ref = np.zeros((c['T'], c['n']))
+            oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q, ql.astype(np.float64), ref, 1)
+            want = (ref.reshape(c['T'] // k, k, c['n']).mean(axis=1) if k > 1 else ref).astype(np.float32)
+            assert np.allclose(outs['slabs'][0][f], want, rtol=3e-7, atol=1e-30), f
+        assert parity_error(outs['slabs'][1], q) < TOL
+
+
+def test_ensemble_mode_batched_members_equal_single_member_runs(tmp_path, monkeypatch):
+    """runoff_processing_mode='ensemble' on the real library: the batched device calls write, for every member, the bytes
+    a single-member run writes, and the final state is numpy's member-order mean of the members' states."""
+    c = _stream_case(tmp_path, n=4000, T=40, files=4, f32=True, seed=7)
+    monkeypatch.setenv('RR_ROUTER_SLAB_ROWS', '16')
+    ens_dir = tmp_path / 'ens'
+    ens_dir.mkdir()
+    r = rr.RapidMuskingum(params_file=c['params'], qlateral_files=c['files'], discharge_dir=str(ens_dir),
+                          channel_state_init_file=c['state'], runoff_processing_mode='ensemble', log=False).route()
+    states = []
+    for f, path in enumerate(c['files']):
+        one = tmp_path / f'one_{f}'
+        one.mkdir()
+        s = rr.RapidMuskingum(params_file=c['params'], qlateral_files=[path], discharge_dir=str(one),
+                              channel_state_init_file=c['state'], log=False).route()
+        states.append(s.channel_state.copy())
+        assert np.array_equal(_read_q(ens_dir / f'discharge_ql_{f}.nc'), _read_q(one / f'discharge_ql_{f}.nc')), f
+    assert np.array_equal(np.array(r._ensemble_member_states), np.array(states))
+    assert np.array_equal(r.channel_state, np.array(states).mean(axis=0))

@@ -17,11 +17,16 @@
 cudaError_t rr_launch_wavefront(int mode, const rr_route_params &P, int grid, int block, cudaStream_t stream);
 int rr_wavefront_occupancy(int mode, int block);
 // rr_direct.cu: the pipeline of level-sorted plans with one substep per row
-cudaError_t rr_launch_direct(int mode, const rr_route_params &P, int grid, cudaStream_t stream);
-int rr_direct_occupancy(int mode);
+cudaError_t rr_launch_direct(int mode, int max_deg, const rr_route_params &P, int grid, cudaStream_t stream);
+int rr_direct_occupancy(int mode, int max_deg);
 int rr_stage_in(const void *src, int src_f32, int64_t lds, double *lat_w, double *out_w, const int32_t *inv, int64_t n, int64_t T,
                 int64_t tile_rows, int64_t n_blocks, int64_t hw_cut, const double *c3, const double *c4,
                 const double *q_init, double *q_final, int sm_count, cudaStream_t stream);
+int rr_stage_out_unit(const double *out_w, const double *lat, int64_t ldl, void *dst, int dst_f32, int64_t ldd, const int32_t *inv,
+                      const int32_t *subset, int64_t n_out, int64_t T, int64_t tile_rows, int64_t n_blocks, int64_t hw_slots,
+                      cudaStream_t stream);
+int rr_unit_state_to_user(const double *qs_w, const double *qf_w, const int32_t *inv, int64_t n, int64_t hw_slots, int last,
+                          const double *lat_last, double *q_state, double *q_full, cudaStream_t stream);
 int rr_stage_out(const double *out_w, void *dst, int dst_f32, int64_t ldd, const int32_t *inv, const int32_t *subset,
                  int64_t n_out, int64_t T, int64_t tile_rows, int64_t n_blocks, cudaStream_t stream);
 
@@ -252,7 +257,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
                         int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
                         int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream, int tile_major = 0,
                         int out_layout = 0, int direct = 0, int64_t rows_in = 0, int64_t first_block = 0, int pipeline = 0,
-                        int64_t q_init_stride = 0) {
+                        int64_t q_init_stride = 0, const double *qf_init = nullptr, int64_t hw_slots = 0) {
     if (mode < 0 || mode > 2) { rr_set_error("unknown router mode"); return 100; }
     if (T <= 0 || K <= 0 || T > 0x7fffffff || K > 0x7fffffff) { rr_set_error("T and substeps must be positive"); return 100; }
     if (n_members < 1 || n_members > RR_MAX_MEMBERS) { rr_set_error("n_members must be in [1, 64]"); return 100; }
@@ -355,6 +360,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.raw_pitch = (int32_t)pitch; P.n_members = n_members; P.first_call = first_call; P.last_call = last_call;
     P.ldl = ldl; P.ldo = ldo;
     P.raw = d->raw; P.done = d->done; P.ticket = d->ticket; P.prof = d->prof; P.q_init = q_init; P.q_init_stride = q_init_stride;
+    P.qf_init = qf_init; P.hw_slots = hw_slots;
     for (int m = 0; m < n_members; ++m) {
         P.lateral[m] = lateral ? lateral[m] : nullptr;
         P.out[m] = out[m];
@@ -381,7 +387,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     if (pipeline) {
         // rr_direct.cu: done[] counts 16-row groups; 8 warps per CTA share 32 KB of output staging
         if (!d->occ_direct[mode]) {
-            d->occ_direct[mode] = rr_direct_occupancy(mode);
+            d->occ_direct[mode] = rr_direct_occupancy(mode, p->max_deg);
             if (d->occ_direct[mode] <= 0) { rr_set_error("occupancy query failed for the direct wavefront kernel"); return 200; }
         }
         const int64_t total = kt->n_items * n_members;
@@ -390,7 +396,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
         if (grid_cap) g = std::min<int64_t>(g, grid_cap);
         {
             rr_timer tm(0, stream);
-            CK(rr_launch_direct(mode, P, (int)g, stream));
+            CK(rr_launch_direct(mode, p->max_deg, P, (int)g, stream));
         }
         rr_count_launch(1);
         return 0;
@@ -547,11 +553,11 @@ struct rr_out_spec {
 };
 
 // The rr_direct.cu pipeline serves level-sorted plans whose blocks are all fast-path eligible, one substep per row,
-// RapidMuskingum / Muskingum, tile lengths that are whole 16-row groups.
+// tile lengths that are whole 16-row groups (all three routers).
 static bool pipeline_ok(const rr_plan *p, int mode, int64_t K) {
     const int st = p->opts.staging;
-    return !p->perm.empty() && p->all_fast && K == 1 && mode != RR_MODE_UNIT && (st == 0 || st == 6 || st == 7) &&
-           (p->opts.time_tile % RR_FLAG_ROWS) == 0;
+    (void)mode;
+    return !p->perm.empty() && p->all_fast && K == 1 && (st == 0 || st == 6 || st == 7) && (p->opts.time_tile % RR_FLAG_ROWS) == 0;
 }
 
 // Route with all arrays in the caller's (params_file) order, whatever order the plan works in.
@@ -583,7 +589,7 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     const int layout = !tiled ? 0 : (p->opts.staging == 3 ? 1 : (p->opts.staging == 5 ? 3 : 2));
     // "direct exchange": the working discharge array (reach-major tiles, raw values) is the exchange buffer
     // (default for level-sorted plans with one substep per row; staging 2 / 4 / 5 keep the exchange rings)
-    const bool direct = tiled && !unit && (p->opts.staging == 6 || p->opts.staging == 0 || p->opts.staging == 7);
+    const bool direct = tiled && (!unit || pipeline) && (p->opts.staging == 6 || p->opts.staging == 0 || p->opts.staging == 7);
     const int out_layout = !tiled ? 0 : ((p->opts.staging == 4 || direct) ? 2 : 1);
     int64_t trows = tiled ? tile_rows_for(p, T, K) : 0;
     // the pipeline's tiles are whole 16-row groups (short calls get one padded tile)
@@ -596,9 +602,12 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     if (has_lat && (rc = grow(&d->p_lat, &d->p_lat_cap, (size_t)n_members * member_elems + 64))) return rc;
     if ((rc = grow(&d->p_out, &d->p_out_cap, (size_t)n_members * member_elems + 64))) return rc;
     // state scratch: [start-of-call state: one shared, or one per member on continued calls][member states][member q_full]
-    if ((rc = grow(&d->p_q, &d->p_q_cap, (size_t)(3 * n_members) * ldp))) return rc;
+    //                [start-of-call q_full of continued UnitMuskingum pipeline calls]
+    if ((rc = grow(&d->p_q, &d->p_q_cap, (size_t)(4 * n_members) * ldp))) return rc;
     double *w_init = d->p_q;
+    double *wf_init = d->p_q + (size_t)(3 * n_members) * ldp;
     const int64_t init_stride = (direct && !first_call) ? ldp : 0;
+    const bool unit_pipe = unit && pipeline;
     const double *lat_w[RR_MAX_MEMBERS];
     double *out_w[RR_MAX_MEMBERS], *qs_w[RR_MAX_MEMBERS], *qf_w[RR_MAX_MEMBERS];
     // whole blocks of headwaters are routed by the staging kernel of the pipeline (RapidMuskingum: their lateral rows
@@ -616,7 +625,7 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
             // direct exchange reads upstream start-of-call values during the launch, so the running state (which the
             // launch overwrites in place) is first copied to the shared, read-only initial-state vector
             if ((rc = permute(true, q_state[m], n, direct ? w_init + (size_t)m * ldp : qs_w[m], ldp, d->inv, n, 1, stream))) return rc;
-            if (unit && (rc = permute(true, q_full[m], n, qf_w[m], ldp, d->inv, n, 1, stream))) return rc;
+            if (unit && (rc = permute(true, q_full[m], n, unit_pipe ? wf_init + (size_t)m * ldp : qf_w[m], ldp, d->inv, n, 1, stream))) return rc;
         }
         if (has_lat && pipeline) {
             rr_timer tm(1, stream);
@@ -628,9 +637,23 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     }
     rc = launch_route(p, mode, n_members, w_init, has_lat ? lat_w : nullptr, ldp, out_w, ldp, qs_w, qf_w, T, K,
                       direct ? 1 : first_call, last_call, stream, layout, out_layout, direct ? 1 : 0, pipeline ? trows : 0,
-                      hw_cut / RR_BLOCK, pipeline ? 1 : 0, init_stride);
+                      (unit_pipe ? p->lvl0_slots : hw_cut) / RR_BLOCK, pipeline ? 1 : 0, init_stride,
+                      unit_pipe ? (first_call ? w_init : wf_init) : nullptr, unit_pipe ? p->lvl0_slots : 0);
     if (rc) return rc;
     for (int m = 0; m < n_members; ++m) {
+        if (unit_pipe) {
+            {
+                rr_timer tm(2, stream);
+                if (spec) rc = rr_stage_out_unit(out_w[m], lateral[m], ldl, spec[m].dst, spec[m].f32, spec[m].ld, d->inv, spec[m].subset,
+                                                 spec[m].n_out, T, trows, p->n_blocks, p->lvl0_slots, stream);
+                else rc = rr_stage_out_unit(out_w[m], lateral[m], ldl, out[m], 0, ldo, d->inv, nullptr, n, T, trows, p->n_blocks,
+                                            p->lvl0_slots, stream);
+            }
+            if (rc) return rc;
+            if ((rc = rr_unit_state_to_user(qs_w[m], qf_w[m], d->inv, n, p->lvl0_slots, last_call, lateral[m] + (size_t)(T - 1) * ldl,
+                                            q_state[m], q_full[m], stream))) return rc;
+            continue;
+        }
         if (pipeline) {
             rr_timer tm(2, stream);
             if (spec) rc = rr_stage_out(out_w[m], spec[m].dst, spec[m].f32, spec[m].ld, d->inv, spec[m].subset, spec[m].n_out, T, trows, p->n_blocks, stream);
@@ -940,7 +963,7 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
     const size_t need_f64 = (size_t)chunk * ldd * 8;
     // float32 lateral inflows: the direct pipeline's staging kernel upcasts them on the fly; other paths get an exact
     // upcast into the fp64 scratch first
-    const bool lat_cast = !grid && has_lat && src.lat_f32 && !pipeline_ok(p, mode, substeps);
+    const bool lat_cast = !grid && has_lat && src.lat_f32 && (!pipeline_ok(p, mode, substeps) || mode == RR_MODE_UNIT);
     if ((grid || lat_cast) && (rc = grow_bytes((void **)&d->s_lat, &d->s_lat_cap, need_f64))) return rc;
     if (uh && (rc = grow_bytes((void **)&d->s_conv, &d->s_conv_cap, need_f64))) return rc;
     if (post && !fused && (rc = grow_bytes((void **)&d->s_route, &d->s_route_cap, need_f64))) return rc;

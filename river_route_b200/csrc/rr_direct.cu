@@ -183,17 +183,201 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
     if (c.valid) P.q_state[c.m][c.i] = q;
 }
 
-// reaches with three or four upstreams are rare: their (register-hungry) instantiations live in a function of their own
-// so that they do not set the register allocation -- and the spills -- of the common paths
-template <int MODE>
-__device__ __noinline__ void direct_item_wide(const rr_route_params &P, const dctx &c, double *stage, int max_deg) {
-    if (max_deg == 3) direct_item<MODE, 3>(P, c, stage);
-    else direct_item<MODE, 4>(P, c, stage);
+
+// -----------------------------------------------------------------------------------------------------------------
+// UnitMuskingum (unit_route, _numba_kernels.py:88-171) in the same pipeline.  Headwater reaches (level 0) pass their
+// convolved lateral inflow through (:122-123) and never enter the wavefront: their blocks are left out of the schedule
+// and stage_out writes their rows.  An inner reach reads, per upstream reach, its lateral series (lateral tiles) and --
+// for inner upstreams -- its q_ch series (discharge tiles, raw); q_full of an upstream before a step is its q_ch plus its
+// lateral of the previous step (:165).  The discharge tiles hold q_ch; stage_out forms max(q_ch + lateral, 0) (:165-171).
+// -----------------------------------------------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void unit_item(const rr_route_params &P, const dctx &c, double qf, double *stage) {
+    constexpr int NA = NS > 0 ? NS : 1;
+    const double c1 = c.c1, c2 = c.c2, c3 = c.c3;
+    const int TT = c.TT, j = c.j, lane = c.lane;
+    const int32_t gbase = j * P.gpt;
+    const bool inner = c.deg > 0;
+    double q = c.q;
+    const double *ex[NA], *lu[NA];
+    bool has[NA], hw[NA];
+    double qfo[NA];                 // upstream q_full before the next step
+    d4 exn[NA], exf[NA], lun[NA];   // upstream q_ch: rows s.., s+4.. (s+8.. in flight); upstream lateral: rows s.. (s+4.. in flight)
+    bool full = !c.prog;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        has[k] = k < c.deg;
+        hw[k] = false;
+        ex[k] = P.out[c.m];
+        lu[k] = P.lateral[c.m];
+        qfo[k] = 0.0;
+        exn[k] = exf[k] = lun[k] = d4{0, 0, 0, 0};
+        if (has[k]) {
+            const int64_t u = c.up_u[k];
+            hw[k] = u < P.hw_slots;
+            lu[k] = tile_of(P.lateral[c.m], P, j, u);
+            lun[k] = ld_sector_ro(lu[k]);
+            if (!hw[k]) {
+                ex[k] = tile_of(P.out[c.m], P, j, u);
+                qfo[k] = j == 0 ? P.qf_init[(size_t)c.m * P.q_init_stride + u]
+                                : tile_of(P.out[c.m], P, j - 1, u)[P.tile_rows - 1] + tile_of(P.lateral[c.m], P, j - 1, u)[P.tile_rows - 1];
+                exn[k] = ld_sector(ex[k]);
+                if (4 < TT) exf[k] = ld_sector(ex[k] + 4);
+            }
+        }
+    }
+    const double *lat = c.lat0;
+    auto own = [&](int s0) -> d4 { return (c.valid && s0 < TT) ? ld_sector_ro(lat + s0) : d4{0, 0, 0, 0}; };
+    d4 lcur = own(0), lnxt = own(4);
+    double *st = stage + lane;
+    for (int s = 0; s < TT; s += 4) {
+        if (NS > 0 && !full && (s & 15) == 0 && s > 0) {
+            wait_groups(c, gbase + (s >> 4) + 1, gbase + P.gpt, full);
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (has[k] && !hw[k]) {
+                    exn[k] = ld_sector(ex[k] + s);
+                    if (s + 4 < TT) exf[k] = ld_sector(ex[k] + s + 4);
+                }
+        }
+        const bool ahead = full || ((s + 8) >> 4) == (s >> 4);
+        d4 exr[NA], lur[NA];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            exr[k] = lur[k] = d4{0, 0, 0, 0};
+            if (has[k] && s + 4 < TT) lur[k] = ld_sector_ro(lu[k] + s + 4);
+            if (has[k] && !hw[k] && ahead && s + 8 < TT) exr[k] = ld_sector(ex[k] + s + 8);
+        }
+        const d4 lfar = own(s + 8);
+        const double lv[4] = {lcur.a, lcur.b, lcur.c, lcur.d};
+        double r4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double a_in = 0.0, a_hw = 0.0;                               // :126-139, ascending upstream per class
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const double l = u == 0 ? lun[k].a : (u == 1 ? lun[k].b : (u == 2 ? lun[k].c : lun[k].d));
+                if (has[k]) { if (hw[k]) a_hw += l; else a_in += l; }
+            }
+            double r = c1 * (a_in + a_hw) + c2 * a_hw;                   // :142-143, :151
+            r = r + c3 * q;
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (has[k] && !hw[k]) r = fma(c2, qfo[k], r);            // :152-156  c2 * q_full_old[upstream]
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const double qn = u == 0 ? exn[k].a : (u == 1 ? exn[k].b : (u == 2 ? exn[k].c : exn[k].d));
+                if (has[k] && !hw[k]) r = fma(c1, qn, r);                // :159-162  lhs_off = -c1
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const double qn = u == 0 ? exn[k].a : (u == 1 ? exn[k].b : (u == 2 ? exn[k].c : exn[k].d));
+                const double l = u == 0 ? lun[k].a : (u == 1 ? lun[k].b : (u == 2 ? lun[k].c : lun[k].d));
+                qfo[k] = qn + l;                                         // the upstream's q_full after this step (:165-166)
+            }
+            r4[u] = r;
+            if (s + u < TT && inner) { q = r; qf = r + lv[u]; }
+        }
+        const int rr = s & 15;
+        st[(rr + 0) * RR_BLOCK] = r4[0];
+        st[(rr + 1) * RR_BLOCK] = r4[1];
+        st[(rr + 2) * RR_BLOCK] = r4[2];
+        st[(rr + 3) * RR_BLOCK] = r4[3];
+        if (rr == 12 || s + 4 >= TT) {
+            if (c.valid) {
+                double *o = c.out0 + (s - rr);
+#pragma unroll
+                for (int v = 0; v < 16; v += 4)
+                    if (v <= rr) st_sector(o + v, st[(v + 0) * RR_BLOCK], st[(v + 1) * RR_BLOCK], st[(v + 2) * RR_BLOCK], st[(v + 3) * RR_BLOCK]);
+            }
+            if (c.narrow && s + 4 < TT) {
+                jitter_delay(P.jitter, c.b, j, 1 + (s >> 4));
+                __syncwarp();
+                if (lane == 0) st_release(c.done + c.b, gbase + (s >> 4) + 1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { exn[k] = exf[k]; exf[k] = exr[k]; lun[k] = lur[k]; }
+        lcur = lnxt;
+        lnxt = lfar;
+    }
+    if (c.valid && inner) { P.q_state[c.m][c.i] = q; P.q_full[c.m][c.i] = qf; }
 }
 
 }  // namespace
 
-template <int MODE>
+template <int MAXNS>
+__global__ void __launch_bounds__(256, 2) rr_direct_unit_kernel(const __grid_constant__ rr_route_params P) {
+    __shared__ double stage_all[8][16 * RR_BLOCK];
+    const int lane = threadIdx.x & 31;
+    double *stage = stage_all[threadIdx.x >> 5];
+    int m, b, j, dep_lo, dep_hi;
+    while (next_ticket(P, lane, m, b, j, dep_lo, dep_hi)) {
+        dctx c;
+        const int64_t i = (int64_t)b * RR_BLOCK + lane;
+        const bool valid = i < P.n;
+        const int64_t ic = valid ? i : P.n - 1;
+        c.m = m; c.b = b; c.j = j; c.lane = lane; c.i = i; c.valid = valid;
+        c.c1 = __ldg(P.c1 + ic); c.c2 = __ldg(P.c2 + ic); c.c3 = __ldg(P.c3 + ic); c.c4 = 0.0;
+        const int e0 = __ldg(P.up_ptr + ic);
+        c.deg = valid ? __ldg(P.up_ptr + ic + 1) - e0 : 0;
+        const rr_blk_meta M = P.meta[b];
+        c.narrow = (M.int_mask & RR_META_NARROW) != 0;
+        c.TT = min(P.tile_rows, P.T - j * P.tile_rows);
+        c.dep_blk = dep_lo + lane < dep_hi ? __ldg(P.dep_idx + dep_lo + lane) : -1;
+#pragma unroll
+        for (int k = 0; k < MAXNS; ++k) c.up_u[k] = k < c.deg ? __ldg(P.up_idx + e0 + k) : 0;
+        c.done = P.done + (size_t)m * P.n_blocks;
+        c.lat0 = tile_of(P.lateral[m], P, j, i);
+        c.out0 = const_cast<double *>(tile_of(P.out[m], P, j, i));
+        const int32_t full_want = (j + 1) * P.gpt;
+        jitter_delay(P.jitter, b, j, 100);
+        if (lane == 0 && j > 0) wait_ge(c.done + b, j * P.gpt);
+        c.prog = false;
+        if (c.narrow && dep_hi - dep_lo <= 32 && dep_hi > dep_lo) {
+            bool full = false;
+            wait_groups(c, j * P.gpt + 1, full_want, full);
+            c.prog = !full;
+        } else {
+            if (c.dep_blk >= 0) wait_ge(c.done + c.dep_blk, full_want);
+            for (int e = dep_lo + 32 + lane; e < dep_hi; e += 32) wait_ge(c.done + __ldg(P.dep_idx + e), full_want);
+        }
+        __syncwarp();
+        c.q = 0.0;
+        double qf = 0.0;
+        if (valid) {
+            c.q = (j == 0) ? P.q_init[(size_t)m * P.q_init_stride + i] : P.q_state[m][i];
+            qf = (j == 0) ? P.qf_init[(size_t)m * P.q_init_stride + i] : P.q_full[m][i];
+        }
+        if (MAXNS <= 2) {
+            switch (M.max_deg) {
+                case 0: unit_item<0>(P, c, qf, stage); break;
+                case 1: unit_item<1>(P, c, qf, stage); break;
+                default: unit_item<2>(P, c, qf, stage); break;
+            }
+        } else {
+            switch (M.max_deg) {
+                case 0: unit_item<0>(P, c, qf, stage); break;
+                case 1: unit_item<1>(P, c, qf, stage); break;
+                case 2: unit_item<2>(P, c, qf, stage); break;
+                case 3: unit_item<3>(P, c, qf, stage); break;
+                default: unit_item<RR_MAX_FAST_DEG>(P, c, qf, stage); break;
+            }
+        }
+        jitter_delay(P.jitter, b, j, 200);
+        __syncwarp();
+        if (lane == 0) st_release(c.done + b, full_want);
+        __syncwarp();
+    }
+}
+
+namespace {
+}  // namespace
+
+// MAXNS: largest in-degree of the network, 2 or RR_MAX_FAST_DEG.  Networks with confluences of three or four rivers get
+// a kernel of their own so that the register-hungry instantiations do not set the register allocation -- and the
+// spills -- of the common case (at most two upstream reaches).
+template <int MODE, int MAXNS>
 __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant__ rr_route_params P) {
     __shared__ double stage_all[8][16 * RR_BLOCK];
     constexpr bool HAS_LAT = (MODE == RR_MODE_RAPID);
@@ -216,7 +400,7 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
         c.TT = min(P.tile_rows, P.T - t0);
         c.dep_blk = dep_lo + lane < dep_hi ? __ldg(P.dep_idx + dep_lo + lane) : -1;
 #pragma unroll
-        for (int k = 0; k < RR_MAX_FAST_DEG; ++k) c.up_u[k] = k < c.deg ? __ldg(P.up_idx + e0 + k) : 0;
+        for (int k = 0; k < MAXNS; ++k) c.up_u[k] = k < c.deg ? __ldg(P.up_idx + e0 + k) : 0;
         c.done = P.done + (size_t)m * P.n_blocks;
         c.lat0 = HAS_LAT ? tile_of(P.lateral[m], P, j, i) : nullptr;
         c.out0 = const_cast<double *>(tile_of(P.out[m], P, j, i));
@@ -237,11 +421,20 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
         __syncwarp();
         c.q = 0.0;
         if (valid) c.q = (j == 0) ? P.q_init[(size_t)m * P.q_init_stride + i] : P.q_state[m][i];
-        switch (M.max_deg) {
-            case 0: direct_item<MODE, 0>(P, c, stage); break;
-            case 1: direct_item<MODE, 1>(P, c, stage); break;
-            case 2: direct_item<MODE, 2>(P, c, stage); break;
-            default: direct_item_wide<MODE>(P, c, stage, M.max_deg); break;
+        if (MAXNS <= 2) {
+            switch (M.max_deg) {
+                case 0: direct_item<MODE, 0>(P, c, stage); break;
+                case 1: direct_item<MODE, 1>(P, c, stage); break;
+                default: direct_item<MODE, 2>(P, c, stage); break;
+            }
+        } else {
+            switch (M.max_deg) {
+                case 0: direct_item<MODE, 0>(P, c, stage); break;
+                case 1: direct_item<MODE, 1>(P, c, stage); break;
+                case 2: direct_item<MODE, 2>(P, c, stage); break;
+                case 3: direct_item<MODE, 3>(P, c, stage); break;
+                default: direct_item<MODE, RR_MAX_FAST_DEG>(P, c, stage); break;
+            }
         }
         jitter_delay(P.jitter, b, j, 200);
         __syncwarp();
@@ -250,20 +443,34 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
     }
 }
 
-cudaError_t rr_launch_direct(int mode, const rr_route_params &P, int grid, cudaStream_t stream) {
-    switch (mode) {
-        case RR_MODE_MUSKINGUM: rr_direct_kernel<RR_MODE_MUSKINGUM><<<grid, 256, 0, stream>>>(P); break;
-        case RR_MODE_RAPID: rr_direct_kernel<RR_MODE_RAPID><<<grid, 256, 0, stream>>>(P); break;
-        default: return cudaErrorInvalidValue;
-    }
+cudaError_t rr_launch_direct(int mode, int max_deg, const rr_route_params &P, int grid, cudaStream_t stream) {
+    const bool wide = max_deg > 2;
+    if (mode == RR_MODE_UNIT) {
+        if (wide) rr_direct_unit_kernel<RR_MAX_FAST_DEG><<<grid, 256, 0, stream>>>(P);
+        else rr_direct_unit_kernel<2><<<grid, 256, 0, stream>>>(P);
+    } else if (mode == RR_MODE_MUSKINGUM) {
+        if (wide) rr_direct_kernel<RR_MODE_MUSKINGUM, RR_MAX_FAST_DEG><<<grid, 256, 0, stream>>>(P);
+        else rr_direct_kernel<RR_MODE_MUSKINGUM, 2><<<grid, 256, 0, stream>>>(P);
+    } else if (mode == RR_MODE_RAPID) {
+        if (wide) rr_direct_kernel<RR_MODE_RAPID, RR_MAX_FAST_DEG><<<grid, 256, 0, stream>>>(P);
+        else rr_direct_kernel<RR_MODE_RAPID, 2><<<grid, 256, 0, stream>>>(P);
+    } else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
-int rr_direct_occupancy(int mode) {
+int rr_direct_occupancy(int mode, int max_deg) {
     int nb = 0;
-    cudaError_t e = mode == RR_MODE_MUSKINGUM
-                        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM>, 256, 0)
-                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID>, 256, 0);
+    const bool wide = max_deg > 2;
+    cudaError_t e;
+    if (mode == RR_MODE_UNIT)
+        e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_unit_kernel<RR_MAX_FAST_DEG>, 256, 0)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_unit_kernel<2>, 256, 0);
+    else if (mode == RR_MODE_MUSKINGUM)
+        e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM, RR_MAX_FAST_DEG>, 256, 0)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM, 2>, 256, 0);
+    else
+        e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID, RR_MAX_FAST_DEG>, 256, 0)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID, 2>, 256, 0);
     return e == cudaSuccess ? nb : -1;
 }
 
@@ -343,6 +550,60 @@ __global__ void __launch_bounds__(256) stage_out_kernel(const double *__restrict
         }
 }
 
+// UnitMuskingum: the discharge tiles hold q_ch of the inner reaches.  Output = the convolved lateral inflow itself for
+// headwaters (unclamped, _numba_kernels.py:122-123), max(q_ch + lateral, 0) for inner reaches (:165-171, one substep
+// per row); the lateral rows are read from the caller's array (coalesced, column i = segment i).
+template <typename OT>
+__global__ void __launch_bounds__(256) stage_out_unit_kernel(const double *__restrict__ out_w, const double *__restrict__ lat,
+                                                             int64_t ldl, OT *__restrict__ dst, int64_t ldd,
+                                                             const int32_t *__restrict__ inv, const int32_t *__restrict__ subset,
+                                                             int64_t n_out, int64_t T, int64_t tile_rows, int64_t pitch,
+                                                             int64_t n_blocks, int64_t hw_slots) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_out) return;
+    const int64_t i = subset ? (int64_t)__ldg(subset + s) : s;
+    const int64_t k = __ldg(inv + i);
+    const int64_t t0 = (int64_t)blockIdx.y * 16;
+    const bool hw = k < hw_slots;
+    double v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = 0.0;
+    if (!hw) {
+        const double *p = out_w + tile_index(t0, k, tile_rows, pitch, n_blocks);
+#pragma unroll
+        for (int r = 0; r < 16; r += 4) {
+            const d4 x = ld_sector_ro(p + r);
+            v[r] = x.a; v[r + 1] = x.b; v[r + 2] = x.c; v[r + 3] = x.d;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+        if (t0 + r < T) {
+            const double l = __ldg(lat + (t0 + r) * ldl + i);
+            double val = l;
+            if (!hw) { val = v[r] + l; val = val > 0.0 ? val : 0.0; }
+            dst[(t0 + r) * ldd + s] = (OT)val;
+        }
+}
+
+// UnitMuskingum state hand-back in the caller's order.  last != 0: the recombined vector of UnitMuskingum.py:94-98
+// (headwaters: lateral inflow of the last row, inner: q_full).  Otherwise the kernel-level pair: q_ch and q_full of the
+// inner reaches; headwater entries are left untouched.
+__global__ void __launch_bounds__(256) unit_state_kernel(const double *__restrict__ qs_w, const double *__restrict__ qf_w,
+                                                         const int32_t *__restrict__ inv, int64_t n, int64_t hw_slots, int last,
+                                                         const double *__restrict__ lat_last, double *__restrict__ q_state,
+                                                         double *__restrict__ q_full) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t k = __ldg(inv + i);
+    if (k < hw_slots) {
+        if (last) q_state[i] = __ldg(lat_last + i);
+        return;
+    }
+    if (last) q_state[i] = qf_w[k];
+    else { q_state[i] = qs_w[k]; q_full[i] = qf_w[k]; }
+}
+
 }  // namespace
 
 #define CKD(call)                                                                                  \
@@ -384,6 +645,30 @@ int rr_stage_out(const double *out_w, void *dst, int dst_f32, int64_t ldd, const
         stage_out_kernel<float><<<grid, 256, 0, stream>>>(out_w, (float *)dst, ldd, inv, subset, n_out, T, tile_rows, pitch, n_blocks);
     else
         stage_out_kernel<double><<<grid, 256, 0, stream>>>(out_w, (double *)dst, ldd, inv, subset, n_out, T, tile_rows, pitch, n_blocks);
+    CKD(cudaGetLastError());
+    rr_count_launch(1);
+    return 0;
+}
+
+int rr_stage_out_unit(const double *out_w, const double *lat, int64_t ldl, void *dst, int dst_f32, int64_t ldd, const int32_t *inv,
+                      const int32_t *subset, int64_t n_out, int64_t T, int64_t tile_rows, int64_t n_blocks, int64_t hw_slots,
+                      cudaStream_t stream) {
+    const int64_t pitch = (tile_rows + 3) & ~(int64_t)3;
+    dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)((T + 15) / 16));
+    if (dst_f32)
+        stage_out_unit_kernel<float><<<grid, 256, 0, stream>>>(out_w, lat, ldl, (float *)dst, ldd, inv, subset, n_out, T, tile_rows,
+                                                               pitch, n_blocks, hw_slots);
+    else
+        stage_out_unit_kernel<double><<<grid, 256, 0, stream>>>(out_w, lat, ldl, (double *)dst, ldd, inv, subset, n_out, T, tile_rows,
+                                                                pitch, n_blocks, hw_slots);
+    CKD(cudaGetLastError());
+    rr_count_launch(1);
+    return 0;
+}
+
+int rr_unit_state_to_user(const double *qs_w, const double *qf_w, const int32_t *inv, int64_t n, int64_t hw_slots, int last,
+                          const double *lat_last, double *q_state, double *q_full, cudaStream_t stream) {
+    unit_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(qs_w, qf_w, inv, n, hw_slots, last, lat_last, q_state, q_full);
     CKD(cudaGetLastError());
     rr_count_launch(1);
     return 0;

@@ -53,6 +53,8 @@ struct rr_route_params {
     unsigned long long *prof;   // optional [8] cycle counters (RR_PROFILE builds), else nullptr
     const double *q_init;                       // start-of-call state: member m reads q_init + m * q_init_stride
     int64_t q_init_stride;                      // 0: one state shared by all members (TransformMuskingum.py:121-126)
+    const double *qf_init;                      // UNIT pipeline: start-of-call q_full (same member stride); == q_init at a file start
+    int64_t hw_slots;                           // UNIT pipeline: working slots below this index are headwaters (level 0)
     const double *lateral[RR_MAX_MEMBERS];
     double *out[RR_MAX_MEMBERS];
     double *q_state[RR_MAX_MEMBERS];            // per-member running / final state (UNIT: q_ch)

@@ -560,7 +560,6 @@ class TransformMuskingum(Muskingum):
                     self._set_network_and_time_dependent_vectors(dates)
                     T = self.num_runoff_steps
                     k = self.num_runoff_steps_per_discharge if self.dt_discharge > self.dt_runoff else 1
-                    dates_out = dates[::k] if k > 1 else dates
                     unit = int(np.lcm(16, k))
                     G = int(max(1, min(M - done, 64, budget // max(1, unit * n * srcs[0].dtype.itemsize))))
                     for f in range(done + 1, done + G):
@@ -568,14 +567,15 @@ class TransformMuskingum(Muskingum):
                     for src, (lat_file, _) in zip(srcs, pairs[done:done + G]):
                         self.logger.info(f'Routing qlateral: {lat_file}')
                         self._check_lateral_shape(src.shape, n)
-                        if not np.array_equal(src.dates, dates):
-                            raise ValueError('ensemble members must share one time axis')
+                        if src.dates.shape != dates.shape or (len(dates) > 1 and src.dates[1] - src.dates[0] != dates[1] - dates[0]):
+                            raise ValueError('ensemble members must have the same number of time steps and time step')
                     dtype = srcs[0].dtype if all(s_.dtype == srcs[0].dtype for s_ in srcs) else np.dtype(np.float64)
                     slab = self._slab_rows(T, k, G * n * dtype.itemsize)
                     starts = list(range(0, T, slab))
                     lat = [[self._pinned(('elat', b, m), (slab, n), dtype) for m in range(G)] for b in range(2)]
                     out = [[self._pinned(('eout', b, m), (slab // k, n), np.float32) for m in range(G)] for b in range(2)]
-                    files = [self._open_discharge_file(dates_out, n, pairs[done + m][1], pairs[done + m][0]) for m in range(G)]
+                    files = [self._open_discharge_file(srcs[m].dates[::k] if k > 1 else srcs[m].dates, n, pairs[done + m][1],
+                                                       pairs[done + m][0]) for m in range(G)]
                     try:
                         def read(s_):
                             t0, t1 = starts[s_], min(T, starts[s_] + slab)

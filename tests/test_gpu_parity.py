@@ -323,3 +323,43 @@ def test_device_api_and_ensemble(renumber):
     mean_ref = np.array(qrefs).mean(axis=0)
     mean_gpu = torch.stack(d_qf).mean(dim=0).cpu().numpy()
     assert parity_error(mean_gpu, mean_ref) < TOL
+
+
+@pytest.mark.parametrize('max_in', [3, 4, 6])
+@pytest.mark.parametrize('staging', ['auto', 'direct'])
+def test_confluences_of_many_rivers(max_in, staging):
+    """Networks with confluences of three and four reaches run the wide instantiation of the direct kernel (upstream
+    sums still in ascending params-file index); beyond four upstreams the plan leaves the direct pipeline and the general
+    path takes over."""
+    n, T = 20000, 40
+    rng = np.random.default_rng(max_in)
+    down = np.full(n, -1, dtype=np.int32)
+    indeg = np.zeros(n, dtype=np.int64)
+    for i in range(n - 1):
+        if rng.random() < 0.002:
+            continue                                   # an outlet
+        for _ in range(8):
+            d = int(rng.integers(i + 1, min(n, i + 400)))
+            if indeg[d] < max_in:
+                down[i] = d
+                indeg[d] += 1
+                break
+    assert indeg.max() == max_in
+    k, x = synth.muskingum_params(n, 2)
+    a = network_arrays(down, k, x, 3600, 3600)
+    plan = rr.Plan(down, renumber='always', staging=staging)
+    assert plan.info['max_indegree'] == max_in and plan.info['all_fast'] == int(max_in <= 4)
+    plan.set_coefficients(a['c1'], a['c2'], a['c3'], a['c4_dt'])
+    q0 = rng.uniform(0, 50, n)
+    ql = synth.lateral_volumes(T, n, 5)
+    q_ref, ref = q0.copy(), np.zeros((T, n))
+    oracle.rapid_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], a['c4_dt'], q_ref, ql, ref, 1)
+    q, out = q0.copy(), np.full((T, n), np.nan)
+    plan.route_host(rr.MODE_RAPID, q, ql, out, 1)
+    assert parity_error(out, ref) < TOL and parity_error(q, q_ref) < TOL
+    q_ref, ref = q0.copy(), np.zeros((T, n))
+    oracle.muskingum_route(a['indptr'], a['indices'], a['lhs_off'], a['c2'], a['c3'], q_ref, ref, T, 1)
+    q, out = q0.copy(), np.full((T, n), np.nan)
+    plan.route_host(rr.MODE_MUSKINGUM, q, None, out, 1)
+    assert parity_error(out, ref) < TOL and parity_error(q, q_ref) < TOL
+    plan.close()

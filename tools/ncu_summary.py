@@ -109,7 +109,7 @@ def traffic_step(report, reaches, rows_, variant, out_path):
     hdr, units, rows = raw(report)
     col = {h: i for i, h in enumerate(hdr)}
     per = float(reaches) * float(rows_)
-    classes = {'route': 'rr_wavefront', 'permute_to_working': 'permute_to_working|stage_in', 'permute_to_user': 'permute_to_user|stage_out'}
+    classes = {'route': 'rr_wavefront|rr_direct', 'permute_to_working': 'permute_to_working|stage_in', 'permute_to_user': 'permute_to_user|stage_out'}
     entry = {'reaches': int(reaches), 'rows': int(rows_), 'source': f'ncu --set full --clock-control none, {report}'}
     for cls, pat in classes.items():
         best = None

@@ -279,6 +279,32 @@ def measured_peak():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def pcie_ceiling(world, e2e_value):
+    """The measured concurrent pinned H2D + D2H rate of this pool's boxes at this rank count
+    (tools/pcie_ceiling_probe.py -> profiles/r02_pcie_ceiling.jsonl) and the e2e value as a fraction of what it allows
+    for 8 B in / 4 B out per reach-timestep."""
+    try:
+        best = None
+        with open(os.path.join(ROOT, 'profiles', 'r02_pcie_ceiling.jsonl')) as f:
+            for line in f:
+                d = json.loads(line)
+                if d.get('n_gpus') == world:
+                    best = d
+        if best is None:
+            return None
+        h2d = best['h2d_only']['GBps_aggregate_per_direction'] * 1e9 / 8.0      # 8 B enter the GPU per reach-timestep
+        both = best['both']['GBps_aggregate_per_direction'] * 1e9 / 8.0         # ... while as many bytes leave it
+        return {'GBps_h2d_only': best['h2d_only']['GBps_aggregate_per_direction'],
+                'GBps_d2h_only': best['d2h_only']['GBps_aggregate_per_direction'],
+                'GBps_each_direction_when_both_run': best['both']['GBps_aggregate_per_direction'],
+                'reach_steps_per_s_at_h2d_only_rate': h2d, 'reach_steps_per_s_at_both_directions_rate': both,
+                'e2e_frac_of_h2d_only_ceiling': e2e_value / h2d,
+                'note': 'e2e moves 8 B in and 4 B out per reach-timestep: its ceiling lies between the two rates',
+                'source': 'profiles/r02_pcie_ceiling.jsonl (tools/pcie_ceiling_probe.py, same pool, all ranks at once)'}
+    except Exception:
+        return None
+
+
 def ncu_traffic(variant):
     """DRAM bytes per reach-timestep of each kernel class from the committed ncu capture of this kernel variant."""
     try:
@@ -288,24 +314,29 @@ def ncu_traffic(variant):
         return None
 
 
-def roofline_block(ktimes, steps, n, rows, tile_rows, value, variant, peak, peak_src):
+def roofline_block(ktimes, steps, n, rows, tile_rows, value, variant, peak, peak_src, n_in_kernel=None):
     """All fractions are of the measured copy peak.  `frac`: the contract's 56 B (a model ratio: > 1 is possible);
     `frac_dram`: DRAM bytes ncu counted for this variant / CUDA-event time; `frac_min`: bytes a time-tiled kernel must
     move (8 lateral + 8 discharge + 40 B of coefficients / topology once per tile)."""
     units = float(n) * float(rows)
+    # reach-timesteps ONE launch of the wavefront kernel processes: with the headwater blocks routed by the staging
+    # kernel (pipeline, RapidMuskingum, >= 2^18 reaches) that is the non-headwater share of the network
+    k_units = float(n_in_kernel if n_in_kernel is not None else n) * float(rows)
     kernel_ms = ktimes['route']['ms'] / max(ktimes['route']['launches'], 1)
     b_min = 16.0 + 40.0 / max(tile_rows, 1)
     tr = ncu_traffic(variant) or {}
 
-    def gbs(bytes_per_unit, ms):
-        return bytes_per_unit * units / (ms * 1e-3) / 1e9
-    achieved = gbs(B_ALG, kernel_ms)
-    r_bytes = (tr.get('route') or {}).get('dram_bytes_per_reach_step')
+    def gbs(bytes_per_unit, ms, u=None):
+        return bytes_per_unit * (units if u is None else u) / (ms * 1e-3) / 1e9
+    achieved = gbs(B_ALG, kernel_ms, k_units)
+    r_bytes = (tr.get('route') or {}).get('dram_bytes_per_reach_step')     # per reach-timestep of the WHOLE network
     block = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+             'units_per_launch': k_units, 'units_note': 'reach-timesteps the wavefront launch itself advances',
              'traffic': r_bytes * units if r_bytes else None,
              'frac_dram': gbs(r_bytes, kernel_ms) / peak if r_bytes else None,
-             'frac_min': gbs(b_min, kernel_ms) / peak,
-             'kernel': 'rr_wavefront_kernel<RAPID>', 'kernel_ms': kernel_ms, 'tile_rows': tile_rows,
+             'frac_min': gbs(b_min, kernel_ms, k_units) / peak,
+             'kernel': 'rr_direct_kernel<RAPID>' if variant == 'pipeline' else 'rr_wavefront_kernel<RAPID>', 'kernel_ms': kernel_ms,
+             'tile_rows': tile_rows,
              'algorithmic_bytes_per_reach_step': B_ALG, 'min_bytes_per_reach_step': b_min,
              'dram_bytes_per_reach_step': r_bytes, 'peak_source': peak_src,
              'traffic_source': (f"{tr.get('source')} ({tr.get('reaches')} reaches x {tr.get('rows')} rows, variant "
@@ -489,7 +520,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        variant = {'auto': 'direct', 'direct': 'direct', 'registers-tiled': 'ring'}.get(args.staging, args.staging)
+        variant = {'auto': 'pipeline', 'direct': 'pipeline', 'registers-tiled': 'ring'}.get(args.staging, args.staging)
         tile_rows = plan.tile_rows(rows, 1)
         line = {
             'metric': 'reach-timesteps/sec (RapidMuskingum, fp64)', 'value': value, 'unit': 'reach-timesteps/s',
@@ -497,13 +528,16 @@ def main():
             'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': workload_config(args),
             'run': {'rows_per_step': rows, 'reaches_rank0': n, 'plan': {k_: int(v) for k_, v in info.items()}},
-            'roofline': roofline_block(ktimes, args.steps, n, rows, tile_rows, value, variant, peak, peak_src),
+            'roofline': roofline_block(ktimes, args.steps, n, rows, tile_rows, value, variant, peak, peak_src,
+                                       n - int(info['n_headwaters']) if (variant == 'pipeline' and args.staging != 'direct-nohw' and
+                                                                         (n >= (1 << 18) or args.staging == 'direct')) else n),
             'e2e': {'value': e2e_value, 'unit': 'reach-timesteps/s', 'h2d_bytes_per_step': int(n * er * 8 + n * 8),
                     'd2h_bytes_per_step': int(n * er * 4 + n * 8), 'rows_per_step': er, 'steps': args.e2e_steps,
                     'api': 'Plan.route_host with a float32 output array -> rr_route_host_ex: pinned fp64 lateral inflows '
                            'in, route, float32 cast on the device (TransformMuskingum.py:146), float32 discharge out; '
                            'chunked cudaMemcpyAsync on three streams',
-                    'host_equals_device_path': host_equals_dev, 'numa_bound': numa_bound, 'variants': variants},
+                    'host_equals_device_path': host_equals_dev, 'numa_bound': numa_bound, 'variants': variants,
+                    'pcie_ceiling': pcie_ceiling(world, e2e_value)},
             'gpu_launches': int(launches), 'kernel_phase_cycles': prof,
             'clocks': clocks,
             'checks': checks,
@@ -648,7 +682,65 @@ def e2e_variants(args, rr, plan, timed_host, h_q, h_lat, h_out32, er, n, local_d
         'api': 'Plan.set_output_subset + Plan.runoff_route_host (all reaches routed, outlet columns copied back)'}
     plan.set_output_subset(None)
     tf.close()
+    del h_grid, h_out_sub
+    # (d) lateral inflows stored as float32 (a qlateral variable may be; the reference upcasts on the host,
+    #     TransformMuskingum.py:36): the rows cross PCIe as stored and are upcast -- exactly -- by the staging kernel
+    h_lat32 = rr.pinned_empty((er, n), dtype=np.float32)
+    for t0 in range(0, er, 32):
+        h_lat32[t0:t0 + 32] = h_lat[t0:t0 + 32]
+    variants['f32_lateral_in_f32_out'] = {
+        'value': timed_host(lambda: plan.route_host(rr.MODE_RAPID, h_q, h_lat32, h_out32, 1)),
+        'h2d_bytes_per_step': int(n * er * 4 + n * 8), 'd2h_bytes_per_step': int(n * er * 4 + n * 8),
+        'api': 'Plan.route_host with a float32 lateral array -> rr_route_host_typed'}
+    # (e) the class API on files: RapidMuskingum(config).route() with a float32 qlateral netCDF and the discharge
+    #     netCDF on tmpfs.  Slabs go file -> pinned buffer -> GPU -> pinned buffer -> file; the network plan is reused by
+    #     the second (timed) route().  On this image the files are classic netCDF through scipy (big-endian on disk, no
+    #     netCDF4 / HDF5 stack), so the number is bounded by single-threaded byte swapping, not by PCIe.
+    try:
+        variants['router_files'] = router_files_variant(args, rr, n, local_down, h_lat32, min(er, 64))
+    except Exception as e:                                   # optional variant: never takes the bench line down
+        variants['router_files'] = {'error': f'{type(e).__name__}: {e}'}
     return variants
+
+
+def router_files_variant(args, rr, n, local_down, h_lat32, rows):
+    import shutil
+    import tempfile
+    import pandas as pd
+    from river_route_b200 import ncio, synth
+    tmp = tempfile.mkdtemp(prefix='rr_bench_', dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
+    try:
+        ids = np.arange(n, dtype=np.int64) + 1
+        k, x = synth.muskingum_params(args.reaches, 4)
+        pd.DataFrame({'river_id': ids, 'downstream_river_id': np.where(local_down >= 0, ids[np.where(local_down >= 0, local_down, 0)], -1),
+                      'k': k[:n], 'x': x[:n]}).to_parquet(os.path.join(tmp, 'params.parquet'))
+        with ncio.open_nc(os.path.join(tmp, 'ql.nc'), 'w') as nc:
+            nc.createDimension('time', rows)
+            nc.createDimension('river_id', n)
+            tv = nc.createVariable('time', 'f8', ('time',))
+            tv.units = 'seconds since 2022-01-01 00:00:00'
+            tv[:] = np.arange(rows) * float(DT)
+            nc.createVariable('river_id', 'i4', ('river_id',))[:] = ids.astype(np.int32)
+            nc.createVariable('qlateral', 'f4', ('time', 'river_id'))[:] = h_lat32[:rows]
+        r = rr.RapidMuskingum(params_file=os.path.join(tmp, 'params.parquet'), qlateral_files=[os.path.join(tmp, 'ql.nc')],
+                              discharge_dir=tmp, log=False)
+        t0 = time.perf_counter()
+        r.route()                                             # builds the plan, pins the slab buffers
+        first = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        r._set_network_dependent_vectors()
+        setup = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        r._execute_routing()
+        execute = time.perf_counter() - t0
+        size = os.path.getsize(os.path.join(tmp, 'discharge_ql.nc'))
+        return {'value': n * rows / execute, 'rows': rows, 'first_route_s': first, 'params_read_and_plan_reuse_s': setup,
+                'execute_routing_s': execute, 'h2d_bytes_per_step': int(n * rows * 4 + n * 8),
+                'd2h_bytes_per_step': int(n * rows * 4 + n * 8), 'discharge_file_bytes': int(size), 'netcdf_backend': ncio.backend(),
+                'api': 'RapidMuskingum(params_file, qlateral_files, discharge_dir).route(): float32 qlateral netCDF in, '
+                       'discharge netCDF out, both on tmpfs; value = reaches x rows / _execute_routing wall time'}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 if __name__ == '__main__':

@@ -970,6 +970,12 @@ class _LateralFile:
 
     def read(self, t0, t1, out):
         """rows [t0, t1) -> out[:t1 - t0] (masked entries become NaN like the reference's xarray read)."""
+        raw = getattr(self.var, 'data', None)
+        if self.time_major and isinstance(raw, np.ndarray) and \
+                not any(k in getattr(self.var, '_attributes', {}) for k in ('missing_value', '_FillValue', 'scale_factor', 'add_offset')):
+            # classic file through scipy, plain values: one byte-swapping copy straight from the memory map
+            np.copyto(out[:t1 - t0], raw[t0:t1], casting='unsafe')
+            return out[:t1 - t0]
         if self.time_major:
             a = self.var[t0:t1]
         else:

@@ -375,45 +375,85 @@ def bench_coefficients(k, x, dt=3600):
 
 
 def c5():
-    """51 members x 360 steps, device resident: members are routed one after the other from the same initial state
-    (time tiling already amortises the parameters, which is what batching members as columns was for in a
-    per-timestep formulation).  Member inputs = one base series x lognormal(0, 0.3) per member."""
+    """Ensemble forecast, 51 members x 360 hourly steps x 7M reaches.  51 x 360 x 7M x 8 B = 1 TB of lateral inflows do
+    not fit one GPU, so the members stream from (pinned) host memory whatever is done on the device; two figures:
+    (1) device resident: 5 members x 120 rows routed by ONE batched call (rr_route_ensemble_dev: stage_in / stage_out
+        per member, one wavefront launch over tickets x members), per-member parity on whole basins, against the same
+        5 members routed one call each;
+    (2) host arrays: rr_route_ensemble_host, 6 members x 96 rows of pinned float32 inflows in, float32 discharge out,
+        members of a chunk in one launch, mean state on the device (TransformMuskingum.py:121-126, :145-146).
+    Member inputs = one base series x lognormal(0, 0.3) per member."""
     n, down, k, x = c4_network()
     plan = rr.Plan(down)
     plan.set_coefficients(*bench_coefficients(k, x))
-    T, M = 360, 51
-    ld = n
-    base = torch.from_numpy(synth.lateral_volumes(24, n, 6)).to(dev)
-    d_lat = torch.empty((T, ld), dtype=torch.float64, device=dev)
-    d_out = torch.empty((T, ld), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
     q_init = np.random.default_rng(6).uniform(0, 30, n)
     d_q0 = torch.from_numpy(q_init).to(dev)
-    d_mean = torch.zeros(n, dtype=torch.float64, device=dev)
-    scale = np.random.default_rng(7).lognormal(0, 0.3, M)
-    stream = torch.cuda.current_stream().cuda_stream
-    checks = []
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    route_ms = 0.0
-    for mbr in range(M):
+    scale = np.random.default_rng(7).lognormal(0, 0.3, 51)
+    base = torch.from_numpy(synth.lateral_volumes(24, n, 6)).to(dev)
+    # ---- (1) device resident ----
+    G, T = 5, 120
+    lats = [torch.empty((T, n), dtype=torch.float64, device=dev) for _ in range(G)]
+    outs = [torch.empty((T, n), dtype=torch.float64, device=dev) for _ in range(G)]
+    finals = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(G)]
+    for m in range(G):
         for r in range(0, T, 24):
-            d_lat[r:r + 24] = base * float(scale[mbr]) * (1.0 + 0.01 * (r // 24))
-        d_q = d_q0.clone()
-        e0.record()
-        plan.route_dev(rr.MODE_RAPID, d_q.data_ptr(), d_lat.data_ptr(), ld, d_out.data_ptr(), ld, T, 1, stream)
-        e1.record()
-        torch.cuda.synchronize()
-        route_ms += e0.elapsed_time(e1)
-        d_mean += d_q                                                         # member-order sum, then / M (:145-146)
-        if mbr in (0, M - 1):
-            m = first_basins(down, 60_000)
-            p_out, p_q = subset_parity(down, k, x, m, d_lat[:, :m].cpu().numpy(), d_out[:, :m].cpu().numpy(),
-                                       q_init[:m], d_q[:m].cpu().numpy())
-            checks.append(dict(member=mbr, parity_reaches=m, parity=p_out, parity_state=p_q))
-    d_mean /= M
-    emit(config='C5', stage='ensemble', members=M, reaches=n, steps=T, route_ms_total=route_ms,
-         reach_steps_members_per_s=n * T * M / (route_ms * 1e-3), checks=checks,
-         mean_state_finite=bool(torch.isfinite(d_mean).all().item()), mean_state_sum=float(d_mean.sum().item()))
+            lats[m][r:r + 24] = base * float(scale[m]) * (1.0 + 0.01 * (r // 24))
+
+    def timed(fn, reps=3):
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    batched_ms = timed(lambda: plan.route_ensemble_dev(rr.MODE_RAPID, d_q0.data_ptr(), [t.data_ptr() for t in lats], n,
+                                                       [t.data_ptr() for t in outs], n, [t.data_ptr() for t in finals], T, 1, stream))
+    m_chk = first_basins(down, 60_000)
+    checks = []
+    for m in (0, G - 1):
+        p_out, p_q = subset_parity(down, k, x, m_chk, lats[m][:, :m_chk].cpu().numpy(), outs[m][:, :m_chk].cpu().numpy(),
+                                   q_init[:m_chk], finals[m][:m_chk].cpu().numpy())
+        checks.append(dict(member=m, parity_reaches=m_chk, parity=p_out, parity_state=p_q))
+    keep = outs[G - 1].clone()
+    d_q = torch.empty(n, dtype=torch.float64, device=dev)
+
+    def one_by_one():
+        for m in range(G):
+            d_q.copy_(d_q0)
+            plan.route_dev(rr.MODE_RAPID, d_q.data_ptr(), lats[m].data_ptr(), n, outs[m].data_ptr(), n, T, 1, stream)
+    single_ms = timed(one_by_one)
+    same = bool(torch.equal(keep, outs[G - 1]))
+    emit(config='C5', stage='ensemble_device_resident', members_per_call=G, reaches=n, steps=T, batched_ms=batched_ms,
+         one_call_per_member_ms=single_ms, reach_steps_members_per_s=n * T * G / (batched_ms * 1e-3),
+         one_call_per_member_rate=n * T * G / (single_ms * 1e-3), batched_equals_single_bitwise=same, checks=checks)
+    del lats, outs, keep
+    torch.cuda.empty_cache()
+    # ---- (2) host arrays, float32 in / float32 out ----
+    G, T = 6, 96
+    base_h = base.cpu().numpy()
+    h_lat = [rr.pinned_empty((T, n), dtype=np.float32) for _ in range(G)]
+    h_out = [rr.pinned_empty((T, n), dtype=np.float32) for _ in range(G)]
+    for m in range(G):
+        for r in range(0, T, 24):
+            h_lat[m][r:r + 24] = (base_h * float(scale[m]) * (1.0 + 0.01 * (r // 24))).astype(np.float32)
+    states = np.empty((G, n))
+    plan.route_ensemble_host(rr.MODE_RAPID, q_init, h_lat, h_out, 1, q_final=states)          # warm (allocates buffers)
+    t = time.perf_counter()
+    mean = plan.route_ensemble_host(rr.MODE_RAPID, q_init, h_lat, h_out, 1, q_final=states)
+    wall = time.perf_counter() - t
+    p_out, p_q = subset_parity(down, k, x, m_chk, h_lat[G - 1][:, :m_chk].astype(np.float64), h_out[G - 1][:, :m_chk].astype(np.float64),
+                               q_init[:m_chk], states[G - 1][:m_chk])
+    emit(config='C5', stage='ensemble_host_f32', members_per_call=G, reaches=n, steps=T, wall_s=wall,
+         reach_steps_members_per_s=n * T * G / wall, h2d_bytes=int(G * T * n * 4), d2h_bytes=int(G * T * n * 4),
+         mean_equals_numpy=bool(np.array_equal(mean, np.array(list(states)).mean(axis=0))),
+         float32_parity_vs_oracle=p_out, state_parity=p_q,
+         full_c5_estimate_s=51 * 360 * n / (n * T * G / wall))
     plan.close()
 
 

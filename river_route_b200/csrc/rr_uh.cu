@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "rr_internal.h"
@@ -115,6 +116,73 @@ __global__ void __launch_bounds__(128) uh_conv_kernel_reg(int64_t n, int n_ks, i
     }
 }
 
+
+// Long kernels (more than 16 taps): the taps live in shared memory ([tap][thread], read back by the thread that wrote
+// them, so no barrier is needed) and each iteration produces 16 outputs.  Round 1 kept up to 48 taps in registers
+// (168 registers, 12 warps per SM) with 8 outputs per iteration, and every iteration re-loaded its whole input window:
+// 56 loads of 8 bytes per 8 outputs, i.e. 56 B of L1/L2 traffic per output for 16 B of algorithmic traffic.  With 16
+// outputs per iteration the window costs 63 loads per 16 outputs, the tap costs one LDS per 16 DFMA, and ~90 registers
+// give 16 warps per SM.  Same accumulation order: old state first, then inputs from the oldest to the newest.
+// SAFE: the iteration's whole input window lies inside [0, T) -- no per-load bounds predicates.
+template <int TB>
+__global__ void __launch_bounds__(128, 4) uh_conv_kernel_smem(int64_t n, int n_ks, int n_groups, int64_t T, int64_t chunk,
+                                                              const double *__restrict__ lat, int64_t ldl,
+                                                              const double *__restrict__ ker, int64_t ldk,
+                                                              const double *__restrict__ state, int64_t lds,
+                                                              double *__restrict__ out, int64_t ldo) {
+    extern __shared__ double sk[];                         // [n_groups * TB][128]
+    const int tid = threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + tid;
+    if (b >= n) return;
+    const int NT = n_groups * TB;
+    for (int k = 0; k < NT; ++k) sk[k * 128 + tid] = k < n_ks ? __ldg(ker + (int64_t)k * ldk + b) : 0.0;
+    const int64_t tb = (int64_t)blockIdx.y * chunk;
+    const int64_t te = min(T, tb + chunk);
+    const double *lb = lat + b;
+    for (int64_t t0 = tb; t0 < te; t0 += TB) {
+        double acc[TB], w[TB];
+#pragma unroll
+        for (int u = 0; u < TB; ++u) {
+            const int64_t t = t0 + u;
+            acc[u] = (t < n_ks && t < te) ? state[t * lds + b] : 0.0;      // UnitHydrograph.py:100
+        }
+        int tau = NT - 1;                                                   // oldest (possibly padded) tap
+        const bool safe = t0 - tau >= 0 && t0 + TB <= T;
+        if (safe) {
+            const double *p0 = lb + (t0 - tau) * ldl;                       // input of output 0 under the oldest tap
+#pragma unroll
+            for (int u = 0; u < TB; ++u) w[u] = __ldg(p0 + u * ldl);
+            const double *pn = p0 + TB * ldl;                               // next input to enter the window
+            for (int g = 0; g < n_groups; ++g) {
+#pragma unroll
+                for (int p = 0; p < TB; ++p, --tau) {
+                    const double kt = sk[tau * 128 + tid];
+#pragma unroll
+                    for (int u = 0; u < TB; ++u) acc[u] = fma(kt, w[(u + p) % TB], acc[u]);
+                    if (tau > 0) w[p] = __ldg(pn);                          // t0 + TB - tau < t0 + TB <= T
+                    pn += ldl;
+                }
+            }
+        } else {
+            auto input = [&](int64_t t) -> double { return (t >= 0 && t < T) ? __ldg(lb + t * ldl) : 0.0; };
+#pragma unroll
+            for (int u = 0; u < TB; ++u) w[u] = input(t0 + u - tau);
+            for (int g = 0; g < n_groups; ++g) {
+#pragma unroll
+                for (int p = 0; p < TB; ++p, --tau) {
+                    const double kt = sk[tau * 128 + tid];
+#pragma unroll
+                    for (int u = 0; u < TB; ++u) acc[u] = fma(kt, w[(u + p) % TB], acc[u]);
+                    w[p] = input(t0 + TB - tau);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TB; ++u)
+            if (t0 + u < te) out[(t0 + u) * ldo + b] = acc[u];
+    }
+}
+
 // Carry-over state: rows 0..n_ks-2 = the full convolution at times T..T+n_ks-2, last row = 0
 // (UnitHydrograph.py:103-105).  Reads of the old state run ahead of the writes (row T+j > j).
 __global__ void __launch_bounds__(128) uh_state_kernel(int64_t n, int n_ks, int64_t T,
@@ -190,6 +258,16 @@ extern "C" int rr_uh_convolve_dev(int64_t n, int64_t n_ks, int64_t T, const doub
     const unsigned gy = (unsigned)((T + chunk - 1) / chunk);
     dim3 grid(gx, gy);
     const int nk = (int)n_ks;
+    const int groups16 = (nk + 15) / 16;
+    const size_t smem_taps = (size_t)groups16 * 16 * 128 * sizeof(double);
+    static const bool reg_only = getenv("RR_UH_REGISTERS") != nullptr;          // A/B switch for measurements
+    if (nk > 16 && smem_taps <= 192 * 1024 && !reg_only) {
+        int64_t chunk16 = std::min<int64_t>(((chunk + 15) / 16) * 16, std::max<int64_t>(T, 1));
+        dim3 grid16(gx, (unsigned)((T + chunk16 - 1) / chunk16));
+        CK(cudaFuncSetAttribute(uh_conv_kernel_smem<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_taps));
+        uh_conv_kernel_smem<16><<<grid16, threads, smem_taps, stream>>>(n, nk, groups16, T, chunk16, lateral, ldl, kernel, ldk, state, lds,
+                                                                      out, ldo);
+    } else
 #define RR_UH_REG(NG) uh_conv_kernel_reg<8, NG><<<grid, threads, 0, stream>>>(n, nk, T, chunk, lateral, ldl, kernel, ldk, state, lds, out, ldo)
     switch ((nk + 7) / 8) {
         case 1: RR_UH_REG(1); break;

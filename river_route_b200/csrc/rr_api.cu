@@ -27,6 +27,8 @@ int rr_stage_out_unit(const double *out_w, const double *lat, int64_t ldl, void 
                       cudaStream_t stream);
 int rr_unit_state_to_user(const double *qs_w, const double *qf_w, const int32_t *inv, int64_t n, int64_t hw_slots, int last,
                           const double *lat_last, double *q_state, double *q_full, cudaStream_t stream);
+int rr_stage_out_sub(const double *out_w, void *dst, int dst_f32, int64_t ldd, const int32_t *inv, const int32_t *subset,
+                     int64_t n_out, int64_t T, int64_t tile_rows, int64_t pitch, int64_t n_blocks, int K, cudaStream_t stream);
 int rr_stage_out(const double *out_w, void *dst, int dst_f32, int64_t ldd, const int32_t *inv, const int32_t *subset,
                  int64_t n_out, int64_t T, int64_t tile_rows, int64_t n_blocks, cudaStream_t stream);
 
@@ -248,8 +250,10 @@ static int64_t tile_rows_for(const rr_plan *p, int64_t T, int64_t K) {
 static bool pipeline_ok(const rr_plan *p, int mode, int64_t K);
 extern "C" int64_t rr_plan_tile_rows(const rr_plan *p, int64_t T, int64_t substeps) {
     if (!p || T <= 0 || substeps <= 0) return 0;
-    if (pipeline_ok(p, RR_MODE_RAPID, substeps))
+    if (pipeline_ok(p, RR_MODE_RAPID, substeps)) {
+        if (substeps > 1) return std::max<int64_t>(1, std::min<int64_t>(p->opts.time_tile / substeps, T));
         return std::min<int64_t>(p->opts.time_tile / RR_FLAG_ROWS * RR_FLAG_ROWS, (T + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS * RR_FLAG_ROWS);
+    }
     return tile_rows_for(p, T, substeps);
 }
 
@@ -303,7 +307,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     // tile about gpt of them.  With that stride the fronts of all tiles in flight share a ticket key and fit the
     // resident warps; with stride 1 they spread over 3 x n_tiles keys and most of them wait for a warp (C2: the 3000-level
     // stem ran 23 tiles in batches of ~7).
-    const int32_t delta_use = pipeline ? (p->opts.tile_stride > 0 ? p->opts.tile_stride : (int32_t)((rows + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS))
+    const int32_t delta_use = pipeline ? (p->opts.tile_stride > 0 ? p->opts.tile_stride : (int32_t)((rows * K + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS))
                                        : d->sched.delta;
     rr_device_state::key_table *kt = nullptr;
     for (auto &k : d->keys) if (k.n_tiles == n_tiles && k.first_block == first_block && k.delta == delta_use) kt = &k;
@@ -379,11 +383,19 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.direct = direct;
     P.tile_pitch = (int32_t)((rows + 3) & ~(int64_t)3);
     P.gpt = (int32_t)((rows + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS);
+    P.lat_pitch = P.tile_pitch;
+    if (pipeline) {   // tiles hold rows x K routing substeps, padded to whole 16-entry groups
+        P.gpt = (int32_t)((rows * K + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS);
+        P.tile_pitch = P.gpt * RR_FLAG_ROWS;
+        if (K == 1) P.lat_pitch = P.tile_pitch;
+    }
     // stress-test hooks (tests/test_gpu_stress.py): fewer persistent CTAs than the device holds, and pseudo-random delays
     // around the flag operations -- any grid size and any timing must give the same bits
     int64_t grid_cap = 0;
     if (const char *env = getenv("RR_GRID_CTAS")) grid_cap = std::max(1, atoi(env));
     if (const char *env = getenv("RR_JITTER")) P.jitter = std::max(0, atoi(env));
+    P.spin_ns = 32;
+    if (const char *env = getenv("RR_PROG_SPIN_NS")) P.spin_ns = std::max(0, atoi(env));
     if (pipeline) {
         // rr_direct.cu: done[] counts 16-row groups; 8 warps per CTA share 32 KB of output staging
         if (!d->occ_direct[mode]) {
@@ -556,8 +568,11 @@ struct rr_out_spec {
 // tile lengths that are whole 16-row groups (all three routers).
 static bool pipeline_ok(const rr_plan *p, int mode, int64_t K) {
     const int st = p->opts.staging;
-    (void)mode;
-    return !p->perm.empty() && p->all_fast && K == 1 && (st == 0 || st == 6 || st == 7) && (p->opts.time_tile % RR_FLAG_ROWS) == 0;
+    // several routing substeps per row: RapidMuskingum / Muskingum, at least one whole row per tile.  Opt-in
+    // (staging='direct' / 'direct-nohw'): on C1 with 12 substeps the substep-tile pipeline measured 38.4 ms against 30.8 ms
+    // for the ring path (stage_out_sub re-reads all K substeps of every row; the wavefront itself takes the same time)
+    if (K > 1 && (mode == RR_MODE_UNIT || K > p->opts.time_tile || !(st == 6 || st == 7))) return false;
+    return !p->perm.empty() && p->all_fast && (st == 0 || st == 6 || st == 7) && (p->opts.time_tile % RR_FLAG_ROWS) == 0;
 }
 
 // Route with all arrays in the caller's (params_file) order, whatever order the plan works in.
@@ -565,7 +580,7 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
                      int64_t ldl, double *const *out, int64_t ldo, double *const *q_state, double *const *q_full,
                      int64_t T, int64_t K, int first_call, int last_call, cudaStream_t stream,
                      const rr_out_spec *spec = nullptr /* one per member */, int lat_f32 = 0) {
-    if (lat_f32 && !(pipeline_ok(p, mode, K) && !p->perm.empty())) { rr_set_error("internal: float32 lateral inflows need the direct pipeline"); return 101; }
+    if (lat_f32 && !(pipeline_ok(p, mode, K) && K == 1 && !p->perm.empty())) { rr_set_error("internal: float32 lateral inflows need the direct pipeline"); return 101; }
     if (p->perm.empty()) {
         if (spec) { rr_set_error("internal: fused output needs a level-sorted plan"); return 101; }
         return launch_route(p, mode, n_members, q_init, lateral, ldl, out, ldo, q_state, q_full, T, K, first_call,
@@ -583,7 +598,7 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     if (spec && !pipeline) { rr_set_error("internal: fused output is a feature of the direct pipeline"); return 101; }
     // working arrays: row-major (staging 1, substeps), [tile][block][row][lane] for the TMA-staged
     // kernel (3), [tile][block][lane][row] otherwise (register path: whole-sector accesses everywhere)
-    const bool tiled = (K == 1 && p->opts.staging != 1 && !(unit && p->opts.staging == 3));
+    const bool tiled = pipeline || (K == 1 && p->opts.staging != 1 && !(unit && p->opts.staging == 3));
     // lateral: reach-major tiles (whole-sector scatter in the permute, 256-bit loads in the kernel); discharge:
     // row-major tiles (coalesced row stores in the kernel, sector-sharing gathers in the permute) -- measured best
     const int layout = !tiled ? 0 : (p->opts.staging == 3 ? 1 : (p->opts.staging == 5 ? 3 : 2));
@@ -596,10 +611,14 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     // (the per-call tile model of tile_rows_for does not apply: narrow levels hand results on every 16 rows whatever
     // the tile length, so long tiles cost no latency and save per-item setup)
     if (pipeline) trows = std::min<int64_t>(p->opts.time_tile / RR_FLAG_ROWS * RR_FLAG_ROWS, (T + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS * RR_FLAG_ROWS);
-    const int64_t tpitch = ((trows + 3) & ~(int64_t)3);
+    // several substeps per row: a tile is as many whole rows as fit time_tile substeps; the discharge tiles hold substeps
+    if (pipeline && K > 1) trows = std::max<int64_t>(1, std::min<int64_t>(p->opts.time_tile / K, T));
+    const int64_t lpitch = ((trows + 3) & ~(int64_t)3);                                                  // lateral tile: rows
+    const int64_t tpitch = pipeline ? (trows * K + RR_FLAG_ROWS - 1) / RR_FLAG_ROWS * RR_FLAG_ROWS : lpitch;   // discharge tile
     const int64_t n_tiles = tiled ? (T + trows - 1) / trows : 0;
     const size_t member_elems = tiled ? (size_t)n_tiles * p->n_blocks * tpitch * RR_BLOCK : (size_t)T * ldp;
-    if (has_lat && (rc = grow(&d->p_lat, &d->p_lat_cap, (size_t)n_members * member_elems + 64))) return rc;
+    const size_t lat_elems = (pipeline && K > 1) ? (size_t)n_tiles * p->n_blocks * lpitch * RR_BLOCK : member_elems;
+    if (has_lat && (rc = grow(&d->p_lat, &d->p_lat_cap, (size_t)n_members * lat_elems + 64))) return rc;
     if ((rc = grow(&d->p_out, &d->p_out_cap, (size_t)n_members * member_elems + 64))) return rc;
     // state scratch: [start-of-call state: one shared, or one per member on continued calls][member states][member q_full]
     //                [start-of-call q_full of continued UnitMuskingum pipeline calls]
@@ -613,11 +632,11 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
     // whole blocks of headwaters are routed by the staging kernel of the pipeline (RapidMuskingum: their lateral rows
     // pass through its registers anyway); small networks keep them in the wavefront (staging 7 forces that, 6 the former)
     int64_t hw_cut = 0;
-    if (pipeline && mode == RR_MODE_RAPID && p->opts.staging != 7 && (p->opts.staging == 6 || n >= (1 << 18)))
+    if (pipeline && K == 1 && mode == RR_MODE_RAPID && p->opts.staging != 7 && (p->opts.staging == 6 || n >= (1 << 18)))
         hw_cut = p->lvl0_slots;   // level 0 fills whole blocks (headwaters + padding)
     if (first_call && (rc = permute(true, q_init, n, w_init, ldp, d->inv, n, 1, stream))) return rc;
     for (int m = 0; m < n_members; ++m) {
-        lat_w[m] = has_lat ? d->p_lat + (size_t)m * member_elems : nullptr;
+        lat_w[m] = has_lat ? d->p_lat + (size_t)m * lat_elems : nullptr;
         out_w[m] = d->p_out + (size_t)m * member_elems;
         qs_w[m] = d->p_q + (size_t)(n_members + m) * ldp;
         qf_w[m] = d->p_q + (size_t)(2 * n_members + m) * ldp;
@@ -627,13 +646,13 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
             if ((rc = permute(true, q_state[m], n, direct ? w_init + (size_t)m * ldp : qs_w[m], ldp, d->inv, n, 1, stream))) return rc;
             if (unit && (rc = permute(true, q_full[m], n, unit_pipe ? wf_init + (size_t)m * ldp : qf_w[m], ldp, d->inv, n, 1, stream))) return rc;
         }
-        if (has_lat && pipeline) {
+        if (has_lat && pipeline && K == 1) {
             rr_timer tm(1, stream);
-            rc = rr_stage_in(lateral[m], lat_f32, ldl, d->p_lat + (size_t)m * member_elems, out_w[m], d->inv, n, T, trows, p->n_blocks,
+            rc = rr_stage_in(lateral[m], lat_f32, ldl, d->p_lat + (size_t)m * lat_elems, out_w[m], d->inv, n, T, trows, p->n_blocks,
                              hw_cut, d->coef + 2 * p->n_work, d->coef + 3 * p->n_work, w_init + (size_t)m * init_stride, qs_w[m],
                              d->sm_count, stream);
             if (rc) return rc;
-        } else if (has_lat && (rc = permute(true, lateral[m], ldl, d->p_lat + (size_t)m * member_elems, ldp, d->inv, n, T, stream, trows, p->n_blocks, layout))) return rc;
+        } else if (has_lat && (rc = permute(true, lateral[m], ldl, d->p_lat + (size_t)m * lat_elems, ldp, d->inv, n, T, stream, trows, p->n_blocks, layout))) return rc;
     }
     rc = launch_route(p, mode, n_members, w_init, has_lat ? lat_w : nullptr, ldp, out_w, ldp, qs_w, qf_w, T, K,
                       direct ? 1 : first_call, last_call, stream, layout, out_layout, direct ? 1 : 0, pipeline ? trows : 0,
@@ -654,7 +673,13 @@ static int route_any(rr_plan *p, int mode, int n_members, const double *q_init, 
                                             q_state[m], q_full[m], stream))) return rc;
             continue;
         }
-        if (pipeline) {
+        if (pipeline && K > 1) {
+            rr_timer tm(2, stream);
+            if (spec) rc = rr_stage_out_sub(out_w[m], spec[m].dst, spec[m].f32, spec[m].ld, d->inv, spec[m].subset, spec[m].n_out, T, trows,
+                                            tpitch, p->n_blocks, (int)K, stream);
+            else rc = rr_stage_out_sub(out_w[m], out[m], 0, ldo, d->inv, nullptr, n, T, trows, tpitch, p->n_blocks, (int)K, stream);
+            if (rc) return rc;
+        } else if (pipeline) {
             rr_timer tm(2, stream);
             if (spec) rc = rr_stage_out(out_w[m], spec[m].dst, spec[m].f32, spec[m].ld, d->inv, spec[m].subset, spec[m].n_out, T, trows, p->n_blocks, stream);
             else rc = rr_stage_out(out_w[m], out[m], 0, ldo, d->inv, nullptr, n, T, trows, p->n_blocks, stream);
@@ -963,7 +988,7 @@ static int stream_route_impl(rr_plan *p, int mode, double *q_state, double *q_fu
     const size_t need_f64 = (size_t)chunk * ldd * 8;
     // float32 lateral inflows: the direct pipeline's staging kernel upcasts them on the fly; other paths get an exact
     // upcast into the fp64 scratch first
-    const bool lat_cast = !grid && has_lat && src.lat_f32 && (!pipeline_ok(p, mode, substeps) || mode == RR_MODE_UNIT);
+    const bool lat_cast = !grid && has_lat && src.lat_f32 && (!pipeline_ok(p, mode, substeps) || mode == RR_MODE_UNIT || substeps > 1);
     if ((grid || lat_cast) && (rc = grow_bytes((void **)&d->s_lat, &d->s_lat_cap, need_f64))) return rc;
     if (uh && (rc = grow_bytes((void **)&d->s_conv, &d->s_conv_cap, need_f64))) return rc;
     if (post && !fused && (rc = grow_bytes((void **)&d->s_route, &d->s_route_cap, need_f64))) return rc;
@@ -1139,7 +1164,7 @@ static int ensemble_host_impl(rr_plan *p, int mode, const double *q_init, int64_
     if (ldo < n || (has_lat && ldl < n) || (q_final && ldq < n) || (ld_init != 0 && ld_init < n)) { rr_set_error("leading dimension smaller than n"); return 100; }
     const bool pipe = pipeline_ok(p, mode, K);
     const bool fused = pipe && resample == 1;
-    const bool cast_first = has_lat && lat_f32 && !pipe;
+    const bool cast_first = has_lat && lat_f32 && !(pipe && K == 1);
     const size_t es_in = lat_f32 ? 4 : 8, es_out = out_f32 ? 4 : 8;
     // chunk rows: all members of a chunk are resident at once -- transfer buffers (x2), working tiles and scratch
     const double per_row = (double)M * (double)ldd * (2.0 * es_in + 2.0 * es_out + 16.0 + ((!fused) ? 8.0 : 0.0) + (cast_first ? 8.0 : 0.0));

@@ -33,6 +33,10 @@ __device__ __forceinline__ const double *tile_of(const double *base, const rr_ro
     return base + (((size_t)jj * P.n_blocks + (size_t)(u >> 5)) * RR_BLOCK + (size_t)(u & 31)) * (size_t)P.tile_pitch;
 }
 
+__device__ __forceinline__ const double *lat_tile_of(const double *base, const rr_route_params &P, int jj, int64_t u) {
+    return base + (((size_t)jj * P.n_blocks + (size_t)(u >> 5)) * RR_BLOCK + (size_t)(u & 31)) * (size_t)P.lat_pitch;
+}
+
 struct dctx {
     int m, b, j, lane, TT, deg;
     int64_t i;
@@ -40,6 +44,9 @@ struct dctx {
     double c1, c2, c3, c4, q;
     int32_t up_u[RR_MAX_FAST_DEG];
     int32_t dep_blk;             // this lane's entry of the block's upstream-block list (-1: none)
+    int32_t dep_more, dep_hi;    // further entries of this lane: dep_more, dep_more + 32, ... < dep_hi (blocks with > 32 upstream blocks)
+    const int32_t *dep_idx;
+    int32_t spin_ns;
     int32_t *done;               // this member's progress counters
     const double *lat0;
     double *out0;
@@ -50,15 +57,18 @@ struct dctx {
 // a relaxed poll would add one more L2 round trip per level (the L1 invalidation an acquire costs does not matter to a
 // warp that is waiting anyway).
 __device__ __forceinline__ void wait_groups(const dctx &c, int32_t want, int32_t full_want, bool &full) {
-    unsigned ns = 32;
+    unsigned ns = (unsigned)c.spin_ns;
     for (;;) {
-        const int32_t p = c.dep_blk >= 0 ? ld_acquire(c.done + c.dep_blk) : 0x7fffffff;
+        int32_t p = c.dep_blk >= 0 ? ld_acquire(c.done + c.dep_blk) : 0x7fffffff;
+        for (int e = c.dep_more; e < c.dep_hi; e += 32) p = min(p, ld_acquire(c.done + __ldg(c.dep_idx + e)));
         if (__all_sync(RR_FULL_MASK, p >= want)) {
             full = __all_sync(RR_FULL_MASK, p >= full_want);
             break;
         }
-        __nanosleep(ns);
-        if (ns < 256) ns <<= 1;
+        if (ns) {
+            __nanosleep(ns);
+            if (ns < 256) ns <<= 1;
+        }
     }
     __syncwarp();
 }
@@ -68,7 +78,10 @@ __device__ __forceinline__ void wait_groups(const dctx &c, int32_t want, int32_t
 // rows (four back-to-back 256-bit stores per reach): a line written one sector per ~600 cycles left L2 partially
 // dirty and cost DRAM read-modify-write traffic (ncu: 11.5 B written + 1.6 B read more than the 8 + 17.4 B the
 // kernel asks for, per reach-timestep).
-template <int MODE, int NS>
+// SUB: more than one routing substep per row (dt_routing < dt_runoff).  The tiles then hold the raw SUBSTEP series
+// (tile_rows x K entries per reach), the lateral value changes every K entries, and the interval mean of
+// _numba_kernels.py:41-46 / :79-84 is formed by stage_out from the raw substeps (same order: sum, then x 1/K).
+template <int MODE, int NS, bool SUB>
 __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx &c, double *stage) {
     constexpr bool HAS_LAT = (MODE == RR_MODE_RAPID);
     constexpr int NA = NS > 0 ? NS : 1;
@@ -90,7 +103,7 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
         if (has[k]) {
             up[k] = tile_of(P.out[c.m], P, j, c.up_u[k]);
             // value before the tile's first row: the start-of-call state, or the last row of the previous tile
-            old[k] = j == 0 ? P.q_init[(size_t)c.m * P.q_init_stride + c.up_u[k]] : tile_of(P.out[c.m], P, j - 1, c.up_u[k])[P.tile_rows - 1];
+            old[k] = j == 0 ? P.q_init[(size_t)c.m * P.q_init_stride + c.up_u[k]] : tile_of(P.out[c.m], P, j - 1, c.up_u[k])[P.tile_rows * P.K - 1];
             nxt[k] = ld_sector(up[k]);                       // rows 0..7 are in group 0, which is published
             if (4 < TT) fut[k] = ld_sector(up[k] + 4);
         }
@@ -98,6 +111,15 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
     const double *lat = c.lat0;
     auto lat_group = [&](int s0) -> d4 {
         if (!(HAS_LAT && c.valid) || s0 >= TT) return d4{0, 0, 0, 0};
+        if (SUB) {                                       // substeps s0..s0+3 take the lateral value of row (s0 + u) / K
+            const int K = P.K, r0 = s0 / K, o0 = s0 - r0 * K;
+            d4 v;
+            v.a = __ldg(lat + r0);
+            v.b = __ldg(lat + r0 + (o0 + 1) / K);
+            v.c = __ldg(lat + r0 + (o0 + 2) / K);
+            v.d = __ldg(lat + r0 + (o0 + 3) / K);   // (a row past the tile's last one is read but never used: the pitch covers it)
+            return v;
+        }
         return ld_sector_ro(lat + s0);
     };
     d4 lcur = lat_group(0), lnxt = lat_group(4);
@@ -325,6 +347,7 @@ __global__ void __launch_bounds__(256, 2) rr_direct_unit_kernel(const __grid_con
         c.narrow = (M.int_mask & RR_META_NARROW) != 0;
         c.TT = min(P.tile_rows, P.T - j * P.tile_rows);
         c.dep_blk = dep_lo + lane < dep_hi ? __ldg(P.dep_idx + dep_lo + lane) : -1;
+        c.dep_more = dep_lo + 32 + lane; c.dep_hi = dep_hi; c.dep_idx = P.dep_idx; c.spin_ns = P.spin_ns;
 #pragma unroll
         for (int k = 0; k < MAXNS; ++k) c.up_u[k] = k < c.deg ? __ldg(P.up_idx + e0 + k) : 0;
         c.done = P.done + (size_t)m * P.n_blocks;
@@ -334,7 +357,7 @@ __global__ void __launch_bounds__(256, 2) rr_direct_unit_kernel(const __grid_con
         jitter_delay(P.jitter, b, j, 100);
         if (lane == 0 && j > 0) wait_ge(c.done + b, j * P.gpt);
         c.prog = false;
-        if (c.narrow && dep_hi - dep_lo <= 32 && dep_hi > dep_lo) {
+        if (c.narrow && dep_hi > dep_lo) {
             bool full = false;
             wait_groups(c, j * P.gpt + 1, full_want, full);
             c.prog = !full;
@@ -377,7 +400,7 @@ namespace {
 // MAXNS: largest in-degree of the network, 2 or RR_MAX_FAST_DEG.  Networks with confluences of three or four rivers get
 // a kernel of their own so that the register-hungry instantiations do not set the register allocation -- and the
 // spills -- of the common case (at most two upstream reaches).
-template <int MODE, int MAXNS>
+template <int MODE, int MAXNS, bool SUB>
 __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant__ rr_route_params P) {
     __shared__ double stage_all[8][16 * RR_BLOCK];
     constexpr bool HAS_LAT = (MODE == RR_MODE_RAPID);
@@ -397,12 +420,13 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
         const rr_blk_meta M = P.meta[b];
         c.narrow = (M.int_mask & RR_META_NARROW) != 0;
         const int t0 = j * P.tile_rows;
-        c.TT = min(P.tile_rows, P.T - t0);
+        c.TT = min(P.tile_rows, P.T - t0) * (SUB ? P.K : 1);   // routing substeps in this tile
         c.dep_blk = dep_lo + lane < dep_hi ? __ldg(P.dep_idx + dep_lo + lane) : -1;
+        c.dep_more = dep_lo + 32 + lane; c.dep_hi = dep_hi; c.dep_idx = P.dep_idx; c.spin_ns = P.spin_ns;
 #pragma unroll
         for (int k = 0; k < MAXNS; ++k) c.up_u[k] = k < c.deg ? __ldg(P.up_idx + e0 + k) : 0;
         c.done = P.done + (size_t)m * P.n_blocks;
-        c.lat0 = HAS_LAT ? tile_of(P.lateral[m], P, j, i) : nullptr;
+        c.lat0 = HAS_LAT ? lat_tile_of(P.lateral[m], P, j, i) : nullptr;
         c.out0 = const_cast<double *>(tile_of(P.out[m], P, j, i));
         // ---- dependencies: own previous tile complete; upstream blocks complete, or (narrow levels with at most 32
         //      upstream blocks) their first group published ----
@@ -410,7 +434,7 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
         jitter_delay(P.jitter, b, j, 100);
         if (lane == 0 && j > 0) wait_ge(c.done + b, j * P.gpt);
         c.prog = false;
-        if (c.narrow && dep_hi - dep_lo <= 32 && dep_hi > dep_lo) {
+        if (c.narrow && dep_hi > dep_lo) {
             bool full = false;
             wait_groups(c, j * P.gpt + 1, full_want, full);
             c.prog = !full;
@@ -423,17 +447,17 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
         if (valid) c.q = (j == 0) ? P.q_init[(size_t)m * P.q_init_stride + i] : P.q_state[m][i];
         if (MAXNS <= 2) {
             switch (M.max_deg) {
-                case 0: direct_item<MODE, 0>(P, c, stage); break;
-                case 1: direct_item<MODE, 1>(P, c, stage); break;
-                default: direct_item<MODE, 2>(P, c, stage); break;
+                case 0: direct_item<MODE, 0, SUB>(P, c, stage); break;
+                case 1: direct_item<MODE, 1, SUB>(P, c, stage); break;
+                default: direct_item<MODE, 2, SUB>(P, c, stage); break;
             }
         } else {
             switch (M.max_deg) {
-                case 0: direct_item<MODE, 0>(P, c, stage); break;
-                case 1: direct_item<MODE, 1>(P, c, stage); break;
-                case 2: direct_item<MODE, 2>(P, c, stage); break;
-                case 3: direct_item<MODE, 3>(P, c, stage); break;
-                default: direct_item<MODE, RR_MAX_FAST_DEG>(P, c, stage); break;
+                case 0: direct_item<MODE, 0, SUB>(P, c, stage); break;
+                case 1: direct_item<MODE, 1, SUB>(P, c, stage); break;
+                case 2: direct_item<MODE, 2, SUB>(P, c, stage); break;
+                case 3: direct_item<MODE, 3, SUB>(P, c, stage); break;
+                default: direct_item<MODE, RR_MAX_FAST_DEG, SUB>(P, c, stage); break;
             }
         }
         jitter_delay(P.jitter, b, j, 200);
@@ -444,17 +468,21 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
 }
 
 cudaError_t rr_launch_direct(int mode, int max_deg, const rr_route_params &P, int grid, cudaStream_t stream) {
-    const bool wide = max_deg > 2;
+    const bool wide = max_deg > 2, sub = P.K > 1;
+#define RR_LAUNCH(M) do {                                                                               \
+        if (wide) { if (sub) rr_direct_kernel<M, RR_MAX_FAST_DEG, true><<<grid, 256, 0, stream>>>(P);  \
+                    else rr_direct_kernel<M, RR_MAX_FAST_DEG, false><<<grid, 256, 0, stream>>>(P); }   \
+        else { if (sub) rr_direct_kernel<M, 2, true><<<grid, 256, 0, stream>>>(P);                     \
+               else rr_direct_kernel<M, 2, false><<<grid, 256, 0, stream>>>(P); }                      \
+    } while (0)
     if (mode == RR_MODE_UNIT) {
+        if (sub) return cudaErrorInvalidValue;
         if (wide) rr_direct_unit_kernel<RR_MAX_FAST_DEG><<<grid, 256, 0, stream>>>(P);
         else rr_direct_unit_kernel<2><<<grid, 256, 0, stream>>>(P);
-    } else if (mode == RR_MODE_MUSKINGUM) {
-        if (wide) rr_direct_kernel<RR_MODE_MUSKINGUM, RR_MAX_FAST_DEG><<<grid, 256, 0, stream>>>(P);
-        else rr_direct_kernel<RR_MODE_MUSKINGUM, 2><<<grid, 256, 0, stream>>>(P);
-    } else if (mode == RR_MODE_RAPID) {
-        if (wide) rr_direct_kernel<RR_MODE_RAPID, RR_MAX_FAST_DEG><<<grid, 256, 0, stream>>>(P);
-        else rr_direct_kernel<RR_MODE_RAPID, 2><<<grid, 256, 0, stream>>>(P);
-    } else return cudaErrorInvalidValue;
+    } else if (mode == RR_MODE_MUSKINGUM) RR_LAUNCH(RR_MODE_MUSKINGUM);
+    else if (mode == RR_MODE_RAPID) RR_LAUNCH(RR_MODE_RAPID);
+    else return cudaErrorInvalidValue;
+#undef RR_LAUNCH
     return cudaGetLastError();
 }
 
@@ -465,12 +493,12 @@ int rr_direct_occupancy(int mode, int max_deg) {
     if (mode == RR_MODE_UNIT)
         e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_unit_kernel<RR_MAX_FAST_DEG>, 256, 0)
                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_unit_kernel<2>, 256, 0);
-    else if (mode == RR_MODE_MUSKINGUM)
-        e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM, RR_MAX_FAST_DEG>, 256, 0)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM, 2>, 256, 0);
+    else if (mode == RR_MODE_MUSKINGUM)   // (the substep instantiations have the same launch bounds; 2 CTAs per SM either way)
+        e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM, RR_MAX_FAST_DEG, true>, 256, 0)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM, 2, true>, 256, 0);
     else
-        e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID, RR_MAX_FAST_DEG>, 256, 0)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID, 2>, 256, 0);
+        e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID, RR_MAX_FAST_DEG, true>, 256, 0)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID, 2, true>, 256, 0);
     return e == cudaSuccess ? nb : -1;
 }
 
@@ -548,6 +576,29 @@ __global__ void __launch_bounds__(256) stage_out_kernel(const double *__restrict
             const double val = v[r] > 0.0 ? v[r] : 0.0;              // _numba_kernels.py:44-46 / :82-84
             dst[(t0 + r) * ldd + s] = (OT)val;
         }
+}
+
+// More than one routing substep per row: the tiles hold the raw substep series; an output row is the clamped mean of its K
+// substeps, accumulated in substep order and multiplied by 1/K exactly as _numba_kernels.py:19, :41-46 / :60, :79-84 do.
+template <typename OT>
+__global__ void __launch_bounds__(256) stage_out_sub_kernel(const double *__restrict__ out_w, OT *__restrict__ dst, int64_t ldd,
+                                                            const int32_t *__restrict__ inv, const int32_t *__restrict__ subset,
+                                                            int64_t n_out, int64_t T, int64_t tile_rows, int64_t pitch,
+                                                            int64_t n_blocks, int K) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_out) return;
+    const int64_t i = subset ? (int64_t)__ldg(subset + s) : s;
+    const int64_t k = __ldg(inv + i);
+    const int64_t j = blockIdx.y;                                            // one time tile per grid row
+    const double *p = out_w + ((j * n_blocks + (k >> 5)) * RR_BLOCK + (k & 31)) * pitch;
+    const double inv_k = 1.0 / (double)K;
+    const int64_t t0 = j * tile_rows, rows = min(tile_rows, T - t0);
+    for (int64_t r = 0; r < rows; ++r) {
+        double acc = 0.0;
+        for (int q = 0; q < K; ++q) acc += p[r * K + q];
+        const double val = acc * inv_k;
+        dst[(t0 + r) * ldd + s] = (OT)(val > 0.0 ? val : 0.0);
+    }
 }
 
 // UnitMuskingum: the discharge tiles hold q_ch of the inner reaches.  Output = the convolved lateral inflow itself for
@@ -669,6 +720,18 @@ int rr_stage_out_unit(const double *out_w, const double *lat, int64_t ldl, void 
 int rr_unit_state_to_user(const double *qs_w, const double *qf_w, const int32_t *inv, int64_t n, int64_t hw_slots, int last,
                           const double *lat_last, double *q_state, double *q_full, cudaStream_t stream) {
     unit_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(qs_w, qf_w, inv, n, hw_slots, last, lat_last, q_state, q_full);
+    CKD(cudaGetLastError());
+    rr_count_launch(1);
+    return 0;
+}
+
+int rr_stage_out_sub(const double *out_w, void *dst, int dst_f32, int64_t ldd, const int32_t *inv, const int32_t *subset,
+                     int64_t n_out, int64_t T, int64_t tile_rows, int64_t pitch, int64_t n_blocks, int K, cudaStream_t stream) {
+    dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)((T + tile_rows - 1) / tile_rows));
+    if (dst_f32)
+        stage_out_sub_kernel<float><<<grid, 256, 0, stream>>>(out_w, (float *)dst, ldd, inv, subset, n_out, T, tile_rows, pitch, n_blocks, K);
+    else
+        stage_out_sub_kernel<double><<<grid, 256, 0, stream>>>(out_w, (double *)dst, ldd, inv, subset, n_out, T, tile_rows, pitch, n_blocks, K);
     CKD(cudaGetLastError());
     rr_count_launch(1);
     return 0;

@@ -3,6 +3,7 @@
 // schedule) and the synthetic network generator.  Reference citations are in include/rr_b200.h.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -202,10 +203,12 @@ static int build_structures(rr_plan *p) {
         for (int64_t b = 0; b < nb; ++b) p->lvl_blk[fill[p->blk_level[b]]++] = (int32_t)b;
     }
     p->all_fast = true;
+    int64_t narrow = RR_NARROW_BLOCKS;
+    if (const char *env = getenv("RR_NARROW_BLOCKS")) narrow = atoll(env);   // measurements only
     for (int64_t b = 0; b < nb; ++b) {
         rr_blk_meta &m = p->meta[b];
         if (!(m.int_mask & RR_META_FAST)) p->all_fast = false;
-        if (p->lvl_ptr[m.level + 1] - p->lvl_ptr[m.level] < RR_NARROW_BLOCKS) m.int_mask |= RR_META_NARROW;
+        if (p->lvl_ptr[m.level + 1] - p->lvl_ptr[m.level] < narrow) m.int_mask |= RR_META_NARROW;
     }
     return 0;
 }

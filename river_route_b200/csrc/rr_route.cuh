@@ -37,8 +37,10 @@ struct rr_route_params {
     int32_t out_layout;   // layout of out (same codes); tile_major is the layout of lateral
     int32_t direct;       // 1: out holds the raw series and is the exchange buffer (see rr_route.cu, direct_tile)
     int32_t tile_pitch;   // layout 2: tile_rows rounded up to a multiple of 4
-    int32_t gpt;          // direct pipeline: progress units (16-row groups) of done[] per tile
+    int32_t gpt;          // direct pipeline: progress units (16-substep groups) of done[] per tile
+    int32_t lat_pitch;    // direct pipeline: doubles per reach of a lateral tile (== tile_pitch unless substeps > 1)
     int32_t jitter;       // stress tests (RR_JITTER): pseudo-random delays around the flag operations, 0 = none
+    int32_t spin_ns;      // progressive waits: first back-off in ns (0: poll without sleeping)
     int32_t smem_region;  // > 0: TMA-staged kernel; bytes of shared memory per warp (tile + row slots + mbarrier)
     int32_t row_slots;    // upstream exchange rows a warp's region can hold
     int32_t first_call;   // UNIT: 1 when q_state holds the start-of-file state (q_ch = q_full = state)

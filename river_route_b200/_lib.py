@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, 'librr_b200.so')
+# RR_B200_LIB: measurement builds of the same sources (tools/librr_trace.so); never a different implementation
+LIB_PATH = os.environ.get('RR_B200_LIB') or os.path.join(_PKG_DIR, 'librr_b200.so')
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)

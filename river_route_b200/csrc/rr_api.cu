@@ -27,6 +27,8 @@ int rr_stage_out_unit(const double *out_w, const double *lat, int64_t ldl, void 
                       cudaStream_t stream);
 int rr_unit_state_to_user(const double *qs_w, const double *qf_w, const int32_t *inv, int64_t n, int64_t hw_slots, int last,
                           const double *lat_last, double *q_state, double *q_full, cudaStream_t stream);
+int rr_fill_sentinel(double *out_w, const int32_t *narrow_blocks, int64_t n_narrow, int64_t first_block, int64_t n_blocks,
+                     int64_t n_tiles, int64_t pitch, cudaStream_t stream);
 int rr_stage_out_sub(const double *out_w, void *dst, int dst_f32, int64_t ldd, const int32_t *inv, const int32_t *subset,
                      int64_t n_out, int64_t T, int64_t tile_rows, int64_t pitch, int64_t n_blocks, int K, cudaStream_t stream);
 int rr_stage_out(const double *out_w, void *dst, int dst_f32, int64_t ldd, const int32_t *inv, const int32_t *subset,
@@ -100,6 +102,8 @@ struct rr_device_state {
     int32_t *dep_ptr = nullptr, *dep_idx = nullptr, *down = nullptr, *exp_ro = nullptr, *edge_ro = nullptr;
     uint8_t *skew = nullptr;
     rr_blk_meta *meta = nullptr;
+    int32_t *narrow_blocks = nullptr;   // ids of the blocks of narrow levels (RR_META_NARROW)
+    int64_t n_narrow = 0;
     double *coef = nullptr;  // c1|c2|c3|c4, each n
     uint64_t coeff_version = 0;
     // launch scratch
@@ -167,6 +171,12 @@ static int ensure_device(rr_plan *p) {
         rc |= upload(&d->skew, p->skew, d->bytes);
         rc |= upload(&d->meta, p->meta, d->bytes);
         if (!p->inv.empty()) rc |= upload(&d->inv, p->inv, d->bytes);
+        {
+            std::vector<int32_t> nb;
+            for (int64_t b = 0; b < p->n_blocks; ++b) if (p->meta[b].int_mask & RR_META_NARROW) nb.push_back((int32_t)b);
+            d->n_narrow = (int64_t)nb.size();
+            rc |= upload(&d->narrow_blocks, nb, d->bytes);
+        }
         if (rc) return rc;
         CK(cudaMalloc((void **)&d->coef, sizeof(double) * 4 * (size_t)p->n_work));
         d->bytes += sizeof(double) * 4 * (size_t)p->n_work;
@@ -201,7 +211,7 @@ void rr_device_release(rr_plan *p) {
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {d->up_ptr, d->up_idx, d->slot_src, d->export_id, d->dep_ptr, d->dep_idx, d->down, d->exp_ro, d->edge_ro,
-                    d->skew, d->meta, d->coef, d->raw, d->done, d->ticket, d->prof,
+                    d->skew, d->meta, d->narrow_blocks, d->coef, d->raw, d->done, d->ticket, d->prof,
                     d->s_inb[0], d->s_inb[1], d->s_outb[0], d->s_outb[1], d->s_lat, d->s_conv, d->s_route, d->d_q, d->d_qfull,
                     d->inv, d->p_lat, d->p_out, d->p_q, d->out_subset, d->ens_q};
     for (void *q : ptrs)
@@ -247,6 +257,11 @@ static int64_t tile_rows_for(const rr_plan *p, int64_t T, int64_t K) {
     return std::max<int64_t>(1, std::min<int64_t>(T, tile / K));
 }
 
+#ifdef RR_TRACE
+// tools/trace_chain.py: device buffer [block][group][event][2] the direct kernel stamps (trace builds only)
+static unsigned long long *g_rr_trace = nullptr;
+extern "C" void rr_trace_set(void *dev_buffer) { g_rr_trace = (unsigned long long *)dev_buffer; }
+#endif
 static bool pipeline_ok(const rr_plan *p, int mode, int64_t K);
 extern "C" int64_t rr_plan_tile_rows(const rr_plan *p, int64_t T, int64_t substeps) {
     if (!p || T <= 0 || substeps <= 0) return 0;
@@ -363,7 +378,11 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.T = (int32_t)T; P.K = (int32_t)K; P.tile_rows = (int32_t)rows;
     P.raw_pitch = (int32_t)pitch; P.n_members = n_members; P.first_call = first_call; P.last_call = last_call;
     P.ldl = ldl; P.ldo = ldo;
-    P.raw = d->raw; P.done = d->done; P.ticket = d->ticket; P.prof = d->prof; P.q_init = q_init; P.q_init_stride = q_init_stride;
+    P.raw = d->raw; P.done = d->done; P.ticket = d->ticket; P.prof = d->prof;
+#ifdef RR_TRACE
+    P.prof = g_rr_trace;
+#endif
+ P.q_init = q_init; P.q_init_stride = q_init_stride;
     P.qf_init = qf_init; P.hw_slots = hw_slots;
     for (int m = 0; m < n_members; ++m) {
         P.lateral[m] = lateral ? lateral[m] : nullptr;
@@ -397,6 +416,13 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     P.spin_ns = 32;
     if (const char *env = getenv("RR_PROG_SPIN_NS")) P.spin_ns = std::max(0, atoi(env));
     if (pipeline) {
+        // narrow levels exchange results through the "not written yet" pattern (rr_direct.cu, narrow_item): arm their tiles
+        P.poll_lo = (int32_t)first_block;
+        if (mode != RR_MODE_UNIT)
+            for (int m = 0; m < n_members; ++m) {
+                rr_timer tm(3, stream);
+                if ((rc = rr_fill_sentinel(out[m], d->narrow_blocks, d->n_narrow, first_block, p->n_blocks, n_tiles, P.tile_pitch, stream))) return rc;
+            }
         // rr_direct.cu: done[] counts 16-row groups; 8 warps per CTA share 32 KB of output staging
         if (!d->occ_direct[mode]) {
             d->occ_direct[mode] = rr_direct_occupancy(mode, p->max_deg);

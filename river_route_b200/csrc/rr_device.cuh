@@ -9,7 +9,7 @@
 #define RR_SPIN_NS0 64
 #endif
 #ifndef RR_SPIN_NSMAX
-#define RR_SPIN_NSMAX 4096
+#define RR_SPIN_NSMAX 1024
 #endif
 #define RR_FULL_MASK 0xffffffffu
 

@@ -28,6 +28,26 @@ void rr_count_launch(int64_t k);
 
 namespace {
 
+// RR_TRACE builds (tools/trace_chain.py; never the shipped library): lane 0 stamps {globaltimer, clock64} of six events per
+// (block, 16-row group) into P.prof = [block][group][event][2]
+#ifdef RR_TRACE
+#define RR_NEV 6
+__device__ __forceinline__ void trace_ev(const rr_route_params &P, int lane, int b, int g, int ev) {
+    if (lane == 0 && P.prof) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+        unsigned long long *q = P.prof + (((size_t)b * ((size_t)P.n_tiles * P.gpt) + (size_t)g) * RR_NEV + ev) * 2;
+        q[0] = t;
+        q[1] = (unsigned long long)clock64();
+    }
+}
+#define TR(b, g, ev) trace_ev(P, lane, b, g, ev)
+#define TR_AFTER(x, b, g, ev) do { asm volatile("" ::"d"(x) : "memory"); trace_ev(P, lane, b, g, ev); } while (0)
+#else
+#define TR(b, g, ev) do { } while (0)
+#define TR_AFTER(x, b, g, ev) do { } while (0)
+#endif
+
 // row 0 of working reach u's series in tile jj (reach-major tiles, tile_pitch doubles per reach)
 __device__ __forceinline__ const double *tile_of(const double *base, const rr_route_params &P, int jj, int64_t u) {
     return base + (((size_t)jj * P.n_blocks + (size_t)(u >> 5)) * RR_BLOCK + (size_t)(u & 31)) * (size_t)P.tile_pitch;
@@ -93,7 +113,6 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
     bool has[NA];
     double old[NA];
     d4 nxt[NA], fut[NA];
-    bool full = !c.prog;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         has[k] = k < c.deg;
@@ -125,24 +144,11 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
     d4 lcur = lat_group(0), lnxt = lat_group(4);
     double *st = stage + lane;                     // [row & 15][lane]
     for (int s = 0; s < TT; s += 4) {
-        // Upstream blocks still running (narrow levels): their series is consumed one published 16-row group at a time
-        // and WITHOUT look-ahead into the next group -- waiting at row s for group (s+8)/16 made every level lag its
-        // upstream by a whole extra group (measured on the 3000-reach stem of C2: ~6.5 us per level instead of ~2.5).
-        if (NS > 0 && !full && (s & 15) == 0 && s > 0) {
-            wait_groups(c, gbase + (s >> 4) + 1, gbase + P.gpt, full);
-#pragma unroll
-            for (int k = 0; k < NS; ++k)
-                if (has[k]) {
-                    nxt[k] = ld_sector(up[k] + s);
-                    if (s + 4 < TT) fut[k] = ld_sector(up[k] + s + 4);
-                }
-        }
-        const bool ahead = full || ((s + 8) >> 4) == (s >> 4);   // rows s+8.. lie in a published group
         d4 far[NA];
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             far[k] = d4{0, 0, 0, 0};
-            if (has[k] && s + 8 < TT && ahead) far[k] = ld_sector(up[k] + s + 8);
+            if (has[k] && s + 8 < TT) far[k] = ld_sector(up[k] + s + 8);
         }
         const d4 lfar = lat_group(s + 8);
         double r0, r1, r2, r3;
@@ -177,12 +183,14 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
             r3 = r;
         }
         const int rr = s & 15;
+        if (rr == 0) TR_AFTER(r0, c.b, gbase + (s >> 4), 2);
         st[(rr + 0) * RR_BLOCK] = r0;
         st[(rr + 1) * RR_BLOCK] = r1;
         st[(rr + 2) * RR_BLOCK] = r2;
         st[(rr + 3) * RR_BLOCK] = r3;
         q = (s + 3 < TT) ? r3 : ((s + 2 < TT) ? r2 : ((s + 1 < TT) ? r1 : r0));
         if (rr == 12 || s + 4 >= TT) {
+            TR_AFTER(r3, c.b, gbase + (s >> 4), 3);
             // one whole line (or the tail of the tile) of this reach's series; rows past TT inside the last sector are
             // never read (consumers and stage_out stop at TT)
             if (c.valid) {
@@ -191,16 +199,275 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
                 for (int v = 0; v < 16; v += 4)
                     if (v <= rr) st_sector(o + v, st[(v + 0) * RR_BLOCK], st[(v + 1) * RR_BLOCK], st[(v + 2) * RR_BLOCK], st[(v + 3) * RR_BLOCK]);
             }
-            if (c.narrow && s + 4 < TT) {
-                jitter_delay(P.jitter, c.b, j, 1 + (s >> 4));
-                __syncwarp();
-                if (lane == 0) st_release(c.done + c.b, gbase + (s >> 4) + 1);
-            }
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) { old[k] = nxt[k].d; nxt[k] = fut[k]; fut[k] = far[k]; }
         lcur = lnxt;
         lnxt = lfar;
+    }
+    if (c.valid) P.q_state[c.m][c.i] = q;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// Narrow levels (fewer than RR_NARROW_BLOCKS blocks: the launch is bound by the latency of the dependency chain, not by
+// bandwidth).  The results ARE the message: before the launch the discharge tiles of narrow blocks are filled with a
+// signalling-NaN pattern no arithmetic result can have (fill_sentinel_kernel); a producer writes its series with
+// st.relaxed.gpu, whole 128-byte lines every 16 entries, and never fences inside a tile; a consumer loads the 16 entries of
+// a group with ld.relaxed.gpu (L1 bypassed) and repeats the load until none of them is the pattern (every 8-byte entry
+// is written once and is single-copy atomic).  One L2 round trip per level instead of fence + flag store + flag poll +
+// data load (trace of the 189-level chain of C1, tools/trace_chain.py: 4.6 us per level, of which 0.8 us fence, 1.3 us flag
+// hand-over, 0.8 + 1.8 us two exposed data round trips).  done[block] is still released once per tile: own next tile,
+// consumers on wide levels, and the safety net below.
+// -----------------------------------------------------------------------------------------------------------------
+#define RR_SENTINEL_BITS 0xFFF4A5A5DEADBEEFull   // sign 1, exponent all ones, quiet bit 0: a signalling NaN
+__device__ __forceinline__ bool is_set(double v) { return (unsigned long long)__double_as_longlong(v) != RR_SENTINEL_BITS; }
+__device__ __forceinline__ bool is_set(const d4 &v) { return is_set(v.a) & is_set(v.b) & is_set(v.c) & is_set(v.d); }
+__device__ __forceinline__ d4 ld_sector_strong(const double *p) {
+    d4 v;
+    asm volatile("ld.relaxed.gpu.global.L2::128B.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_strong(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// (two 128-bit stores: ptxas 12.9 narrowed st.relaxed.gpu.global.v4.f64 to a 64-bit STG.E.64.STRONG.GPU in the
+// in-degree-4 instantiations -- cuobjdump showed one double of each sector stored)
+__device__ __forceinline__ void st_sector_strong(double *p, double a, double b, double c, double d) {
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p + 2), "d"(c), "d"(d) : "memory");
+}
+
+// (not inlined: its register allocation -- 64 registers of upstream entries for two upstream reaches -- stays out of the
+// bandwidth path's, which keeps 0 spills)
+//
+// Per 16-entry group: (1) one optimistic fetch of the whole group of every upstream reach; when an entry is still the
+// pattern the warp polls the group's LAST entry only (one sector per lane and upstream reach instead of four: polling
+// the whole group from ~1500 waiting warps saturated L2 and slowed the producers they were waiting for), backing off,
+// and then fetches what is missing; (2) the group's own lateral inflows were brought into the warp's 4 KB of shared memory
+// by cp.async while the warp waited (K == 1), so the 16 dependent steps run from registers and shared memory; (3) the
+// results overwrite the lateral entries in place and leave as four 256-bit strong stores per reach.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// entry e (0..15) of lane l in the warp's buffer: pairs of entries are 16-byte units, [pair][lane] (conflict-free)
+__device__ __forceinline__ int buf_pair(int pair, int lane) { return (pair * RR_BLOCK + lane) * 2; }
+
+template <int MODE, int NS, bool SUB>
+__device__ __noinline__ void narrow_item(const rr_route_params &P, const dctx &c, double *stage) {
+    constexpr bool HAS_LAT = (MODE == RR_MODE_RAPID);
+    constexpr bool LAT_SMEM = HAS_LAT && !SUB;          // lateral group staged through shared memory by cp.async
+    constexpr int NA = NS > 0 ? NS : 1;
+    const double c1 = c.c1, c2 = c.c2, c3 = c.c3, c4 = c.c4;
+    const int TT = c.TT, j = c.j, lane = c.lane;
+    const int32_t gbase = j * P.gpt;
+    (void)gbase;
+    double q = c.q;
+    const double *up[NA];
+    bool has[NA], poll[NA];
+    double old[NA];
+    d4 U[NA][4];
+    const double *lat = c.lat0;
+    // this lane's 16-byte units of the buffer: pair p at stage + buf_pair(p, lane)
+    auto stage_lateral = [&](int s0) {
+        if (!LAT_SMEM) return;
+        if (c.valid) {
+            const uint32_t dst = smem_u32(stage + buf_pair(0, lane));
+#pragma unroll
+            for (int pr = 0; pr < 8; ++pr)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)pr * (RR_BLOCK * 16)), "l"(lat + s0 + 2 * pr) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage_lateral(0);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        has[k] = k < c.deg;
+        poll[k] = false;
+        up[k] = P.out[c.m];
+        old[k] = 0.0;
+        if (has[k]) {
+            const int32_t u = c.up_u[k], ub = u >> 5;
+            // upstream blocks outside the protocol (wide levels, blocks routed by the staging kernel) are complete: the
+            // kernel waited for their tile flags
+            poll[k] = ub >= P.poll_lo && (P.meta[ub].int_mask & RR_META_NARROW) != 0;
+            up[k] = tile_of(P.out[c.m], P, j, u);
+            // value before the tile's first entry: the start-of-call state, or the last entry of the previous tile
+            const double *po = j == 0 ? P.q_init + ((size_t)c.m * P.q_init_stride + u) : tile_of(P.out[c.m], P, j - 1, u) + (P.tile_rows * P.K - 1);
+            old[k] = (j > 0 && poll[k]) ? ld_strong(po) : *po;
+        }
+    }
+    // The series the warp watches while it waits: one reach of the DEEPEST upstream block of the whole warp (the last one
+    // to deliver, as a rule).  All lanes poll that one word -- one L2 request per warp and round -- and only when it is set
+    // fetch and validate their own upstream entries.  (Every lane polling its own upstream reaches cost 64 requests per
+    // warp and round; with ~1500 warps waiting along the chain that was ~5 TB/s of L2 traffic and every round trip in the
+    // kernel took 1-1.4 us instead of the 0.5 us a store -> load hand-over takes on an idle B200, tools/micro/pingpong.cu.)
+    const double *hint = nullptr;
+    if (NS > 0) {
+        int best = -1;
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+            if (poll[k]) {
+                const int lv = P.meta[c.up_u[k] >> 5].level;
+                if (lv > best) { best = lv; hint = up[k]; }
+            }
+        const int wmax = __reduce_max_sync(RR_FULL_MASK, best);
+        const unsigned who = __ballot_sync(RR_FULL_MASK, best == wmax && best >= 0);
+        const int src = who ? __ffs(who) - 1 : 0;
+        hint = reinterpret_cast<const double *>(__shfl_sync(RR_FULL_MASK, (unsigned long long)hint, src));
+        if (!who) hint = nullptr;
+    }
+    // (the previous tile's last entry was read by the warp that ran this block's previous tile before it released the
+    // block's flag, which this warp acquired: it is set -- the loop only guards the argument)
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+        while (j > 0 && poll[k] && !is_set(old[k])) old[k] = ld_strong(tile_of(P.out[c.m], P, j - 1, c.up_u[k]) + (P.tile_rows * P.K - 1));
+    auto lat_group = [&](int s0) -> d4 {                 // SUB only: substeps s0..s0+3 take the lateral value of row (s0 + u) / K
+        if (!(HAS_LAT && SUB && c.valid) || s0 >= TT) return d4{0, 0, 0, 0};
+        const int K = P.K, r0 = s0 / K, o0 = s0 - r0 * K;
+        d4 v;
+        v.a = __ldg(lat + r0);
+        v.b = __ldg(lat + r0 + (o0 + 1) / K);
+        v.c = __ldg(lat + r0 + (o0 + 2) / K);
+        v.d = __ldg(lat + r0 + (o0 + 3) / K);
+        return v;
+    };
+    d4 lcur = lat_group(0), lnxt = lat_group(4);
+    const int32_t full_want = (j + 1) * P.gpt;
+    for (int s0 = 0; s0 < TT; s0 += 16) {
+        const int nv = min(4, (TT - s0 + 3) >> 2);       // 32-byte sectors of this group that hold entries of the tile
+        TR(c.b, gbase + (s0 >> 4), 5);
+        if (NS > 0) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    U[k][v] = d4{0, 0, 0, 0};
+                    if (has[k] && v < nv) {
+                        U[k][v] = poll[k] ? ld_sector_strong(up[k] + s0 + 4 * v) : ld_sector(up[k] + s0 + 4 * v);
+                        if (poll[k]) ok &= is_set(U[k][v]);
+                    }
+                }
+            if (!__all_sync(RR_FULL_MASK, ok)) {
+                const int last = min(s0 + 15, TT - 1);
+                // a warp at the head of a tile may be far ahead of the wave: it backs off further than one inside a tile
+                const unsigned cap = s0 == 0 ? 1024u : 128u;
+                unsigned ns = (unsigned)P.spin_ns, spins = 0;
+                bool accept = false;
+                for (;;) {
+                    // phase 1: the watched word (uniform address: one request per warp)
+                    if (hint) {
+                        while (!is_set(ld_strong(hint + last))) {
+                            if ((++spins & 255u) == 0) {
+                                // safety net: an upstream block that has released this tile has written every entry of
+                                // it -- whatever the entries look like
+                                bool fin = true;
+#pragma unroll
+                                for (int k = 0; k < NS; ++k)
+                                    if (poll[k]) fin &= ld_acquire(c.done + (c.up_u[k] >> 5)) >= full_want;
+                                if (__all_sync(RR_FULL_MASK, fin)) { accept = true; break; }
+                            }
+                            if (ns) {            // (spin_ns == 0: poll without sleeping)
+                                __nanosleep(ns);
+                                if (ns < cap) ns *= 2u;
+                            }
+                        }
+                    }
+                    // phase 2: this lane's own upstream entries (normally all there: one more round trip)
+                    ok = true;
+#pragma unroll
+                    for (int k = 0; k < NS; ++k)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            if (poll[k] && v < nv && (accept || !is_set(U[k][v]))) {
+                                U[k][v] = ld_sector_strong(up[k] + s0 + 4 * v);
+                                ok &= accept || is_set(U[k][v]);
+                            }
+                    if (__all_sync(RR_FULL_MASK, ok)) break;
+                    // another upstream block is later than the watched one: keep going, gently
+                    if ((++spins & 255u) == 0) {
+                        bool fin = true;
+#pragma unroll
+                        for (int k = 0; k < NS; ++k)
+                            if (poll[k]) fin &= ld_acquire(c.done + (c.up_u[k] >> 5)) >= full_want;
+                        if (__all_sync(RR_FULL_MASK, fin)) accept = true;
+                    }
+                    if (P.spin_ns) __nanosleep(64);
+                }
+#ifdef RR_TRACE
+                if (lane == 0 && P.prof) P.prof[(((size_t)c.b * ((size_t)P.n_tiles * P.gpt) + (size_t)(gbase + (s0 >> 4))) * RR_NEV + 0) * 2 + 1] = spins;
+#endif
+            }
+        }
+        TR(c.b, gbase + (s0 >> 4), 1);
+        if (LAT_SMEM) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int s = s0 + 4 * v;
+            if (v < nv) {
+                double2 *bp0 = reinterpret_cast<double2 *>(stage + buf_pair(2 * v, lane));
+                double2 *bp1 = reinterpret_cast<double2 *>(stage + buf_pair(2 * v + 1, lane));
+                d4 lfar = d4{0, 0, 0, 0};
+                if (LAT_SMEM) {
+                    const double2 x = *bp0, y = *bp1;
+                    lcur = d4{x.x, x.y, y.x, y.y};
+                    if (!c.valid) lcur = d4{0, 0, 0, 0};
+                } else {
+                    lfar = lat_group(s + 8);
+                }
+                double r = c3 * q;                                       // _numba_kernels.py:27-28 / :68-69
+                if (HAS_LAT) r = fma(c4, lcur.a, r);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) r = fma(c2, old[k], r);     // :29-33 / :70-74, ascending upstream
+#pragma unroll
+                for (int k = 0; k < NS; ++k) r = fma(c1, U[k][v].a, r);  // :36-39 / :75-78 (lhs_off = -c1)
+                const double r0 = r;
+                if (v == 0) TR_AFTER(r0, c.b, gbase + (s0 >> 4), 2);
+                r = c3 * r0;
+                if (HAS_LAT) r = fma(c4, lcur.b, r);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) r = fma(c2, U[k][v].a, r);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) r = fma(c1, U[k][v].b, r);
+                const double r1 = r;
+                r = c3 * r1;
+                if (HAS_LAT) r = fma(c4, lcur.c, r);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) r = fma(c2, U[k][v].b, r);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) r = fma(c1, U[k][v].c, r);
+                const double r2 = r;
+                r = c3 * r2;
+                if (HAS_LAT) r = fma(c4, lcur.d, r);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) r = fma(c2, U[k][v].c, r);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) r = fma(c1, U[k][v].d, r);
+                const double r3 = r;
+                *bp0 = make_double2(r0, r1);                             // in place of the lateral entries just used
+                *bp1 = make_double2(r2, r3);
+                q = (s + 3 < TT) ? r3 : ((s + 2 < TT) ? r2 : ((s + 1 < TT) ? r1 : r0));
+#pragma unroll
+                for (int k = 0; k < NS; ++k) old[k] = U[k][v].d;
+                if (!LAT_SMEM) { lcur = lnxt; lnxt = lfar; }
+            }
+        }
+        jitter_delay(P.jitter, c.b, j, 1 + (s0 >> 4));
+        TR_AFTER(q, c.b, gbase + (s0 >> 4), 3);
+        if (c.valid) {
+            // one whole line (or the tail of the tile) of this reach's series; entries past TT inside the last sector are
+            // never used (consumers and stage_out stop at TT)
+            double *o = c.out0 + s0;
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+                if (v < nv) {
+                    const double2 x = *reinterpret_cast<const double2 *>(stage + buf_pair(2 * v, lane));
+                    const double2 y = *reinterpret_cast<const double2 *>(stage + buf_pair(2 * v + 1, lane));
+                    st_sector_strong(o + 4 * v, x.x, x.y, y.x, y.y);
+                }
+        }
+        if (s0 + 16 < TT) stage_lateral(s0 + 16);      // lands while the warp waits for the next group's upstream entries
+        TR(c.b, gbase + (s0 >> 4), 4);
     }
     if (c.valid) P.q_state[c.m][c.i] = q;
 }
@@ -432,20 +699,42 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
         //      upstream blocks) their first group published ----
         const int32_t full_want = (j + 1) * P.gpt;
         jitter_delay(P.jitter, b, j, 100);
+        TR(b, j * P.gpt, 0);
         if (lane == 0 && j > 0) wait_ge(c.done + b, j * P.gpt);
+        TR(b, j * P.gpt, 5);
         c.prog = false;
-        if (c.narrow && dep_hi > dep_lo) {
-            bool full = false;
-            wait_groups(c, j * P.gpt + 1, full_want, full);
-            c.prog = !full;
+        if (c.narrow) {
+            // narrow level: upstream blocks of narrow levels hand their series over entry by entry (narrow_item); only
+            // upstream blocks outside that protocol must have finished the tile
+            for (int e = dep_lo + lane; e < dep_hi; e += 32) {
+                const int32_t db = __ldg(P.dep_idx + e);
+                if (!(db >= P.poll_lo && (P.meta[db].int_mask & RR_META_NARROW) != 0)) wait_ge(c.done + db, full_want);
+            }
         } else {
             if (c.dep_blk >= 0) wait_ge(c.done + c.dep_blk, full_want);
             for (int e = dep_lo + 32 + lane; e < dep_hi; e += 32) wait_ge(c.done + __ldg(P.dep_idx + e), full_want);
         }
         __syncwarp();
+        TR(b, j * P.gpt, 1);
         c.q = 0.0;
         if (valid) c.q = (j == 0) ? P.q_init[(size_t)m * P.q_init_stride + i] : P.q_state[m][i];
-        if (MAXNS <= 2) {
+        if (c.narrow) {
+            if (MAXNS <= 2) {
+                switch (M.max_deg) {
+                    case 0: narrow_item<MODE, 0, SUB>(P, c, stage); break;
+                    case 1: narrow_item<MODE, 1, SUB>(P, c, stage); break;
+                    default: narrow_item<MODE, 2, SUB>(P, c, stage); break;
+                }
+            } else {
+                switch (M.max_deg) {
+                    case 0: narrow_item<MODE, 0, SUB>(P, c, stage); break;
+                    case 1: narrow_item<MODE, 1, SUB>(P, c, stage); break;
+                    case 2: narrow_item<MODE, 2, SUB>(P, c, stage); break;
+                    case 3: narrow_item<MODE, 3, SUB>(P, c, stage); break;
+                    default: narrow_item<MODE, RR_MAX_FAST_DEG, SUB>(P, c, stage); break;
+                }
+            }
+        } else if (MAXNS <= 2) {
             switch (M.max_deg) {
                 case 0: direct_item<MODE, 0, SUB>(P, c, stage); break;
                 case 1: direct_item<MODE, 1, SUB>(P, c, stage); break;
@@ -463,6 +752,7 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
         jitter_delay(P.jitter, b, j, 200);
         __syncwarp();
         if (lane == 0) st_release(c.done + b, full_want);
+        TR(b, full_want - 1, 4);
         __syncwarp();
     }
 }
@@ -665,6 +955,27 @@ __global__ void __launch_bounds__(256) unit_state_kernel(const double *__restric
             return 200;                                                                            \
         }                                                                                          \
     } while (0)
+
+// Discharge tiles of the narrow blocks of one member <- the "not written yet" pattern (narrow_item).  One CTA per
+// (narrow block, tile): the block's tile is 32 x pitch contiguous doubles.
+__global__ void __launch_bounds__(256) fill_sentinel_kernel(double *__restrict__ out_w, const int32_t *__restrict__ narrow_blocks,
+                                                            int32_t first_block, int64_t n_blocks, int64_t pitch) {
+    const int32_t b = __ldg(narrow_blocks + blockIdx.x);
+    if (b < first_block) return;
+    double *p = out_w + (((size_t)blockIdx.y * n_blocks + (size_t)b) * RR_BLOCK) * (size_t)pitch;
+    const double sv = __longlong_as_double((long long)RR_SENTINEL_BITS);
+    for (int64_t e = (int64_t)threadIdx.x * 4; e < RR_BLOCK * pitch; e += 256 * 4) st_sector(p + e, sv, sv, sv, sv);
+}
+
+int rr_fill_sentinel(double *out_w, const int32_t *narrow_blocks, int64_t n_narrow, int64_t first_block, int64_t n_blocks,
+                     int64_t n_tiles, int64_t pitch, cudaStream_t stream) {
+    if (n_narrow <= 0) return 0;
+    dim3 grid((unsigned)n_narrow, (unsigned)n_tiles);
+    fill_sentinel_kernel<<<grid, 256, 0, stream>>>(out_w, narrow_blocks, (int32_t)first_block, n_blocks, pitch);
+    CKD(cudaGetLastError());
+    rr_count_launch(1);
+    return 0;
+}
 
 // tile_rows must be a multiple of 16 (the caller checks).  hw_cut = 0 copies every segment's lateral inflows.
 int rr_stage_in(const void *src, int src_f32, int64_t lds, double *lat_w, double *out_w, const int32_t *inv, int64_t n, int64_t T,

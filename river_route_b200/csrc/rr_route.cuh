@@ -41,6 +41,7 @@ struct rr_route_params {
     int32_t lat_pitch;    // direct pipeline: doubles per reach of a lateral tile (== tile_pitch unless substeps > 1)
     int32_t jitter;       // stress tests (RR_JITTER): pseudo-random delays around the flag operations, 0 = none
     int32_t spin_ns;      // progressive waits: first back-off in ns (0: poll without sleeping)
+    int32_t poll_lo;      // direct pipeline: narrow blocks >= poll_lo hand their series over through the sentinel protocol
     int32_t smem_region;  // > 0: TMA-staged kernel; bytes of shared memory per warp (tile + row slots + mbarrier)
     int32_t row_slots;    // upstream exchange rows a warp's region can hold
     int32_t first_call;   // UNIT: 1 when q_state holds the start-of-file state (q_ch = q_full = state)

@@ -413,7 +413,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     int64_t grid_cap = 0;
     if (const char *env = getenv("RR_GRID_CTAS")) grid_cap = std::max(1, atoi(env));
     if (const char *env = getenv("RR_JITTER")) P.jitter = std::max(0, atoi(env));
-    P.spin_ns = 32;
+    P.spin_ns = 0;    // narrow levels watch one word per warp: polling without sleeping costs L2 one request per warp and round trip
     if (const char *env = getenv("RR_PROG_SPIN_NS")) P.spin_ns = std::max(0, atoi(env));
     if (pipeline) {
         // narrow levels exchange results through the "not written yet" pattern (rr_direct.cu, narrow_item): arm their tiles

@@ -248,6 +248,7 @@ __device__ __forceinline__ void st_sector_strong(double *p, double a, double b, 
 // and then fetches what is missing; (2) the group's own lateral inflows were brought into the warp's 4 KB of shared memory
 // by cp.async while the warp waited (K == 1), so the 16 dependent steps run from registers and shared memory; (3) the
 // results overwrite the lateral entries in place and leave as four 256-bit strong stores per reach.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // entry e (0..15) of lane l in the warp's buffer: pairs of entries are 16-byte units, [pair][lane] (conflict-free)
 __device__ __forceinline__ int buf_pair(int pair, int lane) { return (pair * RR_BLOCK + lane) * 2; }
@@ -296,6 +297,18 @@ __device__ __noinline__ void narrow_item(const rr_route_params &P, const dctx &c
             old[k] = (j > 0 && poll[k]) ? ld_strong(po) : *po;
         }
     }
+    // Most upstream reaches of a deep block are headwaters and shallow tributaries whose entries were written hundreds of
+    // microseconds ago and have left L2 (ncu on C1: 52 % L2 read hit rate, 0.7 GB of DRAM reads beyond the lateral inflows):
+    // bring every line two groups ahead of its use into L2, so that the fetch on the critical path is an L2 hit (and the
+    // page walk of its 2 MB page is over) whichever upstream block it comes from.  A line that is not written yet comes
+    // in armed; its producer then writes into L2.
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+        if (has[k]) {
+            prefetch_l2(up[k]);
+            if (16 < TT) prefetch_l2(up[k] + 16);
+        }
+    if (LAT_SMEM && c.valid && 16 < TT) prefetch_l2(lat + 16);
     // The series the warp watches while it waits: one reach of the DEEPEST upstream block of the whole warp (the last one
     // to deliver, as a rule).  All lanes poll that one word -- one L2 request per warp and round -- and only when it is set
     // fetch and validate their own upstream entries.  (Every lane polling its own upstream reaches cost 64 requests per
@@ -336,6 +349,19 @@ __device__ __noinline__ void narrow_item(const rr_route_params &P, const dctx &c
     for (int s0 = 0; s0 < TT; s0 += 16) {
         const int nv = min(4, (TT - s0 + 3) >> 2);       // 32-byte sectors of this group that hold entries of the tile
         TR(c.b, gbase + (s0 >> 4), 5);
+        if (s0 + 32 < TT) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (has[k]) prefetch_l2(up[k] + s0 + 32);
+            if (LAT_SMEM && c.valid) prefetch_l2(lat + s0 + 32);
+        } else if (j + 1 < P.n_tiles) {
+            // the first lines of the block's next tile (another work item, possibly another warp)
+            const int g2 = (s0 + 32 - TT) >> 4;          // 0 or 1
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (has[k]) prefetch_l2(tile_of(P.out[c.m], P, j + 1, c.up_u[k]) + 16 * g2);
+            if (LAT_SMEM && c.valid) prefetch_l2(lat_tile_of(P.lateral[c.m], P, j + 1, c.i) + 16 * g2);
+        }
         if (NS > 0) {
             bool ok = true;
 #pragma unroll
@@ -345,11 +371,18 @@ __device__ __noinline__ void narrow_item(const rr_route_params &P, const dctx &c
                     U[k][v] = d4{0, 0, 0, 0};
                     if (has[k] && v < nv) {
                         U[k][v] = poll[k] ? ld_sector_strong(up[k] + s0 + 4 * v) : ld_sector(up[k] + s0 + 4 * v);
-                        if (poll[k]) ok &= is_set(U[k][v]);
                     }
                 }
+            // the watched word travels with the optimistic fetch: when the group is not complete yet the warp already knows
+            // whether the deepest upstream block has delivered, one round trip earlier
+            const int last = min(s0 + 15, TT - 1);
+            double hv = hint ? ld_strong(hint + last) : 0.0;
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    if (poll[k] && v < nv) ok &= is_set(U[k][v]);
             if (!__all_sync(RR_FULL_MASK, ok)) {
-                const int last = min(s0 + 15, TT - 1);
                 // a warp at the head of a tile may be far ahead of the wave: it backs off further than one inside a tile
                 const unsigned cap = s0 == 0 ? 1024u : 128u;
                 unsigned ns = (unsigned)P.spin_ns, spins = 0;
@@ -357,7 +390,7 @@ __device__ __noinline__ void narrow_item(const rr_route_params &P, const dctx &c
                 for (;;) {
                     // phase 1: the watched word (uniform address: one request per warp)
                     if (hint) {
-                        while (!is_set(ld_strong(hint + last))) {
+                        for (; !is_set(hv); hv = ld_strong(hint + last)) {
                             if ((++spins & 255u) == 0) {
                                 // safety net: an upstream block that has released this tile has written every entry of
                                 // it -- whatever the entries look like

@@ -46,6 +46,44 @@ __global__ void fetch(const double *buf, size_t n_groups_per_warp, int iters, un
     if (lane == 0) out[warp] = t1 - t0;
     if (acc == -1.0) *sink = acc;
 }
+// the same fetch with every lane's lines on a different 2 MB page, pages drawn from the whole buffer (5 GB): what the level-sorted
+// tile layout does to a block whose upstream reaches sit in a dozen blocks of other levels
+template <int KIND, int NUP>
+__global__ void fetch_scattered(const double *buf, size_t n_pages, int span_pages, int iters, unsigned long long *out, double *sink) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    double acc = 0;
+    unsigned long long t0 = clock64();
+    size_t h = (size_t)warp * 7919 + 13;
+    for (int it = 0; it < iters; ++it) {
+        d4 v[NUP][4];
+#pragma unroll
+        for (int k = 0; k < NUP; ++k) {
+            // page: a pseudo-random one out of span_pages pages following a per-iteration base; line inside the page varies too
+            const size_t page = (h + (size_t)((lane * 2 + k) % span_pages) * 97) % n_pages;
+            const double *g = buf + page * (size_t)(1 << 18) + (size_t)((it * 131 + lane * 17 + k * 5) & 4095) * 64;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) v[k][s] = ld<KIND>(g + 4 * s);
+        }
+#pragma unroll
+        for (int k = 0; k < NUP; ++k)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) acc += v[k][s].a + v[k][s].d;
+        h = h * 6364136223846793005ull + 1442695040888963407ull + (acc == -1.0 ? 1 : 0);
+        h >>= 11;
+    }
+    unsigned long long t1 = clock64();
+    if (lane == 0) out[warp] = t1 - t0;
+    if (acc == -1.0) *sink = acc;
+}
+template <int KIND, int NUP>
+static void run_scattered(const double *buf, size_t n_pages, int span, int blocks, int threads, unsigned long long *out, double *sink, double ghz) {
+    const int iters = 2000;
+    fetch_scattered<KIND, NUP><<<blocks, threads>>>(buf, n_pages, span, iters, out, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    double s = 0; int nw = blocks * threads / 32;
+    for (int w = 0; w < nw; ++w) s += (double)out[w];
+    printf("{\"load\": \"relaxed.gpu v4, scattered\", \"pages_per_fetch\": %d, \"warps\": %d, \"ns_per_group_fetch\": %.1f, \"err\": \"%s\"}\n", span, nw, s / nw / iters / ghz, cudaGetErrorString(e));
+}
 template <int KIND, int NUP>
 static void run(const double *buf, const char *name, int blocks, int threads, unsigned long long *out, double *sink, double ghz) {
     const int iters = 2000;
@@ -77,6 +115,9 @@ int main() {
         run<4, 2>(buf, "volatile v4", blocks, threads, out, sink, ghz);
         run<0, 1>(buf, "weak", blocks, threads, out, sink, ghz);
         run<2, 1>(buf, "relaxed.gpu v4", blocks, threads, out, sink, ghz);
+        for (int span : {1, 2, 4, 8, 16, 64}) run_scattered<2, 2>(buf, n * 8 / (2u << 20), span, blocks, threads, out, sink, ghz);
     }
+    // a few hundred warps, like the waiting chain of a small network
+    for (int span : {1, 4, 16, 64}) run_scattered<2, 2>(buf, n * 8 / (2u << 20), span, sms, 64, out, sink, ghz);
     return 0;
 }

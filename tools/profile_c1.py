@@ -24,8 +24,11 @@ a = network_arrays(down, k, x, dt_runoff // K, dt_runoff)
 d_lat = torch.from_numpy(synth.lateral_volumes(T, n, 0)).to(dev)
 d_out = torch.empty((T, n), dtype=torch.float64, device=dev)
 stream = torch.cuda.current_stream().cuda_stream
-for staging, tile in (('auto', 0), ('auto', 128), ('auto', 256), ('registers-tiled', 0)):
-    plan = rr.Plan(down, staging=staging, time_tile=tile)
+VARIANTS = [('auto', 0, 0), ('auto', 128, 0), ('auto', 256, 0), ('auto', 0, 6), ('auto', 0, 8), ('registers-tiled', 0, 0)]
+if K > 1:
+    VARIANTS += [('direct-nohw', 0, 0), ('direct-nohw', 128, 0), ('direct-nohw', 256, 0), ('direct-nohw', 0, 8)]
+for staging, tile, stride in VARIANTS:
+    plan = rr.Plan(down, staging=staging, time_tile=tile, tile_stride=stride)
     plan.set_coefficients(a['c1'], a['c2'], a['c3'], a['c4_dt'])
     res = []
     for rep in range(3):
@@ -37,6 +40,6 @@ for staging, tile in (('auto', 0), ('auto', 128), ('auto', 256), ('registers-til
         t = timing_read(reset=True)
         res.append({c: round(v['ms'], 3) for c, v in t.items()})
     timing_enable(False)
-    print(json.dumps({'config': 'C1', 'substeps': K, 'staging': staging, 'time_tile': tile, 'tile_rows': plan.tile_rows(T, K),
+    print(json.dumps({'config': 'C1', 'substeps': K, 'staging': staging, 'time_tile': tile, 'tile_stride': stride, 'tile_rows': plan.tile_rows(T, K),
                       'ms_by_class_last_rep': res[-1], 'checksum': float(d_out.sum().item())}), flush=True)
     plan.close()

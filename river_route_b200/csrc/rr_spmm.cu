@@ -36,20 +36,26 @@ constexpr int TB = 8;   // time steps per register block == one 32-byte sector o
 // [time block][cell][TB steps]: the TB time steps of one cell are one 32-byte sector (float32), and all the
 // sectors of one time block are contiguous -- n_points x 32 bytes, small enough to stay in L2 while one
 // launch gathers from it (each cell is read by several catchments, in no particular order).
+// One thread per cell and time block: TB coalesced 4- or 8-byte reads down the rows of the time-major array (a warp reads
+// 128 / 256 contiguous bytes per row), one whole 32-byte sector (float32; two for float64) written per thread, 1 KB
+// contiguous per warp.  (Round 1 went through a 32 x 33 shared-memory tile: 3.0 TB/s under ncu; no tile is needed when the
+// block of TB steps is what a thread owns.)
 template <typename XT>
 __global__ void __launch_bounds__(256) transpose_kernel(const XT *__restrict__ x, int64_t ldx, XT *__restrict__ xt,
                                                         int64_t Tp, int64_t T, int64_t n_points) {
-    __shared__ XT tile[32][33];
-    const int64_t c0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
-    for (int r = ty; r < 32; r += 8) {
-        const int64_t t = t0 + r, c = c0 + tx;
-        tile[r][tx] = (t < T && c < n_points) ? x[t * ldx + c] : XT(0);
-    }
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int64_t c = c0 + r, t = t0 + tx;
-        if (c < n_points && t < Tp) xt[((t / TB) * n_points + c) * TB + (t % TB)] = tile[tx][r];
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t0 = (int64_t)blockIdx.y * TB;
+    if (c >= n_points || t0 >= Tp) return;
+    XT v[TB];
+#pragma unroll
+    for (int u = 0; u < TB; ++u) v[u] = (t0 + u < T) ? __ldg(x + (t0 + u) * ldx + c) : XT(0);
+    XT *dst = xt + ((t0 / TB) * n_points + c) * TB;
+    if (sizeof(XT) == 4) {
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"((float)v[0]), "f"((float)v[1]), "f"((float)v[2]),
+                     "f"((float)v[3]), "f"((float)v[4]), "f"((float)v[5]), "f"((float)v[6]), "f"((float)v[7]) : "memory");
+    } else {
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"((double)v[0]), "d"((double)v[1]), "d"((double)v[2]), "d"((double)v[3]) : "memory");
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "d"((double)v[4]), "d"((double)v[5]), "d"((double)v[6]), "d"((double)v[7]) : "memory");
     }
 }
 
@@ -148,7 +154,7 @@ int run_weights(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *in
     }
     CK(cudaMallocAsync((void **)&xt, sizeof(XT) * (size_t)n_points * Tp, stream));
     if (cumulative) CK(cudaMallocAsync((void **)&carry, sizeof(double) * (size_t)n_rivers, stream));
-    dim3 tg((unsigned)((n_points + 31) / 32), (unsigned)((Tp + 31) / 32));
+    dim3 tg((unsigned)((n_points + 255) / 256), (unsigned)(Tp / TB));
     transpose_kernel<XT><<<tg, 256, 0, stream>>>(x, ldx, xt, Tp, T, n_points);
     CK(cudaGetLastError());
     const int threads = 128;
@@ -156,13 +162,26 @@ int run_weights(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *in
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // ONE launch, grid.y = time blocks of TB steps: CTAs are dispatched x-fastest, so the launch sweeps all rivers of one time
+    // block before the next and the cells of the block in flight (n_points x 32 B, 33 MB at C3) stay in L2 while they are
+    // gathered -- each cell is read by several catchments in no particular order.  (A thread that swept all time steps
+    // itself cost 13x the algorithmic DRAM reads; one launch per 32 MB of cells, the round-1 scheme, cost 93 launches of 64 us
+    // with their ramps and tails at C3.)  Cumulative inputs: a block recomputes the aggregate of the step before it.
+    // RR_WEIGHTS_L2_MB selects the launch-per-slab scheme for A/B measurements.
+    int64_t launches = 0;
+    if (getenv("RR_WEIGHTS_L2_MB") == nullptr && (Tp / TB) <= 65535) {
+        dim3 grid(gx, (unsigned)(Tp / TB));
+        weights_kernel<XT><<<grid, threads, 0, stream>>>(n_rivers, n_points, 0, T, TB, indptr, indices, w, xt, y, ldy, cumulative,
+                                                         force_positive, area, t_skip, carry);
+        CK(cudaGetLastError());
+        ++launches;
+    } else {
     // time steps per launch: the gathered cells of those steps (n_points x steps x element) should stay in L2
     // (126 MB on B200, shared with the output stream): about 32 MB; everything at once when it is that small
     int64_t l2_mb = 32;
     if (const char *env = getenv("RR_WEIGHTS_L2_MB")) l2_mb = std::max(1, atoi(env));
     int64_t span = std::max<int64_t>(TB, (((l2_mb << 20) / (int64_t)(n_points * sizeof(XT))) / TB) * TB);
     span = std::min<int64_t>(span, Tp);
-    int64_t launches = 0;
     for (int64_t t_begin = 0; t_begin < T; t_begin += span) {
         const int64_t t_end = std::min<int64_t>(T, t_begin + span), len = t_end - t_begin;
         // few rivers: split the span over grid.y so that the machine is filled
@@ -174,6 +193,7 @@ int run_weights(int64_t n_rivers, int64_t n_points, int64_t T, const int32_t *in
                                                          ldy, cumulative, force_positive, area, t_skip, carry);
         CK(cudaGetLastError());
         ++launches;
+    }
     }
     CK(cudaFreeAsync(xt, stream));
     if (carry) CK(cudaFreeAsync(carry, stream));

@@ -17,7 +17,7 @@
 cudaError_t rr_launch_wavefront(int mode, const rr_route_params &P, int grid, int block, cudaStream_t stream);
 int rr_wavefront_occupancy(int mode, int block);
 // rr_direct.cu: the pipeline of level-sorted plans with one substep per row
-cudaError_t rr_launch_direct(int mode, int max_deg, const rr_route_params &P, int grid, cudaStream_t stream);
+cudaError_t rr_launch_direct(int mode, int max_deg, const rr_route_params &P, int grid, cudaStream_t stream, int sentinel);
 int rr_direct_occupancy(int mode, int max_deg);
 int rr_stage_in(const void *src, int src_f32, int64_t lds, double *lat_w, double *out_w, const int32_t *inv, int64_t n, int64_t T,
                 int64_t tile_rows, int64_t n_blocks, int64_t hw_cut, const double *c3, const double *c4,
@@ -413,12 +413,21 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
     int64_t grid_cap = 0;
     if (const char *env = getenv("RR_GRID_CTAS")) grid_cap = std::max(1, atoi(env));
     if (const char *env = getenv("RR_JITTER")) P.jitter = std::max(0, atoi(env));
-    P.spin_ns = 0;    // narrow levels watch one word per warp: polling without sleeping costs L2 one request per warp and round trip
+    P.spin_ns = 32;
     if (const char *env = getenv("RR_PROG_SPIN_NS")) P.spin_ns = std::max(0, atoi(env));
     if (pipeline) {
-        // narrow levels exchange results through the "not written yet" pattern (rr_direct.cu, narrow_item): arm their tiles
+        // Small networks (at most RR_SENTINEL_MAX_BLOCKS blocks: every level is narrow and the launch is bound by the latency of
+        // the dependency chain) hand results over through the "not written yet" pattern (rr_direct.cu, narrow_item): arm the
+        // tiles.  Larger networks keep per-group progress flags on their narrow levels: there the pattern costs bandwidth --
+        // the fill, and DRAM reads of armed lines by consumers that arrive early -- which the bandwidth-bound part of the
+        // launch pays for (C4: wavefront 6.45 ms with flags, 6.85 - 7.6 ms with the pattern on levels below 256 - 4096
+        // blocks; the N = 8 shard shape 6.7 vs 7.2 - 8.3 ms), while C1 (1674 blocks) runs in 3.55 ms instead of 4.2 ms.
+        int sentinel = (mode != RR_MODE_UNIT && p->n_blocks <= RR_SENTINEL_MAX_BLOCKS) ? 1 : 0;
+        if (const char *env = getenv("RR_SENTINEL")) sentinel = (mode != RR_MODE_UNIT && atoi(env) != 0) ? 1 : 0;   // tests, measurements
         P.poll_lo = (int32_t)first_block;
-        if (mode != RR_MODE_UNIT)
+        P.spin_ns = sentinel ? 0 : 32;   // the pattern is watched through one word per warp: no need to sleep between polls
+        if (const char *env = getenv("RR_PROG_SPIN_NS")) P.spin_ns = std::max(0, atoi(env));
+        if (sentinel)
             for (int m = 0; m < n_members; ++m) {
                 rr_timer tm(3, stream);
                 if ((rc = rr_fill_sentinel(out[m], d->narrow_blocks, d->n_narrow, first_block, p->n_blocks, n_tiles, P.tile_pitch, stream))) return rc;
@@ -434,7 +443,7 @@ static int launch_route(rr_plan *p, int mode, int n_members, const double *q_ini
         if (grid_cap) g = std::min<int64_t>(g, grid_cap);
         {
             rr_timer tm(0, stream);
-            CK(rr_launch_direct(mode, p->max_deg, P, (int)g, stream));
+            CK(rr_launch_direct(mode, p->max_deg, P, (int)g, stream, sentinel));
         }
         rr_count_launch(1);
         return 0;

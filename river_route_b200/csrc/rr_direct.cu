@@ -113,6 +113,7 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
     bool has[NA];
     double old[NA];
     d4 nxt[NA], fut[NA];
+    bool full = !c.prog;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         has[k] = k < c.deg;
@@ -144,11 +145,24 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
     d4 lcur = lat_group(0), lnxt = lat_group(4);
     double *st = stage + lane;                     // [row & 15][lane]
     for (int s = 0; s < TT; s += 4) {
+        // Upstream blocks still running (narrow levels): their series is consumed one published 16-row group at a time
+        // and WITHOUT look-ahead into the next group -- waiting at row s for group (s+8)/16 made every level lag its
+        // upstream by a whole extra group (measured on the 3000-reach stem of C2: ~6.5 us per level instead of ~2.5).
+        if (NS > 0 && !full && (s & 15) == 0 && s > 0) {
+            wait_groups(c, gbase + (s >> 4) + 1, gbase + P.gpt, full);
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (has[k]) {
+                    nxt[k] = ld_sector(up[k] + s);
+                    if (s + 4 < TT) fut[k] = ld_sector(up[k] + s + 4);
+                }
+        }
+        const bool ahead = full || ((s + 8) >> 4) == (s >> 4);   // rows s+8.. lie in a published group
         d4 far[NA];
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             far[k] = d4{0, 0, 0, 0};
-            if (has[k] && s + 8 < TT) far[k] = ld_sector(up[k] + s + 8);
+            if (has[k] && s + 8 < TT && ahead) far[k] = ld_sector(up[k] + s + 8);
         }
         const d4 lfar = lat_group(s + 8);
         double r0, r1, r2, r3;
@@ -183,14 +197,12 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
             r3 = r;
         }
         const int rr = s & 15;
-        if (rr == 0) TR_AFTER(r0, c.b, gbase + (s >> 4), 2);
         st[(rr + 0) * RR_BLOCK] = r0;
         st[(rr + 1) * RR_BLOCK] = r1;
         st[(rr + 2) * RR_BLOCK] = r2;
         st[(rr + 3) * RR_BLOCK] = r3;
         q = (s + 3 < TT) ? r3 : ((s + 2 < TT) ? r2 : ((s + 1 < TT) ? r1 : r0));
         if (rr == 12 || s + 4 >= TT) {
-            TR_AFTER(r3, c.b, gbase + (s >> 4), 3);
             // one whole line (or the tail of the tile) of this reach's series; rows past TT inside the last sector are
             // never read (consumers and stage_out stop at TT)
             if (c.valid) {
@@ -198,6 +210,11 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
 #pragma unroll
                 for (int v = 0; v < 16; v += 4)
                     if (v <= rr) st_sector(o + v, st[(v + 0) * RR_BLOCK], st[(v + 1) * RR_BLOCK], st[(v + 2) * RR_BLOCK], st[(v + 3) * RR_BLOCK]);
+            }
+            if (c.narrow && s + 4 < TT) {
+                jitter_delay(P.jitter, c.b, j, 1 + (s >> 4));
+                __syncwarp();
+                if (lane == 0) st_release(c.done + c.b, gbase + (s >> 4) + 1);
             }
         }
 #pragma unroll
@@ -207,6 +224,7 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
     }
     if (c.valid) P.q_state[c.m][c.i] = q;
 }
+
 
 // -----------------------------------------------------------------------------------------------------------------
 // Narrow levels (fewer than RR_NARROW_BLOCKS blocks: the launch is bound by the latency of the dependency chain, not by
@@ -700,7 +718,7 @@ namespace {
 // MAXNS: largest in-degree of the network, 2 or RR_MAX_FAST_DEG.  Networks with confluences of three or four rivers get
 // a kernel of their own so that the register-hungry instantiations do not set the register allocation -- and the
 // spills -- of the common case (at most two upstream reaches).
-template <int MODE, int MAXNS, bool SUB>
+template <int MODE, int MAXNS, bool SUB, bool SENT>
 __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant__ rr_route_params P) {
     __shared__ double stage_all[8][16 * RR_BLOCK];
     constexpr bool HAS_LAT = (MODE == RR_MODE_RAPID);
@@ -732,26 +750,18 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
         //      upstream blocks) their first group published ----
         const int32_t full_want = (j + 1) * P.gpt;
         jitter_delay(P.jitter, b, j, 100);
-        TR(b, j * P.gpt, 0);
         if (lane == 0 && j > 0) wait_ge(c.done + b, j * P.gpt);
-        TR(b, j * P.gpt, 5);
         c.prog = false;
-        if (c.narrow) {
-            // narrow level: upstream blocks of narrow levels hand their series over entry by entry (narrow_item); only
-            // upstream blocks outside that protocol must have finished the tile
+        if (SENT) {
+            // small networks (every level narrow): upstream blocks hand their series over entry by entry (narrow_item); only
+            // upstream blocks outside that protocol (routed by the staging kernel) must have finished the tile
             for (int e = dep_lo + lane; e < dep_hi; e += 32) {
                 const int32_t db = __ldg(P.dep_idx + e);
                 if (!(db >= P.poll_lo && (P.meta[db].int_mask & RR_META_NARROW) != 0)) wait_ge(c.done + db, full_want);
             }
-        } else {
-            if (c.dep_blk >= 0) wait_ge(c.done + c.dep_blk, full_want);
-            for (int e = dep_lo + 32 + lane; e < dep_hi; e += 32) wait_ge(c.done + __ldg(P.dep_idx + e), full_want);
-        }
-        __syncwarp();
-        TR(b, j * P.gpt, 1);
-        c.q = 0.0;
-        if (valid) c.q = (j == 0) ? P.q_init[(size_t)m * P.q_init_stride + i] : P.q_state[m][i];
-        if (c.narrow) {
+            __syncwarp();
+            c.q = 0.0;
+            if (valid) c.q = (j == 0) ? P.q_init[(size_t)m * P.q_init_stride + i] : P.q_state[m][i];
             if (MAXNS <= 2) {
                 switch (M.max_deg) {
                     case 0: narrow_item<MODE, 0, SUB>(P, c, stage); break;
@@ -767,7 +777,19 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
                     default: narrow_item<MODE, RR_MAX_FAST_DEG, SUB>(P, c, stage); break;
                 }
             }
-        } else if (MAXNS <= 2) {
+        } else {
+        if (c.narrow && dep_hi > dep_lo) {
+            bool full = false;
+            wait_groups(c, j * P.gpt + 1, full_want, full);
+            c.prog = !full;
+        } else {
+            if (c.dep_blk >= 0) wait_ge(c.done + c.dep_blk, full_want);
+            for (int e = dep_lo + 32 + lane; e < dep_hi; e += 32) wait_ge(c.done + __ldg(P.dep_idx + e), full_want);
+        }
+        __syncwarp();
+        c.q = 0.0;
+        if (valid) c.q = (j == 0) ? P.q_init[(size_t)m * P.q_init_stride + i] : P.q_state[m][i];
+        if (MAXNS <= 2) {
             switch (M.max_deg) {
                 case 0: direct_item<MODE, 0, SUB>(P, c, stage); break;
                 case 1: direct_item<MODE, 1, SUB>(P, c, stage); break;
@@ -782,22 +804,25 @@ __global__ void __launch_bounds__(256, 2) rr_direct_kernel(const __grid_constant
                 default: direct_item<MODE, RR_MAX_FAST_DEG, SUB>(P, c, stage); break;
             }
         }
+        }
         jitter_delay(P.jitter, b, j, 200);
         __syncwarp();
         if (lane == 0) st_release(c.done + b, full_want);
-        TR(b, full_want - 1, 4);
         __syncwarp();
     }
 }
 
-cudaError_t rr_launch_direct(int mode, int max_deg, const rr_route_params &P, int grid, cudaStream_t stream) {
+// sentinel != 0: the hand-over of small networks (narrow_item); the kernels without it are the round's bandwidth kernels
+// unchanged, instruction for instruction
+cudaError_t rr_launch_direct(int mode, int max_deg, const rr_route_params &P, int grid, cudaStream_t stream, int sentinel) {
     const bool wide = max_deg > 2, sub = P.K > 1;
-#define RR_LAUNCH(M) do {                                                                               \
-        if (wide) { if (sub) rr_direct_kernel<M, RR_MAX_FAST_DEG, true><<<grid, 256, 0, stream>>>(P);  \
-                    else rr_direct_kernel<M, RR_MAX_FAST_DEG, false><<<grid, 256, 0, stream>>>(P); }   \
-        else { if (sub) rr_direct_kernel<M, 2, true><<<grid, 256, 0, stream>>>(P);                     \
-               else rr_direct_kernel<M, 2, false><<<grid, 256, 0, stream>>>(P); }                      \
+#define RR_LAUNCH2(M, S) do {                                                                               \
+        if (wide) { if (sub) rr_direct_kernel<M, RR_MAX_FAST_DEG, true, S><<<grid, 256, 0, stream>>>(P);  \
+                    else rr_direct_kernel<M, RR_MAX_FAST_DEG, false, S><<<grid, 256, 0, stream>>>(P); }   \
+        else { if (sub) rr_direct_kernel<M, 2, true, S><<<grid, 256, 0, stream>>>(P);                     \
+               else rr_direct_kernel<M, 2, false, S><<<grid, 256, 0, stream>>>(P); }                      \
     } while (0)
+#define RR_LAUNCH(M) do { if (sentinel) RR_LAUNCH2(M, true); else RR_LAUNCH2(M, false); } while (0)
     if (mode == RR_MODE_UNIT) {
         if (sub) return cudaErrorInvalidValue;
         if (wide) rr_direct_unit_kernel<RR_MAX_FAST_DEG><<<grid, 256, 0, stream>>>(P);
@@ -806,6 +831,7 @@ cudaError_t rr_launch_direct(int mode, int max_deg, const rr_route_params &P, in
     else if (mode == RR_MODE_RAPID) RR_LAUNCH(RR_MODE_RAPID);
     else return cudaErrorInvalidValue;
 #undef RR_LAUNCH
+#undef RR_LAUNCH2
     return cudaGetLastError();
 }
 
@@ -817,11 +843,11 @@ int rr_direct_occupancy(int mode, int max_deg) {
         e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_unit_kernel<RR_MAX_FAST_DEG>, 256, 0)
                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_unit_kernel<2>, 256, 0);
     else if (mode == RR_MODE_MUSKINGUM)   // (the substep instantiations have the same launch bounds; 2 CTAs per SM either way)
-        e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM, RR_MAX_FAST_DEG, true>, 256, 0)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM, 2, true>, 256, 0);
+        e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM, RR_MAX_FAST_DEG, true, true>, 256, 0)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_MUSKINGUM, 2, true, true>, 256, 0);
     else
-        e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID, RR_MAX_FAST_DEG, true>, 256, 0)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID, 2, true>, 256, 0);
+        e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID, RR_MAX_FAST_DEG, true, true>, 256, 0)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_direct_kernel<RR_MODE_RAPID, 2, true, true>, 256, 0);
     return e == cudaSuccess ? nb : -1;
 }
 

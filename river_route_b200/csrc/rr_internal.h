@@ -13,6 +13,7 @@
 #define RR_META_NARROW 0x20  // rr_blk_meta::int_mask: fewer than RR_NARROW_BLOCKS blocks in the block's level -- launches are
                              // dependency-latency bound there: such blocks publish and consume progress per 16-row group
 #define RR_NARROW_BLOCKS 4096
+#define RR_SENTINEL_MAX_BLOCKS 4096   // networks of at most this many blocks use the sentinel hand-over (rr_direct.cu, narrow_item)
 #define RR_FLAG_ROWS 16      // direct kernel: rows per progress unit of done[] (one 128-byte line of a reach's series)
 
 void rr_set_error(const std::string &msg);

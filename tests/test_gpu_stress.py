@@ -4,7 +4,9 @@ kernels synchronise through per-block progress counters (st.release / ld.acquire
 make ANY number of persistent CTAs and ANY relative timing safe.  Here the same calls are repeated with the grid capped
 at 1 .. max CTAs (RR_GRID_CTAS), tile lengths 16 .. 64, and pseudo-random delays of up to 16 us injected around the flag
 operations (RR_JITTER), on a deep narrow network (every level consumes its upstream group by group) and a wide one.
-Every run must reproduce the first run bit for bit, and that run must match the CPU oracle.
+Every run must reproduce the first run bit for bit, and that run must match the CPU oracle.  Round 2: small networks hand
+results over without flags (tiles armed with a signalling-NaN pattern, rr_direct.cu narrow_item); both protocols run here
+on both networks and must give the same bits.
 """
 import os
 
@@ -27,6 +29,7 @@ def _cuda():
     yield
     os.environ.pop('RR_GRID_CTAS', None)
     os.environ.pop('RR_JITTER', None)
+    os.environ.pop('RR_SENTINEL', None)
 
 
 NETS = {
@@ -50,6 +53,14 @@ def test_any_grid_size_and_timing_gives_the_same_bits(net, mode, K, staging):
     first = None
     runs = 0
     for tile in (0, 16, 32, 64):
+        # both hand-over protocols of the narrow levels on both networks: per-group progress flags (RR_SENTINEL=0, the
+        # default of networks above 4096 blocks) and the armed-tile pattern (RR_SENTINEL=1, the default below); same bits
+        if tile == 16:
+            os.environ['RR_SENTINEL'] = '0'
+        elif tile == 32:
+            os.environ['RR_SENTINEL'] = '1'
+        else:
+            os.environ.pop('RR_SENTINEL', None)
         plan = rr.Plan(down, renumber='always', staging=staging, time_tile=tile)
         plan.set_coefficients(a['c1'], a['c2'], a['c3'], a['c4_dt'] if mode == 'rapid' else None)
         for ctas in (0, 1, 2, 3, 17, 148, 295):

@@ -9,7 +9,8 @@
 //              reaches' series straight from their discharge tiles ("direct exchange").  done[block] counts finished
 //              16-row groups (one 128-byte line per reach): blocks of narrow levels publish every group and consume
 //              their upstream blocks group by group, so that deep, narrow parts of the network pipeline at a few
-//              microseconds per level instead of one whole work item per level.
+//              microseconds per level instead of one whole work item per level.  Networks of at most 4096 blocks hand
+//              results over without flags inside a tile (narrow_item below).
 //   stage_out  working discharge tiles -> caller's layout with the reference's clamp (:44-46 / :82-84), optionally cast
 //              to float32 (TransformMuskingum.py:146) and restricted to an output subset.
 //
@@ -227,8 +228,10 @@ __device__ __forceinline__ void direct_item(const rr_route_params &P, const dctx
 
 
 // -----------------------------------------------------------------------------------------------------------------
-// Narrow levels (fewer than RR_NARROW_BLOCKS blocks: the launch is bound by the latency of the dependency chain, not by
-// bandwidth).  The results ARE the message: before the launch the discharge tiles of narrow blocks are filled with a
+// Small networks (at most RR_SENTINEL_MAX_BLOCKS blocks, rr_api.cu: every level is narrow and the whole launch is bound by
+// the latency of the dependency chain, not by bandwidth; kernels instantiated with SENT = true).  Larger networks keep the
+// progress flags above: there the pattern costs DRAM bandwidth that the streaming part of the launch pays for
+// (profiles/r02_chain_latency.md).  The results ARE the message: before the launch the discharge tiles of narrow blocks are filled with a
 // signalling-NaN pattern no arithmetic result can have (fill_sentinel_kernel); a producer writes its series with
 // st.relaxed.gpu, whole 128-byte lines every 16 entries, and never fences inside a tile; a consumer loads the 16 entries of
 // a group with ld.relaxed.gpu (L1 bypassed) and repeats the load until none of them is the pattern (every 8-byte entry

@@ -26,8 +26,10 @@ class Deadlock(AssertionError):
     pass
 
 
-def run_model(plan, has_lat, c1, c2, c3, c4, q0, lat, T, rows_tile, n_warps, seed, drain_prob):
-    """Returns (out [T, n] clamped like stage_out, final state [n], stats)."""
+def run_model(plan, has_lat, c1, c2, c3, c4, q0, lat, T, rows_tile, n_warps, seed, drain_prob, protocol='pattern'):
+    """Returns (out [T, n] clamped like stage_out, final state [n], stats).  protocol='flags': the hand-over of large
+    networks' narrow levels (direct_item): a block releases done[block] after every 16-row group and a consumer reads a
+    group of its upstream reaches only after it has acquired the counters of all its upstream blocks."""
     a = plan.arrays()
     perm, inv = a['perm'], a['inv']
     assert perm is not None, 'the direct pipeline works on level-sorted (renumbered) plans'
@@ -110,12 +112,19 @@ def run_model(plan, has_lat, c1, c2, c3, c4, q0, lat, T, rows_tile, n_warps, see
                 sl = slice(e0, e0 + 4)
                 U[:, k, 4 * v:4 * v + 4] = np.where(has[:, k, None], val[j, safe_idx[:, k], sl], 0.0)
                 ok[:, k, v] = ~has[:, k] | ~armed[j, safe_idx[:, k], sl].any(axis=1)
+            if protocol == 'flags' and up_blocks.size:
+                want = j * gpt + s0 // GROUP + 1
+                while (done[up_blocks] < want).any():             # acquire poll of every upstream block's counter
+                    stats['polls'] += 1
+                    yield 'spin'
             for k in range(D):
                 for v in range(nv):
                     fetch(k, v)                                   # optimistic: one "load instruction" per scheduler step
                     yield 'step'
             last = min(s0 + GROUP - 1, TT - 1)
             hv = hint < 0 or not armed[j, hint, last]
+            if protocol == 'flags':
+                assert ok[:, :, :nv].all(), 'flag acquired but an entry of the group is not visible'
             if not ok[:, :, :nv].all():
                 spins, accept = 0, False
                 while True:
@@ -164,9 +173,11 @@ def run_model(plan, has_lat, c1, c2, c3, c4, q0, lat, T, rows_tile, n_warps, see
                     for ln in range(B):
                         bufs[w].append(('o', j, int(lanes[ln]), s0 + e, float(res[ln, e])))
                 yield 'step'
+            if protocol == 'flags' and s0 + GROUP < TT:
+                yield ('release', b, j * gpt + s0 // GROUP + 1, False)   # publish the group: fence, then the counter
         for ln in range(B):
             bufs[w].append(('q', int(lanes[ln]), float(q[ln])))
-        yield ('release', b, full_want)
+        yield ('release', b, full_want, True)
 
     # ---- scheduler ----
     n_items = blocks.shape[0]
@@ -207,7 +218,8 @@ def run_model(plan, has_lat, c1, c2, c3, c4, q0, lat, T, rows_tile, n_warps, see
                 apply(bufs[w][idx])
             bufs[w].clear()
             done[tok[1]] = tok[2]                                 # ... before the flag
-            warps[w] = None
+            if tok[3]:
+                warps[w] = None
     for t in range(T):
         assert not armed[t // rows_tile, :, t % rows_tile].any(), 'an entry of the call was never written'
     # stage_out: working tiles -> caller's rows with the reference's clamp
